@@ -1,0 +1,773 @@
+// dwgsim_gpu.cu -- C ABI of libdwgsim_b200.so (include/dwgsim_gpu.h): host packer, derived tables,
+// batch pipeline (compute stream + copy stream + pinned ring) around the kernels in kernels.cuh.
+// There is no CPU fallback: every entry point that needs a device fails with DWGSIM_GPU_ENODEV / ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/dwgsim_gpu.h"
+#include "kernels.cuh"
+
+using namespace dwg;
+
+namespace {
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+inline double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- symbol table (reference: nst_nt4_table, src/dwgsim.c:56-73); '-' (code 5 there) is folded into N ----
+struct Nt4 {
+    uint8_t t[256];
+    Nt4()
+    {
+        memset(t, 4, sizeof t);
+        t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+        t['-'] = 5;
+    }
+};
+const Nt4 kNt4;
+
+struct HostContig {
+    std::string name;
+    int32_t contig_i = 0, len = 0;
+    int64_t n_pairs = 0;
+    std::vector<uint32_t> ref2, nmask;
+    std::vector<Event> ev[2];
+    std::vector<uint32_t> blk[2];
+    std::vector<uint8_t> pool[2];
+};
+
+struct DeviceTables {
+    uint32_t *isize_cdf = nullptr, *qdelta_cdf = nullptr, *err_thr[2] = {nullptr, nullptr};
+    uint8_t *qbase[2] = {nullptr, nullptr};
+    int8_t *flow_order = nullptr;
+    char *prefix = nullptr;
+};
+
+struct Workspace {
+    int64_t cap_pairs = 0;
+    PairRec *recs = nullptr;
+    uint8_t *seqs = nullptr;
+    unsigned long long *serial = nullptr;
+    uint32_t *lens = nullptr;                 // [3][cap]
+    unsigned long long *blk_rand = nullptr;   // [nblk]
+    unsigned long long *blk_len = nullptr;    // [3][nblk]
+    unsigned long long *totals = nullptr;     // [8]: 0 n_random, 1..3 stream bytes
+    unsigned long long *status = nullptr;     // [2]: error bits, failed attempts
+    char *out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    uint64_t out_cap[3] = {0, 0, 0};
+    unsigned long long *h_totals = nullptr;   // pinned [8 + 2]
+};
+
+}  // namespace
+
+struct dwgsim_gpu {
+    dwgsim_gpu_params_t p{};
+    std::string prefix_s;                     // "pfx_" or ""
+    std::vector<int8_t> flow_order;
+    int device = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string last_error;
+    // derived tables (host + device)
+    std::vector<uint32_t> isize_cdf, qdelta_cdf, err_thr[2];
+    std::vector<uint8_t> qbase[2];
+    uint64_t thr_genomic = 0, thr_hap0 = 0;
+    int32_t isize_lo = 0, qdelta_lo = 0;
+    uint32_t flow_thr[2] = {0, 0};
+    DeviceTables dt;
+    SimParams sp{};
+    // queue / genome
+    std::vector<HostContig> queue;
+    uint8_t *blob = nullptr;
+    uint64_t blob_bytes = 0;
+    bool blob_owned = true;
+    int64_t blob_pairs = 0;
+    int max_name_len = 4;
+    double ms_pack = 0;
+    int64_t h2d_bytes = 0;
+    // global counters carried across runs (ctr / rand_ii of src/dwgsim.c:423)
+    int64_t gidx_origin = 0, rand_serial = 0;
+    // batching
+    int64_t batch_pairs = 1 << 18;
+    int ring = 3;
+    int shard_rank = 0, shard_world = 1;
+    Workspace ws;
+    char *pinned[8][3] = {};
+    uint64_t pinned_cap[3] = {0, 0, 0};
+    int pinned_slots = 0;
+    // last resident batch
+    int last_slot = 0;
+    uint64_t last_bytes[3] = {0, 0, 0};
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            (h)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                       \
+            return _e == cudaErrorMemoryAllocation ? DWGSIM_GPU_ENOMEM : DWGSIM_GPU_ECUDA;              \
+        }                                                                                              \
+    } while (0)
+
+// ---- derived tables: every probability becomes a 32-bit threshold (DESIGN.md "RNG addressing") ----------
+double phi(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+uint32_t thr32(double p)
+{
+    if (!(p > 0.0)) return 0;
+    double v = ceil(p * 4294967296.0);
+    return v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
+}
+uint64_t thr64(double p)
+{
+    if (!(p > 0.0)) return 0;
+    double v = ceil(p * 4294967296.0);
+    return v >= 4294967296.0 ? 4294967296ull : (uint64_t)v;
+}
+
+void derive_tables(dwgsim_gpu *h)
+{
+    const dwgsim_gpu_params_t &p = h->p;
+    // genomic iff rand_read < U (src/dwgsim.c:649)
+    double v = floor(p.rand_read * 4294967296.0);
+    h->thr_genomic = v >= 4294967296.0 ? 4294967297ull : (uint64_t)v + 1ull;
+    h->thr_hap0 = thr64(p.mut_freq);                                        // src/dwgsim.c:716
+    // insert size d = (int)(N(0,1)*std + dist + 0.5) (src/dwgsim.c:657-659): inverse-CDF table
+    h->isize_cdf.clear();
+    if (p.std_dev > 0.0) {
+        int span = (int)ceil(8.0 * p.std_dev) + 1;
+        h->isize_lo = p.dist - span;
+        for (int j = 0; j < 2 * span; ++j)
+            h->isize_cdf.push_back(thr32(phi(((double)(h->isize_lo + j) + 0.5 - (double)p.dist) / p.std_dev)));
+    } else h->isize_lo = p.dist;
+    // quality noise (int)(N(0,1)*qstd + 0.5), truncation toward zero (src/dwgsim.c:911-913)
+    h->qdelta_cdf.clear();
+    h->qdelta_lo = 0;
+    if (p.quality_std > 0.0 && p.fixed_quality == 0) {
+        int span = (int)ceil(8.0 * p.quality_std) + 1;
+        if (span > 32768) span = 32768;
+        h->qdelta_lo = -span;
+        for (int j = 0; j < 2 * span; ++j) {
+            int k = h->qdelta_lo + j;
+            double x = k < 0 ? (double)k - 0.5 : (double)k + 0.5;
+            h->qdelta_cdf.push_back(thr32(phi(x / p.quality_std)));
+        }
+    }
+    for (int e = 0; e < 2; ++e) {
+        int n = p.length[e];
+        if (p.data_type == 2) n = 2 * n + 64;
+        h->err_thr[e].assign((size_t)n + 1, 0);
+        h->qbase[e].assign((size_t)n + 1, 0);
+        for (int j = 0; j < n; ++j) {
+            double pr = p.e_start[e] + p.e_by[e] * j;                       // src/dwgsim.c:237, :906-910
+            h->err_thr[e][j] = thr32(pr);
+            h->qbase[e][j] = pr > 0 ? (uint8_t)(int)(-10.0 * log(pr) / log(10.0) + 0.499) : 40;
+        }
+        h->flow_thr[e] = thr32(p.e_start[e]);
+    }
+}
+
+template <typename T>
+int upload(dwgsim_gpu *h, T **dst, const T *src, size_t n)
+{
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc((void **)dst, bytes));
+    if (n) CUDA_TRY(h, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return DWGSIM_GPU_OK;
+}
+
+int upload_tables(dwgsim_gpu *h)
+{
+    int rc;
+    if ((rc = upload(h, &h->dt.isize_cdf, h->isize_cdf.data(), h->isize_cdf.size()))) return rc;
+    if ((rc = upload(h, &h->dt.qdelta_cdf, h->qdelta_cdf.data(), h->qdelta_cdf.size()))) return rc;
+    for (int e = 0; e < 2; ++e) {
+        if ((rc = upload(h, &h->dt.err_thr[e], h->err_thr[e].data(), h->err_thr[e].size()))) return rc;
+        if ((rc = upload(h, &h->dt.qbase[e], h->qbase[e].data(), h->qbase[e].size()))) return rc;
+    }
+    if ((rc = upload(h, &h->dt.flow_order, h->flow_order.data(), h->flow_order.size()))) return rc;
+    if ((rc = upload(h, &h->dt.prefix, h->prefix_s.data(), h->prefix_s.size()))) return rc;
+    const dwgsim_gpu_params_t &p = h->p;
+    SimParams &s = h->sp;
+    memset(&s, 0, sizeof s);
+    for (int e = 0; e < 2; ++e) {
+        s.len[e] = p.length[e];
+        s.cap[e] = p.data_type == 2 ? 2 * p.length[e] + 64 : p.length[e];
+        s.err_thr[e] = h->dt.err_thr[e];
+        s.qbase[e] = h->dt.qbase[e];
+        s.flow_thr[e] = h->flow_thr[e];
+    }
+    s.is_inner = p.is_inner; s.max_n = p.max_n; s.data_type = p.data_type; s.strandedness = p.strandedness;
+    s.read_one_strand = p.read_one_strand; s.amplicons = p.amplicons;
+    s.seed = (uint32_t)p.seed;
+    s.thr_genomic = h->thr_genomic; s.thr_hap0 = h->thr_hap0;
+    s.isize_lo = h->isize_lo; s.isize_n = (int32_t)h->isize_cdf.size();
+    s.qdelta_lo = h->qdelta_lo; s.qdelta_n = (int32_t)h->qdelta_cdf.size();
+    s.fixed_quality = p.fixed_quality;
+    s.out_bwa = p.reads_output_type != 2; s.out_bfast = p.reads_output_type != 1;
+    s.prefix_len = (int32_t)h->prefix_s.size();
+    s.flow_order_len = p.flow_order_len;
+    s.seq_off1 = (uint32_t)align_up((uint64_t)(s.cap[0] + 1) / 2, 4);
+    s.seq_stride = (uint32_t)align_up((uint64_t)s.seq_off1 + (uint64_t)(s.cap[1] + 1) / 2, 16);
+    s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf;
+    s.flow_order = h->dt.flow_order; s.prefix = h->dt.prefix;
+    return DWGSIM_GPU_OK;
+}
+
+// ---- dense (seq_t + 2 x mutseq_t) -> packed sections ---------------------------------------------------
+// long insertion record of the reference: [tag 1|2|4][length][2-bit bases, first inserted base stored last]
+// (src/mut.c:200-246, :345-365)
+const uint8_t *long_ins_payload(const uint8_t *rec, uint32_t *n)
+{
+    if (rec[0] == 1) { *n = rec[1]; return rec + 2; }
+    if (rec[0] == 2) { uint16_t v; memcpy(&v, rec + 1, 2); *n = v; return rec + 3; }
+    uint32_t v; memcpy(&v, rec + 1, 4); *n = v; return rec + 5;
+}
+
+int pack_contig(dwgsim_gpu *h, HostContig &c, const uint8_t *seq, const uint64_t *hap[2], uint8_t *const *ins[2],
+                const int32_t ins_n[2])
+{
+    const int len = c.len;
+    c.ref2.assign(((size_t)len + 15) / 16 + 1, 0);
+    c.nmask.assign(((size_t)len + 31) / 32 + 1, 0);
+    const int nblk = (len >> kBlkShift) + 2;
+    for (int hh = 0; hh < 2; ++hh) { c.ev[hh].clear(); c.pool[hh].clear(); c.blk[hh].assign((size_t)nblk, 0); }
+    uint64_t pool_bases[2] = {0, 0};
+    for (int p = 0; p < len; ++p) {
+        const uint8_t raw = kNt4.t[seq[p]];
+        if (raw < 4) c.ref2[p >> 4] |= (uint32_t)raw << ((p & 15) << 1);
+        else c.nmask[p >> 5] |= 1u << (p & 31);
+        for (int hh = 0; hh < 2; ++hh) {
+            const uint64_t m = hap[hh][p];
+            if (m == (uint64_t)raw) continue;
+            Event e;
+            e.pos = (uint32_t)p;
+            uint32_t type = (uint32_t)(m >> 4) & 3u, base = (uint32_t)(m & 0xf);
+            if (base > 4) base = 4;
+            uint32_t n = 0;
+            e.payload = 0;
+            if (type == kEvInsert) {
+                n = (uint32_t)(m >> 59) & 0x1fu;
+                if (n) e.payload = (m >> 6) & ((1ull << 52) - 1);
+                else {
+                    const uint64_t idx = (m >> 6) & ((1ull << 52) - 1);
+                    if ((int64_t)idx >= ins_n[hh]) { h->last_error = "long insertion index out of range"; return DWGSIM_GPU_EINVAL; }
+                    const uint8_t *pl = long_ins_payload(ins[hh][idx], &n);
+                    if (n >= (1u << 27)) { h->last_error = "insertion longer than 2^27-1 bases"; return DWGSIM_GPU_EUNSUPPORTED; }
+                    auto src = [&](uint32_t j) { uint32_t at = n - 1 - j; return (uint32_t)(pl[at >> 2] >> ((at & 3) << 1)) & 3u; };
+                    if (n <= kInlineInsMax) {
+                        for (uint32_t j = 0; j < n; ++j) e.payload |= (uint64_t)src(j) << (2 * j);
+                    } else {
+                        e.payload = pool_bases[hh];
+                        c.pool[hh].resize((size_t)((pool_bases[hh] + n + 3) >> 2) + 1, 0);
+                        for (uint32_t j = 0; j < n; ++j) {
+                            uint64_t at = pool_bases[hh] + j;
+                            c.pool[hh][at >> 2] |= (uint8_t)(src(j) << ((at & 3) << 1));
+                        }
+                        pool_bases[hh] += n;
+                    }
+                }
+            }
+            e.meta = type | (base << 2) | (n << 5);
+            c.ev[hh].push_back(e);
+        }
+    }
+    for (int hh = 0; hh < 2; ++hh) {
+        size_t e = 0;
+        for (int b = 0; b < nblk; ++b) {
+            const uint64_t start = (uint64_t)b << kBlkShift;
+            while (e < c.ev[hh].size() && c.ev[hh][e].pos < start) ++e;
+            c.blk[hh][b] = (uint32_t)e;
+        }
+        if (c.pool[hh].empty()) c.pool[hh].assign(4, 0);
+    }
+    return DWGSIM_GPU_OK;
+}
+
+void free_blob(dwgsim_gpu *h)
+{
+    if (h->blob && h->blob_owned) cudaFree(h->blob);
+    h->blob = nullptr; h->blob_bytes = 0; h->blob_pairs = 0; h->blob_owned = true;
+}
+
+// lay the queued contigs out in one blob and upload it
+int finalize_genome(dwgsim_gpu *h)
+{
+    if (h->blob) return DWGSIM_GPU_OK;
+    if (h->queue.empty()) { h->last_error = "no contigs queued"; return DWGSIM_GPU_ESTATE; }
+    const size_t nc = h->queue.size();
+    uint64_t off = align_up(sizeof(BlobHeader), 256);
+    BlobHeader hd{};
+    hd.magic = kBlobMagic; hd.version = 1; hd.n_contigs = (uint32_t)nc;
+    hd.contigs_off = off;
+    off = align_up(off + nc * sizeof(ContigDesc), 256);
+    hd.names_off = off;
+    std::vector<ContigDesc> cds(nc);
+    std::string names;
+    int64_t pair_base = 0, total_len = 0;
+    for (size_t i = 0; i < nc; ++i) {
+        HostContig &c = h->queue[i];
+        ContigDesc &d = cds[i];
+        memset(&d, 0, sizeof d);
+        d.len = c.len; d.contig_i = c.contig_i; d.pair_base = pair_base; d.n_pairs = c.n_pairs;
+        d.name_off = (uint32_t)names.size(); d.name_len = (uint32_t)c.name.size();
+        names += c.name;
+        pair_base += c.n_pairs; total_len += c.len;
+    }
+    off = align_up(off + names.size() + 1, 256);
+    for (size_t i = 0; i < nc; ++i) {
+        HostContig &c = h->queue[i];
+        ContigDesc &d = cds[i];
+        d.ref2_off = off; off = align_up(off + c.ref2.size() * 4, 256);
+        d.nmask_off = off; off = align_up(off + c.nmask.size() * 4, 256);
+        for (int hh = 0; hh < 2; ++hh) {
+            d.n_ev[hh] = (uint32_t)c.ev[hh].size();
+            d.ev_off[hh] = off; off = align_up(off + std::max<size_t>(c.ev[hh].size(), 1) * sizeof(Event), 256);
+            d.blk_off[hh] = off; off = align_up(off + c.blk[hh].size() * 4, 256);
+            d.pool_off[hh] = off; off = align_up(off + c.pool[hh].size(), 256);
+        }
+    }
+    hd.n_bytes = off; hd.total_pairs = pair_base; hd.total_len = total_len;
+    CUDA_TRY(h, cudaMalloc((void **)&h->blob, off));
+    h->blob_owned = true; h->blob_bytes = off; h->blob_pairs = pair_base;
+    auto put = [&](uint64_t at, const void *src, size_t n) -> cudaError_t {
+        h->h2d_bytes += (int64_t)n;
+        return n ? cudaMemcpyAsync(h->blob + at, src, n, cudaMemcpyHostToDevice, h->s_compute) : cudaSuccess;
+    };
+    CUDA_TRY(h, put(0, &hd, sizeof hd));
+    CUDA_TRY(h, put(hd.contigs_off, cds.data(), nc * sizeof(ContigDesc)));
+    CUDA_TRY(h, put(hd.names_off, names.data(), names.size()));
+    for (size_t i = 0; i < nc; ++i) {
+        HostContig &c = h->queue[i];
+        ContigDesc &d = cds[i];
+        CUDA_TRY(h, put(d.ref2_off, c.ref2.data(), c.ref2.size() * 4));
+        CUDA_TRY(h, put(d.nmask_off, c.nmask.data(), c.nmask.size() * 4));
+        for (int hh = 0; hh < 2; ++hh) {
+            CUDA_TRY(h, put(d.ev_off[hh], c.ev[hh].data(), c.ev[hh].size() * sizeof(Event)));
+            CUDA_TRY(h, put(d.blk_off[hh], c.blk[hh].data(), c.blk[hh].size() * 4));
+            CUDA_TRY(h, put(d.pool_off[hh], c.pool[hh].data(), c.pool[hh].size()));
+        }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+    h->queue.clear();
+    h->queue.shrink_to_fit();
+    return DWGSIM_GPU_OK;
+}
+
+// upper bounds of the record sizes (src/dwgsim.c:923-978): name = '@' prefix contig 13 separators,
+// 2 x 10 digits, 4 flags, 6 counts of <= 5 digits, 16 hex digits
+void record_caps(const dwgsim_gpu *h, uint64_t cap[3])
+{
+    const uint64_t name = 1 + h->prefix_s.size() + (uint64_t)std::max(h->max_name_len, 4) + 13 + 20 + 4 + 30 + 16;
+    const SimParams &s = h->sp;
+    for (int e = 0; e < 2; ++e) cap[e] = s.out_bwa && s.len[e] > 0 ? name + 3 + 2ull * s.cap[e] + 4 : 0;
+    cap[2] = 0;
+    if (s.out_bfast)
+        for (int e = 0; e < 2; ++e) if (s.len[e] > 0) cap[2] += name + 1 + 2ull * s.cap[e] + 5;
+}
+
+void free_workspace(dwgsim_gpu *h)
+{
+    Workspace &w = h->ws;
+    cudaFree(w.recs); cudaFree(w.seqs); cudaFree(w.serial); cudaFree(w.lens);
+    cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status);
+    for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(w.out[s][k]);
+    if (w.h_totals) cudaFreeHost(w.h_totals);
+    w = Workspace();
+    for (int s = 0; s < h->pinned_slots; ++s) for (int k = 0; k < 3; ++k) if (h->pinned[s][k]) { cudaFreeHost(h->pinned[s][k]); h->pinned[s][k] = nullptr; }
+    h->pinned_slots = 0;
+}
+
+int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
+{
+    Workspace &w = h->ws;
+    if (w.cap_pairs < n) {
+        free_workspace(h);
+        const int64_t nblk = (n + kScanTile - 1) / kScanTile;
+        CUDA_TRY(h, cudaMalloc((void **)&w.recs, (size_t)n * sizeof(PairRec)));
+        CUDA_TRY(h, cudaMalloc((void **)&w.seqs, (size_t)n * h->sp.seq_stride));
+        CUDA_TRY(h, cudaMalloc((void **)&w.serial, (size_t)n * 8));
+        CUDA_TRY(h, cudaMalloc((void **)&w.lens, (size_t)n * 12));
+        CUDA_TRY(h, cudaMalloc((void **)&w.blk_rand, (size_t)nblk * 8));
+        CUDA_TRY(h, cudaMalloc((void **)&w.blk_len, (size_t)nblk * 24));
+        CUDA_TRY(h, cudaMalloc((void **)&w.totals, 64));
+        CUDA_TRY(h, cudaMalloc((void **)&w.status, 16));
+        CUDA_TRY(h, cudaMemset(w.status, 0, 16));
+        CUDA_TRY(h, cudaMallocHost((void **)&w.h_totals, 128));
+        uint64_t cap[3];
+        record_caps(h, cap);
+        for (int k = 0; k < 3; ++k) {
+            w.out_cap[k] = align_up(cap[k] * (uint64_t)n + 256, 256);
+            if (w.out_cap[k] >= (1ull << 32)) { h->last_error = "batch too large: a stream would exceed 4 GiB"; return DWGSIM_GPU_EINVAL; }
+            for (int s = 0; s < 2; ++s) CUDA_TRY(h, cudaMalloc((void **)&w.out[s][k], w.out_cap[k]));
+        }
+        w.cap_pairs = n;
+    }
+    if (want_pinned && h->pinned_slots == 0) {
+        for (int s = 0; s < h->ring; ++s)
+            for (int k = 0; k < 3; ++k) {
+                h->pinned_cap[k] = w.out_cap[k];
+                CUDA_TRY(h, cudaMallocHost((void **)&h->pinned[s][k], w.out_cap[k]));
+            }
+        h->pinned_slots = h->ring;
+    }
+    return DWGSIM_GPU_OK;
+}
+
+struct BatchResult {
+    uint64_t bytes[3];
+    int64_t n_random, n_failed;
+    uint64_t status;
+    float ms[3];
+    int launches;
+};
+
+// enqueue the kernels of one batch on the compute stream; results land in ws.h_totals after a sync
+int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slot, bool timed, int *launches)
+{
+    Workspace &w = h->ws;
+    const SimParams &sp = h->sp;
+    const int nblk = (n + kScanTile - 1) / kScanTile;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    const int grid = std::min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count * 8);
+    const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15;
+    const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1);
+    const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + ((std::max(sp.cap[0], sp.cap[1]) + 15) & ~15));
+    cudaStream_t st = h->s_compute;
+    CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 16, st));
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[0], st));
+    simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
+    layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
+    layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_rand, nblk, 1, w.totals);
+    layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, w.blk_rand,
+                                                     w.serial, w.lens, w.blk_len);
+    layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
+    layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
+    format_fastq_kernel<<<grid, kThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
+                                                        w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals + 8, w.status, 16, cudaMemcpyDeviceToHost, st));
+    *launches = 7;
+    return DWGSIM_GPU_OK;
+}
+
+int collect_batch(dwgsim_gpu *h, bool timed, BatchResult *r)
+{
+    Workspace &w = h->ws;
+    CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+    r->n_random = (int64_t)w.h_totals[0];
+    for (int k = 0; k < 3; ++k) r->bytes[k] = w.h_totals[1 + k];
+    r->status = w.h_totals[8];
+    r->n_failed = (int64_t)w.h_totals[9];
+    r->ms[0] = r->ms[1] = r->ms[2] = 0;
+    if (timed) for (int k = 0; k < 3; ++k) CUDA_TRY(h, cudaEventElapsedTime(&r->ms[k], h->ev_t[k], h->ev_t[k + 1]));
+    if (r->status & 1ull) {
+        h->last_error = "failed to generate a read after 10001 trials";
+        return DWGSIM_GPU_ETRIALS;
+    }
+    return DWGSIM_GPU_OK;
+}
+
+}  // namespace
+
+// ---- C ABI --------------------------------------------------------------------------------------------
+extern "C" {
+
+int dwgsim_gpu_abi_version(void) { return DWGSIM_GPU_ABI_VERSION; }
+
+const char *dwgsim_gpu_strerror(int code)
+{
+    switch (code) {
+        case DWGSIM_GPU_OK: return "ok";
+        case DWGSIM_GPU_EINVAL: return "invalid argument";
+        case DWGSIM_GPU_ENODEV: return "no CUDA device (the read-pair path has no CPU fallback)";
+        case DWGSIM_GPU_ECUDA: return "CUDA error";
+        case DWGSIM_GPU_ENOMEM: return "out of memory";
+        case DWGSIM_GPU_ETRIALS: return "failed to generate a read after 10001 trials";
+        case DWGSIM_GPU_ESINK: return "output sink failed";
+        case DWGSIM_GPU_EUNSUPPORTED: return "option not supported on the device path";
+        case DWGSIM_GPU_EOVERFLOW: return "Ion Torrent read grew past the device bound";
+        case DWGSIM_GPU_ESTATE: return "call order violated";
+        default: return "unknown error";
+    }
+}
+
+const char *dwgsim_gpu_last_error(const dwgsim_gpu_t *h) { return h ? h->last_error.c_str() : ""; }
+
+int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int device)
+{
+    if (!out || !p) return DWGSIM_GPU_EINVAL;
+    *out = nullptr;
+    // the ranges dwgsim_opt_parse enforces (src/dwgsim_opt.c:307-371)
+    if (p->length[0] < 1 || p->length[1] < 0 || p->dist < 0 || p->std_dev < 0) return DWGSIM_GPU_EINVAL;
+    if (p->data_type < 0 || p->data_type > 2 || p->strandedness < 0 || p->strandedness > 2) return DWGSIM_GPU_EINVAL;
+    if (p->read_one_strand < 0 || p->read_one_strand > 2 || p->max_n < 0) return DWGSIM_GPU_EINVAL;
+    if (p->rand_read < 0 || p->rand_read > 1 || p->mut_freq < 0 || p->mut_freq > 1) return DWGSIM_GPU_EINVAL;
+    if (p->reads_output_type < 0 || p->reads_output_type > 2 || p->quality_std < 0) return DWGSIM_GPU_EINVAL;
+    if (p->data_type == 2 && (!p->flow_order || p->flow_order_len <= 0)) return DWGSIM_GPU_EINVAL;
+    if (p->length[0] > 30000 || p->length[1] > 30000) return DWGSIM_GPU_EUNSUPPORTED;   // 16-bit lengths in PairRec
+    if (p->std_dev > 1.0e6) return DWGSIM_GPU_EUNSUPPORTED;                              // insert-size table size
+    if (p->data_type == 2) return DWGSIM_GPU_EUNSUPPORTED;                               // Ion Torrent kernel: not yet
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return DWGSIM_GPU_ENODEV;
+    dwgsim_gpu *h = new dwgsim_gpu();
+    h->p = *p;
+    h->device = device;
+    if (p->read_prefix) { h->prefix_s = std::string(p->read_prefix) + "_"; }
+    if (p->flow_order) h->flow_order.assign(p->flow_order, p->flow_order + p->flow_order_len);
+    h->p.read_prefix = nullptr; h->p.flow_order = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DWGSIM_GPU_ECUDA; }
+    for (auto &e : h->ev_t) cudaEventCreate(&e);
+    derive_tables(h);
+    int rc = upload_tables(h);
+    if (rc) { dwgsim_gpu_destroy(h); return rc; }
+    *out = h;
+    return DWGSIM_GPU_OK;
+}
+
+void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_workspace(h);
+    free_blob(h);
+    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf);
+    for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_thr[e]); cudaFree(h->dt.qbase[e]); }
+    cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
+    for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    delete h;
+}
+
+int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name, const uint8_t *seq_ascii, int32_t len,
+                          const uint64_t *hap1, const uint64_t *hap2, uint8_t *const *ins1, int32_t ins1_n,
+                          uint8_t *const *ins2, int32_t ins2_n, int64_t n_pairs)
+{
+    if (!h || !name || !seq_ascii || !hap1 || !hap2 || len <= 0 || n_pairs < 0) return DWGSIM_GPU_EINVAL;
+    if (h->blob) { h->last_error = "add_contig after the genome was finalized: call run() first"; return DWGSIM_GPU_ESTATE; }
+    const size_t nl = strlen(name);
+    if (nl + h->prefix_s.size() + 128 > 1024) { h->last_error = "read name too long for the device formatter"; return DWGSIM_GPU_EUNSUPPORTED; }
+    const double t0 = now_ms();
+    h->queue.emplace_back();
+    HostContig &c = h->queue.back();
+    c.name = name; c.contig_i = contig_i; c.len = len; c.n_pairs = n_pairs;
+    const uint64_t *hap[2] = {hap1, hap2};
+    uint8_t *const *ins[2] = {ins1, ins2};
+    const int32_t ins_n[2] = {ins1_n, ins2_n};
+    int rc = pack_contig(h, c, seq_ascii, hap, ins, ins_n);
+    if (rc) { h->queue.pop_back(); return rc; }
+    h->max_name_len = std::max(h->max_name_len, (int)nl);
+    h->ms_pack += now_ms() - t0;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots)
+{
+    if (!h || pairs_per_batch < 1 || pairs_per_batch > (1 << 24) || ring_slots < 2 || ring_slots > 8) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    free_workspace(h);
+    h->batch_pairs = pairs_per_batch; h->ring = ring_slots;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_set_shard(dwgsim_gpu_t *h, int32_t rank, int32_t world)
+{
+    if (!h || world < 1 || rank < 0 || rank >= world) return DWGSIM_GPU_EINVAL;
+    h->shard_rank = rank; h->shard_world = world;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_set_origin(dwgsim_gpu_t *h, int64_t first_pair_index, int64_t first_rand_serial)
+{
+    if (!h || first_pair_index < 0 || first_rand_serial < 0) return DWGSIM_GPU_EINVAL;
+    h->gidx_origin = first_pair_index; h->rand_serial = first_rand_serial;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_genome_finalize(dwgsim_gpu_t *h)
+{
+    if (!h) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    return finalize_genome(h);
+}
+
+int dwgsim_gpu_genome_blob(const dwgsim_gpu_t *h, uint64_t *device_ptr, uint64_t *n_bytes)
+{
+    if (!h || !h->blob) return DWGSIM_GPU_ESTATE;
+    if (device_ptr) *device_ptr = (uint64_t)(uintptr_t)h->blob;
+    if (n_bytes) *n_bytes = h->blob_bytes;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_genome_import(dwgsim_gpu_t *h, uint64_t device_ptr, uint64_t n_bytes, int32_t take_ownership)
+{
+    if (!h || !device_ptr || n_bytes < sizeof(BlobHeader)) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    BlobHeader hd;
+    CUDA_TRY(h, cudaMemcpy(&hd, (const void *)(uintptr_t)device_ptr, sizeof hd, cudaMemcpyDeviceToHost));
+    if (hd.magic != kBlobMagic || hd.n_bytes != n_bytes) { h->last_error = "not a genome blob"; return DWGSIM_GPU_EINVAL; }
+    std::vector<ContigDesc> cds(hd.n_contigs);
+    CUDA_TRY(h, cudaMemcpy(cds.data(), (const uint8_t *)(uintptr_t)device_ptr + hd.contigs_off, hd.n_contigs * sizeof(ContigDesc),
+                           cudaMemcpyDeviceToHost));
+    free_blob(h);
+    h->queue.clear();
+    h->blob = (uint8_t *)(uintptr_t)device_ptr; h->blob_bytes = n_bytes; h->blob_owned = take_ownership != 0;
+    h->blob_pairs = hd.total_pairs;
+    for (auto &d : cds) h->max_name_len = std::max(h->max_name_len, (int)d.name_len);
+    return DWGSIM_GPU_OK;
+}
+
+int64_t dwgsim_gpu_genome_pairs(const dwgsim_gpu_t *h)
+{
+    if (!h) return -1;
+    if (h->blob) return h->blob_pairs;
+    int64_t n = 0;
+    for (auto &c : h->queue) n += c.n_pairs;
+    return n;
+}
+
+void *dwgsim_gpu_cuda_stream(const dwgsim_gpu_t *h) { return h ? (void *)h->s_compute : nullptr; }
+
+int dwgsim_gpu_tables(const dwgsim_gpu_t *h, dwgsim_gpu_tables_t *t)
+{
+    if (!h || !t) return DWGSIM_GPU_EINVAL;
+    t->thr_genomic = h->thr_genomic; t->thr_hap0 = h->thr_hap0;
+    t->isize_lo = h->isize_lo; t->isize_n = (int32_t)h->isize_cdf.size(); t->isize_cdf = h->isize_cdf.data();
+    t->qdelta_lo = h->qdelta_lo; t->qdelta_n = (int32_t)h->qdelta_cdf.size(); t->qdelta_cdf = h->qdelta_cdf.data();
+    for (int e = 0; e < 2; ++e) {
+        t->n_cycles[e] = (int32_t)h->err_thr[e].size() - 1;
+        t->err_thr[e] = h->err_thr[e].data(); t->qbase[e] = h->qbase[e].data();
+        t->flow_thr[e] = h->flow_thr[e];
+    }
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
+{
+    if (!h || !out || n < 1 || first < 0) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    int rc = finalize_genome(h);
+    if (rc) return rc;
+    if (first + n > h->blob_pairs || n > (1 << 24)) return DWGSIM_GPU_EINVAL;
+    if ((rc = ensure_workspace(h, std::max<int64_t>(n, h->ws.cap_pairs), false))) return rc;
+    int launches = 0;
+    if ((rc = launch_batch(h, first, (int)n, rand_serial_base, 0, true, &launches))) return rc;
+    BatchResult r;
+    rc = collect_batch(h, true, &r);
+    memset(out, 0, sizeof *out);
+    for (int k = 0; k < 3; ++k) { out->dev_ptr[k] = (uint64_t)(uintptr_t)h->ws.out[0][k]; out->n_bytes[k] = r.bytes[k]; h->last_bytes[k] = r.bytes[k]; }
+    h->last_slot = 0;
+    out->n_pairs = n; out->n_random = r.n_random; out->n_failed_attempts = r.n_failed;
+    out->ms_simulate = r.ms[0]; out->ms_layout = r.ms[1]; out->ms_format = r.ms[2];
+    out->n_launches = launches;
+    return rc;
+}
+
+int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap)
+{
+    if (!h || file_id < 0 || file_id > 2 || !dst) return DWGSIM_GPU_EINVAL;
+    if (cap < h->last_bytes[file_id]) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpy(dst, h->ws.out[h->last_slot][file_id], h->last_bytes[file_id], cudaMemcpyDeviceToHost));
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats)
+{
+    if (!h || !sink) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    const double t_start = now_ms();
+    dwgsim_gpu_stats_t st;
+    memset(&st, 0, sizeof st);
+    const int64_t h2d_before = h->h2d_bytes;
+    int rc = finalize_genome(h);
+    if (rc) return rc;
+    const int64_t total = h->blob_pairs;
+    const int64_t B = std::min<int64_t>(h->batch_pairs, std::max<int64_t>(total, 1));
+    if ((rc = ensure_workspace(h, B, true))) return rc;
+    Workspace &w = h->ws;
+    cudaEvent_t copied[8];
+    for (int s = 0; s < h->pinned_slots; ++s) cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming);
+    cudaEvent_t computed;
+    cudaEventCreateWithFlags(&computed, cudaEventDisableTiming);
+    struct Pending { bool live = false; uint64_t bytes[3] = {0, 0, 0}; int pslot = 0; } pend;
+    auto drain = [&](Pending &pd) -> int {
+        if (!pd.live) return DWGSIM_GPU_OK;
+        CUDA_TRY(h, cudaEventSynchronize(copied[pd.pslot]));
+        for (int k = 0; k < 3; ++k)
+            if (pd.bytes[k]) {
+                if (sink(user, k, h->pinned[pd.pslot][k], (size_t)pd.bytes[k])) { h->last_error = "sink callback failed"; return DWGSIM_GPU_ESINK; }
+                st.bytes[k] += (int64_t)pd.bytes[k];
+            }
+        pd.live = false;
+        return DWGSIM_GPU_OK;
+    };
+    int64_t bi = 0;
+    int launches = 0;
+    for (int64_t first = 0; first < total && rc == DWGSIM_GPU_OK; first += B, ++bi) {
+        const int n = (int)std::min<int64_t>(B, total - first);
+        const int dslot = (int)(bi & 1), pslot = (int)(bi % h->pinned_slots);
+        // the device slot was last used by batch bi-2, whose copy finished before batch bi-1 was drained
+        int l = 0;
+        if ((rc = launch_batch(h, first, n, h->rand_serial, dslot, true, &l))) break;
+        launches += l;
+        // while the GPU works on this batch, hand the previous one to the sink
+        if ((rc = drain(pend))) break;
+        BatchResult r;
+        if ((rc = collect_batch(h, true, &r))) break;
+        st.ms_simulate += r.ms[0]; st.ms_layout += r.ms[1]; st.ms_format += r.ms[2];
+        st.n_random += r.n_random; st.n_failed_attempts += r.n_failed; st.n_pairs += n;
+        h->rand_serial += r.n_random;
+        CUDA_TRY(h, cudaEventRecord(computed, h->s_compute));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->s_copy, computed, 0));
+        for (int k = 0; k < 3; ++k)
+            if (r.bytes[k]) {
+                CUDA_TRY(h, cudaMemcpyAsync(h->pinned[pslot][k], w.out[dslot][k], r.bytes[k], cudaMemcpyDeviceToHost, h->s_copy));
+                st.d2h_bytes += (int64_t)r.bytes[k];
+            }
+        CUDA_TRY(h, cudaEventRecord(copied[pslot], h->s_copy));
+        pend.live = true; pend.pslot = pslot;
+        for (int k = 0; k < 3; ++k) pend.bytes[k] = r.bytes[k];
+        ++st.n_batches;
+    }
+    if (rc == DWGSIM_GPU_OK) rc = drain(pend);
+    cudaStreamSynchronize(h->s_copy);
+    for (int s = 0; s < h->pinned_slots; ++s) cudaEventDestroy(copied[s]);
+    cudaEventDestroy(computed);
+    h->gidx_origin += total;
+    free_blob(h);
+    st.n_launches = launches;
+    st.h2d_bytes = h->h2d_bytes - h2d_before;
+    st.ms_pack = h->ms_pack; h->ms_pack = 0;
+    st.ms_total = now_ms() - t_start;
+    if (stats) *stats = st;
+    return rc;
+}
+
+int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t, const int32_t *, uint64_t, double, double, double, double)
+{
+    if (h) h->last_error = "synthetic genome generator not built yet";
+    return DWGSIM_GPU_EUNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,700 @@
+// kernels.cuh -- sm_100a kernels of the dwgsim_core read-pair path.
+//
+//   simulate_pairs_kernel   one warp per read pair: reference src/dwgsim.c:649-882 and :983-1001
+//                           (gate, insert size, position, haplotype, strands, the walk through the
+//                           mutation table = __gen_read src/dwgsim.c:75-153, N filter, colour encoding,
+//                           substitution errors) -> 32-byte PairRec + nibble-packed read codes
+//   layout_* kernels        exclusive scans that turn per-pair record lengths (a function of the name
+//                           fields, src/dwgsim.c:923-929) and random-pair flags (rand_ii, :1096) into
+//                           byte offsets of every record in the three output streams
+//   format_fastq_kernel     one warp per pair: quality strings (src/dwgsim.c:899-918) and the three
+//                           record layouts (src/dwgsim.c:920-980) written at their final offsets
+//
+// Integer / byte work only: no tensor cores, no floating point on the device (every probability is a
+// 32-bit threshold built on the host, DESIGN.md "RNG addressing").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "layout.h"
+
+namespace dwg {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kThreads * kScanItems;   // pairs per layout block
+constexpr int kMaxTrials = 10000;                  // src/dwgsim.c:837
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+struct PairKey {                       // what addresses the draws of one attempt at one pair
+    uint32_t seed, lo, hi, attempt;
+};
+__device__ __forceinline__ uint4 draw_block(const PairKey &k, uint32_t stream, uint32_t end, uint32_t blk)
+{
+    return philox4x32_10(k.lo, k.hi, (k.attempt & 0xFFFFu) | (stream << 16) | (end << 24), blk, k.seed, kPhiloxKey1);
+}
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, uint32_t w)
+{
+    return w == 0 ? v.x : (w == 1 ? v.y : (w == 2 ? v.z : v.w));
+}
+// base k of a read uses word (k>>5)&3 of block (k&31) | ((k>>7)<<5): the lane that owns bases
+// lane + 32 r gets four of them per Philox call
+__device__ __forceinline__ uint32_t lane_block(uint32_t k) { return (k & 31u) | ((k >> 7) << 5); }
+
+// #{j < n : u >= cdf[j]} for a non-decreasing table
+__device__ __forceinline__ int table_rank(const uint32_t *__restrict__ cdf, int n, uint32_t u)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (u >= __ldg(cdf + mid)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- genome access ------------------------------------------------------------------------------------
+struct ContigView {
+    int len;
+    const uint32_t *ref2, *nmask;
+    const Event *ev[2];
+    const uint32_t *blk[2];
+    const uint8_t *pool[2];
+    int n_ev[2];
+};
+__device__ __forceinline__ const ContigDesc *find_contig(const uint8_t *blob, int64_t q, int *index)
+{
+    const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
+    const ContigDesc *cd = reinterpret_cast<const ContigDesc *>(blob + hd->contigs_off);
+    int lo = 0, hi = (int)hd->n_contigs - 1;
+    while (lo < hi) {                  // last contig with pair_base <= q
+        int mid = (lo + hi + 1) >> 1;
+        if (cd[mid].pair_base <= q) lo = mid; else hi = mid - 1;
+    }
+    *index = lo;
+    return cd + lo;
+}
+__device__ __forceinline__ ContigView view_of(const uint8_t *blob, const ContigDesc *cd)
+{
+    ContigView v;
+    v.len = cd->len;
+    v.ref2 = reinterpret_cast<const uint32_t *>(blob + cd->ref2_off);
+    v.nmask = reinterpret_cast<const uint32_t *>(blob + cd->nmask_off);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        v.ev[h] = reinterpret_cast<const Event *>(blob + cd->ev_off[h]);
+        v.blk[h] = reinterpret_cast<const uint32_t *>(blob + cd->blk_off[h]);
+        v.pool[h] = blob + cd->pool_off[h];
+        v.n_ev[h] = (int)cd->n_ev[h];
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t ref_code(const ContigView &c, int p)
+{
+    uint32_t w = __ldg(c.ref2 + (p >> 4));
+    uint32_t m = __ldg(c.nmask + (p >> 5));
+    return ((m >> (p & 31)) & 1u) ? 4u : ((w >> ((p & 15) << 1)) & 3u);
+}
+__device__ __forceinline__ uint4 load_event(const Event *ev, int e)
+{
+    return __ldg(reinterpret_cast<const uint4 *>(ev + e));
+}
+__device__ __forceinline__ uint32_t ins_code(const uint4 &ev, const uint8_t *pool, uint32_t n, uint32_t j)
+{
+    uint64_t payload = (uint64_t)ev.z | ((uint64_t)ev.w << 32);
+    if (n <= kInlineInsMax) return (uint32_t)(payload >> (2 * j)) & 3u;
+    uint64_t at = payload + j;
+    return (__ldg(pool + (at >> 2)) >> ((at & 3) << 1)) & 3u;
+}
+
+// ---- the walk (__gen_read, src/dwgsim.c:75-153) over the sparse table -----------------------------------
+// Scalar state (position, emitted count, counters) is warp-uniform; lanes share the emission of each
+// run of plain reference bases and of each insertion.  Returns false when the reference would leave
+// ext_coor negative (ran off the contig, or the predicted left end went below 0 on the minus strand).
+struct Walk {
+    int ext, n_sub, n_indel, n_indel_first;
+};
+__device__ __forceinline__ bool gen_read(const ContigView &c, int h, int start, int strand, int s,
+                                         uint8_t *out, int lane, Walk &w)
+{
+    const int dir = strand ? -1 : 1;
+    const Event *ev = c.ev[h];
+    const int n_ev = c.n_ev[h];
+    w.ext = -10; w.n_sub = w.n_indel = w.n_indel_first = 0;
+    int i = start;
+    if (i < 0 || i >= c.len) return false;
+    int e;
+    if (dir > 0) {
+        e = (int)__ldg(c.blk[h] + (i >> kBlkShift));
+        while (e < n_ev && (int)__ldg(&ev[e].pos) < i) ++e;
+    } else {
+        e = (int)__ldg(c.blk[h] + (i >> kBlkShift) + 1) - 1;
+        while (e >= 0 && (int)__ldg(&ev[e].pos) > i) --e;
+    }
+    bool have = dir > 0 ? (e < n_ev) : (e >= 0);
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (have) cur = load_event(ev, e);
+    // a read may only start on a NOCHANGE / SUBSTITUTE position (src/dwgsim.c:78-82)
+    while (have && (int)cur.x == i) {
+        uint32_t t = cur.y & 3u;
+        if (t != kEvInsert && t != kEvDelete) break;
+        i += dir; e += dir;
+        if (i < 0 || i >= c.len) return false;
+        have = dir > 0 ? (e < n_ev) : (e >= 0);
+        if (have) cur = load_event(ev, e);
+    }
+    int ext = i - (strand ? s - 1 : 0);
+    if (ext < 0) return false;
+    int k = 0;
+    while (k < s) {
+        const int pe = have ? (int)cur.x : (dir > 0 ? c.len : -1);
+        int run = dir > 0 ? pe - i : i - pe;
+        if (run > s - k) run = s - k;
+        for (int j = lane; j < run; j += 32) out[k + j] = (uint8_t)ref_code(c, i + dir * j);
+        k += run; i += dir * run;
+        if (k == s) break;
+        if (!have) return false;                             // walked off the contig
+        const uint32_t t = cur.y & 3u, base = (cur.y >> 2) & 7u, n = cur.y >> 5;
+        if (t == kEvSubst || t == kEvOverride) {
+            if (lane == 0) out[k] = (uint8_t)base;
+            ++k;
+            if (t == kEvSubst) ++w.n_sub;
+        } else if (t == kEvDelete) {
+            ++w.n_indel;
+            if (strand && --ext < 0) return false;
+        } else {
+            ++w.n_indel; ++w.n_indel_first;
+            if (!strand) {
+                if (lane == 0) out[k] = (uint8_t)base;
+                ++k;
+                int m = (int)n < s - k ? (int)n : s - k;
+                for (int j = lane; j < m; j += 32) out[k + j] = (uint8_t)ins_code(cur, c.pool[h], n, (uint32_t)j);
+                k += m;
+            } else {
+                int m = (int)n < s - k ? (int)n : s - k;
+                ext += m;
+                for (int j = lane; j < m; j += 32) out[k + j] = (uint8_t)ins_code(cur, c.pool[h], n, n - 1u - (uint32_t)j);
+                k += m;
+                if (k < s) { if (lane == 0) out[k] = (uint8_t)base; ++k; }
+            }
+        }
+        i += dir; e += dir;
+        have = dir > 0 ? (e < n_ev) : (e >= 0);
+        if (have) cur = load_event(ev, e);
+    }
+    __syncwarp();
+    if (strand)
+        for (int j = lane; j < s; j += 32) { uint8_t v = out[j]; out[j] = v < 4 ? (uint8_t)(3 - v) : (uint8_t)4; }
+    __syncwarp();
+    w.ext = ext;
+    return true;
+}
+
+// colour encoding with adaptor base 0 (src/dwgsim.c:845-858); chunks are processed high to low so that
+// every predecessor is still a base when it is read
+__device__ __forceinline__ void colour_encode(uint8_t *seq, int n, int lane)
+{
+    for (int r = (n - 1) >> 5; r >= 0; --r) {
+        int k = (r << 5) + lane;
+        uint32_t cur = 0, prev = 0;
+        if (k < n) { cur = seq[k]; prev = k ? seq[k - 1] : 0u; }
+        __syncwarp();
+        if (k < n) seq[k] = (uint8_t)((cur >= 4 || prev >= 4) ? 4u : (cur ^ prev));
+        __syncwarp();
+    }
+}
+
+// ---- kernel A: simulate ----------------------------------------------------------------------------------
+// status[0]: error bits (1 = a pair exhausted its 10001 trials), status[1]: rejected attempts
+__global__ void __launch_bounds__(kThreads)
+simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
+                      PairRec *__restrict__ recs, uint8_t *__restrict__ seqs, unsigned long long *__restrict__ status)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cap0 = (P.cap[0] + 15) & ~15, cap1 = (P.cap[1] + 15) & ~15;
+    uint8_t *code[2];
+    code[0] = smem + (size_t)warp * (cap0 + cap1);
+    code[1] = code[0] + cap0;
+    const int warps_total = gridDim.x * kWarpsPerBlock;
+
+    for (int p = blockIdx.x * kWarpsPerBlock + warp; p < n; p += warps_total) {
+        const int64_t q = first + p;
+        int contig_index;
+        const ContigDesc *cd = find_contig(blob, q, &contig_index);
+        const ContigView cv = view_of(blob, cd);
+        const uint64_t gidx = (uint64_t)(gidx_origin + q);
+        PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), 0u};
+        PairRec rec;
+        int s[2] = {P.len[0], P.len[1]};
+        int strand[2] = {0, 0};
+        bool done = false, random_pair = false;
+        int hap = 0;
+        Walk w[2];
+        unsigned failed = 0;
+
+        for (int attempt = 0; attempt <= kMaxTrials && !done; ++attempt) {
+            key.attempt = (uint32_t)attempt;
+            const uint4 b0 = draw_block(key, kStPair, 0, 0);
+            if ((uint64_t)b0.x < P.thr_genomic) { random_pair = true; done = true; break; }   // src/dwgsim.c:649
+            int d, pos;
+            if (P.amplicons) { pos = 0; d = cv.len; }                                          // src/dwgsim.c:650-653
+            else {
+                if (s[1] > 0) {                                                                // src/dwgsim.c:656-664
+                    d = P.isize_lo + table_rank(P.isize_cdf, P.isize_n, b0.y);
+                    const int min_dist = s[0] + s[1];
+                    if (d < min_dist) d = min_dist;
+                    if (d > cv.len) d = cv.len;
+                } else d = 0;
+                const uint64_t range = (uint64_t)((int64_t)cv.len - d + 1);
+                pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);                   // src/dwgsim.c:671
+            }
+            const uint4 b1 = draw_block(key, kStPair, 0, 1);
+            hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;                                       // src/dwgsim.c:716
+            strand[0] = P.read_one_strand == 0 ? ((b1.y >> 31) ? 0 : 1) : (P.read_one_strand == 1 ? 0 : 1);
+            if (P.strandedness == 0) strand[1] = (P.data_type == 0) ? 1 - strand[0] : strand[0];
+            else strand[1] = (P.strandedness == 1) ? strand[0] : 1 - strand[0];
+            // read placement, src/dwgsim.c:745-821
+            int st0, st1 = 0;
+            const int last = cv.len - 1;
+            if (s[1] > 0) {
+                if (strand[0] == strand[1]) {
+                    if (strand[0] == 0) {
+                        st0 = P.amplicons ? last : (P.is_inner ? pos + s[1] + d - 1 : pos + d - s[0]);
+                        st1 = pos;
+                    } else {
+                        st0 = pos + s[0] - 1;
+                        st1 = P.amplicons ? last : (P.is_inner ? pos + s[0] + d + s[1] - 1 : pos + d - 1);
+                    }
+                } else if (strand[0] == 0) {
+                    st0 = pos;
+                    st1 = P.amplicons ? last : (P.is_inner ? pos + s[0] + d + s[1] - 1 : pos + d - 1);
+                } else {
+                    st0 = P.amplicons ? last : (P.is_inner ? pos + s[1] + d + s[0] - 1 : pos + d - 1);
+                    st1 = pos;
+                }
+            } else {
+                st0 = strand[0] == 0 ? pos : (P.amplicons ? last : pos + s[0] - 1);
+            }
+            bool ok = gen_read(cv, hap, st0, strand[0], s[0], code[0], lane, w[0]);
+            if (s[1] > 0) {
+                // the reference always walks both ends before testing (src/dwgsim.c:759-760,833)
+                bool ok1 = gen_read(cv, hap, st1, strand[1], s[1], code[1], lane, w[1]);
+                ok = ok && ok1;
+            } else { w[1].ext = 0; w[1].n_sub = w[1].n_indel = w[1].n_indel_first = 0; }
+            if (ok) {                                                                          // src/dwgsim.c:823-833
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    int nn = 0;
+                    for (int k = lane; k < s[j]; k += 32) nn += code[j][k] == 4;
+                    nn = __reduce_add_sync(0xffffffffu, nn);
+                    if (nn > P.max_n) ok = false;
+                }
+            }
+            if (ok) done = true; else ++failed;
+        }
+
+        rec.attempt = (uint16_t)key.attempt;
+        rec.n_err_first = 0;
+        if (!done) {                                     // 10001 rejected attempts, src/dwgsim.c:837-840
+            if (lane == 0) atomicOr(status, 1ull);
+            random_pair = true;                          // keep the streams well-formed; the host reports the error
+            rec.flags = kRecFailed;
+        } else rec.flags = 0;
+
+        if (random_pair) {                               // src/dwgsim.c:983-1001
+            rec.flags |= kRecRandom;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                rec.pos[j] = 0; rec.len[j] = (uint16_t)s[j];
+                rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
+                uint4 blk = make_uint4(0, 0, 0, 0);
+                int have_blk = -1;
+                for (int k = lane; k < s[j]; k += 32) {
+                    if ((k >> 6) != have_blk) { have_blk = k >> 6; blk = draw_block(key, kStRandBase, j, have_blk); }
+                    code[j][k] = (uint8_t)((word_of(blk, (k >> 4) & 3) >> ((k & 15) << 1)) & 3u);
+                }
+            }
+            __syncwarp();
+            if (P.data_type == 1) { colour_encode(code[0], s[0], lane); colour_encode(code[1], s[1], lane); }
+        } else {
+            if (P.data_type == 1) { colour_encode(code[0], s[0], lane); colour_encode(code[1], s[1], lane); }
+            rec.flags |= (strand[0] ? kRecStrand0 : 0) | (strand[1] ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                rec.pos[j] = (uint32_t)(w[j].ext + 1);
+                rec.len[j] = (uint16_t)s[j];
+                rec.n_sub[j] = (uint16_t)w[j].n_sub;
+                rec.n_indel[j] = (uint16_t)w[j].n_indel;
+                rec.n_indel_first[j] = (uint16_t)w[j].n_indel_first;
+                // substitution errors, src/dwgsim.c:233-244
+                int nerr = 0;
+                uint4 blk = make_uint4(0, 0, 0, 0);
+                int have_blk = -1;
+                for (int k = lane; k < s[j]; k += 32) {
+                    const int lb = (int)lane_block((uint32_t)k);
+                    if (lb != have_blk) { have_blk = lb; blk = draw_block(key, kStErr, j, lb); }
+                    uint32_t c = code[j][k];
+                    if (c < 4 && word_of(blk, (k >> 5) & 3) < __ldg(P.err_thr[j] + k)) {
+                        const uint4 sb = draw_block(key, kStSub, j, lb);
+                        c = (c + 1u + __umulhi(word_of(sb, (k >> 5) & 3), 3u)) & 3u;
+                        code[j][k] = (uint8_t)c;
+                        ++nerr;
+                        if (k == 0) rec.n_err_first |= (uint8_t)(1u << j);
+                    }
+                }
+                rec.n_err[j] = (uint16_t)__reduce_add_sync(0xffffffffu, nerr);
+            }
+            rec.n_err_first = (uint8_t)__shfl_sync(0xffffffffu, (int)rec.n_err_first, 0);   // k == 0 lives in lane 0
+            __syncwarp();
+        }
+        if (lane == 0) {
+            recs[p] = rec;
+            if (failed) atomicAdd(status + 1, (unsigned long long)failed);
+        }
+        // nibble-pack the read codes: 8 per 32-bit word
+        uint32_t *dst = reinterpret_cast<uint32_t *>(seqs + (size_t)p * P.seq_stride);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint32_t *d = dst + (j ? P.seq_off1 >> 2 : 0);
+            const int nw = (s[j] + 7) >> 3;
+            for (int wi = lane; wi < nw; wi += 32) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    int k = wi * 8 + t;
+                    uint32_t c = k < s[j] ? code[j][k] : 0u;
+                    v |= c << (4 * t);
+                }
+                d[wi] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- record geometry shared by the layout and format kernels --------------------------------------------
+__device__ __forceinline__ int ndigits10(uint32_t v)
+{
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+         : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+__device__ __forceinline__ int ndigits16(uint64_t v) { return v ? (67 - __clzll((long long)v)) >> 2 : 1; }
+
+// the 13 numeric fields of a read name (src/dwgsim.c:923-929); variant 1 = SOLiD bwa counts (:945-946)
+__device__ __forceinline__ uint64_t name_field(const PairRec &r, uint64_t serial, int f, int variant)
+{
+    const bool rnd = r.flags & kRecRandom;
+    switch (f) {
+        case 0: return r.pos[0];
+        case 1: return r.pos[1];
+        case 2: return (r.flags & kRecStrand0) ? 1 : 0;
+        case 3: return (r.flags & kRecStrand1) ? 1 : 0;
+        case 4: case 5: return rnd ? 1 : 0;
+        case 6: return r.n_err[0] - (variant ? (r.n_err_first & 1) : 0);
+        case 7: return r.n_sub[0];
+        case 8: return r.n_indel[0] - (variant ? r.n_indel_first[0] : 0);
+        case 9: return r.n_err[1] - (variant ? ((r.n_err_first >> 1) & 1) : 0);
+        case 10: return r.n_sub[1];
+        case 11: return r.n_indel[1] - (variant ? r.n_indel_first[1] : 0);
+        default: return serial;
+    }
+}
+// '@' + prefix + contig + 13 x (separator + digits)
+__device__ __forceinline__ int name_length(const SimParams &P, const PairRec &r, uint64_t serial, int contig_name_len,
+                                           int variant)
+{
+    int n = 1 + P.prefix_len + ((r.flags & kRecRandom) ? 4 : contig_name_len) + 13;
+#pragma unroll
+    for (int f = 0; f < 12; ++f) n += ndigits10((uint32_t)name_field(r, serial, f, variant));
+    return n + ndigits16(serial);
+}
+// bytes of the records of one pair in the three streams (src/dwgsim.c:920-980)
+__device__ __forceinline__ void record_lengths(const SimParams &P, const PairRec &r, uint64_t serial, int contig_name_len,
+                                               uint32_t len[3])
+{
+    const bool solid = P.data_type == 1;
+    const int name_full = name_length(P, r, serial, contig_name_len, 0);
+    const int name_bwa = solid ? name_length(P, r, serial, contig_name_len, 1) : name_full;
+    len[0] = len[1] = len[2] = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int L = r.len[j];
+        if (L <= 0) continue;
+        if (P.out_bwa) len[j] = (uint32_t)(name_bwa + 3 + (solid ? 2 * (L - 1) : 2 * L) + 4);
+        if (P.out_bfast) len[2] += (uint32_t)(name_full + 1 + 2 * L + 4 + (solid ? 1 : 0));
+    }
+}
+
+// ---- layout kernels --------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *total, T *smem_w /* [kWarpsPerBlock] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) smem_w[warp] = inc;
+    __syncthreads();
+    T base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kWarpsPerBlock; ++i) { T x = smem_w[i]; if (i < warp) base += x; tot += x; }
+    *total = tot;
+    return base + inc - v;
+}
+
+// block sums of the random-pair flags
+__global__ void __launch_bounds__(kThreads)
+layout_count_random_kernel(const PairRec *__restrict__ recs, int n, unsigned long long *__restrict__ blk_rand)
+{
+    __shared__ uint32_t sw[kWarpsPerBlock];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int t = 0; t < kScanItems; ++t) if (base + t < n) c += (recs[base + t].flags & kRecRandom) ? 1u : 0u;
+    uint32_t tot;
+    block_exclusive_scan<uint32_t>(c, &tot, sw);
+    if (threadIdx.x == 0) blk_rand[blockIdx.x] = tot;
+}
+
+// single-block exclusive scan of m 64-bit block sums (m <= a few thousand), in place; totals[slot] = sum
+__global__ void __launch_bounds__(1024)
+layout_scan_blocks_kernel(unsigned long long *__restrict__ v, int m, int n_arrays, unsigned long long *__restrict__ totals)
+{
+    __shared__ unsigned long long sw[32];
+    __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int a = 0; a < n_arrays; ++a) {
+        unsigned long long *x = v + (size_t)a * m;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < m; base += 1024) {
+            const int i = base + threadIdx.x;
+            unsigned long long val = i < m ? x[i] : 0ull, inc = val;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) sw[warp] = inc;
+            __syncthreads();
+            unsigned long long wb = 0, tot = 0;
+            for (int j = 0; j < 32; ++j) { unsigned long long t = sw[j]; if (j < warp) wb += t; tot += t; }
+            const unsigned long long c = carry;
+            if (i < m) x[i] = c + wb + inc - val;
+            __syncthreads();
+            if (threadIdx.x == 0) carry = c + tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) totals[a] = carry;
+        __syncthreads();
+    }
+}
+
+// serial (ii or rand_ii) + record lengths per pair, block sums of the lengths
+__global__ void __launch_bounds__(kThreads)
+layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const PairRec *__restrict__ recs, int n,
+                      int64_t first, unsigned long long rand_base, const unsigned long long *__restrict__ blk_rand_excl,
+                      unsigned long long *__restrict__ serial, uint32_t *__restrict__ lens /* [3][n] */,
+                      unsigned long long *__restrict__ blk_len /* [3][nblk] */)
+{
+    __shared__ uint32_t sw[kWarpsPerBlock];
+    __shared__ unsigned long long sw64[kWarpsPerBlock];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    PairRec r[kScanItems];
+    uint32_t c = 0;
+#pragma unroll
+    for (int t = 0; t < kScanItems; ++t) {
+        if (base + t < n) { r[t] = recs[base + t]; c += (r[t].flags & kRecRandom) ? 1u : 0u; }
+        else r[t].flags = 0;
+    }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan<uint32_t>(c, &tot, sw);
+    unsigned long long rs = rand_base + blk_rand_excl[blockIdx.x] + ex;
+    unsigned long long sum[3] = {0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < kScanItems; ++t) {
+        if (base + t >= n) break;
+        const int64_t q = first + base + t;
+        int ci;
+        const ContigDesc *cd = find_contig(blob, q, &ci);
+        unsigned long long ser;
+        if (r[t].flags & kRecRandom) ser = rs++;
+        else ser = (unsigned long long)(q - cd->pair_base);
+        serial[base + t] = ser;
+        uint32_t len[3];
+        record_lengths(P, r[t], ser, (int)cd->name_len, len);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lens[(size_t)k * n + base + t] = len[k]; sum[k] += len[k]; }
+    }
+    const int nblk = gridDim.x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long t2;
+        block_exclusive_scan<unsigned long long>(sum[k], &t2, sw64);
+        if (threadIdx.x == 0) blk_len[(size_t)k * nblk + blockIdx.x] = t2;
+    }
+}
+
+// lengths -> byte offsets inside the batch (in place)
+__global__ void __launch_bounds__(kThreads)
+layout_offsets_kernel(int n, const unsigned long long *__restrict__ blk_len_excl /* [3][nblk] */,
+                      uint32_t *__restrict__ lens /* [3][n] in, offsets out (low 32 bits) */)
+{
+    __shared__ unsigned long long sw64[kWarpsPerBlock];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    const int nblk = gridDim.x;
+    for (int k = 0; k < 3; ++k) {
+        uint32_t l[kScanItems];
+        unsigned long long s = 0;
+#pragma unroll
+        for (int t = 0; t < kScanItems; ++t) { l[t] = base + t < n ? lens[(size_t)k * n + base + t] : 0u; s += l[t]; }
+        unsigned long long tot;
+        unsigned long long ex = block_exclusive_scan<unsigned long long>(s, &tot, sw64) + blk_len_excl[(size_t)k * nblk + blockIdx.x];
+#pragma unroll
+        for (int t = 0; t < kScanItems; ++t) {
+            if (base + t < n) lens[(size_t)k * n + base + t] = (uint32_t)ex;   // batches are < 4 GiB per stream
+            ex += l[t];
+        }
+    }
+}
+
+// ---- kernel B: format ------------------------------------------------------------------------------------
+// name into shared memory; lane f < 13 owns numeric field f
+__device__ __forceinline__ int build_name(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
+                                          int cname_len, int variant, char *buf, int lane)
+{
+    const bool rnd = r.flags & kRecRandom;
+    const int nl = rnd ? 4 : cname_len;
+    const int head = 1 + P.prefix_len + nl;
+    if (lane == 0) buf[0] = '@';
+    for (int j = lane; j < P.prefix_len; j += 32) buf[1 + j] = P.prefix[j];
+    for (int j = lane; j < nl; j += 32) buf[1 + P.prefix_len + j] = rnd ? "rand"[j] : cname[j];
+    uint64_t v = lane < 13 ? name_field(r, serial, lane, variant) : 0;
+    int nd = lane < 12 ? ndigits10((uint32_t)v) : (lane == 12 ? ndigits16(v) : 0);
+    int width = lane < 13 ? nd + 1 : 0, inc = width;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const int total = __shfl_sync(0xffffffffu, inc, 12);
+    if (lane < 13) {
+        char *p = buf + head + inc - width;
+        p[0] = (lane == 7 || lane == 8 || lane == 10 || lane == 11) ? ':' : '_';
+        if (lane < 12) {
+            uint32_t x = (uint32_t)v;
+            for (int d = nd; d >= 1; --d) { p[d] = (char)('0' + x % 10u); x /= 10u; }
+        } else {
+            for (int d = nd; d >= 1; --d) { uint32_t h = (uint32_t)(v & 15u); p[d] = (char)(h < 10 ? '0' + h : 'a' + h - 10); v >>= 4; }
+        }
+    }
+    __syncwarp();
+    return head + total;
+}
+
+__device__ __forceinline__ uint32_t nibble_at(const uint32_t *__restrict__ w, int k)
+{
+    return (__ldg(w + (k >> 3)) >> ((k & 7) << 2)) & 15u;
+}
+
+// one record: name + suffix + sequence line + "+" + quality line (src/dwgsim.c:923-978)
+__device__ __forceinline__ void write_record(char *__restrict__ dst, const char *name, int name_len, const char *suffix,
+                                             int suffix_len, int lead_A, const char *alphabet, const uint32_t *codes,
+                                             const char *qual, int from, int L, int lane)
+{
+    for (int j = lane; j < name_len; j += 32) dst[j] = name[j];
+    dst += name_len;
+    if (lane < suffix_len) dst[lane] = suffix[lane];
+    dst += suffix_len;
+    if (lead_A) { if (lane == 0) dst[0] = 'A'; dst += 1; }
+    const int m = L - from;
+    for (int j = lane; j < m; j += 32) dst[j] = alphabet[nibble_at(codes, from + j)];
+    dst += m;
+    if (lane < 3) dst[lane] = lane == 1 ? '+' : '\n';
+    dst += 3;
+    for (int j = lane; j < m; j += 32) dst[j] = qual[from + j];
+    if (lane == 0) dst[m] = '\n';
+}
+
+__global__ void __launch_bounds__(kThreads)
+format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
+                    const PairRec *__restrict__ recs, const uint8_t *__restrict__ seqs,
+                    const unsigned long long *__restrict__ serial, const uint32_t *__restrict__ offs /* [3][n] */,
+                    char *__restrict__ out0, char *__restrict__ out1, char *__restrict__ out2)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int capq = (max(P.cap[0], P.cap[1]) + 15) & ~15;
+    const int name_cap = 1024;
+    char *name_full = reinterpret_cast<char *>(smem) + (size_t)warp * (2 * name_cap + capq);
+    char *name_bwa = name_full + name_cap;
+    char *qual = name_bwa + name_cap;
+    const bool solid = P.data_type == 1;
+    const int warps_total = gridDim.x * kWarpsPerBlock;
+    const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
+
+    for (int p = blockIdx.x * kWarpsPerBlock + warp; p < n; p += warps_total) {
+        const int64_t q = first + p;
+        int ci;
+        const ContigDesc *cd = find_contig(blob, q, &ci);
+        const char *cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
+        const PairRec r = recs[p];
+        const uint64_t ser = serial[p];
+        const uint64_t gidx = (uint64_t)(gidx_origin + q);
+        const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)r.attempt};
+        const int nfull = build_name(P, r, ser, cname, (int)cd->name_len, 0, name_full, lane);
+        int nbwa = nfull;
+        const char *nb = name_full;
+        if (solid && P.out_bwa) { nbwa = build_name(P, r, ser, cname, (int)cd->name_len, 1, name_bwa, lane); nb = name_bwa; }
+        uint32_t off_bfast = P.out_bfast ? offs[(size_t)2 * n + p] : 0u;
+        for (int j = 0; j < 2; ++j) {
+            const int L = r.len[j];
+            if (L <= 0) continue;
+            // qualities, src/dwgsim.c:899-918 (char arithmetic there; emulated with an int8 wrap)
+            {
+                uint4 blk = make_uint4(0, 0, 0, 0);
+                int have_blk = -1;
+                for (int k = lane; k < L; k += 32) {
+                    int c;
+                    if (P.fixed_quality) c = P.fixed_quality;
+                    else {
+                        c = 33 + (int)__ldg(P.qbase[j] + k);
+                        if (P.qdelta_n > 0) {
+                            const int lb = (int)lane_block((uint32_t)k);
+                            if (lb != have_blk) { have_blk = lb; blk = draw_block(key, kStQual, j, lb); }
+                            const int delta = P.qdelta_lo + table_rank(P.qdelta_cdf, P.qdelta_n, word_of(blk, (k >> 5) & 3));
+                            c = (int)(signed char)((c + delta) & 0xFF);
+                        }
+                        c = c < 33 ? 33 : (c > 73 ? 73 : c);
+                    }
+                    qual[k] = (char)c;
+                }
+            }
+            __syncwarp();
+            const uint32_t *codes = reinterpret_cast<const uint32_t *>(seqs + (size_t)p * P.seq_stride + (j ? P.seq_off1 : 0));
+            if (P.out_bwa) {
+                char *dst = (j == 0 ? out0 : out1) + offs[(size_t)j * n + p];
+                const char *suffix = solid ? (j == 0 ? "/2\n" : "/1\n") : (j == 0 ? "/1\n" : "/2\n");
+                write_record(dst, nb, nbwa, suffix, 3, 0, "ACGTN\0\0\0\0\0\0\0\0\0\0", codes, qual, solid ? 1 : 0, L, lane);
+            }
+            if (P.out_bfast) {
+                char *dst = out2 + off_bfast;
+                write_record(dst, name_full, nfull, "\n", 1, solid ? 1 : 0, solid ? "01234\0\0\0\0\0\0\0\0\0\0" : "ACGTN\0\0\0\0\0\0\0\0\0\0",
+                             codes, qual, 0, L, lane);
+                off_bfast += (uint32_t)(nfull + 1 + 2 * L + 4 + (solid ? 1 : 0));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace dwg

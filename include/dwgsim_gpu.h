@@ -1,0 +1,171 @@
+/*
+ * dwgsim_gpu.h -- C ABI of libdwgsim_b200.so: the dwgsim_core read-pair loop on a B200.
+ *
+ * The reference has no plugin / FFI surface for this path; the loop is inlined in
+ * dwgsim_core (reference src/dwgsim.c:636-1099).  The seam is cut where a maintainer would cut it:
+ * once per contig, right after mut_diref + mut_print (src/dwgsim.c:628-632) and before
+ * mutseq_destroy (src/dwgsim.c:1103-1104).  Everything crossing the boundary is plain C: POD
+ * structs, pointers and sizes.  No torch / CUDA types appear in any signature.
+ *
+ * Error convention: the reference prints to stderr and exit(1)s (src/dwgsim.c:177-180,837-840);
+ * this library never exits: every call returns DWGSIM_GPU_OK (0) or a negative code, and
+ * dwgsim_gpu_strerror() gives the text the host shell prints before exiting 1.
+ *
+ * Threading: callable from the reference's single thread.  The library owns its CUDA streams,
+ * pinned rings and device memory, and never touches libc's drand48 state (the host's mut_diref
+ * depends on it).
+ */
+#ifndef DWGSIM_GPU_H
+#define DWGSIM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWGSIM_GPU_ABI_VERSION 1
+
+enum {
+    DWGSIM_GPU_OK = 0,
+    DWGSIM_GPU_EINVAL = -1,        /* bad argument / option out of the range the reference accepts   */
+    DWGSIM_GPU_ENODEV = -2,        /* no usable CUDA device: there is NO CPU fallback                  */
+    DWGSIM_GPU_ECUDA = -3,         /* CUDA runtime error (text via dwgsim_gpu_last_error)              */
+    DWGSIM_GPU_ENOMEM = -4,
+    DWGSIM_GPU_ETRIALS = -5,       /* "failed to generate a read after 10001 trials" src/dwgsim.c:837 */
+    DWGSIM_GPU_ESINK = -6,         /* the sink callback returned non-zero                              */
+    DWGSIM_GPU_EUNSUPPORTED = -7,  /* option combination not implemented on the device path            */
+    DWGSIM_GPU_EOVERFLOW = -8,     /* Ion Torrent read grew past the device bound (2*len+64)           */
+    DWGSIM_GPU_ESTATE = -9         /* call order violated                                              */
+};
+
+/* file ids handed to the sink: the three gzFiles of dwgsim_opt_t (src/dwgsim_opt.h:51-53) */
+enum { DWGSIM_GPU_FILE_BWA1 = 0, DWGSIM_GPU_FILE_BWA2 = 1, DWGSIM_GPU_FILE_BFAST = 2 };
+
+typedef struct dwgsim_gpu dwgsim_gpu_t;
+
+/* POD copy of the dwgsim_opt_t fields the loop reads (src/dwgsim_opt.h:21-60), after
+ * dwgsim_opt_parse (so e_by is (end-start)/length, src/dwgsim_opt.c:459-460, and flow_order holds
+ * codes 0..3, src/dwgsim_opt.c:404-407). */
+typedef struct {
+    double  e_start[2], e_by[2];   /* error_t of each end, src/dwgsim_opt.h:17-19                 */
+    int32_t is_inner;              /* -i                                                           */
+    int32_t dist;                  /* -d                                                           */
+    double  std_dev;               /* -s                                                           */
+    int32_t length[2];             /* -1 / -2 (length[1] == 0: single end)                         */
+    double  mut_freq;              /* -F                                                           */
+    double  rand_read;             /* -y                                                           */
+    int32_t max_n;                 /* -n                                                           */
+    int32_t data_type;             /* -c 0 Illumina, 1 SOLiD, 2 Ion Torrent                        */
+    int32_t strandedness;          /* -S                                                           */
+    int32_t read_one_strand;       /* -A                                                           */
+    const int8_t *flow_order;      /* -f as codes 0..3 (NULL unless Ion Torrent)                   */
+    int32_t flow_order_len;
+    int32_t seed;                  /* -z (keys the Philox streams; drand48 is never used)          */
+    int32_t fixed_quality;         /* -q: 0 = none, else the character                             */
+    double  quality_std;           /* -Q                                                           */
+    const char *read_prefix;       /* -P or NULL                                                   */
+    int32_t reads_output_type;     /* -o 0 all, 1 bwa only, 2 bfast only                           */
+    int32_t amplicons;             /* -a                                                           */
+} dwgsim_gpu_params_t;
+
+typedef struct {
+    int64_t n_pairs;               /* pairs written (genomic + random)                             */
+    int64_t n_random;              /* of which random (src/dwgsim.c:983-1097)                      */
+    int64_t n_failed_attempts;     /* rejected genomic attempts (src/dwgsim.c:833-842)             */
+    int64_t bytes[3];              /* FASTQ bytes handed to the sink per file id                   */
+    int64_t h2d_bytes, d2h_bytes;  /* bytes copied over PCIe by this call                          */
+    double  ms_simulate, ms_layout, ms_format;   /* device time per kernel group (CUDA events)     */
+    double  ms_pack, ms_total;     /* host packing time; wall time of the call                     */
+    int32_t n_launches;            /* kernels launched by this call                                */
+    int32_t n_batches;
+} dwgsim_gpu_stats_t;
+
+/* receives FASTQ bytes strictly in pair-index order per file id; buf is only valid during the call.
+ * Return 0 to continue, non-zero to abort the run (-> DWGSIM_GPU_ESINK). */
+typedef int (*dwgsim_gpu_sink_fn)(void *user, int file_id, const char *buf, size_t n);
+
+/* -- lifecycle ------------------------------------------------------------------------------ */
+int  dwgsim_gpu_abi_version(void);
+int  dwgsim_gpu_create(dwgsim_gpu_t **h, const dwgsim_gpu_params_t *p, int device);
+void dwgsim_gpu_destroy(dwgsim_gpu_t *h);
+const char *dwgsim_gpu_strerror(int code);
+const char *dwgsim_gpu_last_error(const dwgsim_gpu_t *h);
+
+/* -- the seam (replaces the body of `for (ii...)`, src/dwgsim.c:636-1099) ---------------------- */
+/* Queue one contig: name, seq_t (ASCII, src/mut.h:12-15), both mutseq_t (src/mut.h:42-47: s[len]
+ * of 64-bit mut_t plus the long-insertion byte strings) and the pair budget computed by the
+ * driver (src/dwgsim.c:535-591).  Everything is packed and copied before the call returns, because
+ * the caller frees / reallocs these per contig (src/dwgsim.c:1103-1104). */
+int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name,
+                          const uint8_t *seq_ascii, int32_t len,
+                          const uint64_t *hap1, const uint64_t *hap2,
+                          uint8_t *const *ins1, int32_t ins1_n,
+                          uint8_t *const *ins2, int32_t ins2_n,
+                          int64_t n_pairs);
+/* Simulate every queued pair, stream FASTQ to the sink in pair order, then drop the queued
+ * contigs.  Pair indices (the Philox key), `ctr` and `rand_ii` (src/dwgsim.c:423) carry over to
+ * the next add_contig/run round, so calling run() once per contig or once at the end yields the
+ * same bytes. */
+int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats);
+
+/* -- knobs ---------------------------------------------------------------------------------- */
+/* pairs per device batch (default 1<<20); ring = number of pinned output slots (default 3) */
+int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots);
+/* shard the global pair-index space: this handle simulates batches b with b % world == rank and
+ * skips the others (their random-pair counts must then be supplied, see set_rand_base_fn). */
+int dwgsim_gpu_set_shard(dwgsim_gpu_t *h, int32_t rank, int32_t world);
+/* the first pair index / random-pair serial this handle starts from (default 0 / 0) */
+int dwgsim_gpu_set_origin(dwgsim_gpu_t *h, int64_t first_pair_index, int64_t first_rand_serial);
+
+/* -- device-resident interface (multi-GPU broadcast, benchmarks) ------------------------------ */
+/* Finish packing the queued contigs into ONE position-independent blob in HBM (2-bit reference,
+ * N mask, per-haplotype sparse mutation tables + block index, contig table).  Rank 0 exports it,
+ * the other ranks import a byte-identical copy (e.g. after an NCCL broadcast into their own
+ * device memory): no host data is needed on those ranks. */
+int dwgsim_gpu_genome_finalize(dwgsim_gpu_t *h);
+int dwgsim_gpu_genome_blob(const dwgsim_gpu_t *h, uint64_t *device_ptr, uint64_t *n_bytes);
+int dwgsim_gpu_genome_import(dwgsim_gpu_t *h, uint64_t device_ptr, uint64_t n_bytes, int32_t take_ownership);
+int64_t dwgsim_gpu_genome_pairs(const dwgsim_gpu_t *h);   /* total pairs queued over all contigs */
+
+typedef struct {
+    uint64_t dev_ptr[3];           /* device addresses of the three packed FASTQ streams           */
+    uint64_t n_bytes[3];
+    int64_t  n_pairs, n_random, n_failed_attempts;
+    double   ms_simulate, ms_layout, ms_format;   /* CUDA-event time of each kernel group          */
+    int32_t  n_launches;
+} dwgsim_gpu_batch_t;
+/* Simulate pairs [first, first+n) of the resident genome into device memory and leave them
+ * there (no D2H).  rand_serial_base = number of random pairs before `first`.  Synchronous. */
+int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t rand_serial_base,
+                                 dwgsim_gpu_batch_t *out);
+/* copy one stream of the last resident batch to host memory (tests) */
+int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap);
+/* Fill the queue with a synthetic genome generated ON the device (benchmarks only): contigs of the
+ * given lengths, i.i.d. uniform ACGT with N runs, SNP/indel events at mut_rate; coverage gives the
+ * pair budget (src/dwgsim.c:589). */
+int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t n_contigs, const int32_t *lengths,
+                                uint64_t seed, double mut_rate, double indel_frac, double n_frac,
+                                double coverage);
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
+void *dwgsim_gpu_cuda_stream(const dwgsim_gpu_t *h);
+
+/* -- derived tables (exposed so tests can compare them with the oracle's) ---------------------- */
+typedef struct {
+    uint64_t thr_genomic, thr_hap0;
+    int32_t  isize_lo, isize_n;
+    const uint32_t *isize_cdf;
+    int32_t  qdelta_lo, qdelta_n;
+    const uint32_t *qdelta_cdf;
+    int32_t  n_cycles[2];
+    const uint32_t *err_thr[2];
+    const uint8_t  *qbase[2];
+    uint32_t flow_thr[2];
+} dwgsim_gpu_tables_t;
+int dwgsim_gpu_tables(const dwgsim_gpu_t *h, dwgsim_gpu_tables_t *out);   /* host copies */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

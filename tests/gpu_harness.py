@@ -1,0 +1,52 @@
+"""Shared helpers of the -m gpu parity tests: play the role of the reference host at the seam.
+
+The oracle (Philox backend) produces the expected FASTQ bytes AND, with keep=True, the dense seq_t /
+mutseq_t arrays a reference host would hold after mut_diref; those arrays are handed to the C ABI exactly
+as dwgsim_core would (include/dwgsim_gpu.h), and the product's bytes must equal the oracle's.
+"""
+import os
+
+FILE_NAMES = ["bwa.read1.fastq", "bwa.read2.fastq", "bfast.fastq"]
+GPU_KEYS = ("e", "E", "is_inner", "dist", "std_dev", "length", "mut_freq", "rand_read", "max_n", "data_type",
+            "strandedness", "read_one_strand", "flow_order", "seed", "fixed_quality", "quality_std", "read_prefix",
+            "reads_output_type", "amplicons")
+
+
+def oracle_expected(oracle, opts, fasta, prefix):
+    """run the oracle with Philox draws; returns (session kept open, [bytes x3])"""
+    sess = oracle.Session(oracle.make_opt(**opts), fasta, prefix, mode=oracle.RNG_PHILOX, keep=True)
+    want = []
+    for f in FILE_NAMES:
+        p = prefix + "." + f
+        want.append(open(p, "rb").read() if os.path.exists(p) else b"")
+    return sess, want
+
+
+def gpu_actual(sess, opts, batch=None, per_contig_runs=False):
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    params = params_from_options(**{k: v for k, v in opts.items() if k in GPU_KEYS})
+    got = [[], [], []]
+    stats = []
+    with DwgsimGpu(params) as gpu:
+        if batch:
+            gpu.set_batch(batch, 2)
+        for k in range(sess.n_contigs):
+            c = sess.contig(k)
+            if c["n_pairs"] == 0 and not per_contig_runs:
+                pass
+            gpu.add_contig(c["contig_i"], c["name"], c["seq"], c["len"], c["hap"][0], c["hap"][1],
+                           c["ins"][0], c["n_ins"][0], c["ins"][1], c["n_ins"][1], c["n_pairs"])
+            if per_contig_runs:
+                stats.append(gpu.run(lambda fid, data: got[fid].append(data)))
+        if not per_contig_runs:
+            stats.append(gpu.run(lambda fid, data: got[fid].append(data)))
+    return [b"".join(g) for g in got], stats
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            lo = a.rfind(b"\n@", 0, i) + 1
+            return "byte %d: want %r / got %r" % (i, a[lo:i + 80], b[lo:i + 80])
+    return "lengths differ: want %d got %d; tail want %r got %r" % (len(a), len(b), a[n - 60:n + 60], b[n - 60:n + 60])

@@ -1,0 +1,72 @@
+"""-m gpu: the CUDA path through the C ABI must equal the oracle (Philox backend) byte for byte."""
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import gpu_harness as gh  # noqa: E402
+import make_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+CASES = {k: v for k, v in make_golden.MATRIX.items()
+         if v.get("data_type", 0) != 2 and v.get("output_type", 0) == 0 and k != "coverage_zero"}
+
+
+def check(oracle, opts, fasta, tmp_path, **kw):
+    sess, want = gh.oracle_expected(oracle, opts, fasta, str(tmp_path / "orc"))
+    try:
+        assert sess.stats.error == 0
+        got, stats = gh.gpu_actual(sess, opts, **kw)
+        for i, name in enumerate(gh.FILE_NAMES):
+            assert got[i] == want[i], "%s: %s" % (name, gh.first_diff(want[i], got[i]))
+        assert sum(s.n_pairs for s in stats) == sess.stats.n_pairs_total
+        assert sum(s.n_random for s in stats) == sess.stats.n_random
+        assert sum(s.n_failed_attempts for s in stats) == sess.stats.n_failed_attempts
+        return stats
+    finally:
+        sess.close()
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_matrix_case_bit_exact(oracle, synth_fa, tmp_path, case):
+    check(oracle, CASES[case], synth_fa, tmp_path)
+
+
+def test_reference_golden_config_bit_exact(oracle, ex1_fa, tmp_path):
+    """the reference's own test configuration (testdata/test.sh:18) with Philox draws"""
+    check(oracle, dict(seed=13, N=10000), ex1_fa, tmp_path)
+
+
+def test_config1_2x100(oracle, ex1_fa, tmp_path):
+    """BASELINE.json configs[0]: ex1.fa 2x100bp -N 10000 Illumina"""
+    check(oracle, dict(seed=13, N=10000, length=(100, 100), data_type=0), ex1_fa, tmp_path)
+
+
+def test_small_batches_and_per_contig_runs_give_same_bytes(oracle, synth_fa, tmp_path):
+    """output must not depend on the batch size or on calling run() once per contig (pair-indexed Philox)"""
+    opts = dict(seed=3, N=5000, length=(100, 100), mut_rate=0.02, indel_frac=0.5, indel_extend=0.7)
+    check(oracle, opts, synth_fa, tmp_path, batch=777)
+    check(oracle, opts, synth_fa, tmp_path, batch=1024, per_contig_runs=True)
+
+
+def test_derived_tables_equal_oracle(oracle):
+    """the 32-bit threshold tables the kernels sample from == the oracle's own derivation"""
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    opts = dict(seed=1, C=1, length=(150, 120), e="0.001-0.01", E="0.0-0.3", std_dev=37.5, dist=420, quality_std=3.3,
+                rand_read=0.123, mut_freq=0.37)
+    o = oracle.make_opt(**opts)
+    t = oracle.lib().orc_tables_build(o).contents
+    with DwgsimGpu(params_from_options(**{k: v for k, v in opts.items() if k in gh.GPU_KEYS})) as gpu:
+        g = gpu.tables()
+        assert (g.thr_genomic, g.thr_hap0) == (t.thr_genomic, t.thr_hap0)
+        assert (g.isize_lo, g.isize_n, g.qdelta_lo, g.qdelta_n) == (t.isize_lo, t.isize_n, t.qdelta_lo, t.qdelta_n)
+        assert [g.isize_cdf[i] for i in range(g.isize_n)] == [t.isize_cdf[i] for i in range(t.isize_n)]
+        assert [g.qdelta_cdf[i] for i in range(g.qdelta_n)] == [t.qdelta_cdf[i] for i in range(t.qdelta_n)]
+        for e in range(2):
+            n = opts["length"][e]
+            assert [g.err_thr[e][i] for i in range(n)] == [t.err_thr[e][i] for i in range(n)]
+            assert [g.qbase[e][i] for i in range(n)] == [t.qbase[e][i] for i in range(n)]
