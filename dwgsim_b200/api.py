@@ -137,6 +137,23 @@ class DwgsimGpu:
         self._check(rc)
         return st
 
+    def run_count(self):
+        """run() with the library's own counting sink (no Python in the data path); returns Stats"""
+        counts = (C.c_int64 * 4)()
+        st = Stats()
+        cb = C.cast(self._L.dwgsim_gpu_sink_count, _lib.SINK_FN)
+        self._check(self._L.dwgsim_gpu_run(self._h, cb, C.cast(counts, C.c_void_p), C.byref(st)))
+        assert list(counts[:3]) == list(st.bytes)
+        return st
+
+    def run_to_fds(self, fds):
+        """run() writing each stream to a file descriptor (-1 discards); returns Stats"""
+        arr = (C.c_int * 3)(*fds)
+        st = Stats()
+        cb = C.cast(self._L.dwgsim_gpu_sink_fd, _lib.SINK_FN)
+        self._check(self._L.dwgsim_gpu_run(self._h, cb, C.cast(arr, C.c_void_p), C.byref(st)))
+        return st
+
     def run_collect(self):
         """run() into three bytes objects (tests)"""
         parts = ([], [], [])

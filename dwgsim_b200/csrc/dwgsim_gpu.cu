@@ -2,6 +2,7 @@
 // batch pipeline (compute stream + copy stream + pinned ring) around the kernels in kernels.cuh.
 // There is no CPU fallback: every entry point that needs a device fails with DWGSIM_GPU_ENODEV / ECUDA.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -764,10 +765,126 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
     return rc;
 }
 
-int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t, const int32_t *, uint64_t, double, double, double, double)
+// ---- synthetic genome (benchmarks): built procedurally on the host, then packed like any other ---------
+namespace {
+struct SplitMix {
+    uint64_t s;
+    explicit SplitMix(uint64_t seed) : s(seed) {}
+    uint64_t next() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+    double unif() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+void synth_contig(HostContig &c, uint64_t seed, double mut_rate, double indel_frac, double n_frac)
 {
-    if (h) h->last_error = "synthetic genome generator not built yet";
-    return DWGSIM_GPU_EUNSUPPORTED;
+    const int len = c.len;
+    const size_t nw2 = ((size_t)len + 15) / 16 + 1, nwm = ((size_t)len + 31) / 32 + 1;
+    c.ref2.resize(nw2); c.nmask.assign(nwm, 0);
+    SplitMix rng(seed * 0x100000001B3ull + (uint64_t)c.contig_i * 0x9E3779B97F4A7C15ull + 1);
+    for (size_t w = 0; w + 1 < nw2; w += 2) { uint64_t r = rng.next(); c.ref2[w] = (uint32_t)r; c.ref2[w + 1] = (uint32_t)(r >> 32); }
+    c.ref2[nw2 - 1] = (uint32_t)rng.next();
+    // N runs: 10 kb telomeres and one long run a third of the way in (together ~n_frac of the contig)
+    auto set_n = [&](int64_t a, int64_t b) {
+        a = std::max<int64_t>(a, 0); b = std::min<int64_t>(b, len);
+        for (int64_t p = a; p < b; ++p) { c.nmask[p >> 5] |= 1u << (p & 31); c.ref2[p >> 4] &= ~(3u << ((p & 15) << 1)); }
+    };
+    if (n_frac > 0 && len > 100000) {
+        const int64_t tel = 10000, mid = std::max<int64_t>((int64_t)(n_frac * len) - 2 * tel, 0);
+        set_n(0, tel); set_n(len - tel, len); set_n(len / 3, len / 3 + mid);
+    }
+    auto is_n = [&](int64_t p) { return (c.nmask[p >> 5] >> (p & 31)) & 1u; };
+    auto base_at = [&](int64_t p) { return (c.ref2[p >> 4] >> ((p & 15) << 1)) & 3u; };
+    const int nblk = (len >> kBlkShift) + 2;
+    for (int hh = 0; hh < 2; ++hh) { c.ev[hh].clear(); c.pool[hh].assign(4, 0); c.blk[hh].assign((size_t)nblk, 0); }
+    if (mut_rate > 0) {
+        const double lg = log1p(-std::min(mut_rate, 0.999999));
+        int64_t p = -1;
+        for (;;) {
+            double u = rng.unif();
+            if (u <= 0) u = 1e-300;
+            p += 1 + (int64_t)floor(log(u) / lg);
+            if (p >= len) break;
+            if (is_n(p)) continue;
+            const uint64_t r = rng.next();
+            const int which = (r & 0xff) < 85 ? 3 : (((r >> 8) & 1) ? 1 : 2);     // 1/3 homozygous
+            const uint32_t rb = base_at(p);
+            if (rng.unif() >= indel_frac) {
+                Event e{(uint32_t)p, kEvSubst | (((rb + 1 + (uint32_t)((r >> 16) % 3)) & 3u) << 2), 0};
+                for (int hh = 0; hh < 2; ++hh) if (which & (1 << hh)) c.ev[hh].push_back(e);
+            } else if ((r >> 20) & 1) {
+                int L = 1;
+                while (rng.unif() < 0.3) ++L;
+                int64_t q = p;
+                for (; q < p + L && q < len && !is_n(q); ++q) {
+                    Event e{(uint32_t)q, kEvDelete | (base_at(q) << 2), 0};
+                    for (int hh = 0; hh < 2; ++hh) if (which & (1 << hh)) c.ev[hh].push_back(e);
+                }
+                p = q - 1;
+            } else {
+                uint32_t n = 1;
+                while (rng.unif() < 0.3 && n < 26) ++n;
+                Event e{(uint32_t)p, kEvInsert | (rb << 2) | (n << 5), rng.next() & ((n >= 32) ? ~0ull : ((1ull << (2 * n)) - 1))};
+                for (int hh = 0; hh < 2; ++hh) if (which & (1 << hh)) c.ev[hh].push_back(e);
+            }
+        }
+    }
+    for (int hh = 0; hh < 2; ++hh) {
+        size_t e = 0;
+        for (int b = 0; b < nblk; ++b) {
+            const uint64_t start = (uint64_t)b << kBlkShift;
+            while (e < c.ev[hh].size() && c.ev[hh][e].pos < start) ++e;
+            c.blk[hh][b] = (uint32_t)e;
+        }
+    }
+}
+
+struct CountSink { int64_t bytes[3]; int64_t calls; uint64_t first_bytes[3]; };
+}  // namespace
+
+int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t n_contigs, const int32_t *lengths, uint64_t seed, double mut_rate,
+                                double indel_frac, double n_frac, double coverage)
+{
+    if (!h || n_contigs < 1 || !lengths || mut_rate < 0 || mut_rate >= 1 || coverage < 0) return DWGSIM_GPU_EINVAL;
+    if (h->blob) { h->last_error = "genome already finalized"; return DWGSIM_GPU_ESTATE; }
+    const double t0 = now_ms();
+    const size_t base = h->queue.size();
+    h->queue.resize(base + (size_t)n_contigs);
+    for (int i = 0; i < n_contigs; ++i) {
+        HostContig &c = h->queue[base + i];
+        c.name = "chr" + std::to_string(i + 1);
+        c.contig_i = (int32_t)(base + i); c.len = lengths[i];
+        // pair budget by coverage, src/dwgsim.c:589
+        c.n_pairs = (int64_t)(uint64_t)(c.len * coverage / ((long double)(h->p.length[0] + h->p.length[1])) / (1.0 - h->p.rand_read) + 0.5);
+        h->max_name_len = std::max(h->max_name_len, (int)c.name.size());
+    }
+    std::vector<std::thread> th;
+    const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_contigs));
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() { for (int i = (int)t; i < n_contigs; i += (int)nt) synth_contig(h->queue[base + i], seed, mut_rate, indel_frac, n_frac); });
+    for (auto &x : th) x.join();
+    h->ms_pack += now_ms() - t0;
+    return DWGSIM_GPU_OK;
+}
+
+// ---- ready-made sinks (plain C callbacks a host can pass to dwgsim_gpu_run) --------------------------------
+// user = int64_t[4]: bytes per file id, number of calls
+int dwgsim_gpu_sink_count(void *user, int file_id, const char *buf, size_t n)
+{
+    int64_t *c = (int64_t *)user;
+    (void)buf;
+    c[file_id] += (int64_t)n; c[3] += 1;
+    return 0;
+}
+// user = int[3]: one file descriptor per file id (-1 = discard)
+int dwgsim_gpu_sink_fd(void *user, int file_id, const char *buf, size_t n)
+{
+    const int fd = ((const int *)user)[file_id];
+    if (fd < 0) return 0;
+    while (n) {
+        ssize_t w = write(fd, buf, n);
+        if (w <= 0) return 1;
+        buf += w; n -= (size_t)w;
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -142,14 +142,21 @@ int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int6
                                  dwgsim_gpu_batch_t *out);
 /* copy one stream of the last resident batch to host memory (tests) */
 int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap);
-/* Fill the queue with a synthetic genome generated ON the device (benchmarks only): contigs of the
- * given lengths, i.i.d. uniform ACGT with N runs, SNP/indel events at mut_rate; coverage gives the
- * pair budget (src/dwgsim.c:589). */
+/* Queue a synthetic genome built procedurally inside the library (benchmarks only; no dense
+ * host arrays are needed): contigs "chr1".. of the given lengths, i.i.d. uniform ACGT, N runs
+ * covering n_frac of each contig (10 kb telomeres + one long run), SNP / deletion / insertion
+ * events at mut_rate with 1/3 homozygous; coverage gives the pair budget (src/dwgsim.c:589). */
 int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t n_contigs, const int32_t *lengths,
                                 uint64_t seed, double mut_rate, double indel_frac, double n_frac,
                                 double coverage);
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
 void *dwgsim_gpu_cuda_stream(const dwgsim_gpu_t *h);
+
+/* -- ready-made sinks for dwgsim_gpu_run ---------------------------------------------------------- */
+/* user = int64_t[4]: bytes per file id and the number of calls */
+int dwgsim_gpu_sink_count(void *user, int file_id, const char *buf, size_t n);
+/* user = int[3]: a file descriptor per file id (-1 discards); write(2)s every chunk */
+int dwgsim_gpu_sink_fd(void *user, int file_id, const char *buf, size_t n);
 
 /* -- derived tables (exposed so tests can compare them with the oracle's) ---------------------- */
 typedef struct {
