@@ -446,7 +446,8 @@ int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slo
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
     const int grid = std::min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count * 8);
     const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15;
-    const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1);
+    const int flr = (sp.flow_order_len + 15) & ~15;
+    const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
     const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + ((std::max(sp.cap[0], sp.cap[1]) + 15) & ~15));
     cudaStream_t st = h->s_compute;
     CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 16, st));
@@ -483,6 +484,10 @@ int collect_batch(dwgsim_gpu *h, bool timed, BatchResult *r)
     if (r->status & 1ull) {
         h->last_error = "failed to generate a read after 10001 trials";
         return DWGSIM_GPU_ETRIALS;
+    }
+    if (r->status & 2ull) {
+        h->last_error = "Ion Torrent read grew past 2*len+64 bases";
+        return DWGSIM_GPU_EOVERFLOW;
     }
     return DWGSIM_GPU_OK;
 }
@@ -526,11 +531,20 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
     if (p->data_type == 2 && (!p->flow_order || p->flow_order_len <= 0)) return DWGSIM_GPU_EINVAL;
     if (p->length[0] > 30000 || p->length[1] > 30000) return DWGSIM_GPU_EUNSUPPORTED;   // 16-bit lengths in PairRec
     if (p->std_dev > 1.0e6) return DWGSIM_GPU_EUNSUPPORTED;                              // insert-size table size
-    if (p->data_type == 2) return DWGSIM_GPU_EUNSUPPORTED;                               // Ion Torrent kernel: not yet
+    if (p->data_type == 2) {
+        // every base must have a flow (the reference loops forever otherwise, src/dwgsim.c:283-286)
+        int seen = 0;
+        if (p->flow_order_len > 1024) return DWGSIM_GPU_EUNSUPPORTED;
+        for (int i = 0; i < p->flow_order_len; ++i) if (p->flow_order[i] >= 0 && p->flow_order[i] < 4) seen |= 1 << p->flow_order[i];
+        if (seen != 15) return DWGSIM_GPU_EUNSUPPORTED;
+        for (int e = 0; e < 2; ++e)                                                      // src/dwgsim_opt.c:338-343
+            if (p->length[e] > 0 && p->e_by[e] != 0.0) return DWGSIM_GPU_EINVAL;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return DWGSIM_GPU_ENODEV;
     dwgsim_gpu *h = new dwgsim_gpu();
     h->p = *p;
+    for (int e = 0; e < 2; ++e) if (p->length[e] == 0) h->p.e_by[e] = 0.0;   // the reference leaves 0/0 here (src/dwgsim_opt.c:460)
     h->device = device;
     if (p->read_prefix) { h->prefix_s = std::string(p->read_prefix) + "_"; }
     if (p->flow_order) h->flow_order.assign(p->flow_order, p->flow_order + p->flow_order_len);
@@ -541,6 +555,17 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
     derive_tables(h);
     int rc = upload_tables(h);
     if (rc) { dwgsim_gpu_destroy(h); return rc; }
+    {   // shared memory per CTA: read codes (+ flow mask) per warp; names + qualities per warp
+        const SimParams &sp = h->sp;
+        const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15, flr = (sp.flow_order_len + 15) & ~15;
+        const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
+        const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + std::max(cap0, cap1));
+        if (smem_a > 227 * 1024 || smem_b > 227 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
+        if (cudaFuncSetAttribute(simulate_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess ||
+            cudaFuncSetAttribute(format_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess) {
+            dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;
+        }
+    }
     *out = h;
     return DWGSIM_GPU_OK;
 }

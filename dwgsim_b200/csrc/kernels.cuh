@@ -217,6 +217,131 @@ __device__ __forceinline__ void colour_encode(uint8_t *seq, int n, int lane)
     }
 }
 
+// ---- Ion Torrent flow model (generate_errors_flows, src/dwgsim.c:246-417) -------------------------------
+// The model is sequential per read (every error shifts the rest of the read and the flow phase), so the
+// scalar control flow runs warp-uniform (all lanes execute the same decisions on the same sequential FLOW
+// draws) and the lanes share the work that is parallel: N removal, reversal, and the shifts of the read tail.
+struct FlowRng {
+    PairKey key;
+    uint32_t end, next;
+    uint4 blk;
+    int have;
+    __device__ __forceinline__ uint32_t draw()
+    {
+        const int b = (int)(next >> 2);
+        if (b != have) { have = b; blk = draw_block(key, kStFlow, end, (uint32_t)b); }
+        return word_of(blk, next++ & 3u);
+    }
+};
+__device__ __forceinline__ void warp_reverse(uint8_t *seq, int len, int lane)
+{
+    for (int j = lane; j < (len >> 1); j += 32) { uint8_t a = seq[j], b = seq[len - 1 - j]; seq[j] = b; seq[len - 1 - j] = a; }
+    __syncwarp();
+}
+// seq[j + n] = seq[j] for j in [i, len), highest chunk first
+__device__ __forceinline__ void warp_shift_up(uint8_t *seq, int i, int len, int n, int lane)
+{
+    for (int top = len; top > i; top -= 32) {
+        const int j = top - 1 - lane;
+        uint8_t v = 0;
+        if (j >= i) v = seq[j];
+        __syncwarp();
+        if (j >= i) seq[j + n] = v;
+        __syncwarp();
+    }
+}
+// seq[j] = seq[j + n] for j in [i, len - n), lowest chunk first
+__device__ __forceinline__ void warp_shift_down(uint8_t *seq, int i, int len, int n, int lane)
+{
+    for (int a = i; a < len - n; a += 32) {
+        const int j = a + lane;
+        uint8_t v = 0;
+        if (j < len - n) v = seq[j + n];
+        __syncwarp();
+        if (j < len - n) seq[j] = v;
+        __syncwarp();
+    }
+}
+// returns the new length, -1 when the first base is not in the flow order (src/dwgsim.c:275-278);
+// *overflow is set when the read would grow past `cap` symbols
+__device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int strand, uint32_t thr, const int8_t *fo,
+                                           int fl, uint8_t *mask, FlowRng &rng, int *n_err_out, int *overflow, int lane)
+{
+    for (int j = lane; j < len; j += 32) if (seq[j] >= 4) seq[j] = 0;          // src/dwgsim.c:253-257
+    for (int j = lane; j < fl; j += 32) mask[j] = 0;                            // per-read mask
+    __syncwarp();
+    if (strand) warp_reverse(seq, len, lane);
+    int i, flow_i;
+    {
+        const int c = len > 0 ? seq[0] : 0;
+        for (i = 0; i < fl; ++i) if (c == fo[i]) break;
+        if (i == fl) return -1;
+    }
+    flow_i = i;
+    int prev_c = 4;
+    for (i = 0; i < len; ++i) {                                                  // src/dwgsim.c:281-364
+        const int c = seq[i];
+        while (c != fo[flow_i]) { if (lane == 0) mask[flow_i] = 0; flow_i = flow_i + 1 == fl ? 0 : flow_i + 1; }
+        if (prev_c != c) {
+            if (lane == 0) mask[flow_i] = 0;
+            int n_err = 0;
+            while (rng.draw() < thr) ++n_err;
+            if (n_err > 0) {
+                if (!(rng.draw() >> 31)) {                                       // U < 0.5: insertion
+                    if (len + n_err >= cap) { *overflow = 1; return len; }
+                    __syncwarp();
+                    warp_shift_up(seq, i, len, n_err, lane);
+                    for (int j = i + lane; j < i + n_err; j += 32) seq[j] = (uint8_t)c;
+                    __syncwarp();
+                    len += n_err;
+                } else {                                                         // deletion, bounded by the homopolymer
+                    int hp_l = 0, next_c = 4;
+                    for (int j = i; j < len; ++j, ++hp_l) { next_c = seq[j]; if (c != next_c) break; }
+                    if (hp_l < n_err) n_err = hp_l;
+                    __syncwarp();
+                    warp_shift_down(seq, i, len, n_err, lane);
+                    len -= n_err;
+                    if (lane == 0) mask[flow_i] = 1;
+                    if (n_err == hp_l && (i == 0 || prev_c == next_c)) {         // dot-fill, src/dwgsim.c:342-358
+                        int j = 0;
+                        while (next_c != fo[(flow_i + j) % fl]) ++j;
+                        if (j <= 0) { *overflow = 2; return len; }
+                        const int k = (int)__umulhi(rng.draw(), (uint32_t)j);
+                        if (len + 1 >= cap) { *overflow = 1; return len; }
+                        warp_shift_up(seq, i, len, 1, lane);
+                        if (lane == 0) seq[i] = (uint8_t)fo[(flow_i + k) % fl];
+                        __syncwarp();
+                        len += 1;
+                    }
+                }
+                *n_err_out += n_err;
+            }
+            prev_c = c;
+        }
+    }
+    __syncwarp();
+    for (i = 0; i < len; ++i) {                                                  // src/dwgsim.c:366-406
+        const int c = seq[i];
+        while (c != fo[flow_i]) {
+            int n_err = 0;
+            while (rng.draw() < thr) ++n_err;
+            if (n_err > 0 && mask[flow_i] == 0) {
+                if (len + n_err >= cap) { *overflow = 1; return len; }
+                __syncwarp();
+                warp_shift_up(seq, i, len, n_err, lane);
+                for (int j = i + lane; j < i + n_err; j += 32) seq[j] = (uint8_t)fo[flow_i];
+                __syncwarp();
+                len += n_err;
+                *n_err_out += n_err;
+            }
+            flow_i = flow_i + 1 == fl ? 0 : flow_i + 1;
+        }
+    }
+    __syncwarp();
+    if (strand) warp_reverse(seq, len, lane);
+    return len;
+}
+
 // ---- kernel A: simulate ----------------------------------------------------------------------------------
 // status[0]: error bits (1 = a pair exhausted its 10001 trials), status[1]: rejected attempts
 __global__ void __launch_bounds__(kThreads)
@@ -226,9 +351,14 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cap0 = (P.cap[0] + 15) & ~15, cap1 = (P.cap[1] + 15) & ~15;
+    const int flr = (P.flow_order_len + 15) & ~15;
     uint8_t *code[2];
-    code[0] = smem + (size_t)warp * (cap0 + cap1);
+    code[0] = smem + (size_t)warp * (cap0 + cap1 + flr);
     code[1] = code[0] + cap0;
+    uint8_t *flow_mask = code[1] + cap1;
+    int8_t *flow_order = reinterpret_cast<int8_t *>(smem + (size_t)kWarpsPerBlock * (cap0 + cap1 + flr));
+    for (int j = threadIdx.x; j < P.flow_order_len; j += kThreads) flow_order[j] = P.flow_order[j];
+    __syncthreads();
     const int warps_total = gridDim.x * kWarpsPerBlock;
 
     for (int p = blockIdx.x * kWarpsPerBlock + warp; p < n; p += warps_total) {
@@ -340,6 +470,19 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
                 rec.n_sub[j] = (uint16_t)w[j].n_sub;
                 rec.n_indel[j] = (uint16_t)w[j].n_indel;
                 rec.n_indel_first[j] = (uint16_t)w[j].n_indel_first;
+                if (P.data_type == 2) {                      // Ion Torrent, src/dwgsim.c:861-864
+                    int nerr = 0, ovf = 0, nl = 0;
+                    if (s[j] > 0) {
+                        FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
+                        nl = flow_errors(code[j], s[j], P.cap[j], strand[j], P.flow_thr[j], flow_order, P.flow_order_len,
+                                         flow_mask, rng, &nerr, &ovf, lane);
+                    }
+                    if (ovf && lane == 0) atomicOr(status, 2ull);
+                    s[j] = nl > 0 ? nl : 0;
+                    rec.len[j] = (uint16_t)s[j];
+                    rec.n_err[j] = (uint16_t)nerr;
+                    continue;
+                }
                 // substitution errors, src/dwgsim.c:233-244
                 int nerr = 0;
                 uint4 blk = make_uint4(0, 0, 0, 0);

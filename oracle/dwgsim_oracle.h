@@ -88,7 +88,7 @@ typedef struct {
     int64_t n_failed_attempts;  /* rejected genomic attempts                                      */
     int64_t n_contigs, n_contigs_skipped;
     int64_t bytes_bwa1, bytes_bwa2, bytes_bfast;
-    int32_t error;              /* 0 ok; 1 = 10000-failure abort; 2 = io; 3 = ion first flow      */
+    int32_t error;              /* 0 ok; 1 = 10001-failure abort; 2 = io; 4 = Ion read overflow   */
 } orc_stats_t;
 
 typedef struct orc_session orc_session_t;

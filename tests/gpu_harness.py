@@ -14,7 +14,9 @@ GPU_KEYS = ("e", "E", "is_inner", "dist", "std_dev", "length", "mut_freq", "rand
 
 def oracle_expected(oracle, opts, fasta, prefix):
     """run the oracle with Philox draws; returns (session kept open, [bytes x3])"""
-    sess = oracle.Session(oracle.make_opt(**opts), fasta, prefix, mode=oracle.RNG_PHILOX, keep=True)
+    opt = oracle.make_opt(**opts)
+    sess = oracle.Session(opt, fasta, prefix, mode=oracle.RNG_PHILOX, keep=True)
+    sess.opt = opt
     want = []
     for f in FILE_NAMES:
         p = prefix + "." + f
@@ -22,9 +24,14 @@ def oracle_expected(oracle, opts, fasta, prefix):
     return sess, want
 
 
-def gpu_actual(sess, opts, batch=None, per_contig_runs=False):
+def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None):
     from dwgsim_b200 import DwgsimGpu, params_from_options
     params = params_from_options(**{k: v for k, v in opts.items() if k in GPU_KEYS})
+    if orc_opt is not None:
+        # -B (Ion Torrent base-error calibration) rescales e in option parsing (src/dwgsim_opt.c:415-457), i.e. on the
+        # host before the seam: hand the device the calibrated profile the host holds
+        for i in range(2):
+            params.e_start[i], params.e_by[i] = orc_opt.e_start[i], orc_opt.e_by[i]
     got = [[], [], []]
     stats = []
     with DwgsimGpu(params) as gpu:

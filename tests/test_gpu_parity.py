@@ -12,15 +12,14 @@ import make_golden  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-CASES = {k: v for k, v in make_golden.MATRIX.items()
-         if v.get("data_type", 0) != 2 and v.get("output_type", 0) == 0 and k != "coverage_zero"}
+CASES = {k: v for k, v in make_golden.MATRIX.items() if v.get("output_type", 0) == 0 and k != "coverage_zero"}
 
 
 def check(oracle, opts, fasta, tmp_path, **kw):
     sess, want = gh.oracle_expected(oracle, opts, fasta, str(tmp_path / "orc"))
     try:
         assert sess.stats.error == 0
-        got, stats = gh.gpu_actual(sess, opts, **kw)
+        got, stats = gh.gpu_actual(sess, opts, orc_opt=sess.opt, **kw)
         for i, name in enumerate(gh.FILE_NAMES):
             assert got[i] == want[i], "%s: %s" % (name, gh.first_diff(want[i], got[i]))
         assert sum(s.n_pairs for s in stats) == sess.stats.n_pairs_total
@@ -51,6 +50,16 @@ def test_small_batches_and_per_contig_runs_give_same_bytes(oracle, synth_fa, tmp
     opts = dict(seed=3, N=5000, length=(100, 100), mut_rate=0.02, indel_frac=0.5, indel_extend=0.7)
     check(oracle, opts, synth_fa, tmp_path, batch=777)
     check(oracle, opts, synth_fa, tmp_path, batch=1024, per_contig_runs=True)
+
+
+def test_ion_torrent_config5_shape(oracle, synth_fa, tmp_path):
+    """BASELINE.json configs[4]: Ion Torrent 400 bp single-end, 32-flow order, -e 0.01"""
+    check(oracle, dict(seed=5, C=4, data_type=2, length=(400, 0), e=0.01, flow_order=make_golden.FLOW), synth_fa, tmp_path)
+
+
+def test_ion_torrent_heavy_errors_many_shifts(oracle, synth_fa, tmp_path):
+    check(oracle, dict(seed=6, N=3000, data_type=2, length=(150, 80), e=0.12, E=0.2, flow_order="TACGTACGTCTGAGCATCGATCGATGTACAGC",
+                       dist=300, std_dev=30), synth_fa, tmp_path)
 
 
 def test_derived_tables_equal_oracle(oracle):
