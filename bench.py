@@ -223,7 +223,7 @@ def dense_contig(n_bases, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -290,16 +290,23 @@ def main():
     stream = torch.cuda.ExternalStream(gpu.cuda_stream(), device=torch.device("cuda", local_rank))
     rand_base = 0
 
+    exchange = None
+    if world > 1:
+        from dwgsim_b200 import shard
+        exchange = shard.make_exchange()
+
     def step(k):
         nonlocal rand_base
         first = ((k % n_steps_avail) * world + rank) * B
-        b = gpu.simulate_resident(first, B, rand_base)
-        if world > 1:   # the one exchange of the path: random-pair counts, so rand_ii is global (src/dwgsim.c:1096)
-            cnt = torch.tensor([b.n_random], dtype=torch.int64, device="cuda")
-            allc = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(allc, cnt)
-            rand_base += int(sum(int(x.item()) for x in allc))
+        if world > 1:
+            # the one exchange of the path: random-pair counts of the round (all-gather over NCCL), so that rand_ii
+            # in the names stays the global running count (src/dwgsim.c:1096)
+            cnt = gpu.resident_begin(first, B, True)
+            before, tot = exchange(k, cnt)
+            b = gpu.resident_finish(rand_base + before)
+            rand_base += tot
         else:
+            b = gpu.simulate_resident(first, B, rand_base)
             rand_base += b.n_random
         return b
 

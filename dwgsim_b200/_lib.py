@@ -51,6 +51,7 @@ class Tables(C.Structure):
 
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_char), C.c_size_t)
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64))
 
 # every symbol include/dwgsim_gpu.h declares: (restype, argtypes)
 _P = C.c_void_p
@@ -65,6 +66,9 @@ SYMBOLS = {
     "dwgsim_gpu_run": (C.c_int, [_P, SINK_FN, _P, C.POINTER(Stats)]),
     "dwgsim_gpu_set_batch": (C.c_int, [_P, C.c_int64, C.c_int32]),
     "dwgsim_gpu_set_shard": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "dwgsim_gpu_set_exchange": (C.c_int, [_P, EXCHANGE_FN, _P]),
+    "dwgsim_gpu_resident_begin": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "dwgsim_gpu_resident_finish": (C.c_int, [_P, C.c_int64, C.POINTER(Batch)]),
     "dwgsim_gpu_set_origin": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "dwgsim_gpu_genome_finalize": (C.c_int, [_P]),
     "dwgsim_gpu_genome_blob": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

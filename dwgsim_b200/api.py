@@ -167,6 +167,19 @@ class DwgsimGpu:
     def set_shard(self, rank, world):
         self._check(self._L.dwgsim_gpu_set_shard(self._h, rank, world))
 
+    def set_exchange(self, fn):
+        """fn(round, my_random) -> (before_me, round_total); called once per round on every rank (a collective)"""
+        def _cb(user, rnd, mine, before, total):
+            try:
+                b, t = fn(int(rnd), int(mine))
+                before[0], total[0] = int(b), int(t)
+                return 0
+            except Exception as e:
+                self._exchange_error = e
+                return 1
+        self._exchange_cb = _lib.EXCHANGE_FN(_cb)      # keep alive
+        self._check(self._L.dwgsim_gpu_set_exchange(self._h, self._exchange_cb, None))
+
     def set_origin(self, first_pair_index, first_rand_serial=0):
         self._check(self._L.dwgsim_gpu_set_origin(self._h, first_pair_index, first_rand_serial))
 
@@ -193,6 +206,16 @@ class DwgsimGpu:
     def simulate_resident(self, first, n, rand_serial_base=0):
         b = Batch()
         self._check(self._L.dwgsim_gpu_simulate_resident(self._h, first, n, rand_serial_base, C.byref(b)))
+        return b
+
+    def resident_begin(self, first, n, want_count=True):
+        c = C.c_int64()
+        self._check(self._L.dwgsim_gpu_resident_begin(self._h, first, n, C.byref(c) if want_count else None))
+        return c.value
+
+    def resident_finish(self, rand_serial_base):
+        b = Batch()
+        self._check(self._L.dwgsim_gpu_resident_finish(self._h, rand_serial_base, C.byref(b)))
         return b
 
     def copy_stream(self, file_id, n_bytes):

@@ -79,7 +79,7 @@ struct dwgsim_gpu {
     std::vector<int8_t> flow_order;
     int device = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     // derived tables (host + device)
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_thr[2];
@@ -104,6 +104,9 @@ struct dwgsim_gpu {
     int64_t batch_pairs = 1 << 18;
     int ring = 3;
     int shard_rank = 0, shard_world = 1;
+    dwgsim_gpu_exchange_fn exchange = nullptr;
+    void *exchange_user = nullptr;
+    int64_t pending_first = -1; int pending_n = 0;
     Workspace ws;
     char *pinned[8][3] = {};
     uint64_t pinned_cap[3] = {0, 0, 0};
@@ -436,8 +439,9 @@ struct BatchResult {
     int launches;
 };
 
-// enqueue the kernels of one batch on the compute stream; results land in ws.h_totals after a sync
-int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slot, bool timed, int *launches)
+// phase 1 of a batch: simulate + count the random pairs (their number is needed before any name can be laid out,
+// because rand_ii is a running count over all earlier pairs, src/dwgsim.c:1096)
+int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launches)
 {
     Workspace &w = h->ws;
     const SimParams &sp = h->sp;
@@ -448,7 +452,6 @@ int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slo
     const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15;
     const int flr = (sp.flow_order_len + 15) & ~15;
     const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
-    const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + ((std::max(sp.cap[0], sp.cap[1]) + 15) & ~15));
     cudaStream_t st = h->s_compute;
     CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 16, st));
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[0], st));
@@ -456,6 +459,35 @@ int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slo
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
     layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_rand, nblk, 1, w.totals);
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[5], st));
+    CUDA_TRY(h, cudaGetLastError());
+    *launches = 3;
+    return DWGSIM_GPU_OK;
+}
+
+// number of random pairs of the batch simulated last (synchronises the compute stream)
+int read_random_count(dwgsim_gpu *h, int64_t *n_random)
+{
+    Workspace &w = h->ws;
+    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 8, cudaMemcpyDeviceToHost, h->s_compute));
+    CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+    *n_random = (int64_t)w.h_totals[0];
+    return DWGSIM_GPU_OK;
+}
+
+// phase 2: record lengths -> offsets -> FASTQ text; results land in ws.h_totals after a sync
+int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slot, bool timed, int *launches)
+{
+    Workspace &w = h->ws;
+    const SimParams &sp = h->sp;
+    const int nblk = (n + kScanTile - 1) / kScanTile;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    const int grid = std::min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count * 8);
+    const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15;
+    const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + std::max(cap0, cap1));
+    cudaStream_t st = h->s_compute;
+    if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[4], st));
     layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, w.blk_rand,
                                                      w.serial, w.lens, w.blk_len);
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
@@ -467,7 +499,16 @@ int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slo
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(w.h_totals + 8, w.status, 16, cudaMemcpyDeviceToHost, st));
-    *launches = 7;
+    *launches = 4;
+    return DWGSIM_GPU_OK;
+}
+
+int launch_batch(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slot, bool timed, int *launches)
+{
+    int l1 = 0, l2 = 0, rc;
+    if ((rc = launch_simulate(h, first, n, timed, &l1))) return rc;
+    if ((rc = launch_format(h, first, n, rand_base, slot, timed, &l2))) return rc;
+    *launches = l1 + l2;
     return DWGSIM_GPU_OK;
 }
 
@@ -480,7 +521,14 @@ int collect_batch(dwgsim_gpu *h, bool timed, BatchResult *r)
     r->status = w.h_totals[8];
     r->n_failed = (int64_t)w.h_totals[9];
     r->ms[0] = r->ms[1] = r->ms[2] = 0;
-    if (timed) for (int k = 0; k < 3; ++k) CUDA_TRY(h, cudaEventElapsedTime(&r->ms[k], h->ev_t[k], h->ev_t[k + 1]));
+    if (timed) {
+        float a = 0, b = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&r->ms[0], h->ev_t[0], h->ev_t[1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&a, h->ev_t[4], h->ev_t[2]));        // lengths + scan + offsets
+        CUDA_TRY(h, cudaEventElapsedTime(&b, h->ev_t[1], h->ev_t[5]));        // count + scan
+        r->ms[1] = a + b;
+        CUDA_TRY(h, cudaEventElapsedTime(&r->ms[2], h->ev_t[2], h->ev_t[3]));
+    }
     if (r->status & 1ull) {
         h->last_error = "failed to generate a read after 10001 trials";
         return DWGSIM_GPU_ETRIALS;
@@ -688,16 +736,30 @@ int dwgsim_gpu_tables(const dwgsim_gpu_t *h, dwgsim_gpu_tables_t *t)
     return DWGSIM_GPU_OK;
 }
 
-int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
+int dwgsim_gpu_resident_begin(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t *n_random)
 {
-    if (!h || !out || n < 1 || first < 0) return DWGSIM_GPU_EINVAL;
+    if (!h || n < 1 || first < 0) return DWGSIM_GPU_EINVAL;
     cudaSetDevice(h->device);
     int rc = finalize_genome(h);
     if (rc) return rc;
     if (first + n > h->blob_pairs || n > (1 << 24)) return DWGSIM_GPU_EINVAL;
     if ((rc = ensure_workspace(h, std::max<int64_t>(n, h->ws.cap_pairs), false))) return rc;
     int launches = 0;
-    if ((rc = launch_batch(h, first, (int)n, rand_serial_base, 0, true, &launches))) return rc;
+    if ((rc = launch_simulate(h, first, (int)n, true, &launches))) return rc;
+    h->pending_first = first; h->pending_n = (int)n;
+    if (n_random) return read_random_count(h, n_random);
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
+{
+    if (!h || !out || h->pending_first < 0) return DWGSIM_GPU_ESTATE;
+    cudaSetDevice(h->device);
+    int launches = 0, rc;
+    const int64_t first = h->pending_first;
+    const int n = h->pending_n;
+    h->pending_first = -1;
+    if ((rc = launch_format(h, first, n, rand_serial_base, 0, true, &launches))) return rc;
     BatchResult r;
     rc = collect_batch(h, true, &r);
     memset(out, 0, sizeof *out);
@@ -705,8 +767,23 @@ int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int6
     h->last_slot = 0;
     out->n_pairs = n; out->n_random = r.n_random; out->n_failed_attempts = r.n_failed;
     out->ms_simulate = r.ms[0]; out->ms_layout = r.ms[1]; out->ms_format = r.ms[2];
-    out->n_launches = launches;
+    out->n_launches = launches + 3;
     return rc;
+}
+
+int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
+{
+    if (!out) return DWGSIM_GPU_EINVAL;
+    int rc = dwgsim_gpu_resident_begin(h, first, n, nullptr);      // no host sync between the phases
+    if (rc) return rc;
+    return dwgsim_gpu_resident_finish(h, rand_serial_base, out);
+}
+
+int dwgsim_gpu_set_exchange(dwgsim_gpu_t *h, dwgsim_gpu_exchange_fn fn, void *user)
+{
+    if (!h) return DWGSIM_GPU_EINVAL;
+    h->exchange = fn; h->exchange_user = user;
+    return DWGSIM_GPU_OK;
 }
 
 int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap)
@@ -748,22 +825,47 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
         pd.live = false;
         return DWGSIM_GPU_OK;
     };
-    int64_t bi = 0;
     int launches = 0;
-    for (int64_t first = 0; first < total && rc == DWGSIM_GPU_OK; first += B, ++bi) {
-        const int n = (int)std::min<int64_t>(B, total - first);
-        const int dslot = (int)(bi & 1), pslot = (int)(bi % h->pinned_slots);
-        // the device slot was last used by batch bi-2, whose copy finished before batch bi-1 was drained
+    const int world = h->shard_world, rank = h->shard_rank;
+    if (world > 1 && !h->exchange) { h->last_error = "sharded run needs dwgsim_gpu_set_exchange"; return DWGSIM_GPU_ESTATE; }
+    const int64_t n_batches = (total + B - 1) / B;
+    const int64_t n_rounds = (n_batches + world - 1) / world;
+    int64_t mine = 0;                                           // batches this rank has processed
+    for (int64_t round = 0; round < n_rounds && rc == DWGSIM_GPU_OK; ++round) {
+        const int64_t bi = round * world + rank;               // batch index owned by this rank in this round
+        const bool active = bi < n_batches;
+        const int64_t first = bi * B;
+        const int n = active ? (int)std::min<int64_t>(B, total - first) : 0;
+        const int dslot = (int)(mine & 1), pslot = (int)(mine % h->pinned_slots);
         int l = 0;
-        if ((rc = launch_batch(h, first, n, h->rand_serial, dslot, true, &l))) break;
-        launches += l;
-        // while the GPU works on this batch, hand the previous one to the sink
-        if ((rc = drain(pend))) break;
+        int64_t rand_base = h->rand_serial, my_random = 0, round_total = 0;
+        if (world == 1) {
+            // the device slot was last used two batches ago, whose copy finished before the previous batch was drained
+            if ((rc = launch_batch(h, first, n, rand_base, dslot, true, &l))) break;
+            launches += l;
+            if ((rc = drain(pend))) break;                     // the sink works on the previous batch meanwhile
+        } else {
+            if (active) {
+                if ((rc = launch_simulate(h, first, n, true, &l))) break;
+                launches += l;
+            }
+            if ((rc = drain(pend))) break;
+            if (active && (rc = read_random_count(h, &my_random))) break;
+            // the one exchange of the path: random-pair counts of this round, in batch order
+            int64_t before_me = 0;
+            if (h->exchange(h->exchange_user, round, my_random, &before_me, &round_total)) { h->last_error = "exchange callback failed"; rc = DWGSIM_GPU_ESINK; break; }
+            rand_base = h->rand_serial + before_me;
+            if (active) {
+                if ((rc = launch_format(h, first, n, rand_base, dslot, true, &l))) break;
+                launches += l;
+            }
+        }
+        if (!active) { h->rand_serial += round_total; continue; }
         BatchResult r;
         if ((rc = collect_batch(h, true, &r))) break;
         st.ms_simulate += r.ms[0]; st.ms_layout += r.ms[1]; st.ms_format += r.ms[2];
         st.n_random += r.n_random; st.n_failed_attempts += r.n_failed; st.n_pairs += n;
-        h->rand_serial += r.n_random;
+        h->rand_serial += world == 1 ? r.n_random : round_total;
         CUDA_TRY(h, cudaEventRecord(computed, h->s_compute));
         CUDA_TRY(h, cudaStreamWaitEvent(h->s_copy, computed, 0));
         for (int k = 0; k < 3; ++k)
@@ -774,7 +876,7 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
         CUDA_TRY(h, cudaEventRecord(copied[pslot], h->s_copy));
         pend.live = true; pend.pslot = pslot;
         for (int k = 0; k < 3; ++k) pend.bytes[k] = r.bytes[k];
-        ++st.n_batches;
+        ++st.n_batches; ++mine;
     }
     if (rc == DWGSIM_GPU_OK) rc = drain(pend);
     cudaStreamSynchronize(h->s_copy);

@@ -113,9 +113,17 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
 /* -- knobs ---------------------------------------------------------------------------------- */
 /* pairs per device batch (default 1<<20); ring = number of pinned output slots (default 3) */
 int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots);
-/* shard the global pair-index space: this handle simulates batches b with b % world == rank and
- * skips the others (their random-pair counts must then be supplied, see set_rand_base_fn). */
+/* shard the pair-index space: dwgsim_gpu_run simulates the batches b with b % world == rank and hands
+ * only those to the sink (in order); concatenating the ranks' batches round-robin gives the bytes of
+ * the unsharded run.  rand_ii (src/dwgsim.c:1096) is a running count over ALL pairs, so every round
+ * the ranks exchange how many random pairs their batch held: */
 int dwgsim_gpu_set_shard(dwgsim_gpu_t *h, int32_t rank, int32_t world);
+/* called once per round by every rank (a collective: e.g. an all-gather of my_random over NCCL);
+ * must return in *before_me the sum over the lower ranks and in *round_total the sum over all ranks.
+ * Return 0 on success. */
+typedef int (*dwgsim_gpu_exchange_fn)(void *user, int64_t round, int64_t my_random,
+                                      int64_t *before_me, int64_t *round_total);
+int dwgsim_gpu_set_exchange(dwgsim_gpu_t *h, dwgsim_gpu_exchange_fn fn, void *user);
 /* the first pair index / random-pair serial this handle starts from (default 0 / 0) */
 int dwgsim_gpu_set_origin(dwgsim_gpu_t *h, int64_t first_pair_index, int64_t first_rand_serial);
 
@@ -140,6 +148,10 @@ typedef struct {
  * there (no D2H).  rand_serial_base = number of random pairs before `first`.  Synchronous. */
 int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t rand_serial_base,
                                  dwgsim_gpu_batch_t *out);
+/* the same in two phases, for sharded runs: begin() simulates and reports the batch's random-pair
+ * count (pass NULL to skip the host sync), finish() lays the records out from rand_serial_base */
+int dwgsim_gpu_resident_begin(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t *n_random);
+int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim_gpu_batch_t *out);
 /* copy one stream of the last resident batch to host memory (tests) */
 int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap);
 /* Queue a synthetic genome built procedurally inside the library (benchmarks only; no dense
