@@ -162,7 +162,7 @@ def reference_arm(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_pairs = 12000
+    n_pairs = int(max(3000, min(12000, 600000 // max(args.steps, 1))))
     sample = ("oracle/_ref/dwgsim_ref (unmodified reference, gcc -O3), %d concurrent single-threaded processes x -N %d pairs "
               "per step on a 2 Mbp sample of the synthetic reference, all three .fastq.gz outputs; prologue "
               "(census + mut_diref, measured with -C 0) subtracted" % (cores, n_pairs))
@@ -359,7 +359,7 @@ def main():
         seq, hap = dense_contig(E2E_CONTIG_LEN, 7 + rank)
         n_pairs_c = int(E2E_CONTIG_LEN * COVERAGE / 300.0 / 0.95 + 0.5)
         g2 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
-        g2.set_batch(1 << 19, 3)
+        g2.set_batch(1 << 17, 3)
 
         def e2e_step(i):
             g2.add_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,

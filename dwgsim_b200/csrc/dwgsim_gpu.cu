@@ -50,7 +50,8 @@ struct HostContig {
 };
 
 struct DeviceTables {
-    uint32_t *isize_cdf = nullptr, *qdelta_cdf = nullptr, *err_thr[2] = {nullptr, nullptr};
+    uint32_t *isize_cdf = nullptr, *qdelta_cdf = nullptr, *err_gap[2] = {nullptr, nullptr}, *err_acc[2] = {nullptr, nullptr};
+    uint16_t *qguide = nullptr;
     uint8_t *qbase[2] = {nullptr, nullptr};
     int8_t *flow_order = nullptr;
     char *prefix = nullptr;
@@ -59,7 +60,7 @@ struct DeviceTables {
 struct Workspace {
     int64_t cap_pairs = 0;
     PairRec *recs = nullptr;
-    uint8_t *seqs = nullptr;
+    uint32_t *seqs = nullptr;                 // nibble-packed read codes, word-major [nw0 + nw1][n]
     unsigned long long *serial = nullptr;
     uint32_t *lens = nullptr;                 // [3][cap]
     unsigned long long *blk_rand = nullptr;   // [nblk]
@@ -82,7 +83,8 @@ struct dwgsim_gpu {
     cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     // derived tables (host + device)
-    std::vector<uint32_t> isize_cdf, qdelta_cdf, err_thr[2];
+    std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
+    std::vector<uint16_t> qguide;
     std::vector<uint8_t> qbase[2];
     uint64_t thr_genomic = 0, thr_hap0 = 0;
     int32_t isize_lo = 0, qdelta_lo = 0;
@@ -101,7 +103,7 @@ struct dwgsim_gpu {
     // global counters carried across runs (ctr / rand_ii of src/dwgsim.c:423)
     int64_t gidx_origin = 0, rand_serial = 0;
     // batching
-    int64_t batch_pairs = 1 << 18;
+    int64_t batch_pairs = 1 << 17;
     int ring = 3;
     int shard_rank = 0, shard_world = 1;
     dwgsim_gpu_exchange_fn exchange = nullptr;
@@ -170,14 +172,25 @@ void derive_tables(dwgsim_gpu *h)
             h->qdelta_cdf.push_back(thr32(phi(x / p.quality_std)));
         }
     }
+    // acceleration only (not part of the sampling rule): rank of each 2^22-wide bucket's lower bound
+    h->qguide.assign(1024, 0);
+    for (uint32_t g = 0; g < 1024; ++g)
+        h->qguide[g] = (uint16_t)(std::upper_bound(h->qdelta_cdf.begin(), h->qdelta_cdf.end(), g << 22) - h->qdelta_cdf.begin());
     for (int e = 0; e < 2; ++e) {
         int n = p.length[e];
         if (p.data_type == 2) n = 2 * n + 64;
-        h->err_thr[e].assign((size_t)n + 1, 0);
+        h->err_gap[e].assign((size_t)n + 1, 0);
+        h->err_acc[e].assign((size_t)n + 1, 0);
         h->qbase[e].assign((size_t)n + 1, 0);
+        // per-cycle Bernoulli(start + by*i) errors (src/dwgsim.c:237) by thinning: candidates arrive with geometric
+        // gaps at the largest per-cycle rate, a candidate at cycle i is kept with probability p_i / pmax
+        double pmax = 0.0;
+        for (int j = 0; j < p.length[e]; ++j) pmax = std::max(pmax, p.e_start[e] + p.e_by[e] * j);
+        if (pmax > 1.0) pmax = 1.0;
         for (int j = 0; j < n; ++j) {
             double pr = p.e_start[e] + p.e_by[e] * j;                       // src/dwgsim.c:237, :906-910
-            h->err_thr[e][j] = thr32(pr);
+            h->err_gap[e][j] = thr32(1.0 - pow(1.0 - pmax, (double)(j + 1)));
+            h->err_acc[e][j] = (pmax > 0.0 && pr > 0.0) ? thr32(pr / pmax) : 0;
             h->qbase[e][j] = pr > 0 ? (uint8_t)(int)(-10.0 * log(pr) / log(10.0) + 0.499) : 40;
         }
         h->flow_thr[e] = thr32(p.e_start[e]);
@@ -198,8 +211,10 @@ int upload_tables(dwgsim_gpu *h)
     int rc;
     if ((rc = upload(h, &h->dt.isize_cdf, h->isize_cdf.data(), h->isize_cdf.size()))) return rc;
     if ((rc = upload(h, &h->dt.qdelta_cdf, h->qdelta_cdf.data(), h->qdelta_cdf.size()))) return rc;
+    if ((rc = upload(h, &h->dt.qguide, h->qguide.data(), h->qguide.size()))) return rc;
     for (int e = 0; e < 2; ++e) {
-        if ((rc = upload(h, &h->dt.err_thr[e], h->err_thr[e].data(), h->err_thr[e].size()))) return rc;
+        if ((rc = upload(h, &h->dt.err_gap[e], h->err_gap[e].data(), h->err_gap[e].size()))) return rc;
+        if ((rc = upload(h, &h->dt.err_acc[e], h->err_acc[e].data(), h->err_acc[e].size()))) return rc;
         if ((rc = upload(h, &h->dt.qbase[e], h->qbase[e].data(), h->qbase[e].size()))) return rc;
     }
     if ((rc = upload(h, &h->dt.flow_order, h->flow_order.data(), h->flow_order.size()))) return rc;
@@ -210,7 +225,8 @@ int upload_tables(dwgsim_gpu *h)
     for (int e = 0; e < 2; ++e) {
         s.len[e] = p.length[e];
         s.cap[e] = p.data_type == 2 ? 2 * p.length[e] + 64 : p.length[e];
-        s.err_thr[e] = h->dt.err_thr[e];
+        s.err_gap[e] = h->dt.err_gap[e]; s.err_acc[e] = h->dt.err_acc[e];
+        s.nw[e] = (s.cap[e] + 7) / 8;
         s.qbase[e] = h->dt.qbase[e];
         s.flow_thr[e] = h->flow_thr[e];
     }
@@ -224,9 +240,8 @@ int upload_tables(dwgsim_gpu *h)
     s.out_bwa = p.reads_output_type != 2; s.out_bfast = p.reads_output_type != 1;
     s.prefix_len = (int32_t)h->prefix_s.size();
     s.flow_order_len = p.flow_order_len;
-    s.seq_off1 = (uint32_t)align_up((uint64_t)(s.cap[0] + 1) / 2, 4);
-    s.seq_stride = (uint32_t)align_up((uint64_t)s.seq_off1 + (uint64_t)(s.cap[1] + 1) / 2, 16);
-    s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf;
+    s.tile_pairs = 32;
+    s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide;
     s.flow_order = h->dt.flow_order; s.prefix = h->dt.prefix;
     return DWGSIM_GPU_OK;
 }
@@ -241,63 +256,143 @@ const uint8_t *long_ins_payload(const uint8_t *rec, uint32_t *n)
     uint32_t v; memcpy(&v, rec + 1, 4); *n = v; return rec + 5;
 }
 
+// one worker's share of a contig: positions [p0, p1), p0 a multiple of 128 so no output word is shared
+struct PackPart {
+    std::vector<Event> ev[2];
+    std::vector<uint8_t> pool[2];      // 2-bit packed, part-local base offsets
+    uint64_t pool_bases[2] = {0, 0};
+    int rc = DWGSIM_GPU_OK;
+    const char *err = nullptr;
+};
+
+void pack_range(HostContig &c, const uint8_t *seq, const uint64_t *const hap[2], uint8_t *const *const ins[2],
+                const int32_t ins_n[2], int p0, int p1, PackPart &out)
+{
+    for (int w0 = p0; w0 < p1; w0 += 32) {
+        const int wend = std::min(w0 + 32, p1);
+        uint32_t lo = 0, hi = 0, nm = 0;
+        for (int p = w0; p < wend; ++p) {
+            const uint8_t raw = kNt4.t[seq[p]];
+            const int b = p - w0;
+            if (raw < 4) { if (b < 16) lo |= (uint32_t)raw << (b << 1); else hi |= (uint32_t)raw << ((b - 16) << 1); }
+            else nm |= 1u << b;
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint64_t m = hap[hh][p];
+                if (m == (uint64_t)raw) continue;
+                Event e;
+                e.pos = (uint32_t)p;
+                uint32_t type = (uint32_t)(m >> 4) & 3u, base = (uint32_t)(m & 0xf);
+                if (base > 4) base = 4;
+                uint32_t n = 0;
+                e.payload = 0;
+                if (type == kEvInsert) {
+                    n = (uint32_t)(m >> 59) & 0x1fu;
+                    if (n) e.payload = (m >> 6) & ((1ull << 52) - 1);
+                    else {
+                        const uint64_t idx = (m >> 6) & ((1ull << 52) - 1);
+                        if ((int64_t)idx >= ins_n[hh]) { out.rc = DWGSIM_GPU_EINVAL; out.err = "long insertion index out of range"; return; }
+                        const uint8_t *pl = long_ins_payload(ins[hh][idx], &n);
+                        if (n >= (1u << 27)) { out.rc = DWGSIM_GPU_EUNSUPPORTED; out.err = "insertion longer than 2^27-1 bases"; return; }
+                        auto src = [&](uint32_t j) { uint32_t at = n - 1 - j; return (uint32_t)(pl[at >> 2] >> ((at & 3) << 1)) & 3u; };
+                        if (n <= kInlineInsMax) {
+                            for (uint32_t j = 0; j < n; ++j) e.payload |= (uint64_t)src(j) << (2 * j);
+                        } else {
+                            // pool entries start on a byte boundary so parts can be concatenated
+                            out.pool_bases[hh] = (out.pool_bases[hh] + 3) & ~3ull;
+                            e.payload = out.pool_bases[hh];
+                            out.pool[hh].resize((size_t)((out.pool_bases[hh] + n + 3) >> 2), 0);
+                            for (uint32_t j = 0; j < n; ++j) {
+                                uint64_t at = out.pool_bases[hh] + j;
+                                out.pool[hh][at >> 2] |= (uint8_t)(src(j) << ((at & 3) << 1));
+                            }
+                            out.pool_bases[hh] += n;
+                        }
+                    }
+                }
+                e.meta = type | (base << 2) | (n << 5);
+                out.ev[hh].push_back(e);
+            }
+        }
+        c.ref2[w0 >> 4] = lo;
+        if (w0 + 16 < p1 || hi) c.ref2[(w0 >> 4) + 1] = hi;
+        c.nmask[w0 >> 5] = nm;
+    }
+}
+
 int pack_contig(dwgsim_gpu *h, HostContig &c, const uint8_t *seq, const uint64_t *hap[2], uint8_t *const *ins[2],
                 const int32_t ins_n[2])
 {
     const int len = c.len;
-    c.ref2.assign(((size_t)len + 15) / 16 + 1, 0);
+    c.ref2.assign(((size_t)len + 15) / 16 + 2, 0);
     c.nmask.assign(((size_t)len + 31) / 32 + 1, 0);
     const int nblk = (len >> kBlkShift) + 2;
-    for (int hh = 0; hh < 2; ++hh) { c.ev[hh].clear(); c.pool[hh].clear(); c.blk[hh].assign((size_t)nblk, 0); }
-    uint64_t pool_bases[2] = {0, 0};
-    for (int p = 0; p < len; ++p) {
-        const uint8_t raw = kNt4.t[seq[p]];
-        if (raw < 4) c.ref2[p >> 4] |= (uint32_t)raw << ((p & 15) << 1);
-        else c.nmask[p >> 5] |= 1u << (p & 31);
-        for (int hh = 0; hh < 2; ++hh) {
-            const uint64_t m = hap[hh][p];
-            if (m == (uint64_t)raw) continue;
-            Event e;
-            e.pos = (uint32_t)p;
-            uint32_t type = (uint32_t)(m >> 4) & 3u, base = (uint32_t)(m & 0xf);
-            if (base > 4) base = 4;
-            uint32_t n = 0;
-            e.payload = 0;
-            if (type == kEvInsert) {
-                n = (uint32_t)(m >> 59) & 0x1fu;
-                if (n) e.payload = (m >> 6) & ((1ull << 52) - 1);
-                else {
-                    const uint64_t idx = (m >> 6) & ((1ull << 52) - 1);
-                    if ((int64_t)idx >= ins_n[hh]) { h->last_error = "long insertion index out of range"; return DWGSIM_GPU_EINVAL; }
-                    const uint8_t *pl = long_ins_payload(ins[hh][idx], &n);
-                    if (n >= (1u << 27)) { h->last_error = "insertion longer than 2^27-1 bases"; return DWGSIM_GPU_EUNSUPPORTED; }
-                    auto src = [&](uint32_t j) { uint32_t at = n - 1 - j; return (uint32_t)(pl[at >> 2] >> ((at & 3) << 1)) & 3u; };
-                    if (n <= kInlineInsMax) {
-                        for (uint32_t j = 0; j < n; ++j) e.payload |= (uint64_t)src(j) << (2 * j);
-                    } else {
-                        e.payload = pool_bases[hh];
-                        c.pool[hh].resize((size_t)((pool_bases[hh] + n + 3) >> 2) + 1, 0);
-                        for (uint32_t j = 0; j < n; ++j) {
-                            uint64_t at = pool_bases[hh] + j;
-                            c.pool[hh][at >> 2] |= (uint8_t)(src(j) << ((at & 3) << 1));
-                        }
-                        pool_bases[hh] += n;
-                    }
-                }
-            }
-            e.meta = type | (base << 2) | (n << 5);
-            c.ev[hh].push_back(e);
-        }
+    // split into 128-base aligned ranges, one per worker thread
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (len < (1 << 20)) nt = 1;
+    const int per = (int)((((int64_t)len + nt - 1) / nt + 127) & ~127ll);
+    std::vector<PackPart> parts(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) {
+        const int p0 = (int)std::min<int64_t>((int64_t)t * per, len), p1 = (int)std::min<int64_t>((int64_t)(t + 1) * per, len);
+        if (p0 >= p1) continue;
+        if (nt == 1) pack_range(c, seq, hap, ins, ins_n, p0, p1, parts[t]);
+        else th.emplace_back([&, t, p0, p1]() { pack_range(c, seq, hap, ins, ins_n, p0, p1, parts[t]); });
     }
+    for (auto &x : th) x.join();
     for (int hh = 0; hh < 2; ++hh) {
+        size_t total = 0;
+        for (auto &pt : parts) total += pt.ev[hh].size();
+        c.ev[hh].clear(); c.ev[hh].reserve(total);
+        c.pool[hh].clear();
+        for (auto &pt : parts) {
+            if (pt.rc) { h->last_error = pt.err ? pt.err : "pack failed"; return pt.rc; }
+            const uint64_t base_bases = (uint64_t)c.pool[hh].size() * 4;
+            for (Event e : pt.ev[hh]) {
+                if ((e.meta & 3u) == kEvInsert && (e.meta >> 5) > kInlineInsMax) e.payload += base_bases;
+                c.ev[hh].push_back(e);
+            }
+            c.pool[hh].insert(c.pool[hh].end(), pt.pool[hh].begin(), pt.pool[hh].end());
+        }
+        c.blk[hh].assign((size_t)nblk, 0);
         size_t e = 0;
         for (int b = 0; b < nblk; ++b) {
             const uint64_t start = (uint64_t)b << kBlkShift;
             while (e < c.ev[hh].size() && c.ev[hh][e].pos < start) ++e;
             c.blk[hh][b] = (uint32_t)e;
         }
-        if (c.pool[hh].empty()) c.pool[hh].assign(4, 0);
+        c.pool[hh].resize(c.pool[hh].size() + 4, 0);
     }
+    return DWGSIM_GPU_OK;
+}
+
+// upper bounds of the record sizes (src/dwgsim.c:923-978): name = '@' prefix contig 13 separators,
+// 2 x 10 digits, 4 flags, 6 counts of <= 5 digits, 16 hex digits
+uint64_t name_cap_of(const dwgsim_gpu *h)
+{
+    return 1 + h->prefix_s.size() + (uint64_t)std::max(h->max_name_len, 4) + 13 + 20 + 4 + 30 + 16;
+}
+void record_caps(const dwgsim_gpu *h, uint64_t cap[3])
+{
+    const uint64_t name = name_cap_of(h);
+    const SimParams &s = h->sp;
+    for (int e = 0; e < 2; ++e) cap[e] = s.out_bwa && s.len[e] > 0 ? name + 3 + 2ull * s.cap[e] + 4 : 0;
+    cap[2] = 0;
+    if (s.out_bfast)
+        for (int e = 0; e < 2; ++e) if (s.len[e] > 0) cap[2] += name + 1 + 2ull * s.cap[e] + 5;
+}
+// record geometry that depends on the longest contig name: kernel parameters + shared memory of the format kernel
+int update_caps(dwgsim_gpu *h)
+{
+    uint64_t cap[3];
+    record_caps(h, cap);
+    h->sp.name_cap = (int32_t)((name_cap_of(h) + 15) & ~15ull);
+    for (int k = 0; k < 3; ++k) h->sp.rec_cap[k] = (int32_t)cap[k];
+    // tile of the format kernel: as many pairs as fit ~110 KB of shared memory (two CTAs per SM), at most 32
+    h->sp.tile_pairs = 32;
+    while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 110 * 1024) h->sp.tile_pairs >>= 1;
+    const FormatSmem L = format_smem_layout(h->sp);
+    if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
+    CUDA_TRY(h, cudaFuncSetAttribute(format_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     return DWGSIM_GPU_OK;
 }
 
@@ -312,6 +407,7 @@ int finalize_genome(dwgsim_gpu *h)
 {
     if (h->blob) return DWGSIM_GPU_OK;
     if (h->queue.empty()) { h->last_error = "no contigs queued"; return DWGSIM_GPU_ESTATE; }
+    { int rc0 = update_caps(h); if (rc0) return rc0; }
     const size_t nc = h->queue.size();
     uint64_t off = align_up(sizeof(BlobHeader), 256);
     BlobHeader hd{};
@@ -371,18 +467,6 @@ int finalize_genome(dwgsim_gpu *h)
     return DWGSIM_GPU_OK;
 }
 
-// upper bounds of the record sizes (src/dwgsim.c:923-978): name = '@' prefix contig 13 separators,
-// 2 x 10 digits, 4 flags, 6 counts of <= 5 digits, 16 hex digits
-void record_caps(const dwgsim_gpu *h, uint64_t cap[3])
-{
-    const uint64_t name = 1 + h->prefix_s.size() + (uint64_t)std::max(h->max_name_len, 4) + 13 + 20 + 4 + 30 + 16;
-    const SimParams &s = h->sp;
-    for (int e = 0; e < 2; ++e) cap[e] = s.out_bwa && s.len[e] > 0 ? name + 3 + 2ull * s.cap[e] + 4 : 0;
-    cap[2] = 0;
-    if (s.out_bfast)
-        for (int e = 0; e < 2; ++e) if (s.len[e] > 0) cap[2] += name + 1 + 2ull * s.cap[e] + 5;
-}
-
 void free_workspace(dwgsim_gpu *h)
 {
     Workspace &w = h->ws;
@@ -402,7 +486,7 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         free_workspace(h);
         const int64_t nblk = (n + kScanTile - 1) / kScanTile;
         CUDA_TRY(h, cudaMalloc((void **)&w.recs, (size_t)n * sizeof(PairRec)));
-        CUDA_TRY(h, cudaMalloc((void **)&w.seqs, (size_t)n * h->sp.seq_stride));
+        CUDA_TRY(h, cudaMalloc((void **)&w.seqs, (size_t)n * 4 * (size_t)(h->sp.nw[0] + h->sp.nw[1] + 1)));
         CUDA_TRY(h, cudaMalloc((void **)&w.serial, (size_t)n * 8));
         CUDA_TRY(h, cudaMalloc((void **)&w.lens, (size_t)n * 12));
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_rand, (size_t)nblk * 8));
@@ -455,7 +539,12 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
     cudaStream_t st = h->s_compute;
     CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 16, st));
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[0], st));
-    simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+    if (sp.data_type == 2)
+        simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+    else {
+        const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * 16);
+        simulate_pairs_tp_kernel<<<grid_tp, kTpThreads, 0, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+    }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
     layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_rand, nblk, 1, w.totals);
@@ -485,7 +574,8 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
     const int grid = std::min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count * 8);
     const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15;
-    const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + std::max(cap0, cap1));
+    const size_t smem_b = (size_t)format_smem_layout(sp).total;
+    (void)cap0; (void)cap1;
     cudaStream_t st = h->s_compute;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[4], st));
     layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, w.blk_rand,
@@ -493,8 +583,11 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
-    format_fastq_kernel<<<grid, kThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
-                                                        w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+    const int ntiles = (n + sp.tile_pairs - 1) / sp.tile_pairs;
+    const int grid_f = std::min(ntiles, sm_count * 4);
+    (void)grid;
+    format_fastq_kernel<<<grid_f, kFmtThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
+                                                             w.totals + 1, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 32, cudaMemcpyDeviceToHost, st));
@@ -607,10 +700,8 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         const SimParams &sp = h->sp;
         const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15, flr = (sp.flow_order_len + 15) & ~15;
         const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
-        const size_t smem_b = (size_t)kWarpsPerBlock * (2 * 1024 + std::max(cap0, cap1));
-        if (smem_a > 227 * 1024 || smem_b > 227 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
-        if (cudaFuncSetAttribute(simulate_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess ||
-            cudaFuncSetAttribute(format_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess) {
+        if (smem_a > 227 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
+        if (cudaFuncSetAttribute(simulate_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) {
             dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;
         }
     }
@@ -624,8 +715,8 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     cudaSetDevice(h->device);
     free_workspace(h);
     free_blob(h);
-    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf);
-    for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_thr[e]); cudaFree(h->dt.qbase[e]); }
+    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide);
+    for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
     cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
@@ -708,7 +799,7 @@ int dwgsim_gpu_genome_import(dwgsim_gpu_t *h, uint64_t device_ptr, uint64_t n_by
     h->blob = (uint8_t *)(uintptr_t)device_ptr; h->blob_bytes = n_bytes; h->blob_owned = take_ownership != 0;
     h->blob_pairs = hd.total_pairs;
     for (auto &d : cds) h->max_name_len = std::max(h->max_name_len, (int)d.name_len);
-    return DWGSIM_GPU_OK;
+    return update_caps(h);
 }
 
 int64_t dwgsim_gpu_genome_pairs(const dwgsim_gpu_t *h)
@@ -729,8 +820,8 @@ int dwgsim_gpu_tables(const dwgsim_gpu_t *h, dwgsim_gpu_tables_t *t)
     t->isize_lo = h->isize_lo; t->isize_n = (int32_t)h->isize_cdf.size(); t->isize_cdf = h->isize_cdf.data();
     t->qdelta_lo = h->qdelta_lo; t->qdelta_n = (int32_t)h->qdelta_cdf.size(); t->qdelta_cdf = h->qdelta_cdf.data();
     for (int e = 0; e < 2; ++e) {
-        t->n_cycles[e] = (int32_t)h->err_thr[e].size() - 1;
-        t->err_thr[e] = h->err_thr[e].data(); t->qbase[e] = h->qbase[e].data();
+        t->n_cycles[e] = (int32_t)h->err_gap[e].size() - 1;
+        t->err_gap[e] = h->err_gap[e].data(); t->err_acc[e] = h->err_acc[e].data(); t->qbase[e] = h->qbase[e].data();
         t->flow_thr[e] = h->flow_thr[e];
     }
     return DWGSIM_GPU_OK;

@@ -1,14 +1,19 @@
 // kernels.cuh -- sm_100a kernels of the dwgsim_core read-pair path.
 //
-//   simulate_pairs_kernel   one warp per read pair: reference src/dwgsim.c:649-882 and :983-1001
-//                           (gate, insert size, position, haplotype, strands, the walk through the
-//                           mutation table = __gen_read src/dwgsim.c:75-153, N filter, colour encoding,
-//                           substitution errors) -> 32-byte PairRec + nibble-packed read codes
+//   simulate_pairs_tp_kernel   Illumina / SOLiD, one THREAD per read pair (no work is replicated across lanes):
+//                           reference src/dwgsim.c:649-882 and :983-1001 (gate, insert size, position,
+//                           haplotype, strands, the walk through the mutation table = __gen_read
+//                           src/dwgsim.c:75-153 eight bases at a time with bit-parallel 2-bit -> nibble
+//                           expansion, N filter, colour encoding, substitution errors)
+//                           -> 32-byte PairRec + nibble-packed read codes (word-major, coalesced)
+//   simulate_pairs_kernel   Ion Torrent, one warp per read pair: same sampling and walk, then the
+//                           flow-space error model (generate_errors_flows, src/dwgsim.c:246-417)
 //   layout_* kernels        exclusive scans that turn per-pair record lengths (a function of the name
 //                           fields, src/dwgsim.c:923-929) and random-pair flags (rand_ii, :1096) into
 //                           byte offsets of every record in the three output streams
-//   format_fastq_kernel     one warp per pair: quality strings (src/dwgsim.c:899-918) and the three
-//                           record layouts (src/dwgsim.c:920-980) written at their final offsets
+//   format_fastq_kernel     one CTA per tile of pairs, one thread per 8-base group: quality strings
+//                           (src/dwgsim.c:899-918) and the three record layouts (src/dwgsim.c:920-980)
+//                           staged in shared memory and copied out with aligned 16-byte stores
 //
 // Integer / byte work only: no tensor cores, no floating point on the device (every probability is a
 // 32-bit threshold built on the host, DESIGN.md "RNG addressing").
@@ -51,9 +56,6 @@ __device__ __forceinline__ uint32_t word_of(const uint4 &v, uint32_t w)
 {
     return w == 0 ? v.x : (w == 1 ? v.y : (w == 2 ? v.z : v.w));
 }
-// base k of a read uses word (k>>5)&3 of block (k&31) | ((k>>7)<<5): the lane that owns bases
-// lane + 32 r gets four of them per Philox call
-__device__ __forceinline__ uint32_t lane_block(uint32_t k) { return (k & 31u) | ((k >> 7) << 5); }
 
 // #{j < n : u >= cdf[j]} for a non-decreasing table
 __device__ __forceinline__ int table_rank(const uint32_t *__restrict__ cdf, int n, uint32_t u)
@@ -346,7 +348,7 @@ __device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int s
 // status[0]: error bits (1 = a pair exhausted its 10001 trials), status[1]: rejected attempts
 __global__ void __launch_bounds__(kThreads)
 simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
-                      PairRec *__restrict__ recs, uint8_t *__restrict__ seqs, unsigned long long *__restrict__ status)
+                      PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -483,23 +485,7 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
                     rec.n_err[j] = (uint16_t)nerr;
                     continue;
                 }
-                // substitution errors, src/dwgsim.c:233-244
-                int nerr = 0;
-                uint4 blk = make_uint4(0, 0, 0, 0);
-                int have_blk = -1;
-                for (int k = lane; k < s[j]; k += 32) {
-                    const int lb = (int)lane_block((uint32_t)k);
-                    if (lb != have_blk) { have_blk = lb; blk = draw_block(key, kStErr, j, lb); }
-                    uint32_t c = code[j][k];
-                    if (c < 4 && word_of(blk, (k >> 5) & 3) < __ldg(P.err_thr[j] + k)) {
-                        const uint4 sb = draw_block(key, kStSub, j, lb);
-                        c = (c + 1u + __umulhi(word_of(sb, (k >> 5) & 3), 3u)) & 3u;
-                        code[j][k] = (uint8_t)c;
-                        ++nerr;
-                        if (k == 0) rec.n_err_first |= (uint8_t)(1u << j);
-                    }
-                }
-                rec.n_err[j] = (uint16_t)__reduce_add_sync(0xffffffffu, nerr);
+                rec.n_err[j] = 0;                            // substitution errors: simulate_pairs_tp_kernel
             }
             rec.n_err_first = (uint8_t)__shfl_sync(0xffffffffu, (int)rec.n_err_first, 0);   // k == 0 lives in lane 0
             __syncwarp();
@@ -508,11 +494,10 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
             recs[p] = rec;
             if (failed) atomicAdd(status + 1, (unsigned long long)failed);
         }
-        // nibble-pack the read codes: 8 per 32-bit word
-        uint32_t *dst = reinterpret_cast<uint32_t *>(seqs + (size_t)p * P.seq_stride);
+        // nibble-pack the read codes: 8 per 32-bit word, word-major
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            uint32_t *d = dst + (j ? P.seq_off1 >> 2 : 0);
+            uint32_t *d = seqw + (size_t)(j ? P.nw[0] : 0) * n + p;
             const int nw = (s[j] + 7) >> 3;
             for (int wi = lane; wi < nw; wi += 32) {
                 uint32_t v = 0;
@@ -522,11 +507,278 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
                     uint32_t c = k < s[j] ? code[j][k] : 0u;
                     v |= c << (4 * t);
                 }
-                d[wi] = v;
+                d[(size_t)wi * n] = v;
             }
         }
         __syncwarp();
     }
+}
+
+// ---- kernel A (Illumina / SOLiD): one thread per pair ------------------------------------------------------
+// 8 consecutive bases of the 2-bit reference -> 8 nibble codes (0-3, 4 = N), optionally reversed + complemented
+__device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, int i, int dir, int m)
+{
+    const int j = dir > 0 ? i : i - m + 1;                    // lowest position of the group
+    const uint32_t w0 = __ldg(c.ref2 + (j >> 4)), w1 = __ldg(c.ref2 + (j >> 4) + 1);
+    const uint32_t n0 = __ldg(c.nmask + (j >> 5)), n1 = __ldg(c.nmask + (j >> 5) + 1);
+    uint32_t x = __funnelshift_r(w0, w1, (j & 15) << 1) & ((1u << (2 * m)) - 1u);
+    uint32_t y = __funnelshift_r(n0, n1, j & 31) & ((1u << m) - 1u);
+    if (dir < 0) {
+        x = __brev(x) >> (32 - 2 * m);
+        x = ((x >> 1) & 0x5555u) | ((x & 0x5555u) << 1);
+        x ^= (1u << (2 * m)) - 1u;
+        y = __brev(y) >> (32 - m);
+    }
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;
+    y = (y | (y << 12)) & 0x000F000Fu; y = (y | (y << 6)) & 0x03030303u; y = (y | (y << 3)) & 0x11111111u;
+    return (x & ~(y * 3u)) | (y << 2);
+}
+
+struct Emit {                          // emission state of one read
+    uint32_t *dst; size_t stride;      // word w of this read goes to dst[w * stride]
+    uint64_t acc; int na, w;           // pending nibbles, their count, next word index
+    int k, nN;                         // symbols emitted, N bases seen (src/dwgsim.c:823-831)
+    int solid; uint32_t prev;          // colour space: previous base, adaptor = 0 (src/dwgsim.c:845-858)
+    int next_err, n_err, err_first;    // substitution errors (src/dwgsim.c:233-244) by thinning
+    uint32_t cand; uint4 cur;
+    const uint32_t *gap, *accp; int s; PairKey key; uint32_t end;
+};
+__device__ __forceinline__ void err_next(Emit &E)
+{
+    E.cur = draw_block(E.key, kStErr, E.end, E.cand);
+    E.next_err += 1 + table_rank(E.gap, E.s, E.cur.x);
+}
+__device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, size_t stride, int s, int solid, bool errors,
+                                           const SimParams &P, const PairKey &key, int end)
+{
+    E.dst = dst; E.stride = stride; E.acc = 0; E.na = 0; E.w = 0; E.k = 0; E.nN = 0;
+    E.solid = solid; E.prev = 0; E.n_err = 0; E.err_first = 0; E.cand = 0; E.s = s;
+    E.gap = P.err_gap[end]; E.accp = P.err_acc[end]; E.key = key; E.end = (uint32_t)end;
+    E.cur = make_uint4(0, 0, 0, 0);
+    E.next_err = -1;
+    if (errors) err_next(E); else E.next_err = 0x7fffffff;
+}
+// append m <= 8 base codes (nibbles in the low bits of `codes`, zero above)
+__device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
+{
+    E.nN += __popc(codes & 0x44444444u);
+    if (E.solid) {
+        const uint32_t prevs = (codes << 4) | E.prev;
+        E.prev = (codes >> (4 * (m - 1))) & 15u;
+        const uint32_t x = (codes ^ prevs) & 0x33333333u, nf = (codes | prevs) & 0x44444444u;
+        codes = ((x & ~((nf >> 2) * 3u)) | nf) & (m == 8 ? 0xFFFFFFFFu : ((1u << (4 * m)) - 1u));
+    }
+    while (E.next_err < E.k + m) {
+        const int sh = (E.next_err - E.k) << 2;
+        uint32_t c = (codes >> sh) & 15u;
+        if (c < 4 && E.cur.y < __ldg(E.accp + E.next_err)) {
+            c = (c + 1u + __umulhi(E.cur.z, 3u)) & 3u;
+            codes = (codes & ~(15u << sh)) | (c << sh);
+            ++E.n_err;
+            if (E.next_err == 0) E.err_first = 1;
+        }
+        ++E.cand;
+        err_next(E);
+    }
+    E.acc |= (uint64_t)codes << (4 * E.na);
+    E.na += m; E.k += m;
+    if (E.na >= 8) { E.dst[(size_t)E.w * E.stride] = (uint32_t)E.acc; ++E.w; E.acc >>= 32; E.na -= 8; }
+}
+__device__ __forceinline__ void emit_end(Emit &E)
+{
+    if (E.na > 0) { E.dst[(size_t)E.w * E.stride] = (uint32_t)E.acc; ++E.w; }
+}
+
+// the walk of gen_read() above, executed by one thread, eight plain bases at a time
+__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w)
+{
+    const int dir = strand ? -1 : 1;
+    const Event *ev = c.ev[h];
+    const int n_ev = c.n_ev[h];
+    w.ext = -10; w.n_sub = w.n_indel = w.n_indel_first = 0;
+    int i = start;
+    if (i < 0 || i >= c.len) return false;
+    int e;
+    if (dir > 0) {
+        e = (int)__ldg(c.blk[h] + (i >> kBlkShift));
+        while (e < n_ev && (int)__ldg(&ev[e].pos) < i) ++e;
+    } else {
+        e = (int)__ldg(c.blk[h] + (i >> kBlkShift) + 1) - 1;
+        while (e >= 0 && (int)__ldg(&ev[e].pos) > i) --e;
+    }
+    bool have = dir > 0 ? (e < n_ev) : (e >= 0);
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (have) cur = load_event(ev, e);
+    while (have && (int)cur.x == i) {                            // src/dwgsim.c:78-82
+        const uint32_t t = cur.y & 3u;
+        if (t != kEvInsert && t != kEvDelete) break;
+        i += dir; e += dir;
+        if (i < 0 || i >= c.len) return false;
+        have = dir > 0 ? (e < n_ev) : (e >= 0);
+        if (have) cur = load_event(ev, e);
+    }
+    int ext = i - (strand ? s - 1 : 0);
+    if (ext < 0) return false;
+    const uint32_t comp = strand ? 3u : 0u;                       // base b < 4 -> b ^ comp
+    int k = 0;
+    while (k < s) {
+        const int pe = have ? (int)cur.x : (dir > 0 ? c.len : -1);
+        int run = dir > 0 ? pe - i : i - pe;
+        if (run > s - k) run = s - k;
+        k += run;
+        while (run > 0) {
+            const int m = run < 8 ? run : 8;
+            emit_group(E, fetch_codes(c, i, dir, m), m);
+            i += dir * m; run -= m;
+        }
+        if (k == s) break;
+        if (!have) return false;
+        const uint32_t t = cur.y & 3u, n = cur.y >> 5;
+        uint32_t base = (cur.y >> 2) & 7u;
+        base = base < 4 ? base ^ comp : 4u;
+        if (t == kEvSubst || t == kEvOverride) {
+            emit_group(E, base, 1); ++k;
+            if (t == kEvSubst) ++w.n_sub;
+        } else if (t == kEvDelete) {
+            ++w.n_indel;
+            if (strand && --ext < 0) return false;
+        } else {
+            ++w.n_indel; ++w.n_indel_first;
+            if (!strand) {
+                emit_group(E, base, 1); ++k;
+                const int m = (int)n < s - k ? (int)n : s - k;
+                for (int j = 0; j < m; ++j) emit_group(E, ins_code(cur, c.pool[h], n, (uint32_t)j), 1);
+                k += m;
+            } else {
+                const int m = (int)n < s - k ? (int)n : s - k;
+                ext += m;
+                for (int j = 0; j < m; ++j) emit_group(E, ins_code(cur, c.pool[h], n, n - 1u - (uint32_t)j) ^ 3u, 1);
+                k += m;
+                if (k < s) { emit_group(E, base, 1); ++k; }
+            }
+        }
+        i += dir; e += dir;
+        have = dir > 0 ? (e < n_ev) : (e >= 0);
+        if (have) cur = load_event(ev, e);
+    }
+    w.ext = ext;
+    return true;
+}
+
+constexpr int kTpThreads = 128;
+__global__ void __launch_bounds__(kTpThreads)
+simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
+                         PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
+{
+    const int solid = P.data_type == 1;
+    unsigned failed_total = 0;
+    for (int p = blockIdx.x * kTpThreads + threadIdx.x; p < n; p += gridDim.x * kTpThreads) {
+        const int64_t q = first + p;
+        int contig_index;
+        const ContigDesc *cd = find_contig(blob, q, &contig_index);
+        const ContigView cv = view_of(blob, cd);
+        const uint64_t gidx = (uint64_t)(gidx_origin + q);
+        PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), 0u};
+        const int s0 = P.len[0], s1 = P.len[1];
+        uint32_t *dst0 = seqw + p, *dst1 = seqw + (size_t)P.nw[0] * n + p;
+        int strand0 = 0, strand1 = 0, hap = 0;
+        bool done = false, random_pair = false;
+        Walk w0, w1;
+        Emit E0, E1;
+        E0.n_err = E1.n_err = 0; E0.err_first = E1.err_first = 0;
+        w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
+
+        for (int attempt = 0; attempt <= kMaxTrials && !done; ++attempt) {
+            key.attempt = (uint32_t)attempt;
+            const uint4 b0 = draw_block(key, kStPair, 0, 0);
+            if ((uint64_t)b0.x < P.thr_genomic) { random_pair = true; done = true; break; }   // src/dwgsim.c:649
+            int d, pos;
+            if (P.amplicons) { pos = 0; d = cv.len; }
+            else {
+                if (s1 > 0) {
+                    d = P.isize_lo + table_rank(P.isize_cdf, P.isize_n, b0.y);
+                    const int min_dist = s0 + s1;
+                    if (d < min_dist) d = min_dist;
+                    if (d > cv.len) d = cv.len;
+                } else d = 0;
+                const uint64_t range = (uint64_t)((int64_t)cv.len - d + 1);
+                pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
+            }
+            const uint4 b1 = draw_block(key, kStPair, 0, 1);
+            hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
+            strand0 = P.read_one_strand == 0 ? ((b1.y >> 31) ? 0 : 1) : (P.read_one_strand == 1 ? 0 : 1);
+            if (P.strandedness == 0) strand1 = (P.data_type == 0) ? 1 - strand0 : strand0;
+            else strand1 = (P.strandedness == 1) ? strand0 : 1 - strand0;
+            int st0, st1 = 0;
+            const int last = cv.len - 1;
+            if (s1 > 0) {                                             // src/dwgsim.c:745-810
+                if (strand0 == strand1) {
+                    if (strand0 == 0) { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d - 1 : pos + d - s0); st1 = pos; }
+                    else { st0 = pos + s0 - 1; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
+                } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
+                else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
+            } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
+            emit_begin(E0, dst0, (size_t)n, s0, solid, true, P, key, 0);
+            bool ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0);
+            if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
+            if (s1 > 0) {
+                bool ok1 = false;
+                if (ok) {                                              // a rejected end 0 already rejects the pair
+                    emit_begin(E1, dst1, (size_t)n, s1, solid, true, P, key, 1);
+                    ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1);
+                    if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
+                }
+                ok = ok && ok1;
+            } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; E1.n_err = 0; E1.err_first = 0; }
+            if (ok) done = true; else ++failed_total;
+        }
+
+        PairRec rec;
+        rec.attempt = (uint16_t)key.attempt;
+        rec.n_err_first = 0;
+        rec.flags = 0;
+        if (!done) { atomicOr(status, 1ull); random_pair = true; rec.flags = kRecFailed; }
+        if (random_pair) {                                              // src/dwgsim.c:983-1001
+            rec.flags |= kRecRandom;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int s = j ? s1 : s0;
+                rec.pos[j] = 0; rec.len[j] = (uint16_t)s;
+                rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
+                if (s <= 0) continue;
+                Emit E;
+                emit_begin(E, j ? dst1 : dst0, (size_t)n, s, solid, false, P, key, j);
+                for (int k = 0; k < s; k += 64) {
+                    const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
+#pragma unroll
+                    for (int wd = 0; wd < 4; ++wd) {
+                        const uint32_t word = word_of(blk, wd);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int k0 = k + wd * 16 + half * 8;
+                            if (k0 >= s) break;
+                            const int m = s - k0 < 8 ? s - k0 : 8;
+                            uint32_t x = (word >> (16 * half)) & ((1u << (2 * m)) - 1u);
+                            x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;
+                            emit_group(E, x, m);
+                        }
+                    }
+                }
+                emit_end(E);
+            }
+        } else {
+            rec.flags |= (strand0 ? kRecStrand0 : 0) | (strand1 ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0);
+            rec.pos[0] = (uint32_t)(w0.ext + 1); rec.pos[1] = (uint32_t)(w1.ext + 1);
+            rec.len[0] = (uint16_t)s0; rec.len[1] = (uint16_t)s1;
+            rec.n_sub[0] = (uint16_t)w0.n_sub; rec.n_sub[1] = (uint16_t)w1.n_sub;
+            rec.n_indel[0] = (uint16_t)w0.n_indel; rec.n_indel[1] = (uint16_t)w1.n_indel;
+            rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
+            rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
+            rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
+        }
+        recs[p] = rec;
+    }
+    if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
 }
 
 // ---- record geometry shared by the layout and format kernels --------------------------------------------
@@ -714,129 +966,245 @@ layout_offsets_kernel(int n, const unsigned long long *__restrict__ blk_len_excl
 }
 
 // ---- kernel B: format ------------------------------------------------------------------------------------
-// name into shared memory; lane f < 13 owns numeric field f
-__device__ __forceinline__ int build_name(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
-                                          int cname_len, int variant, char *buf, int lane)
+// A CTA formats a tile of consecutive pairs.  The records of consecutive pairs are contiguous in each output
+// stream, so the tile owns ONE contiguous byte range per stream: it is assembled in shared memory at the same
+// offset modulo 16 as its destination and copied out with aligned 16-byte stores (byte stores only in the two
+// boundary chunks shared with the neighbouring tiles).  Work inside the tile is flattened over the threads:
+//   phase 0  one thread per pair: record geometry + the read name (13 numeric fields, src/dwgsim.c:923-929)
+//   phase 1  one thread per (pair, 8-base group): 8 bases -> ASCII with two PRMTs, 8 qualities from two Philox
+//            blocks (src/dwgsim.c:899-918), scattered into the bwa and bfast records (src/dwgsim.c:920-980)
+//   phase 2  one thread per record: name, "/1", separators
+//   phase 3  all threads: 16-byte copy-out
+
+constexpr int kFmtThreads = 256;
+
+struct TileMeta {                      // per pair, in shared memory
+    uint32_t so[3];                    // start of the pair's bytes in each stream's staging buffer
+    uint16_t len[2];
+    uint16_t nfull, nbwa;              // name lengths: bfast (full counts) and bwa variant
+    uint32_t lo, hi, attempt;          // Philox counter words of the pair
+};
+
+struct FormatSmem {
+    int guide_off, cdf_off, qbase_off[2], meta_off, names_off, stage_off[3], name_cap, total;
+};
+__host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
+{
+    FormatSmem L;
+    const int TP = P.tile_pairs;
+    int o = 0;
+    L.guide_off = o; o += 2048;
+    L.cdf_off = o; o += ((P.qdelta_n > 0 && P.qdelta_n <= 512 ? P.qdelta_n : 0) * 4 + 15) & ~15;
+    for (int e = 0; e < 2; ++e) { L.qbase_off[e] = o; o += (P.cap[e] + 16) & ~15; }
+    L.meta_off = o; o += (TP * (int)sizeof(TileMeta) + 15) & ~15;
+    L.name_cap = P.name_cap;
+    L.names_off = o; o += 2 * TP * P.name_cap;
+    for (int k = 0; k < 3; ++k) { L.stage_off[k] = o; o += (TP * P.rec_cap[k] + 32 + 15) & ~15; }
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ int put_dec(char *p, uint32_t v)      // writes v in decimal, returns the digit count
+{
+    const int nd = ndigits10(v);
+    for (int d = nd - 1; d >= 0; --d) { p[d] = (char)('0' + v % 10u); v /= 10u; }
+    return nd;
+}
+// '@' prefix contig _pos1_pos2_s1_s2_r_r_e:s:i_e:s:i_hex   (src/dwgsim.c:923-929); returns the length
+__device__ __forceinline__ int write_name(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
+                                          int cname_len, int variant, char *buf)
 {
     const bool rnd = r.flags & kRecRandom;
-    const int nl = rnd ? 4 : cname_len;
-    const int head = 1 + P.prefix_len + nl;
-    if (lane == 0) buf[0] = '@';
-    for (int j = lane; j < P.prefix_len; j += 32) buf[1 + j] = P.prefix[j];
-    for (int j = lane; j < nl; j += 32) buf[1 + P.prefix_len + j] = rnd ? "rand"[j] : cname[j];
-    uint64_t v = lane < 13 ? name_field(r, serial, lane, variant) : 0;
-    int nd = lane < 12 ? ndigits10((uint32_t)v) : (lane == 12 ? ndigits16(v) : 0);
-    int width = lane < 13 ? nd + 1 : 0, inc = width;
+    int o = 0;
+    buf[o++] = '@';
+    for (int j = 0; j < P.prefix_len; ++j) buf[o++] = P.prefix[j];
+    if (rnd) { buf[o++] = 'r'; buf[o++] = 'a'; buf[o++] = 'n'; buf[o++] = 'd'; }
+    else for (int j = 0; j < cname_len; ++j) buf[o++] = cname[j];
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    const int total = __shfl_sync(0xffffffffu, inc, 12);
-    if (lane < 13) {
-        char *p = buf + head + inc - width;
-        p[0] = (lane == 7 || lane == 8 || lane == 10 || lane == 11) ? ':' : '_';
-        if (lane < 12) {
-            uint32_t x = (uint32_t)v;
-            for (int d = nd; d >= 1; --d) { p[d] = (char)('0' + x % 10u); x /= 10u; }
-        } else {
-            for (int d = nd; d >= 1; --d) { uint32_t h = (uint32_t)(v & 15u); p[d] = (char)(h < 10 ? '0' + h : 'a' + h - 10); v >>= 4; }
-        }
+    for (int f = 0; f < 12; ++f) {
+        buf[o++] = (f == 7 || f == 8 || f == 10 || f == 11) ? ':' : '_';
+        o += put_dec(buf + o, (uint32_t)name_field(r, serial, f, variant));
     }
-    __syncwarp();
-    return head + total;
+    buf[o++] = '_';
+    const int nd = ndigits16(serial);
+    for (int d = nd - 1; d >= 0; --d) { const uint32_t h = (uint32_t)(serial >> (4 * d)) & 15u; buf[o++] = (char)(h < 10 ? '0' + h : 'a' + h - 10); }
+    return o;
 }
 
-__device__ __forceinline__ uint32_t nibble_at(const uint32_t *__restrict__ w, int k)
+// quality noise: inverse CDF with a 1024-entry guide table (rank of the bucket's lower bound), then a short scan
+__device__ __forceinline__ int qdelta_rank(const uint16_t *guide, const uint32_t *cdf, int n, uint32_t u)
 {
-    return (__ldg(w + (k >> 3)) >> ((k & 7) << 2)) & 15u;
+    int j = guide[u >> 22];
+    while (j < n && u >= cdf[j]) ++j;
+    return j;
 }
 
-// one record: name + suffix + sequence line + "+" + quality line (src/dwgsim.c:923-978)
-__device__ __forceinline__ void write_record(char *__restrict__ dst, const char *name, int name_len, const char *suffix,
-                                             int suffix_len, int lead_A, const char *alphabet, const uint32_t *codes,
-                                             const char *qual, int from, int L, int lane)
-{
-    for (int j = lane; j < name_len; j += 32) dst[j] = name[j];
-    dst += name_len;
-    if (lane < suffix_len) dst[lane] = suffix[lane];
-    dst += suffix_len;
-    if (lead_A) { if (lane == 0) dst[0] = 'A'; dst += 1; }
-    const int m = L - from;
-    for (int j = lane; j < m; j += 32) dst[j] = alphabet[nibble_at(codes, from + j)];
-    dst += m;
-    if (lane < 3) dst[lane] = lane == 1 ? '+' : '\n';
-    dst += 3;
-    for (int j = lane; j < m; j += 32) dst[j] = qual[from + j];
-    if (lane == 0) dst[m] = '\n';
-}
-
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kFmtThreads)
 format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
-                    const PairRec *__restrict__ recs, const uint8_t *__restrict__ seqs,
+                    const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
                     const unsigned long long *__restrict__ serial, const uint32_t *__restrict__ offs /* [3][n] */,
+                    const unsigned long long *__restrict__ totals /* bytes of the batch per stream */,
                     char *__restrict__ out0, char *__restrict__ out1, char *__restrict__ out2)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int capq = (max(P.cap[0], P.cap[1]) + 15) & ~15;
-    const int name_cap = 1024;
-    char *name_full = reinterpret_cast<char *>(smem) + (size_t)warp * (2 * name_cap + capq);
-    char *name_bwa = name_full + name_cap;
-    char *qual = name_bwa + name_cap;
-    const bool solid = P.data_type == 1;
-    const int warps_total = gridDim.x * kWarpsPerBlock;
-    const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
+    const FormatSmem L = format_smem_layout(P);
+    const int TP = P.tile_pairs, tid = threadIdx.x;
+    uint16_t *guide = reinterpret_cast<uint16_t *>(smem + L.guide_off);
+    const bool cdf_in_smem = P.qdelta_n > 0 && P.qdelta_n <= 512;
+    uint32_t *cdf_s = reinterpret_cast<uint32_t *>(smem + L.cdf_off);
+    uint8_t *qbase_s[2] = {smem + L.qbase_off[0], smem + L.qbase_off[1]};
+    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + L.meta_off);
+    char *names = reinterpret_cast<char *>(smem + L.names_off);
+    uint8_t *stage[3] = {smem + L.stage_off[0], smem + L.stage_off[1], smem + L.stage_off[2]};
+    __shared__ int s_shift[3], s_total[3];
 
-    for (int p = blockIdx.x * kWarpsPerBlock + warp; p < n; p += warps_total) {
-        const int64_t q = first + p;
-        int ci;
-        const ContigDesc *cd = find_contig(blob, q, &ci);
-        const char *cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
-        const PairRec r = recs[p];
-        const uint64_t ser = serial[p];
-        const uint64_t gidx = (uint64_t)(gidx_origin + q);
-        const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)r.attempt};
-        const int nfull = build_name(P, r, ser, cname, (int)cd->name_len, 0, name_full, lane);
-        int nbwa = nfull;
-        const char *nb = name_full;
-        if (solid && P.out_bwa) { nbwa = build_name(P, r, ser, cname, (int)cd->name_len, 1, name_bwa, lane); nb = name_bwa; }
-        uint32_t off_bfast = P.out_bfast ? offs[(size_t)2 * n + p] : 0u;
-        for (int j = 0; j < 2; ++j) {
-            const int L = r.len[j];
-            if (L <= 0) continue;
+    for (int j = tid; j < 1024; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? P.qguide[j] : (uint16_t)0;
+    if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) cdf_s[j] = P.qdelta_cdf[j];
+    for (int e = 0; e < 2; ++e) for (int j = tid; j < P.cap[e]; j += kFmtThreads) qbase_s[e][j] = P.qbase[e][j];
+    __syncthreads();
+    const uint32_t *cdf = cdf_in_smem ? cdf_s : P.qdelta_cdf;
+
+    const bool solid = P.data_type == 1;
+    const int from = solid ? 1 : 0;                                 // bwa drops the first colour (src/dwgsim.c:949-953)
+    const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
+    char *outp[3] = {out0, out1, out2};
+    const bool on[3] = {P.out_bwa != 0, P.out_bwa != 0, P.out_bfast != 0};
+    const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1;
+    const int ntiles = (n + TP - 1) / TP;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * TP, np = min(TP, n - p0);
+        // ---- phase 0: geometry + names --------------------------------------------------------------
+        if (tid < 3) {
+            const int k = tid;
+            const uint32_t begin = on[k] ? offs[(size_t)k * n + p0] : 0u;
+            const unsigned long long end = !on[k] ? 0ull : (p0 + np < n ? (unsigned long long)offs[(size_t)k * n + p0 + np] : totals[k]);
+            s_shift[k] = (int)(reinterpret_cast<uintptr_t>(outp[k] + begin) & 15u);
+            s_total[k] = on[k] ? (int)(end - begin) : 0;
+        }
+        __syncthreads();
+        if (tid < np) {
+            const int p = p0 + tid;
+            const int64_t q = first + p;
+            int ci;
+            const ContigDesc *cd = find_contig(blob, q, &ci);
+            const char *cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
+            const PairRec r = recs[p];
+            const uint64_t ser = serial[p];
+            const uint64_t gidx = (uint64_t)(gidx_origin + q);
+            TileMeta m;
+            for (int k = 0; k < 3; ++k) m.so[k] = on[k] ? offs[(size_t)k * n + p] - offs[(size_t)k * n + p0] + (uint32_t)s_shift[k] : 0u;
+            m.len[0] = r.len[0]; m.len[1] = r.len[1];
+            m.lo = (uint32_t)gidx; m.hi = (uint32_t)(gidx >> 32); m.attempt = r.attempt;
+            m.nfull = (uint16_t)write_name(P, r, ser, cname, (int)cd->name_len, 0, names + (size_t)tid * L.name_cap);
+            m.nbwa = m.nfull;
+            if (solid && P.out_bwa)
+                m.nbwa = (uint16_t)write_name(P, r, ser, cname, (int)cd->name_len, 1, names + (size_t)(TP + tid) * L.name_cap);
+            meta[tid] = m;
+        }
+        __syncthreads();
+        // ---- phase 1: bases and qualities, one thread per (pair, 8-base group) ----------------------------
+        for (int it = tid; it < TP * G; it += kFmtThreads) {
+            const int t = it % TP, gi = it / TP;
+            if (t >= np) continue;
+            const int e = gi < g0 ? 0 : 1, g = gi - (e ? g0 : 0);
+            const TileMeta &m = meta[t];
+            const int Le = m.len[e], k0 = g << 3;
+            if (k0 >= Le) continue;
+            const int cnt = min(8, Le - k0);
+            const uint32_t codes = __ldg(seqw + (size_t)((e ? P.nw[0] : 0) + g) * n + (p0 + t));
+            // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
+            const uint32_t a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu), a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
+            uint32_t d_lo = a_lo, d_hi = a_hi;
+            if (solid) { d_lo = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d_hi = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
             // qualities, src/dwgsim.c:899-918 (char arithmetic there; emulated with an int8 wrap)
-            {
-                uint4 blk = make_uint4(0, 0, 0, 0);
-                int have_blk = -1;
-                for (int k = lane; k < L; k += 32) {
-                    int c;
-                    if (P.fixed_quality) c = P.fixed_quality;
-                    else {
-                        c = 33 + (int)__ldg(P.qbase[j] + k);
-                        if (P.qdelta_n > 0) {
-                            const int lb = (int)lane_block((uint32_t)k);
-                            if (lb != have_blk) { have_blk = lb; blk = draw_block(key, kStQual, j, lb); }
-                            const int delta = P.qdelta_lo + table_rank(P.qdelta_cdf, P.qdelta_n, word_of(blk, (k >> 5) & 3));
-                            c = (int)(signed char)((c + delta) & 0xFF);
-                        }
-                        c = c < 33 ? 33 : (c > 73 ? 73 : c);
+            uint32_t q_lo = 0, q_hi = 0;
+            if (P.fixed_quality) { q_lo = q_hi = 0x01010101u * (uint32_t)P.fixed_quality; }
+            else {
+                const PairKey key{P.seed, m.lo, m.hi, m.attempt};
+                uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+                if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); if (cnt > 4) b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int qc = 33 + (int)qbase_s[e][min(k0 + i, P.cap[e] - 1)];
+                    if (P.qdelta_n > 0) {
+                        const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
+                        qc = (int)(signed char)((qc + P.qdelta_lo + qdelta_rank(guide, cdf, P.qdelta_n, u)) & 0xFF);
                     }
-                    qual[k] = (char)c;
+                    qc = qc < 33 ? 33 : (qc > 73 ? 73 : qc);
+                    if (i < 4) q_lo |= (uint32_t)qc << (8 * i); else q_hi |= (uint32_t)qc << (8 * (i - 4));
                 }
             }
-            __syncwarp();
-            const uint32_t *codes = reinterpret_cast<const uint32_t *>(seqs + (size_t)p * P.seq_stride + (j ? P.seq_off1 : 0));
-            if (P.out_bwa) {
-                char *dst = (j == 0 ? out0 : out1) + offs[(size_t)j * n + p];
-                const char *suffix = solid ? (j == 0 ? "/2\n" : "/1\n") : (j == 0 ? "/1\n" : "/2\n");
-                write_record(dst, nb, nbwa, suffix, 3, 0, "ACGTN\0\0\0\0\0\0\0\0\0\0", codes, qual, solid ? 1 : 0, L, lane);
+            // scatter into the records
+            const int rec0 = (P.out_bfast && m.len[0] > 0) ? m.nfull + 1 + (solid ? 1 : 0) + 2 * m.len[0] + 4 : 0;
+            uint8_t *sb = stage[e] + m.so[e];
+            uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
+            const int me = Le - from;
+            const int bwa_seq = m.nbwa + 3 - from, bwa_qual = m.nbwa + 3 + me + 3 - from;   // index by k
+            const int bf_seq = m.nfull + 1 + (solid ? 1 : 0), bf_qual = bf_seq + Le + 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i >= cnt) break;
+                const int k = k0 + i;
+                const uint8_t ch = (uint8_t)((i < 4 ? a_lo : a_hi) >> (8 * (i & 3)));
+                const uint8_t dg = (uint8_t)((i < 4 ? d_lo : d_hi) >> (8 * (i & 3)));
+                const uint8_t qc = (uint8_t)((i < 4 ? q_lo : q_hi) >> (8 * (i & 3)));
+                if (P.out_bwa && k >= from) { sb[bwa_seq + k] = ch; sb[bwa_qual + k] = qc; }
+                if (P.out_bfast) { sf[bf_seq + k] = dg; sf[bf_qual + k] = qc; }
             }
-            if (P.out_bfast) {
-                char *dst = out2 + off_bfast;
-                write_record(dst, name_full, nfull, "\n", 1, solid ? 1 : 0, solid ? "01234\0\0\0\0\0\0\0\0\0\0" : "ACGTN\0\0\0\0\0\0\0\0\0\0",
-                             codes, qual, 0, L, lane);
-                off_bfast += (uint32_t)(nfull + 1 + 2 * L + 4 + (solid ? 1 : 0));
-            }
-            __syncwarp();
         }
+        // ---- phase 2: names, suffixes, separators: one thread per record ----------------------------------
+        for (int it = tid; it < TP * 4; it += kFmtThreads) {
+            const int t = it % TP, rr = it / TP, e = rr & 1, bf = rr >> 1;
+            if (t >= np) continue;
+            const TileMeta &m = meta[t];
+            const int Le = m.len[e];
+            if (Le <= 0) continue;
+            if (!bf) {
+                if (!P.out_bwa) continue;
+                uint8_t *sb = stage[e] + m.so[e];
+                const char *nm = names + (size_t)((solid ? TP : 0) + t) * L.name_cap;
+                const int nn = m.nbwa, me = Le - from;
+                for (int x = 0; x < nn; ++x) sb[x] = (uint8_t)nm[x];
+                sb[nn] = '/'; sb[nn + 1] = (uint8_t)(solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sb[nn + 2] = '\n';
+                sb[nn + 3 + me] = '\n'; sb[nn + 3 + me + 1] = '+'; sb[nn + 3 + me + 2] = '\n';
+                sb[nn + 3 + me + 3 + me] = '\n';
+            } else {
+                if (!P.out_bfast) continue;
+                const int rec0 = m.len[0] > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * m.len[0] + 4 : 0;
+                uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
+                const char *nm = names + (size_t)t * L.name_cap;
+                const int nn = m.nfull;
+                for (int x = 0; x < nn; ++x) sf[x] = (uint8_t)nm[x];
+                sf[nn] = '\n';
+                int o = nn + 1;
+                if (solid) sf[o++] = 'A';
+                sf[o + Le] = '\n'; sf[o + Le + 1] = '+'; sf[o + Le + 2] = '\n';
+                sf[o + Le + 3 + Le] = '\n';
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: copy-out ------------------------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int total = s_total[k];
+            if (total <= 0) continue;
+            const int shift = s_shift[k];
+            const uint32_t begin = offs[(size_t)k * n + p0];
+            char *base = outp[k] + begin - shift;                       // 16-byte aligned
+            const uint8_t *st = stage[k];
+            const int end = shift + total, nchunk = (end + 15) >> 4;
+            for (int c = tid; c < nchunk; c += kFmtThreads) {
+                const int lo = c << 4;
+                if (lo >= shift && lo + 16 <= end) {
+                    *reinterpret_cast<uint4 *>(base + lo) = *reinterpret_cast<const uint4 *>(st + lo);
+                } else {
+                    const int a = lo > shift ? lo : shift, b = lo + 16 < end ? lo + 16 : end;
+                    for (int x = a; x < b; ++x) base[x] = (char)st[x];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -80,11 +80,15 @@ struct SimParams {
     int32_t  prefix_len;                       // strlen(read_prefix)+1 ("pfx_"), 0 if none
     int32_t  flow_order_len;
     uint32_t flow_thr[2];
-    uint32_t seq_stride;                       // bytes of packed read codes per pair (nibbles)
-    uint32_t seq_off1;                         // byte offset of end 1 inside a pair's slot
+    int32_t  nw[2];                            // 32-bit words of nibble-packed read codes per end (8 codes per word);
+                                               // stored word-major: word w of pair p at seqw[(w0[end] + w) * n + p]
+    int32_t  tile_pairs;                       // pairs per CTA tile of the format kernel
+    int32_t  name_cap;                         // bytes reserved per read name in shared memory
+    int32_t  rec_cap[3];                       // upper bound of a pair's bytes per output stream
     // device tables
     const uint32_t *isize_cdf, *qdelta_cdf;
-    const uint32_t *err_thr[2];
+    const uint16_t *qguide;                    // [1024] rank of (g << 22) in qdelta_cdf
+    const uint32_t *err_gap[2], *err_acc[2];   // substitution errors by thinning (DESIGN.md "RNG addressing")
     const uint8_t  *qbase[2];
     const int8_t   *flow_order;
     const char     *prefix;

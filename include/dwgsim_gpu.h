@@ -111,7 +111,7 @@ int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name,
 int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats);
 
 /* -- knobs ---------------------------------------------------------------------------------- */
-/* pairs per device batch (default 1<<20); ring = number of pinned output slots (default 3) */
+/* pairs per device batch (default 1<<17); ring = number of pinned output slots (default 3) */
 int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots);
 /* shard the pair-index space: dwgsim_gpu_run simulates the batches b with b % world == rank and hands
  * only those to the sink (in order); concatenating the ranks' batches round-robin gives the bytes of
@@ -178,7 +178,7 @@ typedef struct {
     int32_t  qdelta_lo, qdelta_n;
     const uint32_t *qdelta_cdf;
     int32_t  n_cycles[2];
-    const uint32_t *err_thr[2];
+    const uint32_t *err_gap[2], *err_acc[2];
     const uint8_t  *qbase[2];
     uint32_t flow_thr[2];
 } dwgsim_gpu_tables_t;

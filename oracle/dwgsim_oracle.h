@@ -77,7 +77,8 @@ typedef struct {
     int32_t  qdelta_n;
     uint32_t *qdelta_cdf;
     int32_t  n_cycles[2];       /* table lengths (read length, or grown for Ion Torrent)          */
-    uint32_t *err_thr[2];       /* substitution error iff u32 < err_thr[end][cycle]               */
+    uint32_t *err_gap[2];       /* candidate gap = #{g : u32 >= err_gap[end][g]}, g < read length  */
+    uint32_t *err_acc[2];       /* candidate at cycle i becomes an error iff u32 < err_acc[end][i] */
     uint8_t  *qbase[2];         /* Phred before noise, 0..40, per cycle                           */
     uint32_t flow_thr[2];       /* Ion Torrent: per-flow error coin of each end, u32 < flow_thr   */
 } orc_tables_t;

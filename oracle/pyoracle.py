@@ -36,7 +36,7 @@ class OrcTables(C.Structure):
         ("thr_genomic", C.c_uint64), ("thr_hap0", C.c_uint64),
         ("isize_lo", C.c_int32), ("isize_n", C.c_int32), ("isize_cdf", C.POINTER(C.c_uint32)),
         ("qdelta_lo", C.c_int32), ("qdelta_n", C.c_int32), ("qdelta_cdf", C.POINTER(C.c_uint32)),
-        ("n_cycles", C.c_int32 * 2), ("err_thr", C.POINTER(C.c_uint32) * 2),
+        ("n_cycles", C.c_int32 * 2), ("err_gap", C.POINTER(C.c_uint32) * 2), ("err_acc", C.POINTER(C.c_uint32) * 2),
         ("qbase", C.POINTER(C.c_uint8) * 2), ("flow_thr", C.c_uint32 * 2),
     ]
 

@@ -77,5 +77,6 @@ def test_derived_tables_equal_oracle(oracle):
         assert [g.qdelta_cdf[i] for i in range(g.qdelta_n)] == [t.qdelta_cdf[i] for i in range(t.qdelta_n)]
         for e in range(2):
             n = opts["length"][e]
-            assert [g.err_thr[e][i] for i in range(n)] == [t.err_thr[e][i] for i in range(n)]
+            assert [g.err_gap[e][i] for i in range(n)] == [t.err_gap[e][i] for i in range(n)]
+            assert [g.err_acc[e][i] for i in range(n)] == [t.err_acc[e][i] for i in range(n)]
             assert [g.qbase[e][i] for i in range(n)] == [t.qbase[e][i] for i in range(n)]
