@@ -63,6 +63,8 @@ struct Workspace {
     uint32_t *seqs = nullptr;                 // nibble-packed read codes, word-major [nw0 + nw1][n]
     unsigned long long *serial = nullptr;
     uint32_t *lens = nullptr;                 // [3][cap]
+    char *names = nullptr;                    // [cap][nvar][name_cap]
+    uint16_t *name_len = nullptr;             // [cap][2]
     unsigned long long *blk_rand = nullptr;   // [nblk]
     unsigned long long *blk_len = nullptr;    // [3][nblk]
     unsigned long long *totals = nullptr;     // [8]: 0 n_random, 1..3 stream bytes
@@ -470,7 +472,7 @@ int finalize_genome(dwgsim_gpu *h)
 void free_workspace(dwgsim_gpu *h)
 {
     Workspace &w = h->ws;
-    cudaFree(w.recs); cudaFree(w.seqs); cudaFree(w.serial); cudaFree(w.lens);
+    cudaFree(w.recs); cudaFree(w.seqs); cudaFree(w.serial); cudaFree(w.lens); cudaFree(w.names); cudaFree(w.name_len);
     cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(w.out[s][k]);
     if (w.h_totals) cudaFreeHost(w.h_totals);
@@ -489,6 +491,8 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         CUDA_TRY(h, cudaMalloc((void **)&w.seqs, (size_t)n * 4 * (size_t)(h->sp.nw[0] + h->sp.nw[1] + 1)));
         CUDA_TRY(h, cudaMalloc((void **)&w.serial, (size_t)n * 8));
         CUDA_TRY(h, cudaMalloc((void **)&w.lens, (size_t)n * 12));
+        CUDA_TRY(h, cudaMalloc((void **)&w.names, (size_t)n * 2 * (size_t)h->sp.name_cap));
+        CUDA_TRY(h, cudaMalloc((void **)&w.name_len, (size_t)n * 4));
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_rand, (size_t)nblk * 8));
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_len, (size_t)nblk * 24));
         CUDA_TRY(h, cudaMalloc((void **)&w.totals, 64));
@@ -543,7 +547,8 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     else {
         const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * 16);
-        simulate_pairs_tp_kernel<<<grid_tp, kTpThreads, 0, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+        const size_t smem_tp = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) * 4;
+        simulate_pairs_tp_kernel<<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
     layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
@@ -579,7 +584,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     cudaStream_t st = h->s_compute;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[4], st));
     layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, w.blk_rand,
-                                                     w.serial, w.lens, w.blk_len);
+                                                     w.serial, w.lens, w.blk_len, w.names, w.name_len);
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
@@ -587,7 +592,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     const int grid_f = std::min(ntiles, sm_count * 4);
     (void)grid;
     format_fastq_kernel<<<grid_f, kFmtThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
-                                                             w.totals + 1, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+                                                             w.totals + 1, w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 32, cudaMemcpyDeviceToHost, st));
@@ -700,6 +705,14 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         const SimParams &sp = h->sp;
         const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15, flr = (sp.flow_order_len + 15) & ~15;
         const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
+        const size_t smem_tp = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) * 4;
+        if (sp.data_type != 2) {
+            // one staging row per thread in shared memory bounds the combined read length (about 3,400 bases)
+            if (smem_tp > 220 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
+            if (cudaFuncSetAttribute(simulate_pairs_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp) != cudaSuccess) {
+                dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;
+            }
+        }
         if (smem_a > 227 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
         if (cudaFuncSetAttribute(simulate_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) {
             dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;

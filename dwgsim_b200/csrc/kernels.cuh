@@ -497,7 +497,7 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
         // nibble-pack the read codes: 8 per 32-bit word, word-major
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            uint32_t *d = seqw + (size_t)(j ? P.nw[0] : 0) * n + p;
+            uint32_t *d = seqw + (size_t)p * (P.nw[0] + P.nw[1]) + (j ? P.nw[0] : 0);
             const int nw = (s[j] + 7) >> 3;
             for (int wi = lane; wi < nw; wi += 32) {
                 uint32_t v = 0;
@@ -507,7 +507,7 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
                     uint32_t c = k < s[j] ? code[j][k] : 0u;
                     v |= c << (4 * t);
                 }
-                d[(size_t)wi * n] = v;
+                d[wi] = v;
             }
         }
         __syncwarp();
@@ -523,19 +523,19 @@ __device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, int i, int 
     const uint32_t n0 = __ldg(c.nmask + (j >> 5)), n1 = __ldg(c.nmask + (j >> 5) + 1);
     uint32_t x = __funnelshift_r(w0, w1, (j & 15) << 1) & ((1u << (2 * m)) - 1u);
     uint32_t y = __funnelshift_r(n0, n1, j & 31) & ((1u << m) - 1u);
-    if (dir < 0) {
-        x = __brev(x) >> (32 - 2 * m);
-        x = ((x >> 1) & 0x5555u) | ((x & 0x5555u) << 1);
-        x ^= (1u << (2 * m)) - 1u;
-        y = __brev(y) >> (32 - m);
-    }
+    // minus strand: reverse the order of the m bases and complement them (computed for every lane, then selected)
+    uint32_t xr = __brev(x) >> (32 - 2 * m);
+    xr = (((xr >> 1) & 0x5555u) | ((xr & 0x5555u) << 1)) ^ ((1u << (2 * m)) - 1u);
+    const uint32_t yr = __brev(y) >> (32 - m);
+    x = dir < 0 ? xr : x;
+    y = dir < 0 ? yr : y;
     x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;
     y = (y | (y << 12)) & 0x000F000Fu; y = (y | (y << 6)) & 0x03030303u; y = (y | (y << 3)) & 0x11111111u;
     return (x & ~(y * 3u)) | (y << 2);
 }
 
 struct Emit {                          // emission state of one read
-    uint32_t *dst; size_t stride;      // word w of this read goes to dst[w * stride]
+    uint32_t *dst;                     // this thread's row of the CTA's shared staging tile (word w at dst[w])
     uint64_t acc; int na, w;           // pending nibbles, their count, next word index
     int k, nN;                         // symbols emitted, N bases seen (src/dwgsim.c:823-831)
     int solid; uint32_t prev;          // colour space: previous base, adaptor = 0 (src/dwgsim.c:845-858)
@@ -548,10 +548,10 @@ __device__ __forceinline__ void err_next(Emit &E)
     E.cur = draw_block(E.key, kStErr, E.end, E.cand);
     E.next_err += 1 + table_rank(E.gap, E.s, E.cur.x);
 }
-__device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, size_t stride, int s, int solid, bool errors,
+__device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int s, int solid, bool errors,
                                            const SimParams &P, const PairKey &key, int end)
 {
-    E.dst = dst; E.stride = stride; E.acc = 0; E.na = 0; E.w = 0; E.k = 0; E.nN = 0;
+    E.dst = dst; E.acc = 0; E.na = 0; E.w = 0; E.k = 0; E.nN = 0;
     E.solid = solid; E.prev = 0; E.n_err = 0; E.err_first = 0; E.cand = 0; E.s = s;
     E.gap = P.err_gap[end]; E.accp = P.err_acc[end]; E.key = key; E.end = (uint32_t)end;
     E.cur = make_uint4(0, 0, 0, 0);
@@ -582,14 +582,16 @@ __device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
     }
     E.acc |= (uint64_t)codes << (4 * E.na);
     E.na += m; E.k += m;
-    if (E.na >= 8) { E.dst[(size_t)E.w * E.stride] = (uint32_t)E.acc; ++E.w; E.acc >>= 32; E.na -= 8; }
+    if (E.na >= 8) { E.dst[E.w] = (uint32_t)E.acc; ++E.w; E.acc >>= 32; E.na -= 8; }
 }
 __device__ __forceinline__ void emit_end(Emit &E)
 {
-    if (E.na > 0) { E.dst[(size_t)E.w * E.stride] = (uint32_t)E.acc; ++E.w; }
+    if (E.na > 0) { E.dst[E.w] = (uint32_t)E.acc; ++E.w; }
 }
 
-// the walk of gen_read() above, executed by one thread, eight plain bases at a time
+// The walk of gen_read() above executed by one thread as ONE loop: every iteration either emits up to eight
+// plain reference bases or consumes one mutation event, so the lanes of a warp stay in the same loop even
+// when their reads cross different events.
 __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w)
 {
     const int dir = strand ? -1 : 1;
@@ -621,48 +623,65 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
     if (ext < 0) return false;
     const uint32_t comp = strand ? 3u : 0u;                       // base b < 4 -> b ^ comp
     int k = 0;
+    int ins_left = 0, ins_at = 0;                                  // insertion being emitted: bases left, next index
+    bool ins_ref_pending = false;                                  // minus strand: reference base follows the insertion
+    bool ok = true;
     while (k < s) {
+        if (ins_left > 0) {                                        // inside an insertion: up to 8 inserted bases
+            const uint32_t n = cur.y >> 5;
+            const int m = ins_left < 8 ? ins_left : 8;
+            uint32_t codes = 0;
+            for (int j = 0; j < m; ++j) {
+                const uint32_t idx = strand ? n - 1u - (uint32_t)(ins_at + j) : (uint32_t)(ins_at + j);
+                codes |= (ins_code(cur, c.pool[h], n, idx) ^ comp) << (4 * j);
+            }
+            emit_group(E, codes, m);
+            k += m; ins_left -= m; ins_at += m;
+            if (ins_left > 0) continue;
+            if (ins_ref_pending) {
+                ins_ref_pending = false;
+                if (k < s) { uint32_t base = (cur.y >> 2) & 7u; emit_group(E, base < 4 ? base ^ comp : 4u, 1); ++k; }
+            }
+            i += dir; e += dir;
+            have = dir > 0 ? (e < n_ev) : (e >= 0);
+            if (have) cur = load_event(ev, e);
+            continue;
+        }
         const int pe = have ? (int)cur.x : (dir > 0 ? c.len : -1);
         int run = dir > 0 ? pe - i : i - pe;
         if (run > s - k) run = s - k;
-        k += run;
-        while (run > 0) {
+        if (run > 0) {                                             // plain reference bases up to the next event
             const int m = run < 8 ? run : 8;
             emit_group(E, fetch_codes(c, i, dir, m), m);
-            i += dir * m; run -= m;
+            i += dir * m; k += m;
+            continue;
         }
-        if (k == s) break;
-        if (!have) return false;
+        if (!have) { ok = false; break; }                         // walked off the contig
         const uint32_t t = cur.y & 3u, n = cur.y >> 5;
         uint32_t base = (cur.y >> 2) & 7u;
         base = base < 4 ? base ^ comp : 4u;
-        if (t == kEvSubst || t == kEvOverride) {
-            emit_group(E, base, 1); ++k;
-            if (t == kEvSubst) ++w.n_sub;
+        if (t == kEvInsert) {
+            ++w.n_indel; ++w.n_indel_first;
+            if (!strand) { emit_group(E, base, 1); ++k; }
+            const int m = (int)n < s - k ? (int)n : s - k;
+            if (strand) { ext += m; ins_ref_pending = true; }
+            ins_left = m; ins_at = 0;
+            if (m > 0) continue;
+            // nothing of the insertion fits (the read ended on the reference base, plus strand): fall through
+            ins_ref_pending = false;
         } else if (t == kEvDelete) {
             ++w.n_indel;
-            if (strand && --ext < 0) return false;
+            if (strand && --ext < 0) { ok = false; break; }
         } else {
-            ++w.n_indel; ++w.n_indel_first;
-            if (!strand) {
-                emit_group(E, base, 1); ++k;
-                const int m = (int)n < s - k ? (int)n : s - k;
-                for (int j = 0; j < m; ++j) emit_group(E, ins_code(cur, c.pool[h], n, (uint32_t)j), 1);
-                k += m;
-            } else {
-                const int m = (int)n < s - k ? (int)n : s - k;
-                ext += m;
-                for (int j = 0; j < m; ++j) emit_group(E, ins_code(cur, c.pool[h], n, n - 1u - (uint32_t)j) ^ 3u, 1);
-                k += m;
-                if (k < s) { emit_group(E, base, 1); ++k; }
-            }
+            emit_group(E, base, 1); ++k;
+            if (t == kEvSubst) ++w.n_sub;
         }
         i += dir; e += dir;
         have = dir > 0 ? (e < n_ev) : (e >= 0);
         if (have) cur = load_event(ev, e);
     }
     w.ext = ext;
-    return true;
+    return ok;
 }
 
 constexpr int kTpThreads = 128;
@@ -670,9 +689,17 @@ __global__ void __launch_bounds__(kTpThreads)
 simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
                          PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
 {
+    // staging tile: one row of nw0+nw1 words per thread, odd row stride => conflict-free; flushed to HBM (pair-major)
+    // by the whole CTA with coalesced stores
+    extern __shared__ __align__(16) uint32_t tile[];
+    const int NW = P.nw[0] + P.nw[1], RS = NW | 1;
+    uint32_t *row = tile + (size_t)threadIdx.x * RS;
     const int solid = P.data_type == 1;
     unsigned failed_total = 0;
-    for (int p = blockIdx.x * kTpThreads + threadIdx.x; p < n; p += gridDim.x * kTpThreads) {
+    const int n_round = (n + kTpThreads - 1) / kTpThreads * kTpThreads;
+    for (int pbase = blockIdx.x * kTpThreads; pbase < n_round; pbase += gridDim.x * kTpThreads) {
+        const int p = pbase + threadIdx.x;
+        if (p < n) {
         const int64_t q = first + p;
         int contig_index;
         const ContigDesc *cd = find_contig(blob, q, &contig_index);
@@ -680,7 +707,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         const uint64_t gidx = (uint64_t)(gidx_origin + q);
         PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), 0u};
         const int s0 = P.len[0], s1 = P.len[1];
-        uint32_t *dst0 = seqw + p, *dst1 = seqw + (size_t)P.nw[0] * n + p;
+        uint32_t *dst0 = row, *dst1 = row + P.nw[0];
         int strand0 = 0, strand1 = 0, hap = 0;
         bool done = false, random_pair = false;
         Walk w0, w1;
@@ -718,13 +745,13 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
                 else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
             } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
-            emit_begin(E0, dst0, (size_t)n, s0, solid, true, P, key, 0);
+            emit_begin(E0, dst0, s0, solid, true, P, key, 0);
             bool ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0);
             if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
             if (s1 > 0) {
                 bool ok1 = false;
                 if (ok) {                                              // a rejected end 0 already rejects the pair
-                    emit_begin(E1, dst1, (size_t)n, s1, solid, true, P, key, 1);
+                    emit_begin(E1, dst1, s1, solid, true, P, key, 1);
                     ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1);
                     if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
                 }
@@ -747,7 +774,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
                 if (s <= 0) continue;
                 Emit E;
-                emit_begin(E, j ? dst1 : dst0, (size_t)n, s, solid, false, P, key, j);
+                emit_begin(E, j ? dst1 : dst0, s, solid, false, P, key, j);
                 for (int k = 0; k < s; k += 64) {
                     const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
 #pragma unroll
@@ -777,6 +804,13 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
         }
         recs[p] = rec;
+        }
+        // flush the staging tile: rows of this CTA's pairs are contiguous in HBM (pair-major, NW words per pair)
+        __syncthreads();
+        const int np = min(kTpThreads, n - pbase);
+        uint32_t *out = seqw + (size_t)pbase * NW;
+        for (int x = threadIdx.x; x < np * NW; x += kTpThreads) out[x] = tile[(size_t)(x / NW) * RS + (x % NW)];
+        __syncthreads();
     }
     if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
 }
@@ -832,6 +866,33 @@ __device__ __forceinline__ void record_lengths(const SimParams &P, const PairRec
         if (P.out_bwa) len[j] = (uint32_t)(name_bwa + 3 + (solid ? 2 * (L - 1) : 2 * L) + 4);
         if (P.out_bfast) len[2] += (uint32_t)(name_full + 1 + 2 * L + 4 + (solid ? 1 : 0));
     }
+}
+
+__device__ __forceinline__ int put_dec(char *p, uint32_t v)      // writes v in decimal, returns the digit count
+{
+    const int nd = ndigits10(v);
+    for (int d = nd - 1; d >= 0; --d) { p[d] = (char)('0' + v % 10u); v /= 10u; }
+    return nd;
+}
+// '@' prefix contig _pos1_pos2_s1_s2_r_r_e:s:i_e:s:i_hex   (src/dwgsim.c:923-929); returns the length
+__device__ __forceinline__ int write_name(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
+                                          int cname_len, int variant, char *buf)
+{
+    const bool rnd = r.flags & kRecRandom;
+    int o = 0;
+    buf[o++] = '@';
+    for (int j = 0; j < P.prefix_len; ++j) buf[o++] = P.prefix[j];
+    if (rnd) { buf[o++] = 'r'; buf[o++] = 'a'; buf[o++] = 'n'; buf[o++] = 'd'; }
+    else for (int j = 0; j < cname_len; ++j) buf[o++] = cname[j];
+#pragma unroll
+    for (int f = 0; f < 12; ++f) {
+        buf[o++] = (f == 7 || f == 8 || f == 10 || f == 11) ? ':' : '_';
+        o += put_dec(buf + o, (uint32_t)name_field(r, serial, f, variant));
+    }
+    buf[o++] = '_';
+    const int nd = ndigits16(serial);
+    for (int d = nd - 1; d >= 0; --d) { const uint32_t h = (uint32_t)(serial >> (4 * d)) & 15u; buf[o++] = (char)(h < 10 ? '0' + h : 'a' + h - 10); }
+    return o;
 }
 
 // ---- layout kernels --------------------------------------------------------------------------------------
@@ -902,7 +963,8 @@ __global__ void __launch_bounds__(kThreads)
 layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const PairRec *__restrict__ recs, int n,
                       int64_t first, unsigned long long rand_base, const unsigned long long *__restrict__ blk_rand_excl,
                       unsigned long long *__restrict__ serial, uint32_t *__restrict__ lens /* [3][n] */,
-                      unsigned long long *__restrict__ blk_len /* [3][nblk] */)
+                      unsigned long long *__restrict__ blk_len /* [3][nblk] */,
+                      char *__restrict__ names /* [n][nvar][name_cap] */, uint16_t *__restrict__ name_len /* [n][2] */)
 {
     __shared__ uint32_t sw[kWarpsPerBlock];
     __shared__ unsigned long long sw64[kWarpsPerBlock];
@@ -928,6 +990,22 @@ layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const
         if (r[t].flags & kRecRandom) ser = rs++;
         else ser = (unsigned long long)(q - cd->pair_base);
         serial[base + t] = ser;
+        {   // the read name(s), written once here and copied by the format kernel
+            const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
+            const char *cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
+            const int nvar = (P.data_type == 1 && P.out_bwa) ? 2 : 1;
+            for (int v = 0; v < nvar; ++v) {
+                char *dst = names + ((size_t)(base + t) * nvar + v) * P.name_cap;   // name_cap is a multiple of 16
+                int nl;
+                if (P.name_cap <= 256) {               // assemble locally, store 16 bytes at a time
+                    __align__(16) char tmp[256];
+                    nl = write_name(P, r[t], ser, cname, (int)cd->name_len, v, tmp);
+                    for (int x = 0; x < nl; x += 16) *reinterpret_cast<uint4 *>(dst + x) = *reinterpret_cast<const uint4 *>(tmp + x);
+                } else nl = write_name(P, r[t], ser, cname, (int)cd->name_len, v, dst);
+                name_len[(size_t)(base + t) * 2 + v] = (uint16_t)nl;
+            }
+            if (nvar == 1) name_len[(size_t)(base + t) * 2 + 1] = name_len[(size_t)(base + t) * 2];
+        }
         uint32_t len[3];
         record_lengths(P, r[t], ser, (int)cd->name_len, len);
 #pragma unroll
@@ -970,19 +1048,25 @@ layout_offsets_kernel(int n, const unsigned long long *__restrict__ blk_len_excl
 // stream, so the tile owns ONE contiguous byte range per stream: it is assembled in shared memory at the same
 // offset modulo 16 as its destination and copied out with aligned 16-byte stores (byte stores only in the two
 // boundary chunks shared with the neighbouring tiles).  Work inside the tile is flattened over the threads:
-//   phase 0  one thread per pair: record geometry + the read name (13 numeric fields, src/dwgsim.c:923-929)
-//   phase 1  one thread per (pair, 8-base group): 8 bases -> ASCII with two PRMTs, 8 qualities from two Philox
-//            blocks (src/dwgsim.c:899-918), scattered into the bwa and bfast records (src/dwgsim.c:920-980)
+//   phase 0  one thread per pair: load the pair's record, serial, stream offsets and name lengths (the names
+//            themselves, src/dwgsim.c:923-929, were written by layout_lengths_kernel)
+//   phase 1  one thread per (pair, end, 8-base group), consecutive lanes = consecutive groups: 8 bases -> ASCII
+//            with two PRMTs, 8 qualities from two Philox blocks (src/dwgsim.c:899-918), written into the bwa and
+//            bfast records (src/dwgsim.c:920-980)
 //   phase 2  one thread per record: name, "/1", separators
 //   phase 3  all threads: 16-byte copy-out
 
 constexpr int kFmtThreads = 256;
 
 struct TileMeta {                      // per pair, in shared memory
+    PairRec rec;
+    unsigned long long serial;
+    const char *cname;
     uint32_t so[3];                    // start of the pair's bytes in each stream's staging buffer
-    uint16_t len[2];
+    uint32_t cname_len;
+    uint32_t lo, hi;                   // Philox counter words of the pair
     uint16_t nfull, nbwa;              // name lengths: bfast (full counts) and bwa variant
-    uint32_t lo, hi, attempt;          // Philox counter words of the pair
+    uint32_t pad;
 };
 
 struct FormatSmem {
@@ -998,37 +1082,10 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     for (int e = 0; e < 2; ++e) { L.qbase_off[e] = o; o += (P.cap[e] + 16) & ~15; }
     L.meta_off = o; o += (TP * (int)sizeof(TileMeta) + 15) & ~15;
     L.name_cap = P.name_cap;
-    L.names_off = o; o += 2 * TP * P.name_cap;
+    L.names_off = o;
     for (int k = 0; k < 3; ++k) { L.stage_off[k] = o; o += (TP * P.rec_cap[k] + 32 + 15) & ~15; }
     L.total = o;
     return L;
-}
-
-__device__ __forceinline__ int put_dec(char *p, uint32_t v)      // writes v in decimal, returns the digit count
-{
-    const int nd = ndigits10(v);
-    for (int d = nd - 1; d >= 0; --d) { p[d] = (char)('0' + v % 10u); v /= 10u; }
-    return nd;
-}
-// '@' prefix contig _pos1_pos2_s1_s2_r_r_e:s:i_e:s:i_hex   (src/dwgsim.c:923-929); returns the length
-__device__ __forceinline__ int write_name(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
-                                          int cname_len, int variant, char *buf)
-{
-    const bool rnd = r.flags & kRecRandom;
-    int o = 0;
-    buf[o++] = '@';
-    for (int j = 0; j < P.prefix_len; ++j) buf[o++] = P.prefix[j];
-    if (rnd) { buf[o++] = 'r'; buf[o++] = 'a'; buf[o++] = 'n'; buf[o++] = 'd'; }
-    else for (int j = 0; j < cname_len; ++j) buf[o++] = cname[j];
-#pragma unroll
-    for (int f = 0; f < 12; ++f) {
-        buf[o++] = (f == 7 || f == 8 || f == 10 || f == 11) ? ':' : '_';
-        o += put_dec(buf + o, (uint32_t)name_field(r, serial, f, variant));
-    }
-    buf[o++] = '_';
-    const int nd = ndigits16(serial);
-    for (int d = nd - 1; d >= 0; --d) { const uint32_t h = (uint32_t)(serial >> (4 * d)) & 15u; buf[o++] = (char)(h < 10 ? '0' + h : 'a' + h - 10); }
-    return o;
 }
 
 // quality noise: inverse CDF with a 1024-entry guide table (rank of the bucket's lower bound), then a short scan
@@ -1044,6 +1101,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                     const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
                     const unsigned long long *__restrict__ serial, const uint32_t *__restrict__ offs /* [3][n] */,
                     const unsigned long long *__restrict__ totals /* bytes of the batch per stream */,
+                    const char *__restrict__ gnames, const uint16_t *__restrict__ gname_len,
                     char *__restrict__ out0, char *__restrict__ out1, char *__restrict__ out2)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1054,7 +1112,6 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
     uint32_t *cdf_s = reinterpret_cast<uint32_t *>(smem + L.cdf_off);
     uint8_t *qbase_s[2] = {smem + L.qbase_off[0], smem + L.qbase_off[1]};
     TileMeta *meta = reinterpret_cast<TileMeta *>(smem + L.meta_off);
-    char *names = reinterpret_cast<char *>(smem + L.names_off);
     uint8_t *stage[3] = {smem + L.stage_off[0], smem + L.stage_off[1], smem + L.stage_off[2]};
     __shared__ int s_shift[3], s_total[3];
 
@@ -1066,15 +1123,16 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
 
     const bool solid = P.data_type == 1;
     const int from = solid ? 1 : 0;                                 // bwa drops the first colour (src/dwgsim.c:949-953)
+    const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
     const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
     char *outp[3] = {out0, out1, out2};
     const bool on[3] = {P.out_bwa != 0, P.out_bwa != 0, P.out_bfast != 0};
-    const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1;
+    const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1, NW = P.nw[0] + P.nw[1];
     const int ntiles = (n + TP - 1) / TP;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int p0 = tile * TP, np = min(TP, n - p0);
-        // ---- phase 0: geometry + names --------------------------------------------------------------
+        // ---- phase 0a: per-pair record, serial, offsets -------------------------------------------------
         if (tid < 3) {
             const int k = tid;
             const uint32_t begin = on[k] ? offs[(size_t)k * n + p0] : 0u;
@@ -1088,31 +1146,26 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
             const int64_t q = first + p;
             int ci;
             const ContigDesc *cd = find_contig(blob, q, &ci);
-            const char *cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
-            const PairRec r = recs[p];
-            const uint64_t ser = serial[p];
             const uint64_t gidx = (uint64_t)(gidx_origin + q);
-            TileMeta m;
+            TileMeta &m = meta[tid];
+            m.rec = recs[p];
+            m.serial = serial[p];
+            m.cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
+            m.cname_len = cd->name_len;
             for (int k = 0; k < 3; ++k) m.so[k] = on[k] ? offs[(size_t)k * n + p] - offs[(size_t)k * n + p0] + (uint32_t)s_shift[k] : 0u;
-            m.len[0] = r.len[0]; m.len[1] = r.len[1];
-            m.lo = (uint32_t)gidx; m.hi = (uint32_t)(gidx >> 32); m.attempt = r.attempt;
-            m.nfull = (uint16_t)write_name(P, r, ser, cname, (int)cd->name_len, 0, names + (size_t)tid * L.name_cap);
-            m.nbwa = m.nfull;
-            if (solid && P.out_bwa)
-                m.nbwa = (uint16_t)write_name(P, r, ser, cname, (int)cd->name_len, 1, names + (size_t)(TP + tid) * L.name_cap);
-            meta[tid] = m;
+            m.lo = (uint32_t)gidx; m.hi = (uint32_t)(gidx >> 32);
+            m.nfull = gname_len[(size_t)p * 2]; m.nbwa = gname_len[(size_t)p * 2 + 1];
         }
         __syncthreads();
-        // ---- phase 1: bases and qualities, one thread per (pair, 8-base group) ----------------------------
-        for (int it = tid; it < TP * G; it += kFmtThreads) {
-            const int t = it % TP, gi = it / TP;
-            if (t >= np) continue;
+        // ---- phase 1: bases and qualities, one thread per (pair, end, 8-base group) -------------------------
+        for (int it = tid; it < np * G; it += kFmtThreads) {
+            const int t = it / G, gi = it - t * G;
             const int e = gi < g0 ? 0 : 1, g = gi - (e ? g0 : 0);
             const TileMeta &m = meta[t];
-            const int Le = m.len[e], k0 = g << 3;
+            const int Le = m.rec.len[e], k0 = g << 3;
             if (k0 >= Le) continue;
             const int cnt = min(8, Le - k0);
-            const uint32_t codes = __ldg(seqw + (size_t)((e ? P.nw[0] : 0) + g) * n + (p0 + t));
+            const uint32_t codes = __ldg(seqw + (size_t)(p0 + t) * NW + (e ? P.nw[0] : 0) + g);
             // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
             const uint32_t a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu), a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
             uint32_t d_lo = a_lo, d_hi = a_hi;
@@ -1121,7 +1174,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
             uint32_t q_lo = 0, q_hi = 0;
             if (P.fixed_quality) { q_lo = q_hi = 0x01010101u * (uint32_t)P.fixed_quality; }
             else {
-                const PairKey key{P.seed, m.lo, m.hi, m.attempt};
+                const PairKey key{P.seed, m.lo, m.hi, (uint32_t)m.rec.attempt};
                 uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
                 if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); if (cnt > 4) b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
 #pragma unroll
@@ -1135,8 +1188,9 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                     if (i < 4) q_lo |= (uint32_t)qc << (8 * i); else q_hi |= (uint32_t)qc << (8 * (i - 4));
                 }
             }
-            // scatter into the records
-            const int rec0 = (P.out_bfast && m.len[0] > 0) ? m.nfull + 1 + (solid ? 1 : 0) + 2 * m.len[0] + 4 : 0;
+            // write into the records
+            const int len0 = m.rec.len[0];
+            const int rec0 = (P.out_bfast && len0 > 0) ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
             uint8_t *sb = stage[e] + m.so[e];
             uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
             const int me = Le - from;
@@ -1154,16 +1208,15 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
             }
         }
         // ---- phase 2: names, suffixes, separators: one thread per record ----------------------------------
-        for (int it = tid; it < TP * 4; it += kFmtThreads) {
-            const int t = it % TP, rr = it / TP, e = rr & 1, bf = rr >> 1;
-            if (t >= np) continue;
+        for (int it = tid; it < np * 4; it += kFmtThreads) {
+            const int t = it >> 2, rr = it & 3, e = rr & 1, bf = rr >> 1;
             const TileMeta &m = meta[t];
-            const int Le = m.len[e];
+            const int Le = m.rec.len[e];
             if (Le <= 0) continue;
             if (!bf) {
                 if (!P.out_bwa) continue;
                 uint8_t *sb = stage[e] + m.so[e];
-                const char *nm = names + (size_t)((solid ? TP : 0) + t) * L.name_cap;
+                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (nvar - 1)) * L.name_cap;
                 const int nn = m.nbwa, me = Le - from;
                 for (int x = 0; x < nn; ++x) sb[x] = (uint8_t)nm[x];
                 sb[nn] = '/'; sb[nn + 1] = (uint8_t)(solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sb[nn + 2] = '\n';
@@ -1171,9 +1224,10 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 sb[nn + 3 + me + 3 + me] = '\n';
             } else {
                 if (!P.out_bfast) continue;
-                const int rec0 = m.len[0] > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * m.len[0] + 4 : 0;
+                const int len0 = m.rec.len[0];
+                const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
                 uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
-                const char *nm = names + (size_t)t * L.name_cap;
+                const char *nm = gnames + (size_t)(p0 + t) * nvar * L.name_cap;
                 const int nn = m.nfull;
                 for (int x = 0; x < nn; ++x) sf[x] = (uint8_t)nm[x];
                 sf[nn] = '\n';
