@@ -29,8 +29,27 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+CLI = os.path.join(HERE, "bin", "dwgsim")
+CLI_SRC = os.path.join(CSRC, "host", "dwgsim_cli.cpp")
+
+
+def build_cli(force=False):
+    """the drop-in `dwgsim` host shell (g++), linked against libdwgsim_b200.so and zlib"""
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) > max(os.path.getmtime(CLI_SRC), os.path.getmtime(SO)):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI, CLI_SRC, "-L" + HERE, "-ldwgsim_b200", "-lz", "-lpthread",
+           "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building the dwgsim host shell")
+    return CLI
+
+
 def build(force=False, verbose=False):
     if not force and not stale():
+        build_cli()
         return SO
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
           [os.path.join(CSRC, s) for s in SOURCES]
@@ -40,6 +59,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libdwgsim_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
+    build_cli(force=True)
     return SO
 
 

@@ -1,0 +1,811 @@
+// dwgsim_cli.cpp -- the host shell: a drop-in `dwgsim [options] <in.ref.fa> <out.prefix>` binary.
+//
+// What stays on the host is what must stay sequential and bit-identical to the reference (north star):
+// option parsing (reference src/dwgsim_opt.c), the FASTA census and per-contig pair budget / skip rules
+// (src/dwgsim.c:465-625), drand48-driven mutation generation (mut_diref, src/mut.c:591-758, with
+// mut_left_justify :481-589) and the .mutations.txt/.vcf writers (mut_print, src/mut.c:781-893).  The read-pair
+// loop (src/dwgsim.c:636-1099) is three calls into libdwgsim_b200.so (include/dwgsim_gpu.h), exactly the
+// binding INTEGRATION.md describes.  FASTQ goes to <prefix>.bwa.read1/2.fastq.gz and <prefix>.bfast.fastq.gz like
+// the reference (src/dwgsim.c:1149-1160), compressed by a block-parallel gzip writer (concatenated gzip members),
+// or uncompressed with --uncompressed.
+//
+// New long options only (the short-option surface is the reference's): --uncompressed, --threads N, --device D,
+// --batch PAIRS.
+#include <getopt.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/dwgsim_gpu.h"
+
+#ifndef PACKAGE_VERSION
+#define PACKAGE_VERSION "0.1.17-b200"
+#endif
+
+namespace {
+
+// ---- glibc-compatible drand48 (seeded as src/dwgsim_opt.c:387-394 does) ---------------------------------------
+struct Drand48 {
+    uint64_t x = 0;
+    void seed(long sv) { x = ((uint64_t)((sv >> 16) & 0xffff) << 32) | ((uint64_t)(sv & 0xffff) << 16) | 0x330e; }
+    inline double next() { x = (x * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull; return std::ldexp((double)x, -48); }
+} g_rng;
+
+enum { ILLUMINA = 0, SOLID = 1, IONTORRENT = 2 };
+enum : uint64_t { T_NOCHANGE = 0x00, T_INSERT = 0x10, T_SUBST = 0x20, T_DELETE = 0x30, TYPE_MASK = 0x30, BASE_TYPE_MASK = 0x3F };
+constexpr int INS_SHIFT = 6, INS_LEN_SHIFT = 59, INS_SHORT_MAX = 26;
+constexpr uint64_t INS_LEN_MASK = 0x1F, INS_PAYLOAD_MASK = (1ull << 52) - 1, INS_LONG_MAX = 0xFFFFFFFFull;
+
+uint8_t g_nt4[256];
+void nt4_init()
+{
+    memset(g_nt4, 4, sizeof g_nt4);
+    g_nt4['A'] = g_nt4['a'] = 0; g_nt4['C'] = g_nt4['c'] = 1; g_nt4['G'] = g_nt4['g'] = 2; g_nt4['T'] = g_nt4['t'] = 3;
+    g_nt4['-'] = 5;
+}
+const char kBase[8] = {'A', 'C', 'G', 'T', 'N', 0, 0, 0};
+
+struct Options {                              // dwgsim_opt_t, src/dwgsim_opt.h:21-60
+    double e_start[2] = {0.02, 0.02}, e_end[2] = {0.02, 0.02}, e_by[2] = {0, 0};
+    int is_inner = 0, dist = 500;
+    double std_dev = 50;
+    long long N = -1;
+    double C = 100;
+    int length[2] = {70, 70};
+    double mut_rate = 0.001, mut_freq = 0.5, indel_frac = 0.1, indel_extend = 0.3;
+    int indel_min = 1;
+    double rand_read = 0.05;
+    int max_n = 0, data_type = ILLUMINA, strandedness = 0, read_one_strand = 0;
+    std::string flow_order;                   // as given, then codes
+    std::vector<int8_t> flow_codes;
+    int use_base_error = 0, is_hap = 0, seed = -1;
+    std::string fixed_quality, read_prefix, fn_muts_input, fn_regions_bed;
+    bool has_prefix = false, has_fixed_quality = false;
+    double quality_std = 2.0;
+    int muts_input_type = -1, reads_output_type = 0, output_type = 0, amplicons = 0;
+    // this build
+    bool uncompressed = false;
+    int threads = 0, device = 0;
+    long long batch = 0;
+};
+
+int usage(const Options &o)
+{
+    fprintf(stderr, "\nProgram: dwgsim (short read simulator; read-pair loop on NVIDIA B200 via libdwgsim_b200)\n");
+    fprintf(stderr, "Version: %s\n\n", PACKAGE_VERSION);
+    fprintf(stderr, "Usage:   dwgsim [options] <in.ref.fa> <out.prefix>\n\n");
+    fprintf(stderr, "Options (same letters, meaning and defaults as nh13/DWGSIM):\n");
+    fprintf(stderr, "         -e FLOAT      per base/color/flow error rate of the first read, or START-END [%.3f]\n", o.e_start[0]);
+    fprintf(stderr, "         -E FLOAT      per base/color/flow error rate of the second read, or START-END [%.3f]\n", o.e_start[1]);
+    fprintf(stderr, "         -i            use the inner distance instead of the outer distance for pairs\n");
+    fprintf(stderr, "         -d INT        distance between the two ends for pairs [%d]\n", o.dist);
+    fprintf(stderr, "         -s INT        standard deviation of the distance for pairs [%.3f]\n", o.std_dev);
+    fprintf(stderr, "         -N INT        number of read pairs (-1 to disable) [%lld]\n", o.N);
+    fprintf(stderr, "         -C FLOAT      mean coverage across available positions (-1 to disable) [%.2f]\n", o.C);
+    fprintf(stderr, "         -1 INT        length of the first read [%d]\n", o.length[0]);
+    fprintf(stderr, "         -2 INT        length of the second read [%d]\n", o.length[1]);
+    fprintf(stderr, "         -r FLOAT      rate of mutations [%.4f]\n", o.mut_rate);
+    fprintf(stderr, "         -F FLOAT      frequency of given mutation (first haplotype) [%.4f]\n", o.mut_freq);
+    fprintf(stderr, "         -R FLOAT      fraction of mutations that are indels [%.2f]\n", o.indel_frac);
+    fprintf(stderr, "         -X FLOAT      probability an indel is extended [%.2f]\n", o.indel_extend);
+    fprintf(stderr, "         -I INT        the minimum length indel [%d]\n", o.indel_min);
+    fprintf(stderr, "         -y FLOAT      probability of a random DNA read [%.2f]\n", o.rand_read);
+    fprintf(stderr, "         -n INT        maximum number of Ns allowed in a given read [%d]\n", o.max_n);
+    fprintf(stderr, "         -c INT        generate reads for 0: Illumina, 1: SOLiD, 2: Ion Torrent [%d]\n", o.data_type);
+    fprintf(stderr, "         -S INT        pair orientation 0: by platform, 1: same strand, 2: opposite strand [%d]\n", o.strandedness);
+    fprintf(stderr, "         -A INT        read one 0: random strand, 1: forward, 2: reverse [%d]\n", o.read_one_strand);
+    fprintf(stderr, "         -f STRING     the flow order for Ion Torrent data\n");
+    fprintf(stderr, "         -B            use a per-base error rate for Ion Torrent data\n");
+    fprintf(stderr, "         -H            haploid mode\n");
+    fprintf(stderr, "         -z INT        random seed (-1 uses the current time) [%d]\n", o.seed);
+    fprintf(stderr, "         -M INT        output 0: reads and mutations, 1: reads only, 2: mutations only [%d]\n", o.output_type);
+    fprintf(stderr, "         -m/-b/-v FILE replay mutations from txt / bed / vcf (not supported by this build)\n");
+    fprintf(stderr, "         -x FILE       the bed of regions to cover (not supported by this build)\n");
+    fprintf(stderr, "         -P STRING     a read prefix to prepend to each read name\n");
+    fprintf(stderr, "         -q STRING     a fixed base quality to apply (single character)\n");
+    fprintf(stderr, "         -Q FLOAT      standard deviation of the base quality scores [%.2f]\n", o.quality_std);
+    fprintf(stderr, "         -o INT        FASTQ files 0: bfast and bwa, 1: bwa only, 2: bfast only [%d]\n", o.reads_output_type);
+    fprintf(stderr, "         -a            assume each contig is an amplicon\n");
+    fprintf(stderr, "         -h            print this message\n");
+    fprintf(stderr, "         --uncompressed  write .fastq instead of .fastq.gz\n");
+    fprintf(stderr, "         --threads INT   gzip worker threads [all cores]\n");
+    fprintf(stderr, "         --device INT    CUDA device [0]\n");
+    fprintf(stderr, "         --batch INT     read pairs per device batch\n\n");
+    return 1;
+}
+
+void parse_rate(const char *str, double *start, double *end)          // src/dwgsim_opt.c:162-179
+{
+    size_t i, n = strlen(str);
+    *start = atof(str);
+    for (i = 0; i < n; i++) if (str[i] == ',' || str[i] == '-') break;
+    if (n > 0 && i < n - 1) *end = atof(str + i + 1); else *end = *start;
+}
+bool is_int(const char *s, bool neg_ok)                               // src/dwgsim_opt.c:181-192
+{
+    size_t len = strlen(s);
+    if (!len) return false;
+    if (s[0] != '+' && !(neg_ok && s[0] == '-') && !isdigit((unsigned char)s[0])) return false;
+    for (size_t i = 1; i < len; i++) if (!isdigit((unsigned char)s[i])) return false;
+    return true;
+}
+int to_int(const char *s, char flag, bool neg_ok)
+{
+    if (!is_int(s, neg_ok)) { fprintf(stderr, "Error: command line option -%c is not a number [%s]\n", flag, s); exit(1); }
+    return atoi(s);
+}
+
+// ---- Ion Torrent flow model on the host: only for the -B calibration of the error rate, which draws from the
+// same drand48 stream as mut_diref and therefore has to run here (src/dwgsim_opt.c:415-457; model src/dwgsim.c:246-417)
+int flow_errors_host(const Options &o, std::vector<uint8_t> &seq, std::vector<uint8_t> &mask, int len, double e, int *n_err_out)
+{
+    const std::vector<int8_t> &fo = o.flow_codes;
+    const int fl = (int)fo.size();
+    auto grow = [&](int need) { if ((int)seq.size() <= need) seq.resize((size_t)need * 2 + 16); };
+    for (int i = 0; i < len; i++) if (seq[i] >= 4) seq[i] = 0;
+    int i, flow_i;
+    for (i = 0; i < fl; i++) { int c = len > 0 ? seq[0] : 0; if (c == fo[i]) break; mask[i] = 0; }
+    if (i == fl) return -1;
+    flow_i = i;
+    int prev_c = 4;
+    for (i = 0; i < len; i++) {
+        const int c = seq[i];
+        while (c != fo[flow_i]) { mask[flow_i] = 0; flow_i = (flow_i + 1) % fl; }
+        if (prev_c != c) {
+            mask[flow_i] = 0;
+            int n_err = 0;
+            while (g_rng.next() < e) n_err++;
+            if (n_err > 0) {
+                if (g_rng.next() < 0.5) {
+                    grow(len + n_err + 1);
+                    for (int j = len - 1; i <= j; j--) seq[j + n_err] = seq[j];
+                    for (int j = i; j < i + n_err; j++) seq[j] = (uint8_t)c;
+                    len += n_err;
+                } else {
+                    int hp_l = 0, next_c = 4;
+                    for (int j = i; j < len; j++, hp_l++) { next_c = seq[j]; if (c != next_c) break; }
+                    if (hp_l < n_err) n_err = hp_l;
+                    for (int j = i; j < len - n_err; j++) seq[j] = seq[j + n_err];
+                    len -= n_err;
+                    mask[flow_i] = 1;
+                    if (n_err == hp_l && (i == 0 || prev_c == next_c)) {
+                        int j = 0;
+                        while (next_c != fo[(flow_i + j) % fl]) j++;
+                        if (j <= 0) return len;
+                        const int k = (int)(g_rng.next() * j);
+                        grow(len + 2);
+                        for (int jj = len - 1; i <= jj; jj--) seq[jj + 1] = seq[jj];
+                        seq[i] = (uint8_t)fo[(flow_i + k) % fl];
+                        len++;
+                    }
+                }
+                *n_err_out += n_err;
+            }
+            prev_c = c;
+        }
+    }
+    for (i = 0; i < len; i++) {
+        const int c = seq[i];
+        while (c != fo[flow_i]) {
+            int n_err = 0;
+            while (g_rng.next() < e) n_err++;
+            if (mask[flow_i] == 0 && n_err > 0) {
+                grow(len + n_err + 1);
+                for (int j = len - 1; i <= j; j--) seq[j + n_err] = seq[j];
+                for (int j = i; j < i + n_err; j++) seq[j] = (uint8_t)fo[flow_i];
+                len += n_err;
+                *n_err_out += n_err;
+            }
+            flow_i = (flow_i + 1) % fl;
+        }
+    }
+    return len;
+}
+
+// returns 1 ok, 0 -> usage
+int parse_options(Options &o, int argc, char **argv, int *first_arg)
+{
+    static const struct option longopts[] = {
+        {"uncompressed", no_argument, nullptr, 1000}, {"threads", required_argument, nullptr, 1001},
+        {"device", required_argument, nullptr, 1002}, {"batch", required_argument, nullptr, 1003}, {nullptr, 0, nullptr, 0}};
+    int c, muts = 0;
+    while ((c = getopt_long(argc, argv, "id:s:N:C:1:2:e:E:r:F:R:X:I:c:S:A:n:y:BHf:z:M:m:b:v:x:P:q:Q:o:ah", longopts, nullptr)) >= 0) {
+        switch (c) {
+            case 'i': o.is_inner = 1; break;
+            case 'd': o.dist = to_int(optarg, 'd', false); break;
+            case 's': o.std_dev = atof(optarg); break;
+            case 'N': o.N = to_int(optarg, 'N', true); o.C = -1; break;
+            case 'C': o.C = atof(optarg); o.N = -1; break;
+            case '1': o.length[0] = to_int(optarg, '1', false); break;
+            case '2': o.length[1] = to_int(optarg, '2', false); break;
+            case 'e': parse_rate(optarg, &o.e_start[0], &o.e_end[0]); break;
+            case 'E': parse_rate(optarg, &o.e_start[1], &o.e_end[1]); break;
+            case 'r': o.mut_rate = atof(optarg); break;
+            case 'F': o.mut_freq = atof(optarg); break;
+            case 'R': o.indel_frac = atof(optarg); break;
+            case 'X': o.indel_extend = atof(optarg); break;
+            case 'I': o.indel_min = to_int(optarg, 'I', false); break;
+            case 'c': o.data_type = to_int(optarg, 'c', false); break;
+            case 'S': o.strandedness = to_int(optarg, 'S', false); break;
+            case 'A': o.read_one_strand = to_int(optarg, 'A', false); break;
+            case 'n': o.max_n = to_int(optarg, 'n', false); break;
+            case 'y': o.rand_read = atof(optarg); break;
+            case 'f': o.flow_order = optarg; break;
+            case 'B': o.use_base_error = 1; break;
+            case 'H': o.is_hap = 1; break;
+            case 'h': return 0;
+            case 'z': o.seed = to_int(optarg, 'z', true); break;
+            case 'M': o.output_type = to_int(optarg, 'M', false); break;
+            case 'm': o.fn_muts_input = optarg; o.muts_input_type = 0; muts |= 1; break;
+            case 'b': o.fn_muts_input = optarg; o.muts_input_type = 1; muts |= 2; break;
+            case 'v': o.fn_muts_input = optarg; o.muts_input_type = 2; muts |= 4; break;
+            case 'x': o.fn_regions_bed = optarg; break;
+            case 'P': o.read_prefix = optarg; o.has_prefix = true; break;
+            case 'q': o.fixed_quality = optarg; o.has_fixed_quality = true; break;
+            case 'Q': o.quality_std = atof(optarg); break;
+            case 'o': o.reads_output_type = atoi(optarg); break;
+            case 'a': o.amplicons = 1; break;
+            case 1000: o.uncompressed = true; break;
+            case 1001: o.threads = atoi(optarg); break;
+            case 1002: o.device = atoi(optarg); break;
+            case 1003: o.batch = atoll(optarg); break;
+            default: fprintf(stderr, "Unrecognized option: -%c\n", c); return 0;
+        }
+    }
+    if (argc - optind < 2) return 0;
+    *first_arg = optind;
+#define CHECK(v, lo, hi, name) do { if ((v) < (lo) || (hi) < (v)) { fprintf(stderr, "Error: command line option %s was out of range\n", name); return 0; } } while (0)
+    CHECK(o.dist, 0, INT32_MAX, "-d"); CHECK(o.std_dev, 0, INT32_MAX, "-s");
+    if (o.N < 0 && o.C < 0) { fprintf(stderr, "Must use one of -N or -C"); return 0; }
+    if (0 < o.N && 0 < o.C) { fprintf(stderr, "Cannot use both -N or -C"); return 0; }
+    if (0 < o.N) { CHECK(o.N, 1, INT32_MAX, "-N"); CHECK(o.C, INT32_MIN, -1, "-C"); }
+    else { CHECK(o.N, INT32_MIN, -1, "-N"); CHECK(o.C, 0, INT32_MAX, "-C"); }
+    CHECK(o.length[0], 1, INT32_MAX, "-1"); CHECK(o.length[1], 0, INT32_MAX, "-2");
+    for (int i = 0; i < 2; i++) {
+        if (o.e_start[i] < 0.0 || 1.0 < o.e_start[i]) { fprintf(stderr, "End %s: the start error is out of range (-e)\n", i ? "two" : "one"); return 0; }
+        if (o.e_end[i] < 0.0 || 1.0 < o.e_end[i]) { fprintf(stderr, "End %s: the end error is out of range (-e)\n", i ? "two" : "one"); return 0; }
+        if (o.data_type == IONTORRENT && o.e_end[i] != o.e_start[i]) {
+            fprintf(stderr, "End %s: a uniform error rate must be given for Ion Torrent data\n", i ? "two" : "one"); return 0;
+        }
+    }
+    CHECK(o.mut_rate, 0, 1.0, "-r"); CHECK(o.indel_frac, 0, 1.0, "-R"); CHECK(o.indel_extend, 0, 1.0, "-X");
+    CHECK(o.indel_min, 1, INT32_MAX, "-I"); CHECK(o.data_type, 0, 2, "-c"); CHECK(o.strandedness, 0, 2, "-S");
+    CHECK(o.read_one_strand, 0, 2, "-A"); CHECK(o.max_n, 0, INT32_MAX, "-n"); CHECK(o.rand_read, 0, 1.0, "-y");
+    if (o.data_type == IONTORRENT && o.flow_order.empty()) { fprintf(stderr, "Error: command line option -f is required\n"); return 0; }
+    if (o.has_fixed_quality && o.fixed_quality.size() != 1) { fprintf(stderr, "Error: command line option -q requires one character\n"); return 0; }
+    CHECK(o.quality_std, 0, INT32_MAX, "-Q");
+    if (o.has_prefix) fprintf(stderr, "Warning: remember to use the -P option with dwgsim_eval\n");
+    CHECK(o.reads_output_type, 0, 2, "-o");
+    if (muts != 0 && muts != 1 && muts != 2 && muts != 4) { fprintf(stderr, "Error: -m/-b/-v cannot be used together\n"); return 0; }
+#undef CHECK
+    g_rng.seed(o.seed == -1 ? (long)time(nullptr) : (long)o.seed);
+    if (o.data_type == IONTORRENT)
+        for (char ch : o.flow_order) o.flow_codes.push_back((int8_t)g_nt4[(uint8_t)ch]);
+    if (o.data_type == IONTORRENT && o.use_base_error == 1) {           // src/dwgsim_opt.c:415-457
+        double sf = 0.0;
+        for (int i = 0; i < 2; i++) {
+            if (o.length[i] <= 0) continue;
+            fprintf(stderr, "[dwgsim_core] Updating error rate for end %d\n", i + 1);
+            if (0 < i && o.length[i] == o.length[1 - i]) {
+                o.e_start[i] = o.e_start[1 - i]; o.e_end[i] = o.e_end[1 - i]; o.e_by[i] = o.e_by[1 - i];
+                fprintf(stderr, "[dwgsim_core] Using scaling factor from previous end\n[dwgsim_core] Updated with scaling factor %.5lf\n", sf);
+                continue;
+            }
+            std::vector<uint8_t> seq((size_t)o.length[i] * 2 + 64), mask(std::max<size_t>(o.flow_codes.size(), (size_t)o.length[i]) + 64, 0);
+            long long n_err = 0, counts = 0;
+            int j;
+            for (j = 0; j < 1000000; j++) {
+                if (j % 10000 == 0) fprintf(stderr, "\r[dwgsim_core] %d", j);
+                for (int k = 0; k < o.length[i]; k++) seq[k] = (uint8_t)((int)(g_rng.next() * 4.0) & 3);
+                int cur = 0;
+                const int s = flow_errors_host(o, seq, mask, o.length[i], o.e_start[i], &cur);
+                n_err += cur; counts += s;
+            }
+            sf = o.e_start[i] / ((int32_t)n_err / (1.0 * (int32_t)counts));
+            o.e_start[i] = o.e_end[i] *= sf;
+            o.e_by[i] = (o.e_end[i] - o.e_start[i]) / o.length[i];
+            fprintf(stderr, "\r[dwgsim_core] %d\n[dwgsim_core] Updated with scaling factor %.5lf!\n", j, sf);
+        }
+    } else {
+        o.e_by[0] = (o.e_end[0] - o.e_start[0]) / o.length[0];
+        o.e_by[1] = (o.e_end[1] - o.e_start[1]) / o.length[1];
+    }
+    if (o.output_type < 0 || o.output_type > 2) { fprintf(stderr, "Error: command line option -M was out of range\n"); return 0; }
+    if (o.amplicons == 1 && !o.fn_regions_bed.empty()) { fprintf(stderr, "Error: cannot use a regions BED file (-x) when simulating amplicons (-a)\n"); return 0; }
+    return 1;
+}
+
+// ---- FASTA (seq_read_fasta, src/mut.c:49-87) over an in-memory file ------------------------------------------------
+struct Fasta {
+    std::vector<char> buf;
+    size_t pos = 0;
+    bool open(const char *path)
+    {
+        FILE *fp = fopen(path, "rb");
+        if (!fp) return false;
+        fseek(fp, 0, SEEK_END);
+        const long sz = ftell(fp);
+        fseek(fp, 0, SEEK_SET);
+        buf.resize((size_t)sz);
+        const bool ok = fread(buf.data(), 1, buf.size(), fp) == buf.size();
+        fclose(fp);
+        return ok;
+    }
+    // next contig into seq (symbols kept as in the file); returns length or -1
+    int64_t next(std::vector<uint8_t> &seq, std::string &name)
+    {
+        const size_t n = buf.size();
+        while (pos < n && buf[pos] != '>') pos++;
+        if (pos >= n) return -1;
+        pos++;
+        name.clear();
+        int c = 0;
+        while (pos < n) { c = (unsigned char)buf[pos++]; if (c == ' ' || c == '\t' || c == '\n') break; if (c != '\r') name.push_back((char)c); }
+        if (c != '\n') while (pos < n && buf[pos++] != '\n') {}
+        seq.clear();
+        while (pos < n && (c = (unsigned char)buf[pos]) != '>') { pos++; if (isalpha(c) || c == '-' || c == '.') seq.push_back((uint8_t)c); }
+        return (int64_t)seq.size();
+    }
+};
+
+// ---- haplotype arrays: the reference's mutseq_t (src/mut.h:42-47), 64-bit mut_t per base ------------------------------
+struct Hap {
+    std::vector<uint64_t> s;
+    std::vector<uint8_t *> ins;
+    ~Hap() { for (auto p : ins) free(p); }
+    void reset(size_t l) { for (auto p : ins) free(p); ins.clear(); s.assign(l + 2, 0); }
+};
+int long_ins_bytes(uint64_t n) { return 1 + (n <= 0xFF ? 1 : (n <= 0xFFFF ? 2 : 4)) + (int)((n + 3) >> 2); }
+uint8_t *long_ins_payload(uint8_t *rec, uint32_t *n)
+{
+    if (rec[0] == 1) { *n = rec[1]; return rec + 2; }
+    if (rec[0] == 2) { uint16_t v; memcpy(&v, rec + 1, 2); *n = v; return rec + 3; }
+    uint32_t v; memcpy(&v, rec + 1, 4); *n = v; return rec + 5;
+}
+uint8_t *long_ins_set_len(uint8_t *rec, uint32_t n)
+{
+    if (n <= 0xFF) { rec[0] = 1; rec[1] = (uint8_t)n; return rec + 2; }
+    if (n <= 0xFFFF) { uint16_t v = (uint16_t)n; rec[0] = 2; memcpy(rec + 1, &v, 2); return rec + 3; }
+    rec[0] = 4; memcpy(rec + 1, &n, 4); return rec + 5;
+}
+bool get_ins(const Hap &h, int64_t i, uint64_t *n, uint64_t *ins)
+{
+    const uint64_t m = h.s[i];
+    *n = (m >> INS_LEN_SHIFT) & INS_LEN_MASK;
+    *ins = (m >> INS_SHIFT) & INS_PAYLOAD_MASK;
+    return *n != 0;
+}
+
+// mut_add_ins with random bases, src/mut.c:282-377
+void add_insertion(const Options &o, Hap &h1, Hap &h2, int64_t i, uint64_t c)
+{
+    uint64_t num = 0, ins = 0;
+    int hap;
+    do { num++; } while (num < INS_LONG_MAX && ((long long)num < o.indel_min || g_rng.next() < o.indel_extend));
+    if (o.is_hap || g_rng.next() < 0.333333) hap = 3;
+    else if (g_rng.next() < 0.5) hap = 1;
+    else hap = 2;
+    if (num <= INS_SHORT_MAX) {
+        for (uint64_t j = 0; j < num; j++) ins = (ins << 2) | (uint64_t)(g_rng.next() * 4.0);
+        const uint64_t v = (num << INS_LEN_SHIFT) | (ins << INS_SHIFT) | T_INSERT | c;
+        if (hap & 1) h1.s[i] = v;
+        if (hap & 2) h2.s[i] = v;
+        return;
+    }
+    Hap *hs[2] = {&h1, &h2};
+    uint8_t *pl[2] = {nullptr, nullptr};
+    for (int x = 0; x < 2; x++) if (hap & (1 << x)) {
+        uint8_t *rec = (uint8_t *)calloc((size_t)long_ins_bytes(num), 1);
+        hs[x]->ins.push_back(rec);
+        pl[x] = long_ins_set_len(rec, (uint32_t)num);
+    }
+    int byte_i = 0, bit_i = 0;
+    for (uint64_t left = num; left > 0; left--) {
+        const uint8_t b = (uint8_t)((int)(g_rng.next() * 4.0) << (bit_i << 1));
+        if (pl[0]) pl[0][byte_i] |= b;
+        if (pl[1]) pl[1][byte_i] |= b;
+        if (++bit_i == 4) { bit_i = 0; byte_i++; }
+    }
+    for (int x = 0; x < 2; x++) if (hap & (1 << x))
+        hs[x]->s[i] = ((uint64_t)(hs[x]->ins.size() - 1) << INS_SHIFT) | T_INSERT | c;
+}
+
+// mut_left_justify_ins, src/mut.c:427-478
+void left_justify_ins(Hap &h, int64_t i)
+{
+    uint64_t n, ins;
+    int64_t j = i;
+    if (get_ins(h, i, &n, &ins)) {
+        while (0 < j && (h.s[j - 1] & TYPE_MASK) == T_NOCHANGE && ((ins >> ((n - 1) << 1)) & 3) == (h.s[j - 1] & 3)) {
+            ins &= ~((uint64_t)3 << ((n - 1) << 1));
+            ins = (ins << 2) | (h.s[j - 1] & 3);
+            h.s[j] &= 3;
+            j--;
+        }
+        h.s[j] = (n << INS_LEN_SHIFT) | (ins << INS_SHIFT) | T_INSERT | (h.s[j] & 3);
+        return;
+    }
+    uint32_t num;
+    uint8_t *p = long_ins_payload(h.ins[ins], &num);
+    const int nb = (int)((num + 3) >> 2);
+    while (0 < j && (h.s[j - 1] & TYPE_MASK) == T_NOCHANGE && (uint64_t)(p[0] & 3) == (h.s[j - 1] & 3)) {
+        for (int b = 0; b < nb; b++) { p[b] >>= 2; if (b + 1 < nb) p[b] |= (uint8_t)((p[b + 1] & 3) << 6); }
+        p[nb - 1] |= (uint8_t)((h.s[j - 1] & 3) << (((num + 3) & 3) << 1));
+        h.s[j] &= 3;
+        j--;
+    }
+    h.s[j] = (ins << INS_SHIFT) | T_INSERT | (h.s[j] & 3);
+}
+
+void shift_del(Hap &h, int64_t i, int del)                              // src/mut.c:540-553
+{
+    for (int64_t j = i - 1; j >= 0; j--) {
+        if ((h.s[j] & TYPE_MASK) == T_NOCHANGE && (h.s[j] & 3) == (h.s[j + del] & 3)) {
+            const uint64_t t = h.s[j];
+            h.s[j] = h.s[j + del];
+            h.s[j + del] = (t | TYPE_MASK) ^ TYPE_MASK;
+        } else break;
+    }
+}
+
+// mut_left_justify, src/mut.c:481-589
+void left_justify(const std::vector<uint8_t> &seq, Hap &h1, Hap &h2)
+{
+    const int64_t l = (int64_t)seq.size();
+    int prev_del[2] = {0, 0};
+    for (int64_t i = 0; i < l; ++i) {
+        const uint64_t c0 = g_nt4[seq[i]], c1 = h1.s[i], c2 = h2.s[i];
+        if (c0 >= 4) continue;
+        const uint64_t t1 = c1 & TYPE_MASK, t2 = c2 & TYPE_MASK;
+        if (t1 == T_NOCHANGE && t2 == T_NOCHANGE) { prev_del[0] = prev_del[1] = 0; continue; }
+        int64_t j;
+        int del;
+        if ((c1 & BASE_TYPE_MASK) == (c2 & BASE_TYPE_MASK)) {
+            if (t1 == T_SUBST) prev_del[0] = prev_del[1] = 0;
+            else if (t1 == T_DELETE) {
+                if (prev_del[0] == 1 || prev_del[1] == 1) continue;
+                prev_del[0] = prev_del[1] = 1;
+                for (j = i + 1, del = 1; j < l && (h1.s[j] & TYPE_MASK) == T_DELETE; j++) del++;
+                if (l <= i + del || i == 0) continue;
+                for (j = i - 1; j >= 0; j--) {
+                    if ((h1.s[j] & TYPE_MASK) != T_INSERT && (h2.s[j] & TYPE_MASK) != T_INSERT && (h1.s[j] & TYPE_MASK) != T_DELETE &&
+                        (h2.s[j] & TYPE_MASK) != T_DELETE && (h1.s[j] & 3) == (h1.s[j + del] & 3) && (h2.s[j] & 3) == (h2.s[j + del] & 3)) {
+                        uint64_t t = h1.s[j]; h1.s[j] = h1.s[j + del]; h1.s[j + del] = (t | TYPE_MASK) ^ TYPE_MASK;
+                        t = h2.s[j]; h2.s[j] = h2.s[j + del]; h2.s[j + del] = (t | TYPE_MASK) ^ TYPE_MASK;
+                    } else break;
+                }
+            } else { prev_del[0] = prev_del[1] = 0; left_justify_ins(h1, i); left_justify_ins(h2, i); }
+        } else {
+            if (t1 == T_SUBST || t2 == T_SUBST) prev_del[0] = prev_del[1] = 0;
+            else if (t1 == T_DELETE) {
+                if (prev_del[0] == 1) continue;
+                prev_del[0] = 1;
+                for (j = i + 1, del = 1; j < l && (h1.s[j] & TYPE_MASK) == T_DELETE; j++) del++;
+                if (l <= i + del || i == 0) continue;
+                shift_del(h1, i, del);
+            } else if (t2 == T_DELETE) {
+                if (prev_del[1] == 1) continue;
+                prev_del[1] = 1;
+                for (j = i + 1, del = 1; j < l && (h2.s[j] & TYPE_MASK) == T_DELETE; j++) del++;
+                if (l <= i + del || i == 0) continue;
+                shift_del(h2, i, del);
+            } else if (t1 == T_INSERT) { prev_del[0] = prev_del[1] = 0; left_justify_ins(h1, i); }
+            else if (t2 == T_INSERT) { prev_del[0] = prev_del[1] = 0; left_justify_ins(h2, i); }
+        }
+    }
+}
+
+// mut_diref, random branch, src/mut.c:591-643 + :752-757.  The common case (no mutation at this base) is one LCG
+// step and one integer compare: drand48() < r  <=>  X < ceil(r * 2^48) for the 48-bit state X.
+void diref(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2)
+{
+    const int64_t l = (int64_t)seq.size();
+    h1.reset((size_t)l); h2.reset((size_t)l);
+    Hap *ret[2] = {&h1, &h2};
+    const uint64_t thr = (uint64_t)std::ceil(std::ldexp(o.mut_rate, 48));
+    int deleting = 0, del_len = 0;
+    for (int64_t i = 0; i < l; ++i) {
+        uint64_t c = h1.s[i] = h2.s[i] = (uint64_t)g_nt4[seq[i]];
+        if (deleting) {
+            if (del_len < o.indel_min || g_rng.next() < o.indel_extend) {
+                if (deleting & 1) h1.s[i] |= T_DELETE | c;
+                if (deleting & 2) h2.s[i] |= T_DELETE | c;
+                del_len++;
+                continue;
+            }
+            deleting = del_len = 0;
+        }
+        if (c >= 4) continue;
+        g_rng.x = (g_rng.x * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull;
+        if (g_rng.x >= thr) continue;                                      // drand48() < mut_rate is false
+        if (g_rng.next() >= o.indel_frac) {
+            const double r = g_rng.next();
+            c = (c + (uint64_t)(r * 3.0 + 1)) & 3;
+            if (o.is_hap || g_rng.next() < 0.333333) h1.s[i] = h2.s[i] = T_SUBST | c;
+            else ret[g_rng.next() < 0.5 ? 0 : 1]->s[i] = T_SUBST | c;
+        } else if (g_rng.next() < 0.5) {
+            if (o.is_hap || g_rng.next() < 0.3333333) { h1.s[i] = h2.s[i] = T_DELETE | c; deleting = 3; }
+            else { deleting = g_rng.next() < 0.5 ? 1 : 2; ret[deleting - 1]->s[i] = T_DELETE | c; }
+            del_len = 1;
+        } else add_insertion(o, h1, h2, i, c);
+    }
+    left_justify(seq, h1, h2);
+}
+
+void print_ins(FILE *fp, const Hap &h, int64_t i)                        // src/mut.c:249-279
+{
+    uint64_t n, ins;
+    if (get_ins(h, i, &n, &ins)) { while (n > 0) { fputc(kBase[ins & 3], fp); ins >>= 2; n--; } return; }
+    uint32_t num = 0;
+    uint8_t *p = long_ins_payload(h.ins[ins], &num);
+    int byte_i = (int)((num + 3) >> 2) - 1, bit_i = (int)((num + 3) & 3);
+    while (0 < num) { fputc(kBase[(p[byte_i] >> (bit_i << 1)) & 3], fp); if (--bit_i < 0) { bit_i = 3; byte_i--; } num--; }
+}
+void print_del_vcf(FILE *vcf, const char *name, const std::vector<uint8_t> &seq, const Hap &h1, const Hap &h2, int64_t i, int which)
+{
+    const int64_t l = (int64_t)seq.size();
+    uint64_t c0 = g_nt4[seq[i]], c1 = h1.s[i], c2 = h2.s[i];
+    fprintf(vcf, "%s\t%lld\t.\t", name, (long long)i);
+    if (0 < i) fputc(kBase[g_nt4[seq[i - 1]]], vcf);
+    for (int64_t j = i; j < l; ++j) {
+        const bool same = (c1 & BASE_TYPE_MASK) == (c2 & BASE_TYPE_MASK);
+        const uint64_t cd = which == 2 ? c2 : c1;
+        if (which == 3 ? !same : same) break;
+        if ((cd & TYPE_MASK) != T_DELETE) break;
+        fputc(kBase[c0], vcf);
+        if (j + 1 < l) { c0 = g_nt4[seq[j + 1]]; c1 = h1.s[j + 1]; c2 = h2.s[j + 1]; }
+    }
+    if (0 < i) fprintf(vcf, "\t%c", kBase[g_nt4[seq[i - 1]]]); else fprintf(vcf, "\t.");
+    fprintf(vcf, "\t100\tPASS\tAF=%s;pl=%d;mt=DELETE\n", which == 3 ? "1.0" : "0.5", which);
+}
+// mut_print, src/mut.c:781-893
+void print_mutations(const char *name, const std::vector<uint8_t> &seq, const Hap &h1, const Hap &h2, FILE *txt, FILE *vcf)
+{
+    const int64_t l = (int64_t)seq.size();
+    int prev[2] = {0, 0};
+    for (int64_t i = 0; i < l; ++i) {
+        const uint64_t c0 = g_nt4[seq[i]], c1 = h1.s[i], c2 = h2.s[i], t1 = c1 & TYPE_MASK, t2 = c2 & TYPE_MASK;
+        if (t1 == T_NOCHANGE && t2 == T_NOCHANGE) { prev[0] = prev[1] = 0; continue; }
+        if (c0 < 4) {
+            fprintf(txt, "%s\t%lld\t", name, (long long)i + 1);
+            if ((c1 & BASE_TYPE_MASK) == (c2 & BASE_TYPE_MASK)) {
+                if (t1 == T_SUBST) {
+                    fprintf(txt, "%c\t%c\t3\n", kBase[c0], kBase[c1 & 0xf]);
+                    fprintf(vcf, "%s\t%lld\t.\t%c\t%c\t100\tPASS\tAF=1.0;pl=3;mt=SUBSTITUTE\n", name, (long long)i + 1, kBase[c0], kBase[c1 & 0xf]);
+                } else if (t1 == T_DELETE) {
+                    fprintf(txt, "%c\t-\t3\n", kBase[c0]);
+                    if (prev[0] == 0 || prev[1] == 0) print_del_vcf(vcf, name, seq, h1, h2, i, 3);
+                } else {
+                    fprintf(txt, "-\t"); print_ins(txt, h1, i); fprintf(txt, "\t3\n");
+                    fprintf(vcf, "%s\t%lld\t.\t%c\t%c", name, (long long)i + 1, kBase[c0], kBase[c0]);
+                    print_ins(vcf, h1, i);
+                    fprintf(vcf, "\t100\tPASS\tAF=1.0;pl=3;mt=INSERT\n");
+                }
+            } else if (t1 == T_SUBST || t2 == T_SUBST) {
+                const int hap = t1 == T_SUBST ? 1 : 2;
+                fprintf(txt, "%c\t%c\t%d\n", kBase[c0], "XACMGRSVTWYHKDBN"[(1 << (c1 & 3)) | (1 << (c2 & 3))], hap);
+                fprintf(vcf, "%s\t%lld\t.\t%c\t%c\t100\tPASS\tAF=0.5;pl=%d;mt=SUBSTITUTE\n", name, (long long)i + 1, kBase[c0],
+                        kBase[(hap == 1 ? c1 : c2) & 0xf], hap);
+            } else if (t1 == T_DELETE) {
+                fprintf(txt, "%c\t-\t1\n", kBase[c0]);
+                if (prev[0] == 0) print_del_vcf(vcf, name, seq, h1, h2, i, 1);
+            } else if (t2 == T_DELETE) {
+                fprintf(txt, "%c\t-\t2\n", kBase[c0]);
+                if (prev[1] == 0) print_del_vcf(vcf, name, seq, h1, h2, i, 2);
+            } else {
+                const Hap &h = t1 == T_INSERT ? h1 : h2;
+                const int hap = t1 == T_INSERT ? 1 : 2;
+                fprintf(txt, "-\t"); print_ins(txt, h, i); fprintf(txt, "\t%d\n", hap);
+                fprintf(vcf, "%s\t%lld\t.\t%c\t%c", name, (long long)i + 1, kBase[c0], kBase[c0]);
+                print_ins(vcf, h, i);
+                fprintf(vcf, "\t100\tPASS\tAF=0.5;pl=%d;mt=INSERT\n", hap);
+            }
+        }
+        prev[0] = t1 != T_NOCHANGE;
+        prev[1] = t2 != T_NOCHANGE;
+    }
+}
+
+// ---- FASTQ writers: plain, or block-parallel gzip (independent gzip members, concatenated) -------------------------
+struct Writer {
+    FILE *fp[3] = {nullptr, nullptr, nullptr};
+    bool gz = true;
+    int threads = 1;
+    static constexpr size_t kBlock = 1 << 20;
+    bool write(int id, const char *buf, size_t n)
+    {
+        if (!fp[id] || n == 0) return true;
+        if (!gz) return fwrite(buf, 1, n, fp[id]) == n;
+        const size_t nblk = (n + kBlock - 1) / kBlock;
+        std::vector<std::vector<uint8_t>> out(nblk);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> ok{true};
+        auto work = [&]() {
+            for (;;) {
+                const size_t b = next.fetch_add(1);
+                if (b >= nblk) return;
+                const size_t off = b * kBlock, len = std::min(kBlock, n - off);
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+                out[b].resize(deflateBound(&zs, (uLong)len) + 64);
+                zs.next_in = (Bytef *)(buf + off); zs.avail_in = (uInt)len;
+                zs.next_out = out[b].data(); zs.avail_out = (uInt)out[b].size();
+                if (deflate(&zs, Z_FINISH) != Z_STREAM_END) ok = false;
+                out[b].resize(zs.total_out);
+                deflateEnd(&zs);
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)std::max(threads, 1), nblk);
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
+        if (!ok) return false;
+        for (auto &o : out) if (fwrite(o.data(), 1, o.size(), fp[id]) != o.size()) return false;
+        return true;
+    }
+    void close_all()
+    {
+        for (auto &f : fp) if (f) {
+            if (gz && ftell(f) == 0) {           // an empty gzip member, like gzclose on an untouched gzFile
+                gzFile g = gzdopen(dup(fileno(f)), "wb");
+                if (g) gzclose(g);
+            }
+            fclose(f); f = nullptr;
+        }
+    }
+};
+int sink_cb(void *user, int id, const char *buf, size_t n) { return ((Writer *)user)->write(id, buf, n) ? 0 : 1; }
+
+FILE *xopen(const std::string &fn, const char *mode)
+{
+    FILE *fp = fopen(fn.c_str(), mode);
+    if (!fp) { fprintf(stderr, "[dwgsim] fail to open file '%s'. Abort!\n", fn.c_str()); exit(1); }
+    return fp;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    nt4_init();
+    Options o;
+    int first = 0;
+    if (!parse_options(o, argc, argv, &first)) return usage(o);
+    if (o.muts_input_type >= 0 || !o.fn_regions_bed.empty()) {
+        fprintf(stderr, "[dwgsim_core] Error: -m/-b/-v/-x are not supported by this build\n");
+        return 1;
+    }
+    const std::string fn_fa = argv[first], prefix = argv[first + 1];
+    Fasta fa;
+    if (!fa.open(fn_fa.c_str())) { fprintf(stderr, "[main] fail to open file '%s'. Abort!\n", fn_fa.c_str()); return 1; }
+    FILE *fp_fai = fopen((fn_fa + ".fai").c_str(), "r");
+    FILE *fp_txt = nullptr, *fp_vcf = nullptr;
+    if (o.output_type != 1) { fp_txt = xopen(prefix + ".mutations.txt", "w"); fp_vcf = xopen(prefix + ".mutations.vcf", "w"); }
+    Writer wr;
+    wr.gz = !o.uncompressed;
+    wr.threads = o.threads > 0 ? o.threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    const char *ext = o.uncompressed ? "" : ".gz";
+    dwgsim_gpu_t *gpu = nullptr;
+    if (o.output_type != 2) {
+        if (o.reads_output_type != 1) wr.fp[2] = xopen(prefix + ".bfast.fastq" + ext, "wb");
+        if (o.reads_output_type != 2) { wr.fp[0] = xopen(prefix + ".bwa.read1.fastq" + ext, "wb"); wr.fp[1] = xopen(prefix + ".bwa.read2.fastq" + ext, "wb"); }
+    }
+    // the device handle is created when the first contig with pairs arrives (a -C 0 run never needs a GPU)
+    auto gpu_open = [&]() {
+        dwgsim_gpu_params_t p;
+        memset(&p, 0, sizeof p);
+        for (int i = 0; i < 2; i++) { p.e_start[i] = o.e_start[i]; p.e_by[i] = o.e_by[i]; p.length[i] = o.length[i]; }
+        p.is_inner = o.is_inner; p.dist = o.dist; p.std_dev = o.std_dev; p.mut_freq = o.mut_freq; p.rand_read = o.rand_read;
+        p.max_n = o.max_n; p.data_type = o.data_type; p.strandedness = o.strandedness; p.read_one_strand = o.read_one_strand;
+        p.flow_order = o.flow_codes.empty() ? nullptr : o.flow_codes.data(); p.flow_order_len = (int32_t)o.flow_codes.size();
+        p.seed = o.seed == -1 ? (int32_t)time(nullptr) : o.seed;
+        p.fixed_quality = o.has_fixed_quality ? (unsigned char)o.fixed_quality[0] : 0;
+        p.quality_std = o.quality_std; p.read_prefix = o.has_prefix ? o.read_prefix.c_str() : nullptr;
+        p.reads_output_type = o.reads_output_type; p.amplicons = o.amplicons;
+        const int rc = dwgsim_gpu_create(&gpu, &p, o.device);
+        if (rc != DWGSIM_GPU_OK) { fprintf(stderr, "\n[dwgsim_core] Error: %s\n", dwgsim_gpu_strerror(rc)); exit(1); }
+        if (o.batch > 0) dwgsim_gpu_set_batch(gpu, o.batch, 3);
+    };
+
+    // census, src/dwgsim.c:465-492
+    std::vector<uint8_t> seq;
+    std::string name;
+    uint64_t tot_len = 0;
+    int n_ref = 0;
+    if (fp_vcf) fprintf(fp_vcf, "##fileformat=VCFv4.1\n");
+    if (fp_fai) {
+        char nm[1024];
+        int l, d0, d1, d2;
+        while (0 < fscanf(fp_fai, "%1023s\t%d\t%d\t%d\t%d", nm, &l, &d0, &d1, &d2)) {
+            fprintf(stderr, "[dwgsim_core] %s length: %d\n", nm, l);
+            tot_len += (uint64_t)l; ++n_ref;
+            if (fp_vcf) fprintf(fp_vcf, "##contig=<ID=%s,length=%d>\n", nm, l);
+        }
+        fclose(fp_fai);
+    } else {
+        int64_t l;
+        while ((l = fa.next(seq, name)) >= 0) {
+            fprintf(stderr, "[dwgsim_core] %s length: %lld\n", name.c_str(), (long long)l);
+            tot_len += (uint64_t)l; ++n_ref;
+            if (fp_vcf) fprintf(fp_vcf, "##contig=<ID=%s,length=%d>\n", name.c_str(), (int)l);
+        }
+    }
+    fprintf(stderr, "[dwgsim_core] %d sequences, total length: %llu\n", n_ref, (unsigned long long)tot_len);
+    fa.pos = 0;
+    if (fp_vcf) {                                                        // src/mut.c:765-771
+        fprintf(fp_vcf, "##INFO=<ID=AF,Number=A,Type=Float,Description=\"Allele Frequency\">\n");
+        fprintf(fp_vcf, "##INFO=<ID=pl,Number=1,Type=Integer,Description=\"Phasing: 1 - HET contig 1, #2 - HET contig #2, 3 - HOM both contigs\">\n");
+        fprintf(fp_vcf, "##INFO=<ID=mt,Number=1,Type=String,Description=\"Variant Type: SUBSTITUTE/INSERT/DELETE\">\n");
+        fprintf(fp_vcf, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n");
+    }
+    fprintf(stderr, o.output_type != 2 ? "[dwgsim_core] Currently on: \n0" : "[dwgsim_core] Currently on:");
+
+    Hap h1, h2;
+    long long n_sim = 0;
+    unsigned long long ctr = 0;
+    int contig_i = 0, prev_skip = 0, rc_exit = 0;
+    const int maxlen = std::max(o.length[0], o.length[1]);
+    int64_t l64;
+    while ((l64 = fa.next(seq, name)) >= 0) {                             // src/dwgsim.c:519-1106
+        const int l = (int)l64;
+        long long n_pairs = 0;
+        n_ref--;
+        if (o.output_type == 2) fprintf(stderr, "\r[dwgsim_core] Currently on: %s", name.c_str());
+        else {
+            if (0 == n_ref && o.C < 0) n_pairs = o.N - n_sim;
+            else if (0 < o.N) {
+                n_pairs = (long long)(uint64_t)((long double)l / tot_len * o.N + 0.5);
+                if (o.N - n_sim < n_pairs) n_pairs = o.N - n_sim;
+            } else n_pairs = (long long)(uint64_t)(l * o.C / ((long double)(o.length[0] + o.length[1])) / (1.0 - o.rand_read) + 0.5);
+            auto skip = [&](const char *fmt_done) { (void)fmt_done; if (0 == prev_skip) fprintf(stderr, "\n"); prev_skip = 1; };
+            if (o.amplicons == 1) {
+                if (l < maxlen) { skip(""); fprintf(stderr, "[dwgsim_core] #2 skip sequence '%s' as it is shorter than the read length %d < %d!\n", name.c_str(), l, maxlen); contig_i++; continue; }
+            } else if (0 < o.length[1] && l < o.dist + 3 * o.std_dev) {
+                skip(""); fprintf(stderr, "[dwgsim_core] #3 skip sequence '%s' as it is shorter than %f!\n", name.c_str(), o.dist + 3 * o.std_dev); contig_i++; continue;
+            } else if (l < o.length[0] || (0 < o.length[1] && l < o.length[1])) {
+                skip(""); fprintf(stderr, "[dwgsim_core] #4 skip sequence '%s' as it is shorter than %d!\n", name.c_str(), l < o.length[0] ? o.length[0] : o.length[1]); contig_i++; continue;
+            } else if (n_pairs < 0) { fprintf(stderr, "[dwgsim_core] #5 skip sequence '%s' as not enough pairs found\n", name.c_str()); continue; }
+            prev_skip = 0;
+        }
+        diref(o, seq, h1, h2);
+        if (o.output_type != 1) print_mutations(name.c_str(), seq, h1, h2, fp_txt, fp_vcf);
+        if (o.output_type != 2 && n_pairs > 0) {
+            if (!gpu) gpu_open();
+            int rc = dwgsim_gpu_add_contig(gpu, contig_i, name.c_str(), seq.data(), l, h1.s.data(), h2.s.data(), h1.ins.data(),
+                                           (int32_t)h1.ins.size(), h2.ins.data(), (int32_t)h2.ins.size(), n_pairs);
+            dwgsim_gpu_stats_t st;
+            if (rc == DWGSIM_GPU_OK) rc = dwgsim_gpu_run(gpu, sink_cb, &wr, &st);
+            if (rc != DWGSIM_GPU_OK) {
+                fprintf(stderr, "\r[dwgsim_core] %s%s%s\n", dwgsim_gpu_strerror(rc), *dwgsim_gpu_last_error(gpu) ? ": " : "", dwgsim_gpu_last_error(gpu));
+                rc_exit = 1;
+                break;
+            }
+            ctr += (unsigned long long)n_pairs; n_sim += n_pairs;
+            fprintf(stderr, "\r[dwgsim_core] %llu", ctr);
+        }
+        contig_i++;
+    }
+    if (!rc_exit) fprintf(stderr, "\n[dwgsim_core] Complete!\n");
+    if (fp_txt) fclose(fp_txt);
+    if (fp_vcf) fclose(fp_vcf);
+    wr.close_all();
+    if (gpu) dwgsim_gpu_destroy(gpu);
+    return rc_exit;
+}

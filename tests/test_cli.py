@@ -1,0 +1,120 @@
+"""The drop-in `dwgsim` host shell (dwgsim_b200/bin/dwgsim).
+
+CPU: option surface, and .mutations.txt/.vcf byte-identical to the reference run with -C 0 / -M 2 (SURVEY.md section 0:
+zero read draws from drand48), checked against the md5 fixtures written from oracle/_ref and against the pinned oracle.
+GPU (-m gpu): whole runs, FASTQ bytes (after gunzip) equal to the oracle's Philox backend."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden  # noqa: E402
+
+FIX = json.load(open(os.path.join(HERE, "golden", "ref_matrix.json")))
+FLOW = make_golden.FLOW
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from dwgsim_b200 import build
+    build.build()
+    return build.build_cli()
+
+
+def md5(path):
+    op = gzip.open if path.endswith(".gz") else open
+    with op(path, "rb") as f:
+        return hashlib.md5(f.read()).hexdigest()
+
+
+def run(cli, args, check=True):
+    return subprocess.run([cli] + [str(a) for a in args], capture_output=True, check=check)
+
+
+@pytest.mark.parametrize("case", ["mutations_only", "coverage_zero"])
+def test_mutation_files_equal_reference_fixture(cli, oracle, synth_fa, tmp_path, case):
+    prefix = str(tmp_path / "out")
+    run(cli, oracle.opt_to_ref_argv(**make_golden.MATRIX[case]) + [synth_fa, prefix])
+    for f in ("mutations.txt", "mutations.vcf"):
+        assert md5(prefix + "." + f) == FIX[case][f]
+    if case == "coverage_zero":            # three empty gzip members, like the reference
+        for f in ("bwa.read1.fastq.gz", "bwa.read2.fastq.gz", "bfast.fastq.gz"):
+            assert os.path.getsize(prefix + "." + f) == 20 and md5(prefix + "." + f) == hashlib.md5(b"").hexdigest()
+
+
+MUT_CASES = {
+    "defaults_ex1": (dict(seed=13), "ex1"),
+    "haploid_indel_min": (dict(seed=31, mut_rate=0.02, indel_frac=0.6, indel_extend=0.5, indel_min=2, is_hap=1), "synth"),
+    "long_insertions": (dict(seed=5, mut_rate=0.01, indel_frac=0.9, indel_extend=0.97, indel_min=3), "synth"),
+    "high_rate": (dict(seed=8, mut_rate=0.2, indel_frac=0.3), "synth"),
+    "ion_base_error_calibration": (dict(seed=28, data_type=2, length=(100, 0), e=0.02, flow_order=FLOW, use_base_error=1), "synth"),
+    "skips_short_contig_paired": (dict(seed=9, dist=3000, std_dev=2000, mut_rate=0.01), "synth"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(MUT_CASES))
+def test_mutation_files_equal_oracle_C0(cli, oracle, synth_fa, ex1_fa, tmp_path, case):
+    opts, which = MUT_CASES[case]
+    fasta = ex1_fa if which == "ex1" else synth_fa
+    opts = dict(opts, C=0)
+    a, b = str(tmp_path / "cli"), str(tmp_path / "orc")
+    run(cli, oracle.opt_to_ref_argv(**opts) + [fasta, a])
+    with oracle.Session(oracle.make_opt(**opts), fasta, b) as s:
+        assert s.stats.error == 0
+    for f in ("mutations.txt", "mutations.vcf"):
+        assert md5(a + "." + f) == md5(b + "." + f), f
+
+
+def test_option_surface(cli, synth_fa, tmp_path):
+    assert run(cli, ["-h"], check=False).returncode == 1
+    assert run(cli, [synth_fa], check=False).returncode == 1                       # needs <ref> <prefix>
+    r = run(cli, ["-N", "5", "-C", "3", synth_fa, str(tmp_path / "x")], check=False)  # -C resets -N: fine
+    assert r.returncode in (0, 1)
+    r = run(cli, ["-c", "7", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
+    assert r.returncode == 1 and b"-c was out of range" in r.stderr
+    r = run(cli, ["-c", "2", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
+    assert r.returncode == 1 and b"-f is required" in r.stderr
+    r = run(cli, ["-m", "muts.txt", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
+    assert r.returncode == 1 and b"not supported" in r.stderr
+    r = run(cli, ["-d", "abc", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
+    assert r.returncode == 1 and b"is not a number" in r.stderr
+
+
+def test_reference_stderr_lines(cli, synth_fa, tmp_path):
+    r = run(cli, ["-C", "0", "-z", "1", synth_fa, str(tmp_path / "x")])
+    err = r.stderr.decode()
+    assert "[dwgsim_core] chrA length: 30000" in err
+    assert "[dwgsim_core] 4 sequences, total length: 50400" in err
+    assert "#3 skip sequence 'tiny' as it is shorter than 650.000000!" in err
+    assert "[dwgsim_core] Complete!" in err
+
+
+GPU_CASES = {
+    "illumina_gz": (dict(seed=7, N=4000, length=(100, 100), mut_rate=0.01, indel_frac=0.3), []),
+    "illumina_plain_config1": (dict(seed=13, N=10000, length=(100, 100), data_type=0), ["--uncompressed"]),
+    "solid_gz": (dict(seed=22, N=3000, data_type=1, length=(50, 50), mut_rate=0.02, indel_frac=0.5), ["--batch", "1000"]),
+    "ion_plain": (dict(seed=25, N=1200, data_type=2, length=(200, 0), e=0.02, flow_order=FLOW), ["--uncompressed"]),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(GPU_CASES))
+def test_whole_run_equals_oracle(cli, oracle, synth_fa, ex1_fa, tmp_path, case):
+    opts, extra = GPU_CASES[case]
+    fasta = ex1_fa if case == "illumina_plain_config1" else synth_fa
+    a, b = str(tmp_path / "cli"), str(tmp_path / "orc")
+    run(cli, oracle.opt_to_ref_argv(**opts) + extra + [fasta, a])
+    with oracle.Session(oracle.make_opt(**opts), fasta, b, mode=oracle.RNG_PHILOX) as s:
+        assert s.stats.error == 0
+    ext = "" if "--uncompressed" in extra else ".gz"
+    for f in ("bwa.read1.fastq", "bwa.read2.fastq", "bfast.fastq"):
+        assert md5(a + "." + f + ext) == md5(b + "." + f), f
+    for f in ("mutations.txt", "mutations.vcf"):
+        assert md5(a + "." + f) == md5(b + "." + f), f
