@@ -37,6 +37,9 @@ MUT_RATE, INDEL_FRAC, N_FRAC = 0.001, 0.1, 0.01
 PAIRS_PER_STEP = 1 << 20
 ALGO_BYTES_PER_PAIR = 1524.0      # 118 B read (2-bit ref + N mask + mutation table) + 1,406 B FASTQ written
 E2E_CONTIG_LEN = 8 << 20          # contig handed over per e2e step (dense host arrays: 17 B/base)
+# dram__bytes_read.sum + dram__bytes_write.sum of the three main kernels of one 2^20-pair step, from the ncu --set full
+# capture profiles/r01_ncu_key_metrics_final.txt (simulate 0.525 GB + layout_lengths 0.124 GB + format 1.768 GB)
+NCU_DRAM_BYTES_PER_STEP = 2.417e9
 
 
 def peak_hbm():
@@ -176,7 +179,7 @@ def reference_arm(args, rank):
                     e2e={"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     except Exception as e:  # the oracle port is the fallback the tier allows
         line.update(unavailable="reference binary could not run: %s" % e)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(n_gpus):
@@ -220,7 +223,27 @@ def dense_contig(n_bases, seed):
     return np.ascontiguousarray(seq), hap
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """the driver reads ONE JSON line from stdout; libraries (NCCL prints its version) must not get in the way:
+    everything written to fd 1 from now on goes to stderr, emit() writes to the real stdout"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -347,7 +370,9 @@ def main():
     achieved = ALGO_BYTES_PER_PAIR * B / (kern_ms * 1e-3) / 1e9
     dom = max(range(3), key=lambda i: ms[i])
     names = ["simulate_pairs_kernel", "layout_* (5 scan kernels)", "format_fastq_kernel"]
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_DRAM_BYTES_PER_STEP if B == PAIRS_PER_STEP else None,
+                "traffic_source": "ncu --set full capture of the same step (profiles/r01_ncu_key_metrics_final.txt), bytes per step",
                 "peak_source": peak_src,
                 "kernel": "whole step = simulate + layout + format (7 launches); dominant: %s" % names[dom],
                 "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "fastq_bytes_per_pair": out_bytes / (B * args.steps),
@@ -410,7 +435,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "setup": {"genome_build_s": setup_s, "nccl_broadcast_s": bcast_s, "genome_pairs": total_pairs,
                           "wall_s_timed_region": t_wall}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     gpu.close()
     del keep
     if world > 1:
