@@ -390,7 +390,10 @@ int update_caps(dwgsim_gpu *h)
     h->sp.name_cap = (int32_t)((name_cap_of(h) + 15) & ~15ull);
     for (int k = 0; k < 3; ++k) h->sp.rec_cap[k] = (int32_t)cap[k];
     // tile of the format kernel: as many pairs as fit ~110 KB of shared memory (two CTAs per SM), at most 32
+    // tile of the format kernel: 32 pairs (measured best for 2x150: 56 KB of staging, 4 CTAs per SM), halved for long
+    // reads until at least two CTAs fit an SM; DWGSIM_TILE_PAIRS overrides it for experiments
     h->sp.tile_pairs = 32;
+    if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(32, atoi(e)));
     while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 110 * 1024) h->sp.tile_pairs >>= 1;
     const FormatSmem L = format_smem_layout(h->sp);
     if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
@@ -546,8 +549,11 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
     if (sp.data_type == 2)
         simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     else {
-        const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * 16);
+        // persistent grid: exactly the CTAs that are resident at once (a partial second wave would idle most SMs)
         const size_t smem_tp = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) * 4;
+        int occ_tp = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel, kTpThreads, smem_tp);
+        const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::max(occ_tp, 1));
         simulate_pairs_tp_kernel<<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
@@ -589,7 +595,9 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
     const int ntiles = (n + sp.tile_pairs - 1) / sp.tile_pairs;
-    const int grid_f = std::min(ntiles, sm_count * 4);
+    int occ_f = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, format_fastq_kernel, kFmtThreads, smem_b);
+    const int grid_f = std::min(ntiles, sm_count * std::max(occ_f, 1));
     (void)grid;
     format_fastq_kernel<<<grid_f, kFmtThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
                                                              w.totals + 1, w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);

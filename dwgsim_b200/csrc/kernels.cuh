@@ -685,7 +685,8 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
 }
 
 constexpr int kTpThreads = 128;
-__global__ void __launch_bounds__(kTpThreads)
+constexpr int kTpMinBlocks = 6;        // <= 80 registers per thread: 24 warps per SM
+__global__ void __launch_bounds__(kTpThreads, kTpMinBlocks)
 simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
                          PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
 {
@@ -1057,6 +1058,12 @@ layout_offsets_kernel(int n, const unsigned long long *__restrict__ blk_len_excl
 //   phase 3  all threads: 16-byte copy-out
 
 constexpr int kFmtThreads = 256;
+#ifndef FMT_COPYNAME16
+#define FMT_COPYNAME16 1
+#endif
+#ifndef FMT_QB8
+#define FMT_QB8 1
+#endif
 
 struct TileMeta {                      // per pair, in shared memory
     PairRec rec;
@@ -1094,6 +1101,21 @@ __device__ __forceinline__ int qdelta_rank(const uint16_t *guide, const uint32_t
     int j = guide[u >> 22];
     while (j < n && u >= cdf[j]) ++j;
     return j;
+}
+
+// name text (16-byte aligned in HBM, padded to a multiple of 16) -> staging buffer at any alignment
+__device__ __forceinline__ void copy_name(uint8_t *dst, const char *src, int n)
+{
+#if !FMT_COPYNAME16
+    for (int x = 0; x < n; ++x) dst[x] = (uint8_t)src[x];
+    return;
+#endif
+    for (int x = 0; x < n; x += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + x));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) if (x + b < n) dst[x + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+    }
 }
 
 __global__ void __launch_bounds__(kFmtThreads)
@@ -1177,9 +1199,14 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 const PairKey key{P.seed, m.lo, m.hi, (uint32_t)m.rec.attempt};
                 uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
                 if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); if (cnt > 4) b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
+                const uint2 qb8 = *reinterpret_cast<const uint2 *>(qbase_s[e] + k0);   // k0 is a multiple of 8
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
+#if FMT_QB8
+                    int qc = 33 + (int)(((i < 4 ? qb8.x : qb8.y) >> (8 * (i & 3))) & 0xFFu);
+#else
                     int qc = 33 + (int)qbase_s[e][min(k0 + i, P.cap[e] - 1)];
+#endif
                     if (P.qdelta_n > 0) {
                         const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
                         qc = (int)(signed char)((qc + P.qdelta_lo + qdelta_rank(guide, cdf, P.qdelta_n, u)) & 0xFF);
@@ -1218,7 +1245,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 uint8_t *sb = stage[e] + m.so[e];
                 const char *nm = gnames + ((size_t)(p0 + t) * nvar + (nvar - 1)) * L.name_cap;
                 const int nn = m.nbwa, me = Le - from;
-                for (int x = 0; x < nn; ++x) sb[x] = (uint8_t)nm[x];
+                copy_name(sb, nm, nn);
                 sb[nn] = '/'; sb[nn + 1] = (uint8_t)(solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sb[nn + 2] = '\n';
                 sb[nn + 3 + me] = '\n'; sb[nn + 3 + me + 1] = '+'; sb[nn + 3 + me + 2] = '\n';
                 sb[nn + 3 + me + 3 + me] = '\n';
@@ -1229,7 +1256,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
                 const char *nm = gnames + (size_t)(p0 + t) * nvar * L.name_cap;
                 const int nn = m.nfull;
-                for (int x = 0; x < nn; ++x) sf[x] = (uint8_t)nm[x];
+                copy_name(sf, nm, nn);
                 sf[nn] = '\n';
                 int o = nn + 1;
                 if (solid) sf[o++] = 'A';
