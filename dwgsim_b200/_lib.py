@@ -79,6 +79,7 @@ SYMBOLS = {
     "dwgsim_gpu_genome_synthetic": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_uint64, C.c_double, C.c_double,
                                               C.c_double, C.c_double]),
     "dwgsim_gpu_cuda_stream": (_P, [_P]),
+    "dwgsim_gpu_gz_host_encode": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "dwgsim_gpu_sink_count": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "dwgsim_gpu_sink_fd": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "dwgsim_gpu_tables": (C.c_int, [_P, C.POINTER(Tables)]),

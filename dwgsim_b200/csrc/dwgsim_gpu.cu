@@ -16,6 +16,7 @@
 
 #include "../../include/dwgsim_gpu.h"
 #include "kernels.cuh"
+#include "gz_host.h"
 
 using namespace dwg;
 
@@ -1101,6 +1102,22 @@ int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t n_contigs, const int32_
         th.emplace_back([&, t]() { for (int i = (int)t; i < n_contigs; i += (int)nt) synth_contig(h->queue[base + i], seed, mut_rate, indel_frac, n_frac); });
     for (auto &x : th) x.join();
     h->ms_pack += now_ms() - t0;
+    return DWGSIM_GPU_OK;
+}
+
+// ---- host reference of the device gzip member format (CPU tests of the Huffman / CRC tables) ------------------
+int dwgsim_gpu_gz_host_encode(const uint8_t *data, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_n)
+{
+    if ((!data && n) || !out || !out_n) return DWGSIM_GPU_EINVAL;
+    uint64_t hist[256] = {0};
+    for (uint64_t i = 0; i < n; ++i) hist[data[i]]++;
+    const GzTables t = gz_build_tables(hist);
+    static const Crc32Tables ct;
+    std::vector<uint8_t> v;
+    gz_encode_host(t, ct, data, (size_t)n, v);
+    if (v.size() > cap) return DWGSIM_GPU_EINVAL;
+    memcpy(out, v.data(), v.size());
+    *out_n = v.size();
     return DWGSIM_GPU_OK;
 }
 

@@ -164,6 +164,11 @@ int dwgsim_gpu_genome_synthetic(dwgsim_gpu_t *h, int32_t n_contigs, const int32_
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
 void *dwgsim_gpu_cuda_stream(const dwgsim_gpu_t *h);
 
+/* Host-side encoder of the gzip member format the device writer emits (one literal-only dynamic-Huffman
+ * block per 64 KiB member, code fitted to the data's byte histogram).  Exists so the Huffman / header / CRC
+ * tables can be validated against zlib without a GPU; not used on the product path. */
+int dwgsim_gpu_gz_host_encode(const uint8_t *data, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_n);
+
 /* -- ready-made sinks for dwgsim_gpu_run ---------------------------------------------------------- */
 /* user = int64_t[4]: bytes per file id and the number of calls */
 int dwgsim_gpu_sink_count(void *user, int file_id, const char *buf, size_t n);
