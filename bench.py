@@ -384,16 +384,18 @@ def main():
         seq, hap = dense_contig(E2E_CONTIG_LEN, 7 + rank)
         n_pairs_c = int(E2E_CONTIG_LEN * COVERAGE / 300.0 / 0.95 + 0.5)
         g2 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
-        g2.set_batch(1 << 17, 3)
+        g2.set_batch(1 << 18, 3)
 
         def e2e_step(i):
             g2.add_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,
                           None, 0, None, 0, n_pairs_c)
             return g2.run_count()
 
-        for i in range(2):
+        # warm-up: the first steps allocate the pinned ring and first-touch its pages (100+ ms stalls on a fresh box)
+        n_warm = 6
+        for i in range(n_warm):
             e2e_step(i)
-        n_e2e = max(3, min(args.steps, 10))
+        n_e2e = max(5, min(args.steps, 20))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -401,7 +403,7 @@ def main():
         h2d = d2h = 0
         pack_ms = 0.0
         for i in range(n_e2e):
-            st = e2e_step(2 + i)
+            st = e2e_step(n_warm + i)
             h2d += st.h2d_bytes; d2h += st.d2h_bytes; pack_ms += st.ms_pack
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - te

@@ -52,7 +52,7 @@ struct HostContig {
 
 struct DeviceTables {
     uint32_t *isize_cdf = nullptr, *qdelta_cdf = nullptr, *err_gap[2] = {nullptr, nullptr}, *err_acc[2] = {nullptr, nullptr};
-    uint16_t *qguide = nullptr;
+    uint16_t *qguide = nullptr, *isize_guide = nullptr, *gap_guide[2] = {nullptr, nullptr};
     uint8_t *qbase[2] = {nullptr, nullptr};
     int8_t *flow_order = nullptr;
     char *prefix = nullptr;
@@ -87,7 +87,7 @@ struct dwgsim_gpu {
     std::string last_error;
     // derived tables (host + device)
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
-    std::vector<uint16_t> qguide;
+    std::vector<uint16_t> qguide, isize_guide, gap_guide[2];
     std::vector<uint8_t> qbase[2];
     uint64_t thr_genomic = 0, thr_hap0 = 0;
     int32_t isize_lo = 0, qdelta_lo = 0;
@@ -122,6 +122,14 @@ struct dwgsim_gpu {
 };
 
 namespace {
+
+// dynamic shared memory of simulate_pairs_tp_kernel: staging tile + sampling tables (see the kernel prologue)
+size_t tp_smem_bytes(const SimParams &sp)
+{
+    size_t words = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) + (sp.isize_n <= 8192 ? ((sp.isize_n + 1) & ~1) : 0);
+    for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);
+    return words * 4 + 3 * 1026 * 2 + 16;
+}
 
 #define CUDA_TRY(h, expr)                                                                              \
     do {                                                                                               \
@@ -179,6 +187,12 @@ void derive_tables(dwgsim_gpu *h)
     h->qguide.assign(1024, 0);
     for (uint32_t g = 0; g < 1024; ++g)
         h->qguide[g] = (uint16_t)(std::upper_bound(h->qdelta_cdf.begin(), h->qdelta_cdf.end(), g << 22) - h->qdelta_cdf.begin());
+    auto make_guide = [](const uint32_t *cdf, size_t n, std::vector<uint16_t> &g) {     // g[b] = rank of (b << 22), b = 0..1024
+        g.assign(1025, 0);
+        for (uint32_t b = 0; b < 1024; ++b) g[b] = (uint16_t)(std::upper_bound(cdf, cdf + n, b << 22) - cdf);
+        g[1024] = (uint16_t)n;
+    };
+    make_guide(h->isize_cdf.data(), h->isize_cdf.size(), h->isize_guide);
     for (int e = 0; e < 2; ++e) {
         int n = p.length[e];
         if (p.data_type == 2) n = 2 * n + 64;
@@ -196,6 +210,7 @@ void derive_tables(dwgsim_gpu *h)
             h->err_acc[e][j] = (pmax > 0.0 && pr > 0.0) ? thr32(pr / pmax) : 0;
             h->qbase[e][j] = pr > 0 ? (uint8_t)(int)(-10.0 * log(pr) / log(10.0) + 0.499) : 40;
         }
+        make_guide(h->err_gap[e].data(), (size_t)p.length[e], h->gap_guide[e]);
         h->flow_thr[e] = thr32(p.e_start[e]);
     }
 }
@@ -215,6 +230,8 @@ int upload_tables(dwgsim_gpu *h)
     if ((rc = upload(h, &h->dt.isize_cdf, h->isize_cdf.data(), h->isize_cdf.size()))) return rc;
     if ((rc = upload(h, &h->dt.qdelta_cdf, h->qdelta_cdf.data(), h->qdelta_cdf.size()))) return rc;
     if ((rc = upload(h, &h->dt.qguide, h->qguide.data(), h->qguide.size()))) return rc;
+    if ((rc = upload(h, &h->dt.isize_guide, h->isize_guide.data(), h->isize_guide.size()))) return rc;
+    for (int e = 0; e < 2; ++e) if ((rc = upload(h, &h->dt.gap_guide[e], h->gap_guide[e].data(), h->gap_guide[e].size()))) return rc;
     for (int e = 0; e < 2; ++e) {
         if ((rc = upload(h, &h->dt.err_gap[e], h->err_gap[e].data(), h->err_gap[e].size()))) return rc;
         if ((rc = upload(h, &h->dt.err_acc[e], h->err_acc[e].data(), h->err_acc[e].size()))) return rc;
@@ -245,6 +262,9 @@ int upload_tables(dwgsim_gpu *h)
     s.flow_order_len = p.flow_order_len;
     s.tile_pairs = 32;
     s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide;
+    s.isize_guide = h->dt.isize_guide; s.gap_guide[0] = h->dt.gap_guide[0]; s.gap_guide[1] = h->dt.gap_guide[1];
+    s.inv_nw = (uint32_t)(4294967296.0 / std::max(s.nw[0] + s.nw[1], 1)) + 1u;
+    s.inv_groups = (uint32_t)(4294967296.0 / std::max((s.cap[0] + 7) / 8 + (s.cap[1] + 7) / 8, 1)) + 1u;
     s.flow_order = h->dt.flow_order; s.prefix = h->dt.prefix;
     return DWGSIM_GPU_OK;
 }
@@ -551,7 +571,7 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     else {
         // persistent grid: exactly the CTAs that are resident at once (a partial second wave would idle most SMs)
-        const size_t smem_tp = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) * 4;
+        const size_t smem_tp = tp_smem_bytes(sp);
         int occ_tp = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel, kTpThreads, smem_tp);
         const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::max(occ_tp, 1));
@@ -714,7 +734,7 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         const SimParams &sp = h->sp;
         const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15, flr = (sp.flow_order_len + 15) & ~15;
         const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
-        const size_t smem_tp = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) * 4;
+        const size_t smem_tp = tp_smem_bytes(sp);
         if (sp.data_type != 2) {
             // one staging row per thread in shared memory bounds the combined read length (about 3,400 bases)
             if (smem_tp > 220 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
@@ -737,7 +757,7 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     cudaSetDevice(h->device);
     free_workspace(h);
     free_blob(h);
-    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide);
+    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
     for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
     cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);

@@ -68,6 +68,18 @@ __device__ __forceinline__ int table_rank(const uint32_t *__restrict__ cdf, int 
     return lo;
 }
 
+// the same rank through a guide: guide[g] = rank of (g << 22), g = 0..1024, so the search is confined to the
+// thresholds inside u's 2^22-wide bucket (none or one in the bulk of a distribution, many only in its tails)
+__device__ __forceinline__ int guided_rank(const uint32_t *cdf, const uint16_t *guide, uint32_t u)
+{
+    int lo = guide[u >> 22], hi = guide[(u >> 22) + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u >= cdf[mid]) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // ---- genome access ------------------------------------------------------------------------------------
 struct ContigView {
     int len;
@@ -541,19 +553,23 @@ struct Emit {                          // emission state of one read
     int solid; uint32_t prev;          // colour space: previous base, adaptor = 0 (src/dwgsim.c:845-858)
     int next_err, n_err, err_first;    // substitution errors (src/dwgsim.c:233-244) by thinning
     uint32_t cand; uint4 cur;
-    const uint32_t *gap, *accp; int s; PairKey key; uint32_t end;
+    const uint32_t *gap, *accp; const uint16_t *gguide; int s; PairKey key; uint32_t end;
 };
 __device__ __forceinline__ void err_next(Emit &E)
 {
     E.cur = draw_block(E.key, kStErr, E.end, E.cand);
-    E.next_err += 1 + table_rank(E.gap, E.s, E.cur.x);
+    E.next_err += 1 + guided_rank(E.gap, E.gguide, E.cur.x);
 }
+struct TpTables {                     // shared-memory copies of the sampling tables of the thread-per-pair kernel
+    const uint32_t *isize_cdf; const uint16_t *isize_guide;
+    const uint32_t *gap[2], *acc[2]; const uint16_t *gap_guide[2];
+};
 __device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int s, int solid, bool errors,
-                                           const SimParams &P, const PairKey &key, int end)
+                                           const TpTables &T, const PairKey &key, int end)
 {
     E.dst = dst; E.acc = 0; E.na = 0; E.w = 0; E.k = 0; E.nN = 0;
     E.solid = solid; E.prev = 0; E.n_err = 0; E.err_first = 0; E.cand = 0; E.s = s;
-    E.gap = P.err_gap[end]; E.accp = P.err_acc[end]; E.key = key; E.end = (uint32_t)end;
+    E.gap = T.gap[end]; E.accp = T.acc[end]; E.gguide = T.gap_guide[end]; E.key = key; E.end = (uint32_t)end;
     E.cur = make_uint4(0, 0, 0, 0);
     E.next_err = -1;
     if (errors) err_next(E); else E.next_err = 0x7fffffff;
@@ -571,7 +587,7 @@ __device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
     while (E.next_err < E.k + m) {
         const int sh = (E.next_err - E.k) << 2;
         uint32_t c = (codes >> sh) & 15u;
-        if (c < 4 && E.cur.y < __ldg(E.accp + E.next_err)) {
+        if (c < 4 && E.cur.y < E.accp[E.next_err]) {
             c = (c + 1u + __umulhi(E.cur.z, 3u)) & 3u;
             codes = (codes & ~(15u << sh)) | (c << sh);
             ++E.n_err;
@@ -695,6 +711,27 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     extern __shared__ __align__(16) uint32_t tile[];
     const int NW = P.nw[0] + P.nw[1], RS = NW | 1;
     uint32_t *row = tile + (size_t)threadIdx.x * RS;
+    // sampling tables behind the tile: insert-size CDF + guide, per end: gap CDF (len entries) + guide, accept thresholds
+    TpTables T;
+    {
+        uint32_t *p32 = tile + (size_t)kTpThreads * RS;
+        const bool isz_smem = P.isize_n <= 8192;          // wider insert-size tables (-s > ~500) stay in HBM / L2
+        uint32_t *isz = p32; p32 += isz_smem ? ((P.isize_n + 1) & ~1) : 0;
+        uint32_t *gp[2], *ac[2];
+        for (int e = 0; e < 2; ++e) { gp[e] = p32; p32 += (P.len[e] + 1) & ~1; ac[e] = p32; p32 += (P.len[e] + 1) & ~1; }
+        uint16_t *p16 = reinterpret_cast<uint16_t *>(p32);
+        uint16_t *ig = p16; p16 += 1026;
+        uint16_t *gg[2] = {p16, p16 + 1026};
+        if (isz_smem) for (int j = threadIdx.x; j < P.isize_n; j += kTpThreads) isz[j] = P.isize_cdf[j];
+        for (int j = threadIdx.x; j < 1025; j += kTpThreads) ig[j] = P.isize_guide[j];
+        for (int e = 0; e < 2; ++e) {
+            for (int j = threadIdx.x; j < P.len[e]; j += kTpThreads) { gp[e][j] = P.err_gap[e][j]; ac[e][j] = P.err_acc[e][j]; }
+            for (int j = threadIdx.x; j < 1025; j += kTpThreads) gg[e][j] = P.gap_guide[e][j];
+        }
+        T.isize_cdf = isz_smem ? isz : P.isize_cdf; T.isize_guide = ig;
+        for (int e = 0; e < 2; ++e) { T.gap[e] = gp[e]; T.acc[e] = ac[e]; T.gap_guide[e] = gg[e]; }
+        __syncthreads();
+    }
     const int solid = P.data_type == 1;
     unsigned failed_total = 0;
     const int n_round = (n + kTpThreads - 1) / kTpThreads * kTpThreads;
@@ -724,7 +761,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             if (P.amplicons) { pos = 0; d = cv.len; }
             else {
                 if (s1 > 0) {
-                    d = P.isize_lo + table_rank(P.isize_cdf, P.isize_n, b0.y);
+                    d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
                     const int min_dist = s0 + s1;
                     if (d < min_dist) d = min_dist;
                     if (d > cv.len) d = cv.len;
@@ -746,13 +783,13 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
                 else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
             } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
-            emit_begin(E0, dst0, s0, solid, true, P, key, 0);
+            emit_begin(E0, dst0, s0, solid, true, T, key, 0);
             bool ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0);
             if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
             if (s1 > 0) {
                 bool ok1 = false;
                 if (ok) {                                              // a rejected end 0 already rejects the pair
-                    emit_begin(E1, dst1, s1, solid, true, P, key, 1);
+                    emit_begin(E1, dst1, s1, solid, true, T, key, 1);
                     ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1);
                     if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
                 }
@@ -775,7 +812,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
                 if (s <= 0) continue;
                 Emit E;
-                emit_begin(E, j ? dst1 : dst0, s, solid, false, P, key, j);
+                emit_begin(E, j ? dst1 : dst0, s, solid, false, T, key, j);
                 for (int k = 0; k < s; k += 64) {
                     const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
 #pragma unroll
@@ -810,7 +847,8 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         __syncthreads();
         const int np = min(kTpThreads, n - pbase);
         uint32_t *out = seqw + (size_t)pbase * NW;
-        for (int x = threadIdx.x; x < np * NW; x += kTpThreads) out[x] = tile[(size_t)(x / NW) * RS + (x % NW)];
+        // tile index of linear word x is x + (x / NW) * (RS - NW); x / NW by a multiply-high with P.inv_nw = 2^32/NW + 1
+        for (int x = threadIdx.x; x < np * NW; x += kTpThreads) out[x] = tile[x + (int)__umulhi((uint32_t)x, P.inv_nw) * (RS - NW)];
         __syncthreads();
     }
     if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
@@ -1058,12 +1096,7 @@ layout_offsets_kernel(int n, const unsigned long long *__restrict__ blk_len_excl
 //   phase 3  all threads: 16-byte copy-out
 
 constexpr int kFmtThreads = 256;
-#ifndef FMT_COPYNAME16
-#define FMT_COPYNAME16 1
-#endif
-#ifndef FMT_QB8
-#define FMT_QB8 1
-#endif
+
 
 struct TileMeta {                      // per pair, in shared memory
     PairRec rec;
@@ -1101,21 +1134,6 @@ __device__ __forceinline__ int qdelta_rank(const uint16_t *guide, const uint32_t
     int j = guide[u >> 22];
     while (j < n && u >= cdf[j]) ++j;
     return j;
-}
-
-// name text (16-byte aligned in HBM, padded to a multiple of 16) -> staging buffer at any alignment
-__device__ __forceinline__ void copy_name(uint8_t *dst, const char *src, int n)
-{
-#if !FMT_COPYNAME16
-    for (int x = 0; x < n; ++x) dst[x] = (uint8_t)src[x];
-    return;
-#endif
-    for (int x = 0; x < n; x += 16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + x));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int b = 0; b < 16; ++b) if (x + b < n) dst[x + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
-    }
 }
 
 __global__ void __launch_bounds__(kFmtThreads)
@@ -1181,7 +1199,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
         __syncthreads();
         // ---- phase 1: bases and qualities, one thread per (pair, end, 8-base group) -------------------------
         for (int it = tid; it < np * G; it += kFmtThreads) {
-            const int t = it / G, gi = it - t * G;
+            const int t = (int)__umulhi((uint32_t)it, P.inv_groups), gi = it - t * G;
             const int e = gi < g0 ? 0 : 1, g = gi - (e ? g0 : 0);
             const TileMeta &m = meta[t];
             const int Le = m.rec.len[e], k0 = g << 3;
@@ -1202,11 +1220,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 const uint2 qb8 = *reinterpret_cast<const uint2 *>(qbase_s[e] + k0);   // k0 is a multiple of 8
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-#if FMT_QB8
                     int qc = 33 + (int)(((i < 4 ? qb8.x : qb8.y) >> (8 * (i & 3))) & 0xFFu);
-#else
-                    int qc = 33 + (int)qbase_s[e][min(k0 + i, P.cap[e] - 1)];
-#endif
                     if (P.qdelta_n > 0) {
                         const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
                         qc = (int)(signed char)((qc + P.qdelta_lo + qdelta_rank(guide, cdf, P.qdelta_n, u)) & 0xFF);
@@ -1234,34 +1248,54 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 if (P.out_bfast) { sf[bf_seq + k] = dg; sf[bf_qual + k] = qc; }
             }
         }
-        // ---- phase 2: names, suffixes, separators: one thread per record ----------------------------------
-        for (int it = tid; it < np * 4; it += kFmtThreads) {
-            const int t = it >> 2, rr = it & 3, e = rr & 1, bf = rr >> 1;
-            const TileMeta &m = meta[t];
-            const int Le = m.rec.len[e];
-            if (Le <= 0) continue;
-            if (!bf) {
-                if (!P.out_bwa) continue;
-                uint8_t *sb = stage[e] + m.so[e];
-                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (nvar - 1)) * L.name_cap;
-                const int nn = m.nbwa, me = Le - from;
-                copy_name(sb, nm, nn);
-                sb[nn] = '/'; sb[nn + 1] = (uint8_t)(solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sb[nn + 2] = '\n';
-                sb[nn + 3 + me] = '\n'; sb[nn + 3 + me + 1] = '+'; sb[nn + 3 + me + 2] = '\n';
-                sb[nn + 3 + me + 3 + me] = '\n';
-            } else {
-                if (!P.out_bfast) continue;
+        // ---- phase 2: names (one thread per record and 16-byte chunk), suffixes and separators -----------------
+        {
+            const int nchunks = L.name_cap >> 4;
+            for (int it = tid; it < np * 4 * nchunks; it += kFmtThreads) {
+                const int c = it % nchunks, rc = it / nchunks, t = rc >> 2, rr = rc & 3, e = rr & 1, bf = rr >> 1;
+                const TileMeta &m = meta[t];
+                const int Le = m.rec.len[e];
+                if (Le <= 0 || (bf ? !P.out_bfast : !P.out_bwa)) continue;
+                const int nn = bf ? m.nfull : m.nbwa, x0 = c << 4;
+                if (x0 >= nn) continue;
                 const int len0 = m.rec.len[0];
                 const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-                uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
-                const char *nm = gnames + (size_t)(p0 + t) * nvar * L.name_cap;
-                const int nn = m.nfull;
-                copy_name(sf, nm, nn);
-                sf[nn] = '\n';
-                int o = nn + 1;
-                if (solid) sf[o++] = 'A';
-                sf[o + Le] = '\n'; sf[o + Le + 1] = '+'; sf[o + Le + 2] = '\n';
-                sf[o + Le + 3 + Le] = '\n';
+                uint8_t *dstb = bf ? stage[2] + m.so[2] + (e ? rec0 : 0) : stage[e] + m.so[e];
+                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (bf ? 0 : nvar - 1)) * L.name_cap;
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nm + x0));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                if (x0 + 16 <= nn) {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) dstb[x0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) if (x0 + b < nn) dstb[x0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+                }
+            }
+            for (int it = tid; it < np * 4; it += kFmtThreads) {
+                const int t = it >> 2, rr = it & 3, e = rr & 1, bf = rr >> 1;
+                const TileMeta &m = meta[t];
+                const int Le = m.rec.len[e];
+                if (Le <= 0) continue;
+                if (!bf) {
+                    if (!P.out_bwa) continue;
+                    uint8_t *sb = stage[e] + m.so[e];
+                    const int nn = m.nbwa, me = Le - from;
+                    sb[nn] = '/'; sb[nn + 1] = (uint8_t)(solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sb[nn + 2] = '\n';
+                    sb[nn + 3 + me] = '\n'; sb[nn + 3 + me + 1] = '+'; sb[nn + 3 + me + 2] = '\n';
+                    sb[nn + 3 + me + 3 + me] = '\n';
+                } else {
+                    if (!P.out_bfast) continue;
+                    const int len0 = m.rec.len[0];
+                    const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
+                    uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
+                    const int nn = m.nfull;
+                    sf[nn] = '\n';
+                    int o = nn + 1;
+                    if (solid) sf[o++] = 'A';
+                    sf[o + Le] = '\n'; sf[o + Le + 1] = '+'; sf[o + Le + 2] = '\n';
+                    sf[o + Le + 3 + Le] = '\n';
+                }
             }
         }
         __syncthreads();

@@ -83,11 +83,13 @@ struct SimParams {
     int32_t  nw[2];                            // 32-bit words of nibble-packed read codes per end (8 codes per word);
                                                // stored word-major: word w of pair p at seqw[(w0[end] + w) * n + p]
     int32_t  tile_pairs;                       // pairs per CTA tile of the format kernel
+    uint32_t inv_nw, inv_groups;               // 2^32 / (nw0+nw1) + 1 and 2^32 / (groups per pair) + 1: divisions by multiply-high
     int32_t  name_cap;                         // bytes reserved per read name in shared memory
     int32_t  rec_cap[3];                       // upper bound of a pair's bytes per output stream
     // device tables
     const uint32_t *isize_cdf, *qdelta_cdf;
     const uint16_t *qguide;                    // [1024] rank of (g << 22) in qdelta_cdf
+    const uint16_t *isize_guide, *gap_guide[2]; // [1025] the same for isize_cdf and err_gap[end] (first len[end] entries)
     const uint32_t *err_gap[2], *err_acc[2];   // substitution errors by thinning (DESIGN.md "RNG addressing")
     const uint8_t  *qbase[2];
     const int8_t   *flow_order;
