@@ -52,7 +52,8 @@ struct HostContig {
 
 struct DeviceTables {
     uint32_t *isize_cdf = nullptr, *qdelta_cdf = nullptr, *err_gap[2] = {nullptr, nullptr}, *err_acc[2] = {nullptr, nullptr};
-    uint16_t *qguide = nullptr, *isize_guide = nullptr, *gap_guide[2] = {nullptr, nullptr};
+    uint16_t *isize_guide = nullptr, *gap_guide[2] = {nullptr, nullptr};
+    uint32_t *qguide = nullptr;
     uint8_t *qbase[2] = {nullptr, nullptr};
     int8_t *flow_order = nullptr;
     char *prefix = nullptr;
@@ -87,7 +88,8 @@ struct dwgsim_gpu {
     std::string last_error;
     // derived tables (host + device)
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
-    std::vector<uint16_t> qguide, isize_guide, gap_guide[2];
+    std::vector<uint16_t> isize_guide, gap_guide[2];
+    std::vector<uint32_t> qguide;
     std::vector<uint8_t> qbase[2];
     uint64_t thr_genomic = 0, thr_hap0 = 0;
     int32_t isize_lo = 0, qdelta_lo = 0;
@@ -183,10 +185,19 @@ void derive_tables(dwgsim_gpu *h)
             h->qdelta_cdf.push_back(thr32(phi(x / p.quality_std)));
         }
     }
-    // acceleration only (not part of the sampling rule): rank of each 2^22-wide bucket's lower bound
-    h->qguide.assign(1024, 0);
-    for (uint32_t g = 0; g < 1024; ++g)
-        h->qguide[g] = (uint16_t)(std::upper_bound(h->qdelta_cdf.begin(), h->qdelta_cdf.end(), g << 22) - h->qdelta_cdf.begin());
+    // acceleration only (not part of the sampling rule): one-load guide, 2048 buckets of 2^21; entry = rank at the
+    // bucket's lower bound << 24 | offset of the single threshold inside the bucket (2^21 = none), bit 23 = several
+    h->qguide.assign(2048, 0);
+    for (uint32_t g = 0; g < 2048; ++g) {
+        const std::vector<uint32_t> &cdf = h->qdelta_cdf;
+        const uint64_t lo = (uint64_t)g << 21, hi = lo + (1ull << 21);
+        const size_t j = (size_t)(std::upper_bound(cdf.begin(), cdf.end(), (uint32_t)lo) - cdf.begin());
+        size_t inside = 0;
+        while (j + inside < cdf.size() && (uint64_t)cdf[j + inside] < hi) ++inside;
+        if (j > 255 || inside > 1) h->qguide[g] = ((uint32_t)std::min<size_t>(j, 255) << 24) | 0x800000u;
+        else if (inside == 1) h->qguide[g] = ((uint32_t)j << 24) | (uint32_t)(cdf[j] - lo);
+        else h->qguide[g] = ((uint32_t)j << 24) | 0x200000u;
+    }
     auto make_guide = [](const uint32_t *cdf, size_t n, std::vector<uint16_t> &g) {     // g[b] = rank of (b << 22), b = 0..1024
         g.assign(1025, 0);
         for (uint32_t b = 0; b < 1024; ++b) g[b] = (uint16_t)(std::upper_bound(cdf, cdf + n, b << 22) - cdf);
@@ -415,6 +426,7 @@ int update_caps(dwgsim_gpu *h)
     // reads until at least two CTAs fit an SM; DWGSIM_TILE_PAIRS overrides it for experiments
     h->sp.tile_pairs = 32;
     if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(32, atoi(e)));
+    else while (h->sp.tile_pairs > 24 && format_smem_layout(h->sp).total > 56 * 1024) --h->sp.tile_pairs;   // 4 CTAs per SM
     while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 110 * 1024) h->sp.tile_pairs >>= 1;
     const FormatSmem L = format_smem_layout(h->sp);
     if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }

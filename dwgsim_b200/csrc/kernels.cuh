@@ -1117,7 +1117,7 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     FormatSmem L;
     const int TP = P.tile_pairs;
     int o = 0;
-    L.guide_off = o; o += 2048;
+    L.guide_off = o; o += 2048 * 4;
     L.cdf_off = o; o += ((P.qdelta_n > 0 && P.qdelta_n <= 512 ? P.qdelta_n : 0) * 4 + 15) & ~15;
     for (int e = 0; e < 2; ++e) { L.qbase_off[e] = o; o += (P.cap[e] + 16) & ~15; }
     L.meta_off = o; o += (TP * (int)sizeof(TileMeta) + 15) & ~15;
@@ -1128,11 +1128,15 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     return L;
 }
 
-// quality noise: inverse CDF with a 1024-entry guide table (rank of the bucket's lower bound), then a short scan
-__device__ __forceinline__ int qdelta_rank(const uint16_t *guide, const uint32_t *cdf, int n, uint32_t u)
+// quality noise: inverse CDF through a 2048-bucket guide.  An entry holds the rank at the bucket's lower bound
+// (bits 24-31) and, when exactly one threshold lies inside the 2^21-wide bucket, its offset (bits 0-21; 2^21 = none):
+// one shared-memory load and one compare.  Bit 23 marks buckets with several thresholds (the tails): scan.
+__device__ __forceinline__ int qdelta_rank(const uint32_t *guide, const uint32_t *cdf, int n, uint32_t u)
 {
-    int j = guide[u >> 22];
-    while (j < n && u >= cdf[j]) ++j;
+    const uint32_t ent = guide[u >> 21];
+    int j = (int)(ent >> 24);
+    if (ent & 0x800000u) { while (j < n && u >= cdf[j]) ++j; }
+    else j += (u & 0x1FFFFFu) >= (ent & 0x3FFFFFu);
     return j;
 }
 
@@ -1147,7 +1151,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
     extern __shared__ __align__(16) uint8_t smem[];
     const FormatSmem L = format_smem_layout(P);
     const int TP = P.tile_pairs, tid = threadIdx.x;
-    uint16_t *guide = reinterpret_cast<uint16_t *>(smem + L.guide_off);
+    uint32_t *guide = reinterpret_cast<uint32_t *>(smem + L.guide_off);
     const bool cdf_in_smem = P.qdelta_n > 0 && P.qdelta_n <= 512;
     uint32_t *cdf_s = reinterpret_cast<uint32_t *>(smem + L.cdf_off);
     uint8_t *qbase_s[2] = {smem + L.qbase_off[0], smem + L.qbase_off[1]};
@@ -1155,7 +1159,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
     uint8_t *stage[3] = {smem + L.stage_off[0], smem + L.stage_off[1], smem + L.stage_off[2]};
     __shared__ int s_shift[3], s_total[3];
 
-    for (int j = tid; j < 1024; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? P.qguide[j] : (uint16_t)0;
+    for (int j = tid; j < 2048; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? P.qguide[j] : 0u;
     if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) cdf_s[j] = P.qdelta_cdf[j];
     for (int e = 0; e < 2; ++e) for (int j = tid; j < P.cap[e]; j += kFmtThreads) qbase_s[e][j] = P.qbase[e][j];
     __syncthreads();

@@ -88,7 +88,7 @@ struct SimParams {
     int32_t  rec_cap[3];                       // upper bound of a pair's bytes per output stream
     // device tables
     const uint32_t *isize_cdf, *qdelta_cdf;
-    const uint16_t *qguide;                    // [1024] rank of (g << 22) in qdelta_cdf
+    const uint32_t *qguide;                    // [2048] one-load guide into qdelta_cdf (see qdelta_rank)
     const uint16_t *isize_guide, *gap_guide[2]; // [1025] the same for isize_cdf and err_gap[end] (first len[end] entries)
     const uint32_t *err_gap[2], *err_acc[2];   // substitution errors by thinning (DESIGN.md "RNG addressing")
     const uint8_t  *qbase[2];
