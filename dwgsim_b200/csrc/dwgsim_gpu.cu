@@ -90,6 +90,7 @@ struct dwgsim_gpu {
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
     std::vector<uint16_t> isize_guide, gap_guide[2];
     std::vector<uint32_t> qguide;
+    bool ion_warp_kernel = false;             // Ion Torrent reads too long for the thread-per-pair rows: warp-per-pair kernel
     std::vector<uint8_t> qbase[2];
     uint64_t thr_genomic = 0, thr_hap0 = 0;
     int32_t isize_lo = 0, qdelta_lo = 0;
@@ -130,7 +131,8 @@ size_t tp_smem_bytes(const SimParams &sp)
 {
     size_t words = (size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) + (sp.isize_n <= 8192 ? ((sp.isize_n + 1) & ~1) : 0);
     for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);
-    return words * 4 + 3 * 1026 * 2 + 16;
+    const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4;
+    return words * 4 + 3 * 1026 * 2 + flow + 32;
 }
 
 #define CUDA_TRY(h, expr)                                                                              \
@@ -579,15 +581,19 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
     cudaStream_t st = h->s_compute;
     CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 16, st));
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[0], st));
-    if (sp.data_type == 2)
+    if (h->ion_warp_kernel)
         simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     else {
         // persistent grid: exactly the CTAs that are resident at once (a partial second wave would idle most SMs)
         const size_t smem_tp = tp_smem_bytes(sp);
         int occ_tp = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel, kTpThreads, smem_tp);
+        if (sp.data_type == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<true>, kTpThreads, smem_tp);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<false>, kTpThreads, smem_tp);
         const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::max(occ_tp, 1));
-        simulate_pairs_tp_kernel<<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+        if (sp.data_type == 2)
+            simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+        else
+            simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
     }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
     layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
@@ -747,12 +753,16 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15, flr = (sp.flow_order_len + 15) & ~15;
         const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
         const size_t smem_tp = tp_smem_bytes(sp);
-        if (sp.data_type != 2) {
-            // one staging row per thread in shared memory bounds the combined read length (about 3,400 bases)
-            if (smem_tp > 220 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
-            if (cudaFuncSetAttribute(simulate_pairs_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp) != cudaSuccess) {
-                dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;
-            }
+        // one staging row per thread in shared memory bounds the combined read length (about 3,400 symbols); Ion Torrent
+        // rows hold 2*len+64 symbols and longer ones fall back to the warp-per-pair kernel
+        const bool tp_fits = smem_tp <= 220 * 1024 && (sp.data_type != 2 || std::max(sp.nw[0], sp.nw[1]) <= kIonRowWordsMax);
+        const char *force = getenv("DWGSIM_ION_KERNEL");
+        h->ion_warp_kernel = sp.data_type == 2 && (!tp_fits || (force && strcmp(force, "warp") == 0));
+        if (sp.data_type != 2 && !tp_fits) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
+        if (!h->ion_warp_kernel &&
+            (sp.data_type == 2 ? cudaFuncSetAttribute(simulate_pairs_tp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp)
+                               : cudaFuncSetAttribute(simulate_pairs_tp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp)) != cudaSuccess) {
+            dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;
         }
         if (smem_a > 227 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
         if (cudaFuncSetAttribute(simulate_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a) != cudaSuccess) {

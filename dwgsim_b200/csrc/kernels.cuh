@@ -563,6 +563,7 @@ __device__ __forceinline__ void err_next(Emit &E)
 struct TpTables {                     // shared-memory copies of the sampling tables of the thread-per-pair kernel
     const uint32_t *isize_cdf; const uint16_t *isize_guide;
     const uint32_t *gap[2], *acc[2]; const uint16_t *gap_guide[2];
+    const int8_t *flow_order; uint32_t *flow_mask;
 };
 __device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int s, int solid, bool errors,
                                            const TpTables &T, const PairKey &key, int end)
@@ -700,8 +701,141 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
     return ok;
 }
 
+// ---- Ion Torrent flow model, one thread per read, on a nibble-packed row (thread-per-pair kernel) ---------------
+// Same algorithm and draw order as flow_errors() above (src/dwgsim.c:246-417); the read lives in the thread's row of
+// the shared staging tile (8 symbols per word), so insertions / deletions are word-wise funnel shifts.
+constexpr int kIonRowWordsMax = 264;           // rows up to 2,112 symbols (reads up to 1,024 bases): bound of the local scratch
+
+__device__ __forceinline__ uint32_t nib_get(const uint32_t *r, int k) { return (r[k >> 3] >> ((k & 7) << 2)) & 15u; }
+__device__ __forceinline__ void nib_set(uint32_t *r, int k, uint32_t v)
+{
+    const int sh = (k & 7) << 2;
+    r[k >> 3] = (r[k >> 3] & ~(15u << sh)) | (v << sh);
+}
+__device__ __forceinline__ uint32_t nib_mask_ge(int k) { return (k & 7) ? ~0u << ((k & 7) << 2) : ~0u; }   // nibbles >= k&7 of k's word
+// symbols [i, len) move up by n, symbols [i, i+n) become v
+__device__ __forceinline__ void nib_insert(uint32_t *r, int i, int len, int n, uint32_t v)
+{
+    const int q = n >> 3, rr = n & 7, first_w = (i + n) >> 3;
+    for (int dw = (len + n - 1) >> 3; dw >= first_w; --dw) {
+        uint32_t x;
+        if (rr == 0) x = r[dw - q];
+        else { const int sw = dw - q - 1; x = __funnelshift_r(sw >= 0 ? r[sw] : 0u, r[sw + 1], (8 - rr) << 2); }
+        if (dw == first_w) { const uint32_t m = nib_mask_ge(i + n); x = (x & m) | (r[dw] & ~m); }
+        r[dw] = x;
+    }
+    for (int j = i; j < i + n; ++j) nib_set(r, j, v);
+}
+// symbols [i+n, len) move down by n
+__device__ __forceinline__ void nib_delete(uint32_t *r, int i, int len, int n)
+{
+    const int q = n >> 3, rr = n & 7, first_w = i >> 3, last_w = (len - n - 1) >> 3;
+    for (int dw = first_w; dw <= last_w; ++dw) {
+        const int sw = dw + q;
+        uint32_t x = rr == 0 ? r[sw] : __funnelshift_r(r[sw], r[sw + 1], rr << 2);
+        if (dw == first_w) { const uint32_t m = nib_mask_ge(i); x = (x & m) | (r[dw] & ~m); }
+        r[dw] = x;
+    }
+}
+__device__ __forceinline__ uint32_t rev_nibbles(uint32_t x)
+{
+    x = __brev(x);
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    return ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
+}
+// in-place reversal of the first len symbols through a thread-local scratch
+__device__ __forceinline__ void nib_reverse(uint32_t *r, int len)
+{
+    uint32_t tmp[kIonRowWordsMax];
+    const int nw = (len + 7) >> 3;
+    for (int dw = 0; dw < nw; ++dw) {
+        const int a = len - 8 - 8 * dw;                       // source symbol of the word's LAST nibble
+        uint32_t x;
+        if (a >= 0) x = (a & 7) ? __funnelshift_r(r[a >> 3], r[(a >> 3) + 1], (a & 7) << 2) : r[a >> 3];
+        else x = r[0] << ((-a) << 2);
+        tmp[dw] = rev_nibbles(x);
+    }
+    for (int dw = 0; dw < nw; ++dw) r[dw] = tmp[dw];
+    if (len & 7) r[nw - 1] &= ~(~0u << ((len & 7) << 2));
+}
+__device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int cap, int strand, uint32_t thr, const int8_t *fo, int fl,
+                                                  uint32_t *mask /* ceil(fl/32) words of this thread */, FlowRng &rng, int *n_err_out,
+                                                  int *overflow)
+{
+    for (int w = 0; w < ((len + 7) >> 3); ++w) { const uint32_t x = row[w]; row[w] = x & ~(((x & 0x44444444u) >> 2) * 15u); }   // N -> A
+    for (int w = 0; w < ((fl + 31) >> 5); ++w) mask[w] = 0;
+    if (strand) nib_reverse(row, len);
+    int i, flow_i;
+    {
+        const int c = len > 0 ? (int)nib_get(row, 0) : 0;
+        for (i = 0; i < fl; ++i) if (c == fo[i]) break;
+        if (i == fl) return -1;
+    }
+    flow_i = i;
+    // Both passes are written as ONE loop each whose iterations either step one flow or consume one base, so the
+    // threads of a warp (32 different reads) stay in the same loop body; the control flow is that of the reference.
+    int prev_c = 4;
+    i = 0;
+    while (i < len) {                                              // pass 1, src/dwgsim.c:281-364
+        const int c = (int)nib_get(row, i);
+        if (c != fo[flow_i]) {                                      // an empty flow
+            mask[flow_i >> 5] &= ~(1u << (flow_i & 31));
+            flow_i = flow_i + 1 == fl ? 0 : flow_i + 1;
+            continue;
+        }
+        if (prev_c != c) {                                          // first base of a homopolymer
+            mask[flow_i >> 5] &= ~(1u << (flow_i & 31));
+            int n_err = 0;
+            while (rng.draw() < thr) ++n_err;
+            if (n_err > 0) {
+                if (!(rng.draw() >> 31)) {
+                    if (len + n_err >= cap) { *overflow = 1; return len; }
+                    nib_insert(row, i, len, n_err, (uint32_t)c);
+                    len += n_err;
+                } else {
+                    int hp_l = 0, next_c = 4;
+                    for (int j = i; j < len; ++j, ++hp_l) { next_c = (int)nib_get(row, j); if (c != next_c) break; }
+                    if (hp_l < n_err) n_err = hp_l;
+                    nib_delete(row, i, len, n_err);
+                    len -= n_err;
+                    mask[flow_i >> 5] |= 1u << (flow_i & 31);
+                    if (n_err == hp_l && (i == 0 || prev_c == next_c)) {
+                        int j = 0;
+                        while (next_c != fo[(flow_i + j) % fl]) ++j;
+                        if (j <= 0) { *overflow = 2; return len; }
+                        const int k = (int)__umulhi(rng.draw(), (uint32_t)j);
+                        if (len + 1 >= cap) { *overflow = 1; return len; }
+                        nib_insert(row, i, len, 1, (uint32_t)fo[(flow_i + k) % fl]);
+                        len += 1;
+                    }
+                }
+                *n_err_out += n_err;
+            }
+            prev_c = c;
+        }
+        ++i;
+    }
+    i = 0;
+    int c2 = len > 0 ? (int)nib_get(row, 0) : 0;                    // the base being matched: read once per position
+    while (i < len) {                                              // pass 2, src/dwgsim.c:366-406
+        if (c2 == fo[flow_i]) { ++i; if (i < len) c2 = (int)nib_get(row, i); continue; }
+        int n_err = 0;
+        while (rng.draw() < thr) ++n_err;
+        if (n_err > 0 && !((mask[flow_i >> 5] >> (flow_i & 31)) & 1u)) {
+            if (len + n_err >= cap) { *overflow = 1; return len; }
+            nib_insert(row, i, len, n_err, (uint32_t)fo[flow_i]);
+            len += n_err;
+            *n_err_out += n_err;
+        }
+        flow_i = flow_i + 1 == fl ? 0 : flow_i + 1;
+    }
+    if (strand) nib_reverse(row, len);
+    return len;
+}
+
 constexpr int kTpThreads = 128;
 constexpr int kTpMinBlocks = 6;        // <= 80 registers per thread: 24 warps per SM
+template <bool kIon>
 __global__ void __launch_bounds__(kTpThreads, kTpMinBlocks)
 simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
                          PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
@@ -730,8 +864,17 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         }
         T.isize_cdf = isz_smem ? isz : P.isize_cdf; T.isize_guide = ig;
         for (int e = 0; e < 2; ++e) { T.gap[e] = gp[e]; T.acc[e] = ac[e]; T.gap_guide[e] = gg[e]; }
+        // Ion Torrent: flow order (codes) and one flow-mask bit vector per thread
+        T.flow_order = nullptr; T.flow_mask = nullptr;
+        if (kIon) {
+            int8_t *fo = reinterpret_cast<int8_t *>(gg[1] + 1026);
+            for (int j = threadIdx.x; j < P.flow_order_len; j += kTpThreads) fo[j] = P.flow_order[j];
+            T.flow_order = fo;
+            T.flow_mask = reinterpret_cast<uint32_t *>(fo + ((P.flow_order_len + 15) & ~15)) + (size_t)threadIdx.x * ((P.flow_order_len + 31) >> 5);
+        }
         __syncthreads();
     }
+    constexpr bool ion = kIon;
     const int solid = P.data_type == 1;
     unsigned failed_total = 0;
     const int n_round = (n + kTpThreads - 1) / kTpThreads * kTpThreads;
@@ -783,13 +926,13 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
                 else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
             } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
-            emit_begin(E0, dst0, s0, solid, true, T, key, 0);
+            emit_begin(E0, dst0, s0, solid, !ion, T, key, 0);
             bool ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0);
             if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
             if (s1 > 0) {
                 bool ok1 = false;
                 if (ok) {                                              // a rejected end 0 already rejects the pair
-                    emit_begin(E1, dst1, s1, solid, true, T, key, 1);
+                    emit_begin(E1, dst1, s1, solid, !ion, T, key, 1);
                     ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1);
                     if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
                 }
@@ -840,6 +983,20 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
             rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
             rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
+            if constexpr (kIon) {                                       // flow-space errors, src/dwgsim.c:861-864
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    const int s = j ? s1 : s0;
+                    if (s <= 0) continue;
+                    int nerr = 0, ovf = 0;
+                    FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
+                    const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_thr[j], T.flow_order,
+                                                      P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
+                    if (ovf) atomicOr(status, 2ull);
+                    rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);
+                    rec.n_err[j] = (uint16_t)nerr;
+                }
+            }
         }
         recs[p] = rec;
         }

@@ -62,6 +62,17 @@ def test_ion_torrent_heavy_errors_many_shifts(oracle, synth_fa, tmp_path):
                        dist=300, std_dev=30), synth_fa, tmp_path)
 
 
+def test_ion_torrent_warp_kernel_fallback(oracle, synth_fa, tmp_path, monkeypatch):
+    """reads too long for the thread-per-pair rows use the warp-per-pair kernel; force it on a short case"""
+    monkeypatch.setenv("DWGSIM_ION_KERNEL", "warp")
+    check(oracle, dict(seed=26, N=1500, data_type=2, length=(200, 100), e=0.05, E=0.03, flow_order=make_golden.FLOW,
+                       mut_rate=0.01, indel_frac=0.4), synth_fa, tmp_path)
+
+
+def test_ion_torrent_long_reads_use_fallback(oracle, synth_fa, tmp_path):
+    check(oracle, dict(seed=27, N=300, data_type=2, length=(1500, 0), e=0.01, flow_order=make_golden.FLOW), synth_fa, tmp_path)
+
+
 def test_derived_tables_equal_oracle(oracle):
     """the 32-bit threshold tables the kernels sample from == the oracle's own derivation"""
     from dwgsim_b200 import DwgsimGpu, params_from_options

@@ -1,6 +1,6 @@
 """Throughput of the other BASELINE configs (SOLiD 2x50, Ion Torrent 400 SE) on the resident synthetic genome."""
 import sys, time, json
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 from dwgsim_b200 import DwgsimGpu, params_from_options
 import bench
