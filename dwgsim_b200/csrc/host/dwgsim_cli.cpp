@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <chrono>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -757,6 +758,10 @@ int main(int argc, char **argv)
     }
     fprintf(stderr, o.output_type != 2 ? "[dwgsim_core] Currently on: \n0" : "[dwgsim_core] Currently on:");
 
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mut = 0, t_print = 0, t_gpu = 0, t_pack = 0, t_kernels = 0;
+    const double t_begin = now();
+    long long bytes_out = 0, bases_in = 0;
     Hap h1, h2;
     long long n_sim = 0;
     unsigned long long ctr = 0;
@@ -784,10 +789,15 @@ int main(int argc, char **argv)
             } else if (n_pairs < 0) { fprintf(stderr, "[dwgsim_core] #5 skip sequence '%s' as not enough pairs found\n", name.c_str()); continue; }
             prev_skip = 0;
         }
+        double t0 = now();
         diref(o, seq, h1, h2);
+        t_mut += now() - t0; t0 = now();
         if (o.output_type != 1) print_mutations(name.c_str(), seq, h1, h2, fp_txt, fp_vcf);
+        t_print += now() - t0;
+        bases_in += l;
         if (o.output_type != 2 && n_pairs > 0) {
             if (!gpu) gpu_open();
+            t0 = now();
             int rc = dwgsim_gpu_add_contig(gpu, contig_i, name.c_str(), seq.data(), l, h1.s.data(), h2.s.data(), h1.ins.data(),
                                            (int32_t)h1.ins.size(), h2.ins.data(), (int32_t)h2.ins.size(), n_pairs);
             dwgsim_gpu_stats_t st;
@@ -797,12 +807,21 @@ int main(int argc, char **argv)
                 rc_exit = 1;
                 break;
             }
+            t_gpu += now() - t0; t_pack += st.ms_pack * 1e-3; t_kernels += (st.ms_simulate + st.ms_layout + st.ms_format) * 1e-3;
+            bytes_out += st.bytes[0] + st.bytes[1] + st.bytes[2];
             ctr += (unsigned long long)n_pairs; n_sim += n_pairs;
             fprintf(stderr, "\r[dwgsim_core] %llu", ctr);
         }
         contig_i++;
     }
     if (!rc_exit) fprintf(stderr, "\n[dwgsim_core] Complete!\n");
+    if (getenv("DWGSIM_STATS")) {
+        const double total = now() - t_begin;
+        fprintf(stderr, "[dwgsim_b200] bases %lld pairs %lld fastq_bytes %lld | total %.3f s: mut_diref %.3f s (%.1f ns/base), mut_print %.3f s, "
+                        "read loop %.3f s (host pack %.3f s, kernels %.3f s, rest = D2H + sink%s) | %.3f Mpairs/s overall, %.3f Mpairs/s in the read loop\n",
+                bases_in, n_sim, bytes_out, total, t_mut, bases_in ? 1e9 * t_mut / bases_in : 0.0, t_print, t_gpu, t_pack, t_kernels,
+                o.uncompressed ? "" : " incl. gzip", total > 0 ? n_sim / total / 1e6 : 0.0, t_gpu > 0 ? n_sim / t_gpu / 1e6 : 0.0);
+    }
     if (fp_txt) fclose(fp_txt);
     if (fp_vcf) fclose(fp_vcf);
     wr.close_all();
