@@ -26,6 +26,7 @@ class Stats(C.Structure):
         ("bytes", C.c_int64 * 3), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_simulate", C.c_double), ("ms_layout", C.c_double), ("ms_format", C.c_double),
         ("ms_pack", C.c_double), ("ms_total", C.c_double), ("n_launches", C.c_int32), ("n_batches", C.c_int32),
+        ("raw_bytes", C.c_int64 * 3),
     ]
 
 
@@ -65,6 +66,7 @@ SYMBOLS = {
                                         C.c_int64]),
     "dwgsim_gpu_run": (C.c_int, [_P, SINK_FN, _P, C.POINTER(Stats)]),
     "dwgsim_gpu_set_batch": (C.c_int, [_P, C.c_int64, C.c_int32]),
+    "dwgsim_gpu_set_compression": (C.c_int, [_P, C.c_int32]),
     "dwgsim_gpu_set_shard": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "dwgsim_gpu_set_exchange": (C.c_int, [_P, EXCHANGE_FN, _P]),
     "dwgsim_gpu_resident_begin": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),

@@ -164,6 +164,10 @@ class DwgsimGpu:
     def set_batch(self, pairs_per_batch, ring_slots=3):
         self._check(self._L.dwgsim_gpu_set_batch(self._h, pairs_per_batch, ring_slots))
 
+    def set_compression(self, mode):
+        """0: FASTQ text to the sink; 1: gzip members written on the device"""
+        self._check(self._L.dwgsim_gpu_set_compression(self._h, mode))
+
     def set_shard(self, rank, world):
         self._check(self._L.dwgsim_gpu_set_shard(self._h, rank, world))
 

@@ -17,6 +17,7 @@
 #include "../../include/dwgsim_gpu.h"
 #include "kernels.cuh"
 #include "gz_host.h"
+#include "gz_device.cuh"
 
 using namespace dwg;
 
@@ -74,6 +75,12 @@ struct Workspace {
     char *out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint64_t out_cap[3] = {0, 0, 0};
     unsigned long long *h_totals = nullptr;   // pinned [8 + 2]
+    // device gzip writer
+    uint8_t *gz_slots[3] = {nullptr, nullptr, nullptr};
+    char *gz_out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    uint64_t gz_cap[3] = {0, 0, 0}, gz_members[3] = {0, 0, 0};
+    unsigned long long *gz_sizes = nullptr, *gz_offs = nullptr, *gz_totals = nullptr, *gz_hist = nullptr;   // [3][members], .., [3], [256]
+    uint64_t gz_members_max = 0;
 };
 
 }  // namespace
@@ -90,7 +97,14 @@ struct dwgsim_gpu {
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
     std::vector<uint16_t> isize_guide, gap_guide[2];
     std::vector<uint32_t> qguide;
-    bool ion_warp_kernel = false;             // Ion Torrent reads too long for the thread-per-pair rows: warp-per-pair kernel
+    bool ion_warp_kernel = false;
+    // device gzip writer: mode, per-stream tables in HBM
+    int gz_mode = 0;
+    bool gz_ready = false;
+    uint32_t *gz_code[3] = {nullptr, nullptr, nullptr};
+    uint8_t *gz_prefix[3] = {nullptr, nullptr, nullptr};
+    uint32_t gz_prefix_bits[3] = {0, 0, 0};
+    uint32_t *gz_crc = nullptr;             // Ion Torrent reads too long for the thread-per-pair rows: warp-per-pair kernel
     std::vector<uint8_t> qbase[2];
     uint64_t thr_genomic = 0, thr_hap0 = 0;
     int32_t isize_lo = 0, qdelta_lo = 0;
@@ -513,6 +527,8 @@ void free_workspace(dwgsim_gpu *h)
     cudaFree(w.recs); cudaFree(w.seqs); cudaFree(w.serial); cudaFree(w.lens); cudaFree(w.names); cudaFree(w.name_len);
     cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(w.out[s][k]);
+    for (int k = 0; k < 3; ++k) { cudaFree(w.gz_slots[k]); cudaFree(w.gz_out[0][k]); cudaFree(w.gz_out[1][k]); }
+    cudaFree(w.gz_sizes); cudaFree(w.gz_offs); cudaFree(w.gz_totals); cudaFree(w.gz_hist);
     if (w.h_totals) cudaFreeHost(w.h_totals);
     w = Workspace();
     for (int s = 0; s < h->pinned_slots; ++s) for (int k = 0; k < 3; ++k) if (h->pinned[s][k]) { cudaFreeHost(h->pinned[s][k]); h->pinned[s][k] = nullptr; }
@@ -543,6 +559,20 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
             w.out_cap[k] = align_up(cap[k] * (uint64_t)n + 256, 256);
             if (w.out_cap[k] >= (1ull << 32)) { h->last_error = "batch too large: a stream would exceed 4 GiB"; return DWGSIM_GPU_EINVAL; }
             for (int s = 0; s < 2; ++s) CUDA_TRY(h, cudaMalloc((void **)&w.out[s][k], w.out_cap[k]));
+        }
+        if (h->gz_mode) {
+            w.gz_members_max = 1;
+            for (int k = 0; k < 3; ++k) {
+                w.gz_members[k] = (w.out_cap[k] + kGzMemberRaw - 1) / kGzMemberRaw + 1;
+                w.gz_members_max = std::max(w.gz_members_max, w.gz_members[k]);
+                w.gz_cap[k] = w.out_cap[k] + w.out_cap[k] / 4 + (1 << 20);
+                CUDA_TRY(h, cudaMalloc((void **)&w.gz_slots[k], w.gz_members[k] * (uint64_t)kGzSlotStride));
+                for (int s2 = 0; s2 < 2; ++s2) CUDA_TRY(h, cudaMalloc((void **)&w.gz_out[s2][k], w.gz_cap[k]));
+            }
+            CUDA_TRY(h, cudaMalloc((void **)&w.gz_sizes, 3 * w.gz_members_max * 8));
+            CUDA_TRY(h, cudaMalloc((void **)&w.gz_offs, 3 * w.gz_members_max * 8));
+            CUDA_TRY(h, cudaMalloc((void **)&w.gz_totals, 64));
+            CUDA_TRY(h, cudaMalloc((void **)&w.gz_hist, 256 * 8));
         }
         w.cap_pairs = n;
     }
@@ -685,6 +715,70 @@ int collect_batch(dwgsim_gpu *h, bool timed, BatchResult *r)
     return DWGSIM_GPU_OK;
 }
 
+
+// fit the per-stream Huffman codes to the first batch and upload the tables
+int gz_calibrate(dwgsim_gpu *h, int dslot, const uint64_t bytes[3])
+{
+    Workspace &w = h->ws;
+    static const Crc32Tables ct;
+    if (!h->gz_crc) {
+        std::vector<uint32_t> v(1024 + 32);
+        for (int s2 = 0; s2 < 4; ++s2) memcpy(&v[(size_t)s2 * 256], ct.t[s2], 1024);
+        memcpy(&v[1024], ct.x2n, 128);
+        int rc = upload(h, &h->gz_crc, v.data(), v.size());
+        if (rc) return rc;
+    }
+    for (int k = 0; k < 3; ++k) {
+        uint64_t hist[256] = {0};
+        if (bytes[k]) {
+            CUDA_TRY(h, cudaMemsetAsync(w.gz_hist, 0, 256 * 8, h->s_compute));
+            gz_histogram_kernel<<<592, 256, 0, h->s_compute>>>((const uint8_t *)w.out[dslot][k], bytes[k], w.gz_hist);
+            CUDA_TRY(h, cudaMemcpyAsync(hist, w.gz_hist, 256 * 8, cudaMemcpyDeviceToHost, h->s_compute));
+            CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+        }
+        const GzTables t = gz_build_tables(hist);
+        cudaFree(h->gz_code[k]); cudaFree(h->gz_prefix[k]);
+        h->gz_code[k] = nullptr; h->gz_prefix[k] = nullptr;
+        int rc = upload(h, &h->gz_code[k], t.code, (size_t)257);
+        if (rc) return rc;
+        std::vector<uint8_t> pre = t.prefix;
+        pre.resize((pre.size() + 11) & ~3ull, 0);               // whole words plus one
+        if ((rc = upload(h, &h->gz_prefix[k], pre.data(), pre.size()))) return rc;
+        h->gz_prefix_bits[k] = t.prefix_bits;
+    }
+    h->gz_ready = true;
+    return DWGSIM_GPU_OK;
+}
+
+// raw streams of device slot `dslot` -> gzip members -> contiguous streams in ws.gz_out[dslot]; sizes in out_bytes
+int gz_batch(dwgsim_gpu *h, int dslot, const uint64_t bytes[3], uint64_t out_bytes[3], int *launches)
+{
+    Workspace &w = h->ws;
+    int rc;
+    if (!h->gz_ready && (rc = gz_calibrate(h, dslot, bytes))) return rc;
+    cudaStream_t st = h->s_compute;
+    CUDA_TRY(h, cudaMemsetAsync(w.gz_totals, 0, 64, st));
+    for (int k = 0; k < 3; ++k) {
+        if (!bytes[k]) continue;
+        const int nm = (int)((bytes[k] + kGzMemberRaw - 1) / kGzMemberRaw);
+        unsigned long long *sizes = w.gz_sizes + (size_t)k * w.gz_members_max, *offs = w.gz_offs + (size_t)k * w.gz_members_max;
+        GzDeviceTables T{h->gz_code[k], h->gz_prefix[k], h->gz_prefix_bits[k]};
+        gz_compress_kernel<<<nm, kGzThreads, 0, st>>>((const uint8_t *)w.out[dslot][k], bytes[k], T, h->gz_crc, w.gz_slots[k], sizes);
+        CUDA_TRY(h, cudaMemcpyAsync(offs, sizes, (size_t)nm * 8, cudaMemcpyDeviceToDevice, st));
+        layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(offs, nm, 1, w.gz_totals + k);
+        gz_compact_kernel<<<nm, 256, 0, st>>>(w.gz_slots[k], sizes, offs, (uint8_t *)w.gz_out[dslot][k]);
+        *launches += 3;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals + 12, w.gz_totals, 24, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) {
+        out_bytes[k] = bytes[k] ? w.h_totals[12 + k] : 0;
+        if (out_bytes[k] > w.gz_cap[k]) { h->last_error = "compressed stream larger than its buffer"; return DWGSIM_GPU_EOVERFLOW; }
+    }
+    return DWGSIM_GPU_OK;
+}
+
 }  // namespace
 
 // ---- C ABI --------------------------------------------------------------------------------------------
@@ -782,6 +876,8 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
     for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
     cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
+    for (int k = 0; k < 3; ++k) { cudaFree(h->gz_code[k]); cudaFree(h->gz_prefix[k]); }
+    cudaFree(h->gz_crc);
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
@@ -816,6 +912,15 @@ int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_
     cudaSetDevice(h->device);
     free_workspace(h);
     h->batch_pairs = pairs_per_batch; h->ring = ring_slots;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_set_compression(dwgsim_gpu_t *h, int32_t mode)
+{
+    if (!h || mode < 0 || mode > 1) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    if (mode != h->gz_mode) free_workspace(h);
+    h->gz_mode = mode;
     return DWGSIM_GPU_OK;
 }
 
@@ -1021,16 +1126,24 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
         st.ms_simulate += r.ms[0]; st.ms_layout += r.ms[1]; st.ms_format += r.ms[2];
         st.n_random += r.n_random; st.n_failed_attempts += r.n_failed; st.n_pairs += n;
         h->rand_serial += world == 1 ? r.n_random : round_total;
+        uint64_t send[3] = {r.bytes[0], r.bytes[1], r.bytes[2]};
+        for (int k = 0; k < 3; ++k) st.raw_bytes[k] += (int64_t)r.bytes[k];
+        if (h->gz_mode) {                                          // gzip members on the device: fewer bytes over PCIe
+            int lz = 0;
+            if ((rc = gz_batch(h, dslot, r.bytes, send, &lz))) break;
+            launches += lz;
+        }
         CUDA_TRY(h, cudaEventRecord(computed, h->s_compute));
         CUDA_TRY(h, cudaStreamWaitEvent(h->s_copy, computed, 0));
         for (int k = 0; k < 3; ++k)
-            if (r.bytes[k]) {
-                CUDA_TRY(h, cudaMemcpyAsync(h->pinned[pslot][k], w.out[dslot][k], r.bytes[k], cudaMemcpyDeviceToHost, h->s_copy));
-                st.d2h_bytes += (int64_t)r.bytes[k];
+            if (send[k]) {
+                CUDA_TRY(h, cudaMemcpyAsync(h->pinned[pslot][k], h->gz_mode ? w.gz_out[dslot][k] : w.out[dslot][k], send[k],
+                                            cudaMemcpyDeviceToHost, h->s_copy));
+                st.d2h_bytes += (int64_t)send[k];
             }
         CUDA_TRY(h, cudaEventRecord(copied[pslot], h->s_copy));
         pend.live = true; pend.pslot = pslot;
-        for (int k = 0; k < 3; ++k) pend.bytes[k] = r.bytes[k];
+        for (int k = 0; k < 3; ++k) pend.bytes[k] = send[k];
         ++st.n_batches; ++mine;
     }
     if (rc == DWGSIM_GPU_OK) rc = drain(pend);

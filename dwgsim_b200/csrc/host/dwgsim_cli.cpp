@@ -6,11 +6,11 @@
 // mut_left_justify :481-589) and the .mutations.txt/.vcf writers (mut_print, src/mut.c:781-893).  The read-pair
 // loop (src/dwgsim.c:636-1099) is three calls into libdwgsim_b200.so (include/dwgsim_gpu.h), exactly the
 // binding INTEGRATION.md describes.  FASTQ goes to <prefix>.bwa.read1/2.fastq.gz and <prefix>.bfast.fastq.gz like
-// the reference (src/dwgsim.c:1149-1160), compressed by a block-parallel gzip writer (concatenated gzip members),
-// or uncompressed with --uncompressed.
+// the reference (src/dwgsim.c:1149-1160): by default as gzip members written on the GPU (dwgsim_gpu_set_compression),
+// with --host-gzip by a block-parallel zlib writer (concatenated members, level 6), or uncompressed with --uncompressed.
 //
-// New long options only (the short-option surface is the reference's): --uncompressed, --threads N, --device D,
-// --batch PAIRS.
+// New long options only (the short-option surface is the reference's): --uncompressed, --host-gzip, --threads N,
+// --device D, --batch PAIRS.
 #include <getopt.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -80,7 +80,7 @@ struct Options {                              // dwgsim_opt_t, src/dwgsim_opt.h:
     double quality_std = 2.0;
     int muts_input_type = -1, reads_output_type = 0, output_type = 0, amplicons = 0;
     // this build
-    bool uncompressed = false;
+    bool uncompressed = false, host_gzip = false;
     int threads = 0, device = 0;
     long long batch = 0;
 };
@@ -124,7 +124,8 @@ int usage(const Options &o)
     fprintf(stderr, "         -a            assume each contig is an amplicon\n");
     fprintf(stderr, "         -h            print this message\n");
     fprintf(stderr, "         --uncompressed  write .fastq instead of .fastq.gz\n");
-    fprintf(stderr, "         --threads INT   gzip worker threads [all cores]\n");
+    fprintf(stderr, "         --host-gzip     compress with zlib on the host (level 6, like the reference) instead of on the GPU\n");
+    fprintf(stderr, "         --threads INT   host gzip worker threads [all cores]\n");
     fprintf(stderr, "         --device INT    CUDA device [0]\n");
     fprintf(stderr, "         --batch INT     read pairs per device batch\n\n");
     return 1;
@@ -223,7 +224,8 @@ int parse_options(Options &o, int argc, char **argv, int *first_arg)
 {
     static const struct option longopts[] = {
         {"uncompressed", no_argument, nullptr, 1000}, {"threads", required_argument, nullptr, 1001},
-        {"device", required_argument, nullptr, 1002}, {"batch", required_argument, nullptr, 1003}, {nullptr, 0, nullptr, 0}};
+        {"device", required_argument, nullptr, 1002}, {"batch", required_argument, nullptr, 1003},
+        {"host-gzip", no_argument, nullptr, 1004}, {nullptr, 0, nullptr, 0}};
     int c, muts = 0;
     while ((c = getopt_long(argc, argv, "id:s:N:C:1:2:e:E:r:F:R:X:I:c:S:A:n:y:BHf:z:M:m:b:v:x:P:q:Q:o:ah", longopts, nullptr)) >= 0) {
         switch (c) {
@@ -265,6 +267,7 @@ int parse_options(Options &o, int argc, char **argv, int *first_arg)
             case 1001: o.threads = atoi(optarg); break;
             case 1002: o.device = atoi(optarg); break;
             case 1003: o.batch = atoll(optarg); break;
+            case 1004: o.host_gzip = true; break;
             default: fprintf(stderr, "Unrecognized option: -%c\n", c); return 0;
         }
     }
@@ -625,7 +628,8 @@ void print_mutations(const char *name, const std::vector<uint8_t> &seq, const Ha
 // ---- FASTQ writers: plain, or block-parallel gzip (independent gzip members, concatenated) -------------------------
 struct Writer {
     FILE *fp[3] = {nullptr, nullptr, nullptr};
-    bool gz = true;
+    bool gz = true;                 // compress here with zlib
+    bool gz_file = true;            // the files are .gz (bytes arrive compressed when gz is false)
     int threads = 1;
     static constexpr size_t kBlock = 1 << 20;
     bool write(int id, const char *buf, size_t n)
@@ -664,7 +668,7 @@ struct Writer {
     void close_all()
     {
         for (auto &f : fp) if (f) {
-            if (gz && ftell(f) == 0) {           // an empty gzip member, like gzclose on an untouched gzFile
+            if (gz_file && ftell(f) == 0) {      // an empty gzip member, like gzclose on an untouched gzFile
                 gzFile g = gzdopen(dup(fileno(f)), "wb");
                 if (g) gzclose(g);
             }
@@ -700,7 +704,8 @@ int main(int argc, char **argv)
     FILE *fp_txt = nullptr, *fp_vcf = nullptr;
     if (o.output_type != 1) { fp_txt = xopen(prefix + ".mutations.txt", "w"); fp_vcf = xopen(prefix + ".mutations.vcf", "w"); }
     Writer wr;
-    wr.gz = !o.uncompressed;
+    wr.gz = !o.uncompressed && o.host_gzip;          // zlib on the host only when asked; default: gzip members from the GPU
+    wr.gz_file = !o.uncompressed;
     wr.threads = o.threads > 0 ? o.threads : (int)std::max(1u, std::thread::hardware_concurrency());
     const char *ext = o.uncompressed ? "" : ".gz";
     dwgsim_gpu_t *gpu = nullptr;
@@ -723,6 +728,7 @@ int main(int argc, char **argv)
         const int rc = dwgsim_gpu_create(&gpu, &p, o.device);
         if (rc != DWGSIM_GPU_OK) { fprintf(stderr, "\n[dwgsim_core] Error: %s\n", dwgsim_gpu_strerror(rc)); exit(1); }
         if (o.batch > 0) dwgsim_gpu_set_batch(gpu, o.batch, 3);
+        if (!o.uncompressed && !o.host_gzip) dwgsim_gpu_set_compression(gpu, 1);
     };
 
     // census, src/dwgsim.c:465-492

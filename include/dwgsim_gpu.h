@@ -80,6 +80,7 @@ typedef struct {
     double  ms_pack, ms_total;     /* host packing time; wall time of the call                     */
     int32_t n_launches;            /* kernels launched by this call                                */
     int32_t n_batches;
+    int64_t raw_bytes[3];          /* uncompressed FASTQ bytes per file id (== bytes[] without compression) */
 } dwgsim_gpu_stats_t;
 
 /* receives FASTQ bytes strictly in pair-index order per file id; buf is only valid during the call.
@@ -113,6 +114,11 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
 /* -- knobs ---------------------------------------------------------------------------------- */
 /* pairs per device batch (default 1<<17); ring = number of pinned output slots (default 3) */
 int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots);
+/* 0 (default): the sink receives FASTQ text.  1: the sink receives gzip (RFC 1952) bytes -- every batch of every
+ * stream is a run of complete gzip members written on the device (64 KiB of FASTQ each, literal-only dynamic-Huffman
+ * block with a per-stream code fitted to the first batch), so appending them to <prefix>.*.fastq.gz gives the file
+ * the reference writes through gzFile (src/dwgsim.c:1151-1157), at a fraction of the PCIe bytes and no host zlib. */
+int dwgsim_gpu_set_compression(dwgsim_gpu_t *h, int32_t mode);
 /* shard the pair-index space: dwgsim_gpu_run simulates the batches b with b % world == rank and hands
  * only those to the sink (in order); concatenating the ranks' batches round-robin gives the bytes of
  * the unsharded run.  rand_ii (src/dwgsim.c:1096) is a running count over ALL pairs, so every round

@@ -24,7 +24,7 @@ def oracle_expected(oracle, opts, fasta, prefix):
     return sess, want
 
 
-def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None):
+def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None, compression=0):
     from dwgsim_b200 import DwgsimGpu, params_from_options
     params = params_from_options(**{k: v for k, v in opts.items() if k in GPU_KEYS})
     if orc_opt is not None:
@@ -37,6 +37,8 @@ def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None):
     with DwgsimGpu(params) as gpu:
         if batch:
             gpu.set_batch(batch, 2)
+        if compression:
+            gpu.set_compression(compression)
         for k in range(sess.n_contigs):
             c = sess.contig(k)
             if c["n_pairs"] == 0 and not per_contig_runs:
@@ -47,7 +49,11 @@ def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None):
                 stats.append(gpu.run(lambda fid, data: got[fid].append(data)))
         if not per_contig_runs:
             stats.append(gpu.run(lambda fid, data: got[fid].append(data)))
-    return [b"".join(g) for g in got], stats
+    out = [b"".join(g) for g in got]
+    if compression:
+        import gzip
+        out = [gzip.decompress(x) if x else b"" for x in out]
+    return out, stats
 
 
 def first_diff(a, b):

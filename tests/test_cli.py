@@ -100,6 +100,7 @@ GPU_CASES = {
     "illumina_gz": (dict(seed=7, N=4000, length=(100, 100), mut_rate=0.01, indel_frac=0.3), []),
     "illumina_plain_config1": (dict(seed=13, N=10000, length=(100, 100), data_type=0), ["--uncompressed"]),
     "solid_gz": (dict(seed=22, N=3000, data_type=1, length=(50, 50), mut_rate=0.02, indel_frac=0.5), ["--batch", "1000"]),
+    "illumina_host_gzip": (dict(seed=8, N=3000, length=(100, 100)), ["--host-gzip"]),
     "ion_plain": (dict(seed=25, N=1200, data_type=2, length=(200, 0), e=0.02, flow_order=FLOW), ["--uncompressed"]),
 }
 

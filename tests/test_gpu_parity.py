@@ -73,6 +73,18 @@ def test_ion_torrent_long_reads_use_fallback(oracle, synth_fa, tmp_path):
     check(oracle, dict(seed=27, N=300, data_type=2, length=(1500, 0), e=0.01, flow_order=make_golden.FLOW), synth_fa, tmp_path)
 
 
+@pytest.mark.parametrize("case", ["illumina_2x150_slope_C", "solid_2x50", "ion_400_se", "illumina_single_end", "illumina_q0_bfast"])
+def test_device_gzip_members_decode_to_the_same_bytes(oracle, synth_fa, tmp_path, case):
+    """sink receives gzip members written on the device; zlib must decode them to the oracle's FASTQ bytes"""
+    stats = check(oracle, CASES[case], synth_fa, tmp_path, compression=1, batch=2500)
+    assert sum(sum(s.bytes) for s in stats) < 0.7 * sum(sum(s.raw_bytes) for s in stats)
+
+
+def test_device_gzip_large_batch(oracle, synth_fa, tmp_path):
+    """several 64 KiB members per stream and batch, ragged last member"""
+    check(oracle, dict(seed=2, N=60000, length=(150, 150), e="0.001-0.01", E="0.001-0.01"), synth_fa, tmp_path, compression=1)
+
+
 def test_derived_tables_equal_oracle(oracle):
     """the 32-bit threshold tables the kernels sample from == the oracle's own derivation"""
     from dwgsim_b200 import DwgsimGpu, params_from_options
