@@ -26,7 +26,7 @@ class Stats(C.Structure):
         ("bytes", C.c_int64 * 3), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_simulate", C.c_double), ("ms_layout", C.c_double), ("ms_format", C.c_double),
         ("ms_pack", C.c_double), ("ms_total", C.c_double), ("n_launches", C.c_int32), ("n_batches", C.c_int32),
-        ("raw_bytes", C.c_int64 * 3),
+        ("raw_bytes", C.c_int64 * 3), ("ms_compress", C.c_double),
     ]
 
 

@@ -91,7 +91,7 @@ struct dwgsim_gpu {
     std::vector<int8_t> flow_order;
     int device = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     // derived tables (host + device)
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
@@ -100,6 +100,7 @@ struct dwgsim_gpu {
     bool ion_warp_kernel = false;
     // device gzip writer: mode, per-stream tables in HBM
     int gz_mode = 0;
+    double ms_gz = 0;
     bool gz_ready = false;
     uint32_t *gz_code[3] = {nullptr, nullptr, nullptr};
     uint8_t *gz_prefix[3] = {nullptr, nullptr, nullptr};
@@ -757,6 +758,7 @@ int gz_batch(dwgsim_gpu *h, int dslot, const uint64_t bytes[3], uint64_t out_byt
     int rc;
     if (!h->gz_ready && (rc = gz_calibrate(h, dslot, bytes))) return rc;
     cudaStream_t st = h->s_compute;
+    CUDA_TRY(h, cudaEventRecord(h->ev_t[6], st));
     CUDA_TRY(h, cudaMemsetAsync(w.gz_totals, 0, 64, st));
     for (int k = 0; k < 3; ++k) {
         if (!bytes[k]) continue;
@@ -770,8 +772,10 @@ int gz_batch(dwgsim_gpu *h, int dslot, const uint64_t bytes[3], uint64_t out_byt
         *launches += 3;
     }
     CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev_t[7], st));
     CUDA_TRY(h, cudaMemcpyAsync(w.h_totals + 12, w.gz_totals, 24, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    { float ms = 0; cudaEventElapsedTime(&ms, h->ev_t[6], h->ev_t[7]); h->ms_gz += ms; }
     for (int k = 0; k < 3; ++k) {
         out_bytes[k] = bytes[k] ? w.h_totals[12 + k] : 0;
         if (out_bytes[k] > w.gz_cap[k]) { h->last_error = "compressed stream larger than its buffer"; return DWGSIM_GPU_EOVERFLOW; }
@@ -1155,6 +1159,7 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
     st.n_launches = launches;
     st.h2d_bytes = h->h2d_bytes - h2d_before;
     st.ms_pack = h->ms_pack; h->ms_pack = 0;
+    st.ms_compress = h->ms_gz; h->ms_gz = 0;
     st.ms_total = now_ms() - t_start;
     if (stats) *stats = st;
     return rc;

@@ -81,6 +81,7 @@ typedef struct {
     int32_t n_launches;            /* kernels launched by this call                                */
     int32_t n_batches;
     int64_t raw_bytes[3];          /* uncompressed FASTQ bytes per file id (== bytes[] without compression) */
+    double  ms_compress;           /* device time of the gzip kernels                               */
 } dwgsim_gpu_stats_t;
 
 /* receives FASTQ bytes strictly in pair-index order per file id; buf is only valid during the call.
