@@ -265,7 +265,14 @@ def main():
     import torch
     import torch.distributed as dist
     from dwgsim_b200 import DwgsimGpu, params_from_options, build
-    build.build()
+    if not os.path.exists(build.SO):          # normally prebuilt in-tree and shipped with the snapshot
+        if rank == 0:
+            build.build()
+        else:
+            for _ in range(600):
+                if os.path.exists(build.SO):
+                    break
+                time.sleep(0.5)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the read-pair path has no CPU fallback")
     torch.cuda.set_device(local_rank)
