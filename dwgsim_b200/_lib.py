@@ -64,6 +64,7 @@ SYMBOLS = {
     "dwgsim_gpu_last_error": (C.c_char_p, [_P]),
     "dwgsim_gpu_add_contig": (C.c_int, [_P, C.c_int32, C.c_char_p, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_int32,
                                         C.c_int64]),
+    "dwgsim_gpu_set_regions": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.c_int32]),
     "dwgsim_gpu_run": (C.c_int, [_P, SINK_FN, _P, C.POINTER(Stats)]),
     "dwgsim_gpu_set_batch": (C.c_int, [_P, C.c_int64, C.c_int32]),
     "dwgsim_gpu_set_compression": (C.c_int, [_P, C.c_int32]),

@@ -118,6 +118,14 @@ class DwgsimGpu:
         self._check(self._L.dwgsim_gpu_add_contig(self._h, contig_i, name, seq, length, hap1, hap2, ins1, ins1_n,
                                                   ins2, ins2_n, n_pairs))
 
+    def set_regions(self, regions, sample_len):
+        """-x for the contig just queued: regions = [(start, end), ...] merged and sorted (BED half-open),
+        sample_len = the reference's `l` after src/dwgsim.c:539-553"""
+        n = len(regions)
+        a = (C.c_uint32 * max(n, 1))(*[r[0] for r in regions])
+        b = (C.c_uint32 * max(n, 1))(*[r[1] for r in regions])
+        self._check(self._L.dwgsim_gpu_set_regions(self._h, a, b, n, sample_len))
+
     def run(self, sink):
         """sink(file_id:int, data:bytes) is called in pair order; returns Stats"""
         err = []

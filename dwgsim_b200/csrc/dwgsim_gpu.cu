@@ -49,6 +49,8 @@ struct HostContig {
     std::vector<Event> ev[2];
     std::vector<uint32_t> blk[2];
     std::vector<uint8_t> pool[2];
+    std::vector<Region> regions;               // -x
+    int32_t sample_len = 0;
 };
 
 struct DeviceTables {
@@ -455,6 +457,7 @@ void free_blob(dwgsim_gpu *h)
 {
     if (h->blob && h->blob_owned) cudaFree(h->blob);
     h->blob = nullptr; h->blob_bytes = 0; h->blob_pairs = 0; h->blob_owned = true;
+    h->sp.regions = 0;
 }
 
 // lay the queued contigs out in one blob and upload it
@@ -466,7 +469,7 @@ int finalize_genome(dwgsim_gpu *h)
     const size_t nc = h->queue.size();
     uint64_t off = align_up(sizeof(BlobHeader), 256);
     BlobHeader hd{};
-    hd.magic = kBlobMagic; hd.version = 1; hd.n_contigs = (uint32_t)nc;
+    hd.magic = kBlobMagic; hd.version = kBlobVersion; hd.n_contigs = (uint32_t)nc;
     hd.contigs_off = off;
     off = align_up(off + nc * sizeof(ContigDesc), 256);
     hd.names_off = off;
@@ -494,10 +497,14 @@ int finalize_genome(dwgsim_gpu *h)
             d.blk_off[hh] = off; off = align_up(off + c.blk[hh].size() * 4, 256);
             d.pool_off[hh] = off; off = align_up(off + c.pool[hh].size(), 256);
         }
+        d.n_reg = (uint32_t)c.regions.size(); d.sample_len = c.sample_len;
+        if (c.sample_len > 0) hd.flags |= 1u;
+        d.reg_off = off; off = align_up(off + c.regions.size() * sizeof(Region), 256);
     }
     hd.n_bytes = off; hd.total_pairs = pair_base; hd.total_len = total_len;
     CUDA_TRY(h, cudaMalloc((void **)&h->blob, off));
     h->blob_owned = true; h->blob_bytes = off; h->blob_pairs = pair_base;
+    h->sp.regions = (int32_t)(hd.flags & 1u);
     auto put = [&](uint64_t at, const void *src, size_t n) -> cudaError_t {
         h->h2d_bytes += (int64_t)n;
         return n ? cudaMemcpyAsync(h->blob + at, src, n, cudaMemcpyHostToDevice, h->s_compute) : cudaSuccess;
@@ -515,6 +522,7 @@ int finalize_genome(dwgsim_gpu *h)
             CUDA_TRY(h, put(d.blk_off[hh], c.blk[hh].data(), c.blk[hh].size() * 4));
             CUDA_TRY(h, put(d.pool_off[hh], c.pool[hh].data(), c.pool[hh].size()));
         }
+        CUDA_TRY(h, put(d.reg_off, c.regions.data(), c.regions.size() * sizeof(Region)));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
     h->queue.clear();
@@ -910,6 +918,28 @@ int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name, c
     return DWGSIM_GPU_OK;
 }
 
+int dwgsim_gpu_set_regions(dwgsim_gpu_t *h, const uint32_t *start, const uint32_t *end, int32_t n, int32_t sample_len)
+{
+    if (!h || n < 0 || (n > 0 && (!start || !end)) || sample_len <= 0) return DWGSIM_GPU_EINVAL;
+    if (h->blob || h->queue.empty()) { h->last_error = "set_regions applies to the contig just queued with add_contig"; return DWGSIM_GPU_ESTATE; }
+    if (h->p.amplicons) { h->last_error = "regions cannot be combined with amplicon mode"; return DWGSIM_GPU_EINVAL; }
+    HostContig &c = h->queue.back();
+    std::vector<Region> r((size_t)n);
+    uint32_t cum = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        // the invariants regions_bed_init leaves behind (src/regions_bed.c:66-97): inside the contig, sorted, merged
+        if (end[i] < start[i] || end[i] > (uint32_t)c.len || (i > 0 && start[i] <= end[i - 1])) {
+            h->last_error = "regions must lie inside the contig, sorted by start and not touch or overlap";
+            return DWGSIM_GPU_EINVAL;
+        }
+        r[(size_t)i] = Region{start[i], end[i], cum, 0u};
+        cum += end[i] - start[i];
+    }
+    c.regions.swap(r);
+    c.sample_len = sample_len;
+    return DWGSIM_GPU_OK;
+}
+
 int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots)
 {
     if (!h || pairs_per_batch < 1 || pairs_per_batch > (1 << 24) || ring_slots < 2 || ring_slots > 8) return DWGSIM_GPU_EINVAL;
@@ -963,7 +993,7 @@ int dwgsim_gpu_genome_import(dwgsim_gpu_t *h, uint64_t device_ptr, uint64_t n_by
     cudaSetDevice(h->device);
     BlobHeader hd;
     CUDA_TRY(h, cudaMemcpy(&hd, (const void *)(uintptr_t)device_ptr, sizeof hd, cudaMemcpyDeviceToHost));
-    if (hd.magic != kBlobMagic || hd.n_bytes != n_bytes) { h->last_error = "not a genome blob"; return DWGSIM_GPU_EINVAL; }
+    if (hd.magic != kBlobMagic || hd.version != kBlobVersion || hd.n_bytes != n_bytes) { h->last_error = "not a genome blob"; return DWGSIM_GPU_EINVAL; }
     std::vector<ContigDesc> cds(hd.n_contigs);
     CUDA_TRY(h, cudaMemcpy(cds.data(), (const uint8_t *)(uintptr_t)device_ptr + hd.contigs_off, hd.n_contigs * sizeof(ContigDesc),
                            cudaMemcpyDeviceToHost));
@@ -971,6 +1001,7 @@ int dwgsim_gpu_genome_import(dwgsim_gpu_t *h, uint64_t device_ptr, uint64_t n_by
     h->queue.clear();
     h->blob = (uint8_t *)(uintptr_t)device_ptr; h->blob_bytes = n_bytes; h->blob_owned = take_ownership != 0;
     h->blob_pairs = hd.total_pairs;
+    h->sp.regions = (int32_t)(hd.flags & 1u);
     for (auto &d : cds) h->max_name_len = std::max(h->max_name_len, (int)d.name_len);
     return update_caps(h);
 }

@@ -116,7 +116,7 @@ int usage(const Options &o)
     fprintf(stderr, "         -z INT        random seed (-1 uses the current time) [%d]\n", o.seed);
     fprintf(stderr, "         -M INT        output 0: reads and mutations, 1: reads only, 2: mutations only [%d]\n", o.output_type);
     fprintf(stderr, "         -m/-b/-v FILE replay mutations from txt / bed / vcf (not supported by this build)\n");
-    fprintf(stderr, "         -x FILE       the bed of regions to cover (not supported by this build)\n");
+    fprintf(stderr, "         -x FILE       the bed of regions to cover [%s]\n", o.fn_regions_bed.empty() ? "not using" : o.fn_regions_bed.c_str());
     fprintf(stderr, "         -P STRING     a read prefix to prepend to each read name\n");
     fprintf(stderr, "         -q STRING     a fixed base quality to apply (single character)\n");
     fprintf(stderr, "         -Q FLOAT      standard deviation of the base quality scores [%.2f]\n", o.quality_std);
@@ -685,6 +685,37 @@ FILE *xopen(const std::string &fn, const char *mode)
     return fp;
 }
 
+// ---- -x regions (src/regions_bed.c) ------------------------------------------------------------------------------------
+struct ContigList { std::vector<std::string> name; std::vector<uint32_t> len; };
+struct Regions {
+    std::vector<uint32_t> contig, start, end;
+    // regions_bed_init, src/regions_bed.c:43-115: contigs in FASTA order, starts sorted, overlapping regions merged
+    void read(const std::string &path, const ContigList &c)
+    {
+        FILE *fp = xopen(path, "r");
+        char name[1024];
+        uint32_t s, e;
+        size_t i = 0;
+        long prev_contig = -1, prev_start = -1, prev_end = -1;
+        while (0 < fscanf(fp, "%1023s\t%u\t%u", name, &s, &e)) {
+            while (i < c.name.size() && c.name[i] != name) i++;
+            if (i == c.name.size()) { fprintf(stderr, "Error: contig not found: %s.  Are you sure your BED is coordinate sorted?\n", name); exit(1); }
+            if (c.len[i] < s || c.len[i] < e) { fprintf(stderr, "Error: start/end was out of range\n"); exit(1); }
+            if (e < s) { fprintf(stderr, "Error: end < start: [%s,%u,%u]\n", name, s, e); exit(1); }
+            if (prev_contig == (long)i && (long)s < prev_start) { fprintf(stderr, "Error: the input was not sorted: [%s,%u,%u]\n", name, s, e); exit(1); }
+            if (prev_contig == (long)i && (long)s <= prev_end && prev_start <= (long)s) {
+                if (prev_end < (long)e) { end.back() = e; prev_end = e; }
+            } else {
+                prev_contig = (long)i; prev_start = s; prev_end = e;
+                contig.push_back((uint32_t)i); start.push_back(s); end.push_back(e);
+            }
+            int b;
+            while (EOF != (b = fgetc(fp))) if ('\n' == b || '\r' == b) break;
+        }
+        fclose(fp);
+    }
+};
+
 }  // namespace
 
 int main(int argc, char **argv)
@@ -693,8 +724,8 @@ int main(int argc, char **argv)
     Options o;
     int first = 0;
     if (!parse_options(o, argc, argv, &first)) return usage(o);
-    if (o.muts_input_type >= 0 || !o.fn_regions_bed.empty()) {
-        fprintf(stderr, "[dwgsim_core] Error: -m/-b/-v/-x are not supported by this build\n");
+    if (o.muts_input_type >= 0) {
+        fprintf(stderr, "[dwgsim_core] Error: -m/-b/-v are not supported by this build\n");
         return 1;
     }
     const std::string fn_fa = argv[first], prefix = argv[first + 1];
@@ -736,6 +767,8 @@ int main(int argc, char **argv)
     std::string name;
     uint64_t tot_len = 0;
     int n_ref = 0;
+    ContigList contigs;
+    if (!o.fn_regions_bed.empty()) fclose(xopen(o.fn_regions_bed, "r"));   // fail before the census, like src/dwgsim.c:460
     if (fp_vcf) fprintf(fp_vcf, "##fileformat=VCFv4.1\n");
     if (fp_fai) {
         char nm[1024];
@@ -743,6 +776,7 @@ int main(int argc, char **argv)
         while (0 < fscanf(fp_fai, "%1023s\t%d\t%d\t%d\t%d", nm, &l, &d0, &d1, &d2)) {
             fprintf(stderr, "[dwgsim_core] %s length: %d\n", nm, l);
             tot_len += (uint64_t)l; ++n_ref;
+            contigs.name.push_back(nm); contigs.len.push_back((uint32_t)l);
             if (fp_vcf) fprintf(fp_vcf, "##contig=<ID=%s,length=%d>\n", nm, l);
         }
         fclose(fp_fai);
@@ -751,6 +785,7 @@ int main(int argc, char **argv)
         while ((l = fa.next(seq, name)) >= 0) {
             fprintf(stderr, "[dwgsim_core] %s length: %lld\n", name.c_str(), (long long)l);
             tot_len += (uint64_t)l; ++n_ref;
+            contigs.name.push_back(name); contigs.len.push_back((uint32_t)l);
             if (fp_vcf) fprintf(fp_vcf, "##contig=<ID=%s,length=%d>\n", name.c_str(), (int)l);
         }
     }
@@ -761,6 +796,13 @@ int main(int argc, char **argv)
         fprintf(fp_vcf, "##INFO=<ID=pl,Number=1,Type=Integer,Description=\"Phasing: 1 - HET contig 1, #2 - HET contig #2, 3 - HOM both contigs\">\n");
         fprintf(fp_vcf, "##INFO=<ID=mt,Number=1,Type=String,Description=\"Variant Type: SUBSTITUTE/INSERT/DELETE\">\n");
         fprintf(fp_vcf, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n");
+    }
+    Regions regions;
+    const bool use_regions = !o.fn_regions_bed.empty();
+    if (use_regions) {                                                   // src/dwgsim.c:499-506
+        regions.read(o.fn_regions_bed, contigs);
+        tot_len = 0;
+        for (size_t i = 0; i < regions.start.size(); i++) tot_len += regions.end[i] - regions.start[i];
     }
     fprintf(stderr, o.output_type != 2 ? "[dwgsim_core] Currently on: \n0" : "[dwgsim_core] Currently on:");
 
@@ -775,12 +817,30 @@ int main(int argc, char **argv)
     const int maxlen = std::max(o.length[0], o.length[1]);
     int64_t l64;
     while ((l64 = fa.next(seq, name)) >= 0) {                             // src/dwgsim.c:519-1106
-        const int l = (int)l64;
+        const int seq_l = (int)l64;
+        int l = seq_l;                                                    // with -x: the total length of the contig's regions
         long long n_pairs = 0;
+        std::vector<uint32_t> reg_start, reg_end;
         n_ref--;
         if (o.output_type == 2) fprintf(stderr, "\r[dwgsim_core] Currently on: %s", name.c_str());
         else {
-            if (0 == n_ref && o.C < 0) n_pairs = o.N - n_sim;
+            if (use_regions)
+                for (size_t i = 0; i < regions.start.size(); i++)
+                    if ((uint32_t)contig_i == regions.contig[i]) { reg_start.push_back(regions.start[i]); reg_end.push_back(regions.end[i]); }
+            if (0 == n_ref && o.C < 0) n_pairs = o.N - n_sim;             // NB: the last contig keeps its full length, also with -x
+            else if (use_regions && [&]() {                               // src/dwgsim.c:539-581
+                     int m = 0, num_n = 0;
+                     for (size_t i = 0; i < reg_start.size(); i++) m += (int)(reg_end[i] - reg_start[i]);
+                     if (0 == m) { fprintf(stderr, "[dwgsim_core] #0 skip sequence '%s' as it is not in the targeted region\n", name.c_str()); return true; }
+                     l = m;
+                     for (size_t i = 0; i < reg_start.size(); i++)
+                         for (uint32_t q = reg_start[i]; q <= reg_end[i]; q++) {     // the reference reads seq[q-1] for q in [start, end]
+                             const int ch = q >= 1 ? seq[q - 1] : 'N';
+                             switch (ch) { case 'a': case 'A': case 'c': case 'C': case 'g': case 'G': case 't': case 'T': break; default: num_n++; }
+                         }
+                     if (0.95 < num_n / (double)l) { fprintf(stderr, "[dwgsim_core] #1 skip sequence '%s' as %d out of %d bases are non-ACGT\n", name.c_str(), num_n, l); return true; }
+                     return false;
+                 }()) { contig_i++; continue; }
             else if (0 < o.N) {
                 n_pairs = (long long)(uint64_t)((long double)l / tot_len * o.N + 0.5);
                 if (o.N - n_sim < n_pairs) n_pairs = o.N - n_sim;
@@ -800,12 +860,13 @@ int main(int argc, char **argv)
         t_mut += now() - t0; t0 = now();
         if (o.output_type != 1) print_mutations(name.c_str(), seq, h1, h2, fp_txt, fp_vcf);
         t_print += now() - t0;
-        bases_in += l;
+        bases_in += seq_l;
         if (o.output_type != 2 && n_pairs > 0) {
             if (!gpu) gpu_open();
             t0 = now();
-            int rc = dwgsim_gpu_add_contig(gpu, contig_i, name.c_str(), seq.data(), l, h1.s.data(), h2.s.data(), h1.ins.data(),
+            int rc = dwgsim_gpu_add_contig(gpu, contig_i, name.c_str(), seq.data(), seq_l, h1.s.data(), h2.s.data(), h1.ins.data(),
                                            (int32_t)h1.ins.size(), h2.ins.data(), (int32_t)h2.ins.size(), n_pairs);
+            if (rc == DWGSIM_GPU_OK && use_regions) rc = dwgsim_gpu_set_regions(gpu, reg_start.data(), reg_end.data(), (int32_t)reg_start.size(), l);
             dwgsim_gpu_stats_t st;
             if (rc == DWGSIM_GPU_OK) rc = dwgsim_gpu_run(gpu, sink_cb, &wr, &st);
             if (rc != DWGSIM_GPU_OK) {

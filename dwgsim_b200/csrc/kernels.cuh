@@ -122,6 +122,43 @@ __device__ __forceinline__ uint32_t ref_code(const ContigView &c, int p)
     uint32_t m = __ldg(c.nmask + (p >> 5));
     return ((m >> (p & 31)) & 1u) ? 4u : ((w >> ((p & 15) << 1)) & 3u);
 }
+// -x: map a position drawn in region space to the contig and require one region to hold the whole fragment
+// (src/dwgsim.c:695-713 with regions_bed_query, src/regions_bed.c:117-141).  Returns false where the reference
+// repeats its draw (returned as -1); here that is a rejected attempt (draws are addressed by attempt).
+// Both helpers look the contig up again instead of keeping its region fields live across the read walk.
+__device__ __noinline__ int region_sample_len(const uint8_t *blob, int64_t q)
+{
+    int index;
+    const ContigDesc *cd = find_contig(blob, q, &index);
+    return cd->sample_len > 0 ? cd->sample_len : cd->len;
+}
+__device__ __noinline__ int map_to_regions(const uint8_t *blob, int64_t q, int pos, int d)
+{
+    int index;
+    const ContigDesc *cd = find_contig(blob, q, &index);
+    if (cd->sample_len <= 0) return pos;                               // a contig queued without -x
+    struct { const Region *reg; int n_reg, len; } c{reinterpret_cast<const Region *>(blob + cd->reg_off), (int)cd->n_reg, cd->len};
+    int lo = 0, hi = c.n_reg - 1, k = -1;
+    while (lo <= hi) {                 // last region with cum <= pos
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&c.reg[mid].cum) <= (uint32_t)pos) { k = mid; lo = mid + 1; } else hi = mid - 1;
+    }
+    int total = 0;
+    if (c.n_reg > 0) { const uint4 r = __ldg(reinterpret_cast<const uint4 *>(c.reg + c.n_reg - 1)); total = (int)(r.z + (r.y - r.x)); }
+    if (k >= 0) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(c.reg + k));
+        const int off = pos - (int)r.z;
+        if (off < (int)(r.y - r.x)) pos = (int)r.x + off - 1;          // "zero-based", src/dwgsim.c:700
+        else pos -= total;                                              // past the last region: left unmapped
+    }
+    if (pos < 0 || pos >= c.len || pos + d - 1 >= c.len) return -1;
+    lo = 0; hi = c.n_reg - 1; k = -1;
+    while (lo <= hi) {                 // last region with start <= pos
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&c.reg[mid].start) <= (uint32_t)pos) { k = mid; lo = mid + 1; } else hi = mid - 1;
+    }
+    return (k >= 0 && (uint32_t)(pos + d) <= __ldg(&c.reg[k].end)) ? pos : -1;
+}
 __device__ __forceinline__ uint4 load_event(const Event *ev, int e)
 {
     return __ldg(reinterpret_cast<const uint4 *>(ev + e));
@@ -397,14 +434,16 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
             int d, pos;
             if (P.amplicons) { pos = 0; d = cv.len; }                                          // src/dwgsim.c:650-653
             else {
+                const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
                 if (s[1] > 0) {                                                                // src/dwgsim.c:656-664
                     d = P.isize_lo + table_rank(P.isize_cdf, P.isize_n, b0.y);
                     const int min_dist = s[0] + s[1];
                     if (d < min_dist) d = min_dist;
-                    if (d > cv.len) d = cv.len;
+                    if (d > slen) d = slen;
                 } else d = 0;
-                const uint64_t range = (uint64_t)((int64_t)cv.len - d + 1);
+                const uint64_t range = (uint64_t)((int64_t)slen - d + 1);
                 pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);                   // src/dwgsim.c:671
+                if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) { ++failed; continue; }
             }
             const uint4 b1 = draw_block(key, kStPair, 0, 1);
             hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;                                       // src/dwgsim.c:716
@@ -903,14 +942,16 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             int d, pos;
             if (P.amplicons) { pos = 0; d = cv.len; }
             else {
+                const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
                 if (s1 > 0) {
                     d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
                     const int min_dist = s0 + s1;
                     if (d < min_dist) d = min_dist;
-                    if (d > cv.len) d = cv.len;
+                    if (d > slen) d = slen;
                 } else d = 0;
-                const uint64_t range = (uint64_t)((int64_t)cv.len - d + 1);
+                const uint64_t range = (uint64_t)((int64_t)slen - d + 1);
                 pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
+                if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) { ++failed_total; continue; }
             }
             const uint4 b1 = draw_block(key, kStPair, 0, 1);
             hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;

@@ -8,11 +8,12 @@ namespace dwg {
 // One position-independent allocation: [BlobHeader][ContigDesc x n][names][per-contig sections...].
 // All offsets are bytes from the blob base, 256-byte aligned.
 constexpr uint32_t kBlobMagic = 0x42475744u;   // "DWGB"
+constexpr uint32_t kBlobVersion = 2;
 constexpr int kBlkShift = 7;                   // mutation block index granularity: 128 bases
 
 struct BlobHeader {
     uint32_t magic, version;
-    uint32_t n_contigs, reserved;
+    uint32_t n_contigs, flags;                 // flags bit 0: some contig carries -x regions
     uint64_t n_bytes;
     uint64_t contigs_off;                      // ContigDesc[n_contigs]
     uint64_t names_off;                        // concatenated contig names
@@ -32,6 +33,16 @@ struct ContigDesc {
     uint64_t pool_off[2];                      // long insertions, 2-bit packed, forward order
     uint32_t n_ev[2];
     uint32_t name_off, name_len;
+    // -x (src/dwgsim.c:539-581,677-713): sample_len > 0 switches the position sampler to region space
+    uint64_t reg_off;                          // Region[n_reg] sorted by start, disjoint (src/regions_bed.c:82-97 merges)
+    uint32_t n_reg;
+    int32_t  sample_len;                       // the `l` the sampler draws in: 0 = no -x (use len)
+};
+
+struct Region {
+    uint32_t start, end;                       // BED half-open
+    uint32_t cum;                              // total length of the contig's regions before this one
+    uint32_t pad;
 };
 
 // One entry of a haplotype's sparse mutation table = one mut_t that differs from the plain
@@ -72,6 +83,7 @@ struct SimParams {
     int32_t  len[2];                           // requested read lengths
     int32_t  cap[2];                           // storage per end (== len, or 2*len+64 for Ion Torrent)
     int32_t  is_inner, max_n, data_type, strandedness, read_one_strand, amplicons;
+    int32_t  regions;                          // the resident genome carries -x regions (BlobHeader.flags bit 0)
     uint32_t seed;
     uint64_t thr_genomic, thr_hap0;
     int32_t  isize_lo, isize_n;

@@ -106,6 +106,15 @@ int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name,
                           uint8_t *const *ins1, int32_t ins1_n,
                           uint8_t *const *ins2, int32_t ins2_n,
                           int64_t n_pairs);
+/* -x (targeted regions) for the contig just queued by add_contig: its regions as regions_bed_init leaves them
+ * (src/regions_bed.c:43-115: BED half-open, sorted by start, overlapping ones merged) and `sample_len`, the `l`
+ * the reference's sampler draws in at that point (src/dwgsim.c:539-553: the total region length, except for the
+ * last contig under -N, which keeps its full length).  The device then restates src/dwgsim.c:677-713: the position
+ * is drawn in [0, sample_len - d], mapped through the regions, and the draw is repeated (as a new attempt) unless
+ * one region holds [pos, pos + d] (regions_bed_query, src/regions_bed.c:117-141).  n = 0 is allowed and, like the
+ * reference, can never place a pair (ETRIALS instead of the reference's endless loop).  n_pairs passed to
+ * add_contig must already be the region-based budget. */
+int dwgsim_gpu_set_regions(dwgsim_gpu_t *h, const uint32_t *start, const uint32_t *end, int32_t n, int32_t sample_len);
 /* Simulate every queued pair, stream FASTQ to the sink in pair order, then drop the queued
  * contigs.  Pair indices (the Philox key), `ctr` and `rand_ii` (src/dwgsim.c:423) carry over to
  * the next add_contig/run round, so calling run() once per contig or once at the end yields the

@@ -64,6 +64,7 @@ typedef struct {
     int32_t output_type;                    /* 0 all, 1 reads, 2 mutations */
     int32_t amplicons;
     int32_t finalized;
+    char    fn_regions_bed[1024];           /* -x: BED of regions to cover ("" = none)              */
 } orc_opt_t;
 
 /* tables the Philox backend (and the GPU) samples from instead of calling log/sqrt per draw */
@@ -118,6 +119,10 @@ int64_t      orc_contig_n_pairs(const orc_session_t *s, int32_t k);
 const uint8_t  *orc_contig_seq(const orc_session_t *s, int32_t k);  /* ASCII                      */
 const uint64_t *orc_contig_hap(const orc_session_t *s, int32_t k, int32_t hap); /* mut_t[len]     */
 int32_t      orc_contig_n_ins(const orc_session_t *s, int32_t k, int32_t hap);
+/* -x regions of the kept contig (merged, sorted): returns their number, fills the two pointers */
+/* the length the position sampler uses: the contig's, or with -x the total length of its regions */
+int32_t      orc_contig_sample_len(const orc_session_t *s, int32_t k);
+int32_t      orc_contig_regions(const orc_session_t *s, int32_t k, const uint32_t **start, const uint32_t **end);
 uint8_t *const *orc_contig_ins(const orc_session_t *s, int32_t k, int32_t hap);
 
 /* derived tables (Philox backend) */

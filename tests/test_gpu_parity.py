@@ -16,6 +16,7 @@ CASES = {k: v for k, v in make_golden.MATRIX.items() if v.get("output_type", 0) 
 
 
 def check(oracle, opts, fasta, tmp_path, **kw):
+    opts = make_golden.materialize(opts, str(tmp_path))
     sess, want = gh.oracle_expected(oracle, opts, fasta, str(tmp_path / "orc"))
     try:
         assert sess.stats.error == 0

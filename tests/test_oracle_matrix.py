@@ -29,7 +29,7 @@ def test_fixture_fasta_is_reproducible(synth_fa):
 
 @pytest.mark.parametrize("case", sorted(make_golden.MATRIX))
 def test_oracle_equals_reference(oracle, synth_fa, tmp_path, case):
-    opts = make_golden.MATRIX[case]
+    opts = make_golden.materialize(make_golden.MATRIX[case], str(tmp_path))
     prefix = str(tmp_path / "orc")
     with oracle.Session(oracle.make_opt(**opts), synth_fa, prefix) as s:
         assert s.stats.error == 0
