@@ -143,6 +143,16 @@ struct dwgsim_gpu {
 
 namespace {
 
+// the format kernel is specialised on colour space and on whether the quality sum can wrap in int8
+typedef void (*format_kernel_t)(const SimParams, const uint8_t *, int64_t, int64_t, int, const PairRec *, const uint32_t *,
+                                const unsigned long long *, const uint32_t *, const unsigned long long *, const char *,
+                                const uint16_t *, char *, char *, char *);
+format_kernel_t format_kernel_of(const SimParams &sp)
+{
+    if (sp.data_type == 1) return sp.q_wrap ? format_fastq_kernel<true, true> : format_fastq_kernel<true, false>;
+    return sp.q_wrap ? format_fastq_kernel<false, true> : format_fastq_kernel<false, false>;
+}
+
 // dynamic shared memory of simulate_pairs_tp_kernel: staging tile + sampling tables (see the kernel prologue)
 size_t tp_smem_bytes(const SimParams &sp)
 {
@@ -204,18 +214,18 @@ void derive_tables(dwgsim_gpu *h)
             h->qdelta_cdf.push_back(thr32(phi(x / p.quality_std)));
         }
     }
-    // acceleration only (not part of the sampling rule): one-load guide, 2048 buckets of 2^21; entry = rank at the
-    // bucket's lower bound << 24 | offset of the single threshold inside the bucket (2^21 = none), bit 23 = several
-    h->qguide.assign(2048, 0);
-    for (uint32_t g = 0; g < 2048; ++g) {
+    // acceleration only (not part of the sampling rule): one-load guide, 1024 buckets of 2^22.  Entry g = {t, r}: r = rank
+    // at the bucket's lower bound; when exactly one threshold c lies inside the bucket t = c - 1 (rank = r + (u > t)),
+    // with none t = 2^32 - 1; with several (the tails) r carries bit 31, t = their number and the kernel scans the CDF
+    h->qguide.assign(2 * 1024, 0);
+    for (uint32_t g = 0; g < 1024; ++g) {
         const std::vector<uint32_t> &cdf = h->qdelta_cdf;
-        const uint64_t lo = (uint64_t)g << 21, hi = lo + (1ull << 21);
+        const uint64_t lo = (uint64_t)g << 22, hi = lo + (1ull << 22);
         const size_t j = (size_t)(std::upper_bound(cdf.begin(), cdf.end(), (uint32_t)lo) - cdf.begin());
         size_t inside = 0;
         while (j + inside < cdf.size() && (uint64_t)cdf[j + inside] < hi) ++inside;
-        if (j > 255 || inside > 1) h->qguide[g] = ((uint32_t)std::min<size_t>(j, 255) << 24) | 0x800000u;
-        else if (inside == 1) h->qguide[g] = ((uint32_t)j << 24) | (uint32_t)(cdf[j] - lo);
-        else h->qguide[g] = ((uint32_t)j << 24) | 0x200000u;
+        h->qguide[2 * g] = inside == 1 ? cdf[j] - 1u : (inside > 1 ? (uint32_t)inside : 0xFFFFFFFFu);
+        h->qguide[2 * g + 1] = (uint32_t)j | (inside > 1 ? 0x80000000u : 0u);
     }
     auto make_guide = [](const uint32_t *cdf, size_t n, std::vector<uint16_t> &g) {     // g[b] = rank of (b << 22), b = 0..1024
         g.assign(1025, 0);
@@ -286,6 +296,8 @@ int upload_tables(dwgsim_gpu *h)
     s.thr_genomic = h->thr_genomic; s.thr_hap0 = h->thr_hap0;
     s.isize_lo = h->isize_lo; s.isize_n = (int32_t)h->isize_cdf.size();
     s.qdelta_lo = h->qdelta_lo; s.qdelta_n = (int32_t)h->qdelta_cdf.size();
+    // the reference adds the noise in `char` (src/dwgsim.c:911-913): only a wide noise table can leave the int8 range
+    s.q_wrap = (73 + (int)h->qdelta_cdf.size() / 2 > 127 || 33 + h->qdelta_lo < -128) ? 1 : 0;
     s.fixed_quality = p.fixed_quality;
     s.out_bwa = p.reads_output_type != 2; s.out_bfast = p.reads_output_type != 1;
     s.prefix_len = (int32_t)h->prefix_s.size();
@@ -439,6 +451,7 @@ int update_caps(dwgsim_gpu *h)
     uint64_t cap[3];
     record_caps(h, cap);
     h->sp.name_cap = (int32_t)((name_cap_of(h) + 15) & ~15ull);
+    h->sp.inv_name_chunks = (uint32_t)(4294967296.0 / std::max(h->sp.name_cap >> 4, 1)) + 1u;
     for (int k = 0; k < 3; ++k) h->sp.rec_cap[k] = (int32_t)cap[k];
     // tile of the format kernel: as many pairs as fit ~110 KB of shared memory (two CTAs per SM), at most 32
     // tile of the format kernel: 32 pairs (measured best for 2x150: 56 KB of staging, 4 CTAs per SM), halved for long
@@ -449,7 +462,7 @@ int update_caps(dwgsim_gpu *h)
     while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 110 * 1024) h->sp.tile_pairs >>= 1;
     const FormatSmem L = format_smem_layout(h->sp);
     if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
-    CUDA_TRY(h, cudaFuncSetAttribute(format_fastq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CUDA_TRY(h, cudaFuncSetAttribute(format_kernel_of(h->sp), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     return DWGSIM_GPU_OK;
 }
 
@@ -674,10 +687,11 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
     const int ntiles = (n + sp.tile_pairs - 1) / sp.tile_pairs;
     int occ_f = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, format_fastq_kernel, kFmtThreads, smem_b);
+    const format_kernel_t fmt = format_kernel_of(sp);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fmt, kFmtThreads, smem_b);
     const int grid_f = std::min(ntiles, sm_count * std::max(occ_f, 1));
     (void)grid;
-    format_fastq_kernel<<<grid_f, kFmtThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
+    fmt<<<grid_f, kFmtThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
                                                              w.totals + 1, w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());

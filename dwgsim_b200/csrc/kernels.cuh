@@ -648,7 +648,13 @@ __device__ __forceinline__ void emit_end(Emit &E)
 // The walk of gen_read() above executed by one thread as ONE loop: every iteration either emits up to eight
 // plain reference bases or consumes one mutation event, so the lanes of a warp stay in the same loop even
 // when their reads cross different events.
-__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w)
+// first load of the walk, issued early by the caller: the block-index entry that brackets `start` (0 when off the contig)
+__device__ __forceinline__ int walk_hint(const ContigView &c, int h, int start, int strand)
+{
+    if (start < 0 || start >= c.len) return 0;
+    return (int)__ldg(c.blk[h] + (start >> kBlkShift) + (strand ? 1 : 0));
+}
+__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w, int hint)
 {
     const int dir = strand ? -1 : 1;
     const Event *ev = c.ev[h];
@@ -658,10 +664,10 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
     if (i < 0 || i >= c.len) return false;
     int e;
     if (dir > 0) {
-        e = (int)__ldg(c.blk[h] + (i >> kBlkShift));
+        e = hint;
         while (e < n_ev && (int)__ldg(&ev[e].pos) < i) ++e;
     } else {
-        e = (int)__ldg(c.blk[h] + (i >> kBlkShift) + 1) - 1;
+        e = hint - 1;
         while (e >= 0 && (int)__ldg(&ev[e].pos) > i) --e;
     }
     bool have = dir > 0 ? (e < n_ev) : (e >= 0);
@@ -874,6 +880,26 @@ __device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int ca
 
 constexpr int kTpThreads = 128;
 constexpr int kTpMinBlocks = 6;        // <= 80 registers per thread: 24 warps per SM
+constexpr int kTpQueueCap = 2 * kTpThreads;
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the sectors of the packed reference and of the N mask that a read of s bases starting at `start` will touch
+__device__ __forceinline__ void prefetch_read(const ContigView &c, int start, int strand, int s)
+{
+    int lo = strand ? start - s + 1 : start, hi = strand ? start : start + s - 1;
+    lo = lo < 0 ? 0 : lo; hi = hi >= c.len ? c.len - 1 : hi;
+    if (lo > hi) return;
+    prefetch_l2(c.ref2 + (lo >> 4)); prefetch_l2(c.ref2 + (hi >> 4));
+    prefetch_l2(c.nmask + (lo >> 5)); prefetch_l2(c.nmask + (hi >> 5));
+}
+
+// One CTA works through its share of the batch in ROUNDS of kTpThreads jobs, one job per thread.  A job is one
+// attempt at one pair (src/dwgsim.c:649-843) or the generation of one random pair (:983-1001).  Fresh pairs start
+// with attempt 0; an attempt that is rejected (N filter, contig end, -x miss) re-enters through the CTA's retry
+// queue with the next attempt number, and a pair whose gate draw says "random" goes to the random queue, so every
+// round runs ONE code path on all of its lanes: retries and random pairs are batched into (nearly) full rounds of
+// their own instead of keeping 31 finished lanes of a warp waiting.  The draws of a pair are addressed by (pair,
+// attempt), so the result does not depend on which round executes a job.
 template <bool kIon>
 __global__ void __launch_bounds__(kTpThreads, kTpMinBlocks)
 simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
@@ -882,6 +908,9 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     // staging tile: one row of nw0+nw1 words per thread, odd row stride => conflict-free; flushed to HBM (pair-major)
     // by the whole CTA with coalesced stores
     extern __shared__ __align__(16) uint32_t tile[];
+    __shared__ uint2 q_retry[kTpQueueCap], q_random[kTpQueueCap];     // (pair index in the batch, attempt | failed << 16)
+    __shared__ int row_pair[kTpThreads];                              // destination pair of each staged row, -1 = none
+    __shared__ int n_retry, n_random;
     const int NW = P.nw[0] + P.nw[1], RS = NW | 1;
     uint32_t *row = tile + (size_t)threadIdx.x * RS;
     // sampling tables behind the tile: insert-size CDF + guide, per end: gap CDF (len entries) + guide, accept thresholds
@@ -911,142 +940,181 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             T.flow_order = fo;
             T.flow_mask = reinterpret_cast<uint32_t *>(fo + ((P.flow_order_len + 15) & ~15)) + (size_t)threadIdx.x * ((P.flow_order_len + 31) >> 5);
         }
+        if (threadIdx.x == 0) { n_retry = 0; n_random = 0; }
         __syncthreads();
     }
     constexpr bool ion = kIon;
     const int solid = P.data_type == 1;
+    const int s0 = P.len[0], s1 = P.len[1];
+    uint32_t *dst0 = row, *dst1 = row + P.nw[0];
     unsigned failed_total = 0;
     const int n_round = (n + kTpThreads - 1) / kTpThreads * kTpThreads;
-    for (int pbase = blockIdx.x * kTpThreads; pbase < n_round; pbase += gridDim.x * kTpThreads) {
-        const int p = pbase + threadIdx.x;
-        if (p < n) {
-        const int64_t q = first + p;
-        int contig_index;
-        const ContigDesc *cd = find_contig(blob, q, &contig_index);
-        const ContigView cv = view_of(blob, cd);
-        const uint64_t gidx = (uint64_t)(gidx_origin + q);
-        PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), 0u};
-        const int s0 = P.len[0], s1 = P.len[1];
-        uint32_t *dst0 = row, *dst1 = row + P.nw[0];
-        int strand0 = 0, strand1 = 0, hap = 0;
-        bool done = false, random_pair = false;
-        Walk w0, w1;
-        Emit E0, E1;
-        E0.n_err = E1.n_err = 0; E0.err_first = E1.err_first = 0;
-        w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
+    int pbase = blockIdx.x * kTpThreads;
 
-        for (int attempt = 0; attempt <= kMaxTrials && !done; ++attempt) {
-            key.attempt = (uint32_t)attempt;
-            const uint4 b0 = draw_block(key, kStPair, 0, 0);
-            if ((uint64_t)b0.x < P.thr_genomic) { random_pair = true; done = true; break; }   // src/dwgsim.c:649
-            int d, pos;
-            if (P.amplicons) { pos = 0; d = cv.len; }
-            else {
-                const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
-                if (s1 > 0) {
-                    d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
-                    const int min_dist = s0 + s1;
-                    if (d < min_dist) d = min_dist;
-                    if (d > slen) d = slen;
-                } else d = 0;
-                const uint64_t range = (uint64_t)((int64_t)slen - d + 1);
-                pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
-                if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) { ++failed_total; continue; }
+    for (;;) {
+        // ---- pick the round (uniform over the CTA): full queue rounds first, then fresh pairs, then the leftovers ----
+        const int cr = n_retry, cq = n_random;
+        int kind;                                           // 0 fresh, 1 retry, 2 random
+        if (cq >= kTpThreads) kind = 2;
+        else if (cr >= kTpThreads) kind = 1;
+        else if (pbase < n_round) kind = 0;
+        else if (cr > 0) kind = 1;
+        else if (cq > 0) kind = 2;
+        else break;
+        int p = -1; uint32_t attempt = 0, failed_flag = 0;
+        if (kind == 0) { p = pbase + threadIdx.x; if (p >= n) p = -1; pbase += gridDim.x * kTpThreads; }
+        else {
+            const int cnt = kind == 1 ? cr : cq, take = cnt < kTpThreads ? cnt : kTpThreads;
+            if ((int)threadIdx.x < take) {
+                const uint2 it = (kind == 1 ? q_retry : q_random)[cnt - take + threadIdx.x];
+                p = (int)it.x; attempt = it.y & 0xFFFFu; failed_flag = it.y >> 16;
             }
-            const uint4 b1 = draw_block(key, kStPair, 0, 1);
-            hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
-            strand0 = P.read_one_strand == 0 ? ((b1.y >> 31) ? 0 : 1) : (P.read_one_strand == 1 ? 0 : 1);
-            if (P.strandedness == 0) strand1 = (P.data_type == 0) ? 1 - strand0 : strand0;
-            else strand1 = (P.strandedness == 1) ? strand0 : 1 - strand0;
-            int st0, st1 = 0;
-            const int last = cv.len - 1;
-            if (s1 > 0) {                                             // src/dwgsim.c:745-810
-                if (strand0 == strand1) {
-                    if (strand0 == 0) { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d - 1 : pos + d - s0); st1 = pos; }
-                    else { st0 = pos + s0 - 1; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
-                } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
-                else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
-            } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
-            emit_begin(E0, dst0, s0, solid, !ion, T, key, 0);
-            bool ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0);
-            if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
-            if (s1 > 0) {
-                bool ok1 = false;
-                if (ok) {                                              // a rejected end 0 already rejects the pair
-                    emit_begin(E1, dst1, s1, solid, !ion, T, key, 1);
-                    ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1);
-                    if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
-                }
-                ok = ok && ok1;
-            } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; E1.n_err = 0; E1.err_first = 0; }
-            if (ok) done = true; else ++failed_total;
+            __syncthreads();                                // every item is read before the counter moves
+            if (threadIdx.x == 0) { if (kind == 1) n_retry = cnt - take; else n_random = cnt - take; }
         }
-
-        PairRec rec;
-        rec.attempt = (uint16_t)key.attempt;
-        rec.n_err_first = 0;
-        rec.flags = 0;
-        if (!done) { atomicOr(status, 1ull); random_pair = true; rec.flags = kRecFailed; }
-        if (random_pair) {                                              // src/dwgsim.c:983-1001
-            rec.flags |= kRecRandom;
+        __syncthreads();
+        int staged = -1;
+        if (p >= 0) {
+            const int64_t q = first + p;
+            const uint64_t gidx = (uint64_t)(gidx_origin + q);
+            PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), attempt};
+            PairRec rec;
+            rec.attempt = (uint16_t)attempt;
+            rec.n_err_first = 0;
+            if (kind == 2) {                                              // random pair, src/dwgsim.c:983-1001
+                rec.flags = (uint8_t)(kRecRandom | (failed_flag ? kRecFailed : 0));
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int s = j ? s1 : s0;
-                rec.pos[j] = 0; rec.len[j] = (uint16_t)s;
-                rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
-                if (s <= 0) continue;
-                Emit E;
-                emit_begin(E, j ? dst1 : dst0, s, solid, false, T, key, j);
-                for (int k = 0; k < s; k += 64) {
-                    const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
-#pragma unroll
-                    for (int wd = 0; wd < 4; ++wd) {
-                        const uint32_t word = word_of(blk, wd);
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const int k0 = k + wd * 16 + half * 8;
-                            if (k0 >= s) break;
-                            const int m = s - k0 < 8 ? s - k0 : 8;
-                            uint32_t x = (word >> (16 * half)) & ((1u << (2 * m)) - 1u);
-                            x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;
-                            emit_group(E, x, m);
-                        }
-                    }
-                }
-                emit_end(E);
-            }
-        } else {
-            rec.flags |= (strand0 ? kRecStrand0 : 0) | (strand1 ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0);
-            rec.pos[0] = (uint32_t)(w0.ext + 1); rec.pos[1] = (uint32_t)(w1.ext + 1);
-            rec.len[0] = (uint16_t)s0; rec.len[1] = (uint16_t)s1;
-            rec.n_sub[0] = (uint16_t)w0.n_sub; rec.n_sub[1] = (uint16_t)w1.n_sub;
-            rec.n_indel[0] = (uint16_t)w0.n_indel; rec.n_indel[1] = (uint16_t)w1.n_indel;
-            rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
-            rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
-            rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
-            if constexpr (kIon) {                                       // flow-space errors, src/dwgsim.c:861-864
-#pragma unroll 1
                 for (int j = 0; j < 2; ++j) {
                     const int s = j ? s1 : s0;
+                    rec.pos[j] = 0; rec.len[j] = (uint16_t)s;
+                    rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
                     if (s <= 0) continue;
-                    int nerr = 0, ovf = 0;
-                    FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
-                    const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_thr[j], T.flow_order,
-                                                      P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
-                    if (ovf) atomicOr(status, 2ull);
-                    rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);
-                    rec.n_err[j] = (uint16_t)nerr;
+                    Emit E;
+                    emit_begin(E, j ? dst1 : dst0, s, solid, false, T, key, j);
+                    for (int k = 0; k < s; k += 64) {
+                        const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
+#pragma unroll
+                        for (int wd = 0; wd < 4; ++wd) {
+                            const uint32_t word = word_of(blk, wd);
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                const int k0 = k + wd * 16 + half * 8;
+                                if (k0 >= s) break;
+                                const int m = s - k0 < 8 ? s - k0 : 8;
+                                uint32_t x = (word >> (16 * half)) & ((1u << (2 * m)) - 1u);
+                                x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;
+                                emit_group(E, x, m);
+                            }
+                        }
+                    }
+                    emit_end(E);
+                }
+                recs[p] = rec;
+                staged = p;
+            } else {
+                const uint4 b0 = draw_block(key, kStPair, 0, 0);
+                if ((uint64_t)b0.x < P.thr_genomic) {                         // src/dwgsim.c:649
+                    q_random[atomicAdd(&n_random, 1)] = make_uint2((uint32_t)p, attempt);
+                } else {
+                    int contig_index;
+                    const ContigDesc *cd = find_contig(blob, q, &contig_index);
+                    const ContigView cv = view_of(blob, cd);
+                    int d, pos;
+                    bool ok = true;
+                    if (P.amplicons) { pos = 0; d = cv.len; }
+                    else {
+                        const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
+                        if (s1 > 0) {
+                            d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
+                            const int min_dist = s0 + s1;
+                            if (d < min_dist) d = min_dist;
+                            if (d > slen) d = slen;
+                        } else d = 0;
+                        const uint64_t range = (uint64_t)((int64_t)slen - d + 1);
+                        pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
+                        if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) ok = false;
+                    }
+                    Walk w0, w1;
+                    Emit E0, E1;
+                    E0.n_err = E1.n_err = 0; E0.err_first = E1.err_first = 0;
+                    w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
+                    int strand0 = 0, strand1 = 0, hap = 0;
+                    if (ok) {
+                        const uint4 b1 = draw_block(key, kStPair, 0, 1);
+                        hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
+                        strand0 = P.read_one_strand == 0 ? ((b1.y >> 31) ? 0 : 1) : (P.read_one_strand == 1 ? 0 : 1);
+                        if (P.strandedness == 0) strand1 = (P.data_type == 0) ? 1 - strand0 : strand0;
+                        else strand1 = (P.strandedness == 1) ? strand0 : 1 - strand0;
+                        int st0, st1 = 0;
+                        const int last = cv.len - 1;
+                        if (s1 > 0) {                                             // src/dwgsim.c:745-810
+                            if (strand0 == strand1) {
+                                if (strand0 == 0) { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d - 1 : pos + d - s0); st1 = pos; }
+                                else { st0 = pos + s0 - 1; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
+                            } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
+                            else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
+                        } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
+                        // start the DRAM accesses of both ends before walking the first one
+                        prefetch_read(cv, st0, strand0, s0);
+                        int hint1 = -1;
+                        if (s1 > 0) { prefetch_read(cv, st1, strand1, s1); hint1 = walk_hint(cv, hap, st1, strand1); }
+                        const int hint0 = walk_hint(cv, hap, st0, strand0);
+                        emit_begin(E0, dst0, s0, solid, !ion, T, key, 0);
+                        ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0, hint0);
+                        if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
+                        if (s1 > 0) {
+                            bool ok1 = false;
+                            if (ok) {                                              // a rejected end 0 already rejects the pair
+                                emit_begin(E1, dst1, s1, solid, !ion, T, key, 1);
+                                ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1);
+                                if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
+                            }
+                            ok = ok && ok1;
+                        } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; E1.n_err = 0; E1.err_first = 0; }
+                    }
+                    if (!ok) {                                                    // src/dwgsim.c:833-842
+                        ++failed_total;
+                        if (attempt >= (uint32_t)kMaxTrials) {                    // 10001 rejected attempts: the host reports it
+                            atomicOr(status, 1ull);
+                            q_random[atomicAdd(&n_random, 1)] = make_uint2((uint32_t)p, attempt | (1u << 16));
+                        } else q_retry[atomicAdd(&n_retry, 1)] = make_uint2((uint32_t)p, attempt + 1u);
+                    } else {
+                        rec.flags = (uint8_t)((strand0 ? kRecStrand0 : 0) | (strand1 ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0));
+                        rec.pos[0] = (uint32_t)(w0.ext + 1); rec.pos[1] = (uint32_t)(w1.ext + 1);
+                        rec.len[0] = (uint16_t)s0; rec.len[1] = (uint16_t)s1;
+                        rec.n_sub[0] = (uint16_t)w0.n_sub; rec.n_sub[1] = (uint16_t)w1.n_sub;
+                        rec.n_indel[0] = (uint16_t)w0.n_indel; rec.n_indel[1] = (uint16_t)w1.n_indel;
+                        rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
+                        rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
+                        rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
+                        if constexpr (kIon) {                                       // flow-space errors, src/dwgsim.c:861-864
+#pragma unroll 1
+                            for (int j = 0; j < 2; ++j) {
+                                const int s = j ? s1 : s0;
+                                if (s <= 0) continue;
+                                int nerr = 0, ovf = 0;
+                                FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
+                                const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_thr[j], T.flow_order,
+                                                                  P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
+                                if (ovf) atomicOr(status, 2ull);
+                                rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);
+                                rec.n_err[j] = (uint16_t)nerr;
+                            }
+                        }
+                        recs[p] = rec;
+                        staged = p;
+                    }
                 }
             }
         }
-        recs[p] = rec;
-        }
-        // flush the staging tile: rows of this CTA's pairs are contiguous in HBM (pair-major, NW words per pair)
+        row_pair[threadIdx.x] = staged;
+        // flush the staged rows (pair-major in HBM, NW words per pair); rows of one fresh round are contiguous there
         __syncthreads();
-        const int np = min(kTpThreads, n - pbase);
-        uint32_t *out = seqw + (size_t)pbase * NW;
         // tile index of linear word x is x + (x / NW) * (RS - NW); x / NW by a multiply-high with P.inv_nw = 2^32/NW + 1
-        for (int x = threadIdx.x; x < np * NW; x += kTpThreads) out[x] = tile[x + (int)__umulhi((uint32_t)x, P.inv_nw) * (RS - NW)];
+        for (int x = threadIdx.x; x < kTpThreads * NW; x += kTpThreads) {
+            const int r = (int)__umulhi((uint32_t)x, P.inv_nw), dp = row_pair[r];
+            if (dp >= 0) seqw[(size_t)dp * NW + (x - r * NW)] = tile[x + r * (RS - NW)];
+        }
         __syncthreads();
     }
     if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
@@ -1315,7 +1383,7 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     FormatSmem L;
     const int TP = P.tile_pairs;
     int o = 0;
-    L.guide_off = o; o += 2048 * 4;
+    L.guide_off = o; o += 1024 * 8;
     L.cdf_off = o; o += ((P.qdelta_n > 0 && P.qdelta_n <= 512 ? P.qdelta_n : 0) * 4 + 15) & ~15;
     for (int e = 0; e < 2; ++e) { L.qbase_off[e] = o; o += (P.cap[e] + 16) & ~15; }
     L.meta_off = o; o += (TP * (int)sizeof(TileMeta) + 15) & ~15;
@@ -1326,18 +1394,36 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     return L;
 }
 
-// quality noise: inverse CDF through a 2048-bucket guide.  An entry holds the rank at the bucket's lower bound
-// (bits 24-31) and, when exactly one threshold lies inside the 2^21-wide bucket, its offset (bits 0-21; 2^21 = none):
-// one shared-memory load and one compare.  Bit 23 marks buckets with several thresholds (the tails): scan.
-__device__ __forceinline__ int qdelta_rank(const uint32_t *guide, const uint32_t *cdf, int n, uint32_t u)
+// ---- explicit shared-memory accesses (32-bit shared-window addresses; the staging areas are selected at run time, and a
+// generic pointer there would turn every byte store into a 64-bit generic ST) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a)
 {
-    const uint32_t ent = guide[u >> 21];
-    int j = (int)(ent >> 24);
-    if (ent & 0x800000u) { while (j < n && u >= cdf[j]) ++j; }
-    else j += (u & 0x1FFFFFu) >= (ent & 0x3FFFFFu);
-    return j;
+    uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v;
+}
+template <int kOff>
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOff) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// quality noise: inverse CDF through a 1024-bucket guide.  An entry {t, r} holds the rank r at the bucket's lower bound
+// and, when exactly one threshold c lies inside the 2^22-wide bucket, t = c - 1 (no threshold: t = 2^32 - 1): one 8-byte
+// shared-memory load and one compare.  r < 0 marks buckets with several thresholds (the tails), t = their number: the
+// scan starts from the side of the bucket where the probability mass is (top of a lower-tail bucket, bottom of an upper).
+__device__ __forceinline__ int qdelta_rank(uint32_t guide_addr, const uint32_t *cdf, uint32_t u)
+{
+    const uint2 ent = lds64(guide_addr + ((u >> 22) << 3));
+    int j = (int)ent.y;
+    if (j < 0) {
+        const int r = j & 0x7fffffff, top = r + (int)ent.x;
+        if (!(u >> 31)) { j = top; while (j > r && u < cdf[j - 1]) --j; }
+        else { j = r; while (j < top && u >= cdf[j]) ++j; }
+        return j;
+    }
+    return j + (u > ent.x ? 1 : 0);
 }
 
+template <bool kSolid, bool kWrap>
 __global__ void __launch_bounds__(kFmtThreads)
 format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
                     const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
@@ -1349,26 +1435,28 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
     extern __shared__ __align__(16) uint8_t smem[];
     const FormatSmem L = format_smem_layout(P);
     const int TP = P.tile_pairs, tid = threadIdx.x;
-    uint32_t *guide = reinterpret_cast<uint32_t *>(smem + L.guide_off);
     const bool cdf_in_smem = P.qdelta_n > 0 && P.qdelta_n <= 512;
     uint32_t *cdf_s = reinterpret_cast<uint32_t *>(smem + L.cdf_off);
-    uint8_t *qbase_s[2] = {smem + L.qbase_off[0], smem + L.qbase_off[1]};
     TileMeta *meta = reinterpret_cast<TileMeta *>(smem + L.meta_off);
-    uint8_t *stage[3] = {smem + L.stage_off[0], smem + L.stage_off[1], smem + L.stage_off[2]};
+    const uint32_t a_base = smem_addr(smem);
+    const uint32_t a_guide = a_base + L.guide_off, a_qb0 = a_base + L.qbase_off[0], a_qb1 = a_base + L.qbase_off[1];
+    const uint32_t a_st0 = a_base + L.stage_off[0], a_st1 = a_base + L.stage_off[1], a_st2 = a_base + L.stage_off[2];
     __shared__ int s_shift[3], s_total[3];
 
-    for (int j = tid; j < 2048; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? P.qguide[j] : 0u;
-    if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) cdf_s[j] = P.qdelta_cdf[j];
-    for (int e = 0; e < 2; ++e) for (int j = tid; j < P.cap[e]; j += kFmtThreads) qbase_s[e][j] = P.qbase[e][j];
+    {
+        uint2 *guide = reinterpret_cast<uint2 *>(smem + L.guide_off);
+        for (int j = tid; j < 1024; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? reinterpret_cast<const uint2 *>(P.qguide)[j] : make_uint2(0u, 0u);
+        if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) cdf_s[j] = P.qdelta_cdf[j];
+        for (int j = tid; j < P.cap[0]; j += kFmtThreads) smem[L.qbase_off[0] + j] = P.qbase[0][j];
+        for (int j = tid; j < P.cap[1]; j += kFmtThreads) smem[L.qbase_off[1] + j] = P.qbase[1][j];
+    }
     __syncthreads();
-    const uint32_t *cdf = cdf_in_smem ? cdf_s : P.qdelta_cdf;
 
-    const bool solid = P.data_type == 1;
-    const int from = solid ? 1 : 0;                                 // bwa drops the first colour (src/dwgsim.c:949-953)
+    constexpr bool solid = kSolid;
+    constexpr int from = kSolid ? 1 : 0;                            // bwa drops the first colour (src/dwgsim.c:949-953)
     const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
     const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
-    char *outp[3] = {out0, out1, out2};
-    const bool on[3] = {P.out_bwa != 0, P.out_bwa != 0, P.out_bfast != 0};
+    const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
     const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1, NW = P.nw[0] + P.nw[1];
     const int ntiles = (n + TP - 1) / TP;
 
@@ -1377,10 +1465,12 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
         // ---- phase 0a: per-pair record, serial, offsets -------------------------------------------------
         if (tid < 3) {
             const int k = tid;
-            const uint32_t begin = on[k] ? offs[(size_t)k * n + p0] : 0u;
-            const unsigned long long end = !on[k] ? 0ull : (p0 + np < n ? (unsigned long long)offs[(size_t)k * n + p0 + np] : totals[k]);
-            s_shift[k] = (int)(reinterpret_cast<uintptr_t>(outp[k] + begin) & 15u);
-            s_total[k] = on[k] ? (int)(end - begin) : 0;
+            const bool on = k == 2 ? on2 : on0;
+            char *outk = k == 0 ? out0 : (k == 1 ? out1 : out2);
+            const uint32_t begin = on ? offs[(size_t)k * n + p0] : 0u;
+            const unsigned long long end = !on ? 0ull : (p0 + np < n ? (unsigned long long)offs[(size_t)k * n + p0 + np] : totals[k]);
+            s_shift[k] = (int)(reinterpret_cast<uintptr_t>(outk + begin) & 15u);
+            s_total[k] = on ? (int)(end - begin) : 0;
         }
         __syncthreads();
         if (tid < np) {
@@ -1394,7 +1484,9 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
             m.serial = serial[p];
             m.cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
             m.cname_len = cd->name_len;
-            for (int k = 0; k < 3; ++k) m.so[k] = on[k] ? offs[(size_t)k * n + p] - offs[(size_t)k * n + p0] + (uint32_t)s_shift[k] : 0u;
+            m.so[0] = on0 ? offs[p] - offs[p0] + (uint32_t)s_shift[0] : 0u;
+            m.so[1] = on0 ? offs[(size_t)n + p] - offs[(size_t)n + p0] + (uint32_t)s_shift[1] : 0u;
+            m.so[2] = on2 ? offs[(size_t)2 * n + p] - offs[(size_t)2 * n + p0] + (uint32_t)s_shift[2] : 0u;
             m.lo = (uint32_t)gidx; m.hi = (uint32_t)(gidx >> 32);
             m.nfull = gname_len[(size_t)p * 2]; m.nbwa = gname_len[(size_t)p * 2 + 1];
         }
@@ -1412,66 +1504,83 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
             const uint32_t a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu), a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
             uint32_t d_lo = a_lo, d_hi = a_hi;
             if (solid) { d_lo = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d_hi = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
-            // qualities, src/dwgsim.c:899-918 (char arithmetic there; emulated with an int8 wrap)
+            // qualities, src/dwgsim.c:899-918 (char arithmetic there; emulated with an int8 wrap where it can matter)
             uint32_t q_lo = 0, q_hi = 0;
             if (P.fixed_quality) { q_lo = q_hi = 0x01010101u * (uint32_t)P.fixed_quality; }
             else {
                 const PairKey key{P.seed, m.lo, m.hi, (uint32_t)m.rec.attempt};
                 uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
                 if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); if (cnt > 4) b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
-                const uint2 qb8 = *reinterpret_cast<const uint2 *>(qbase_s[e] + k0);   // k0 is a multiple of 8
+                const uint2 qb8 = lds64((e ? a_qb1 : a_qb0) + k0);           // k0 is a multiple of 8
+                const int qk = 33 + P.qdelta_lo;
+                const uint32_t *cdf = cdf_in_smem ? cdf_s : P.qdelta_cdf;     // only the tail buckets look at it
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    int qc = 33 + (int)(((i < 4 ? qb8.x : qb8.y) >> (8 * (i & 3))) & 0xFFu);
+                    int qc = (int)__byte_perm(i < 4 ? qb8.x : qb8.y, 0u, 0x4440 + (i & 3));
                     if (P.qdelta_n > 0) {
-                        const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
-                        qc = (int)(signed char)((qc + P.qdelta_lo + qdelta_rank(guide, cdf, P.qdelta_n, u)) & 0xFF);
-                    }
-                    qc = qc < 33 ? 33 : (qc > 73 ? 73 : qc);
+                        qc += qk + qdelta_rank(a_guide, cdf, word_of(i < 4 ? b0 : b1, i & 3));
+                        if (kWrap) qc = (int)(signed char)(qc & 0xFF);
+                    } else qc += 33;
+                    qc = max(33, min(73, qc));
                     if (i < 4) q_lo |= (uint32_t)qc << (8 * i); else q_hi |= (uint32_t)qc << (8 * (i - 4));
                 }
             }
-            // write into the records
+            // write into the records: predicated byte stores at fixed offsets from four section pointers
             const int len0 = m.rec.len[0];
-            const int rec0 = (P.out_bfast && len0 > 0) ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-            uint8_t *sb = stage[e] + m.so[e];
-            uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
+            const int rec0 = (on2 && len0 > 0) ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
+            const uint32_t sb = (e ? a_st1 : a_st0) + m.so[e];
+            const uint32_t sf = a_st2 + m.so[2] + (e ? rec0 : 0);
             const int me = Le - from;
-            const int bwa_seq = m.nbwa + 3 - from, bwa_qual = m.nbwa + 3 + me + 3 - from;   // index by k
-            const int bf_seq = m.nfull + 1 + (solid ? 1 : 0), bf_qual = bf_seq + Le + 3;
+            const uint32_t ps_b = sb + m.nbwa + 3 - from + k0, pq_b = ps_b + me + 3;           // bwa: sequence, qualities
+            const uint32_t ps_f = sf + m.nfull + 1 + (solid ? 1 : 0) + k0, pq_f = ps_f + Le + 3;   // bfast
+            const bool skip0 = solid && k0 == 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (i >= cnt) break;
-                const int k = k0 + i;
-                const uint8_t ch = (uint8_t)((i < 4 ? a_lo : a_hi) >> (8 * (i & 3)));
-                const uint8_t dg = (uint8_t)((i < 4 ? d_lo : d_hi) >> (8 * (i & 3)));
-                const uint8_t qc = (uint8_t)((i < 4 ? q_lo : q_hi) >> (8 * (i & 3)));
-                if (P.out_bwa && k >= from) { sb[bwa_seq + k] = ch; sb[bwa_qual + k] = qc; }
-                if (P.out_bfast) { sf[bf_seq + k] = dg; sf[bf_qual + k] = qc; }
+                const uint32_t ch = (i < 4 ? a_lo : a_hi) >> (8 * (i & 3)), dg = (i < 4 ? d_lo : d_hi) >> (8 * (i & 3));
+                const uint32_t qc = (i < 4 ? q_lo : q_hi) >> (8 * (i & 3));
+                const bool in = i < cnt;
+                if (on0 && in && !(i == 0 && skip0)) {
+                    switch (i) {      // the offset is part of the instruction
+                        case 0: sts8<0>(ps_b, ch); sts8<0>(pq_b, qc); break; case 1: sts8<1>(ps_b, ch); sts8<1>(pq_b, qc); break;
+                        case 2: sts8<2>(ps_b, ch); sts8<2>(pq_b, qc); break; case 3: sts8<3>(ps_b, ch); sts8<3>(pq_b, qc); break;
+                        case 4: sts8<4>(ps_b, ch); sts8<4>(pq_b, qc); break; case 5: sts8<5>(ps_b, ch); sts8<5>(pq_b, qc); break;
+                        case 6: sts8<6>(ps_b, ch); sts8<6>(pq_b, qc); break; default: sts8<7>(ps_b, ch); sts8<7>(pq_b, qc); break;
+                    }
+                }
+                if (on2 && in) {
+                    switch (i) {
+                        case 0: sts8<0>(ps_f, dg); sts8<0>(pq_f, qc); break; case 1: sts8<1>(ps_f, dg); sts8<1>(pq_f, qc); break;
+                        case 2: sts8<2>(ps_f, dg); sts8<2>(pq_f, qc); break; case 3: sts8<3>(ps_f, dg); sts8<3>(pq_f, qc); break;
+                        case 4: sts8<4>(ps_f, dg); sts8<4>(pq_f, qc); break; case 5: sts8<5>(ps_f, dg); sts8<5>(pq_f, qc); break;
+                        case 6: sts8<6>(ps_f, dg); sts8<6>(pq_f, qc); break; default: sts8<7>(ps_f, dg); sts8<7>(pq_f, qc); break;
+                    }
+                }
             }
         }
         // ---- phase 2: names (one thread per record and 16-byte chunk), suffixes and separators -----------------
         {
             const int nchunks = L.name_cap >> 4;
             for (int it = tid; it < np * 4 * nchunks; it += kFmtThreads) {
-                const int c = it % nchunks, rc = it / nchunks, t = rc >> 2, rr = rc & 3, e = rr & 1, bf = rr >> 1;
+                const int rc = (int)__umulhi((uint32_t)it, P.inv_name_chunks), c = it - rc * nchunks, t = rc >> 2, rr = rc & 3, e = rr & 1, bf = rr >> 1;
                 const TileMeta &m = meta[t];
                 const int Le = m.rec.len[e];
-                if (Le <= 0 || (bf ? !P.out_bfast : !P.out_bwa)) continue;
+                if (Le <= 0 || (bf ? !on2 : !on0)) continue;
                 const int nn = bf ? m.nfull : m.nbwa, x0 = c << 4;
                 if (x0 >= nn) continue;
                 const int len0 = m.rec.len[0];
                 const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-                uint8_t *dstb = bf ? stage[2] + m.so[2] + (e ? rec0 : 0) : stage[e] + m.so[e];
+                const uint32_t d = (bf ? a_st2 + m.so[2] + (e ? rec0 : 0) : (e ? a_st1 : a_st0) + m.so[e]) + x0;
                 const char *nm = gnames + ((size_t)(p0 + t) * nvar + (bf ? 0 : nvar - 1)) * L.name_cap;
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nm + x0));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                if (x0 + 16 <= nn) {
+                const int left = nn - x0;
 #pragma unroll
-                    for (int b = 0; b < 16; ++b) dstb[x0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) if (x0 + b < nn) dstb[x0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+                for (int b4 = 0; b4 < 4; ++b4) {
+                    const uint32_t x = w[b4];
+                    if (4 * b4 + 0 < left) sts8(d + 4 * b4, x);
+                    if (4 * b4 + 1 < left) sts8(d + 4 * b4 + 1, x >> 8);
+                    if (4 * b4 + 2 < left) sts8(d + 4 * b4 + 2, x >> 16);
+                    if (4 * b4 + 3 < left) sts8(d + 4 * b4 + 3, x >> 24);
                 }
             }
             for (int it = tid; it < np * 4; it += kFmtThreads) {
@@ -1480,23 +1589,22 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 const int Le = m.rec.len[e];
                 if (Le <= 0) continue;
                 if (!bf) {
-                    if (!P.out_bwa) continue;
-                    uint8_t *sb = stage[e] + m.so[e];
-                    const int nn = m.nbwa, me = Le - from;
-                    sb[nn] = '/'; sb[nn + 1] = (uint8_t)(solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sb[nn + 2] = '\n';
-                    sb[nn + 3 + me] = '\n'; sb[nn + 3 + me + 1] = '+'; sb[nn + 3 + me + 2] = '\n';
-                    sb[nn + 3 + me + 3 + me] = '\n';
+                    if (!on0) continue;
+                    const uint32_t sb = (e ? a_st1 : a_st0) + m.so[e] + m.nbwa;
+                    const int me = Le - from;
+                    sts8(sb, '/'); sts8(sb + 1, solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sts8(sb + 2, '\n');
+                    sts8(sb + 3 + me, '\n'); sts8(sb + 3 + me + 1, '+'); sts8(sb + 3 + me + 2, '\n');
+                    sts8(sb + 3 + me + 3 + me, '\n');
                 } else {
-                    if (!P.out_bfast) continue;
+                    if (!on2) continue;
                     const int len0 = m.rec.len[0];
                     const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-                    uint8_t *sf = stage[2] + m.so[2] + (e ? rec0 : 0);
-                    const int nn = m.nfull;
-                    sf[nn] = '\n';
-                    int o = nn + 1;
-                    if (solid) sf[o++] = 'A';
-                    sf[o + Le] = '\n'; sf[o + Le + 1] = '+'; sf[o + Le + 2] = '\n';
-                    sf[o + Le + 3 + Le] = '\n';
+                    uint32_t sf = a_st2 + m.so[2] + (e ? rec0 : 0) + m.nfull;
+                    sts8(sf, '\n');
+                    sf += 1;
+                    if (solid) { sts8(sf, 'A'); sf += 1; }
+                    sts8(sf + Le, '\n'); sts8(sf + Le + 1, '+'); sts8(sf + Le + 2, '\n');
+                    sts8(sf + Le + 3 + Le, '\n');
                 }
             }
         }
@@ -1508,15 +1616,17 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
             if (total <= 0) continue;
             const int shift = s_shift[k];
             const uint32_t begin = offs[(size_t)k * n + p0];
-            char *base = outp[k] + begin - shift;                       // 16-byte aligned
-            const uint8_t *st = stage[k];
+            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin - shift;   // 16-byte aligned
+            const uint8_t *st = smem + L.stage_off[k];
             const int end = shift + total, nchunk = (end + 15) >> 4;
-            for (int c = tid; c < nchunk; c += kFmtThreads) {
-                const int lo = c << 4;
-                if (lo >= shift && lo + 16 <= end) {
-                    *reinterpret_cast<uint4 *>(base + lo) = *reinterpret_cast<const uint4 *>(st + lo);
-                } else {
-                    const int a = lo > shift ? lo : shift, b = lo + 16 < end ? lo + 16 : end;
+            const int c_first = shift ? 1 : 0, c_full = end >> 4;       // chunks [c_first, c_full) lie wholly inside the tile's range
+            const uint4 *src = reinterpret_cast<const uint4 *>(st);
+            uint4 *dst = reinterpret_cast<uint4 *>(base);
+            for (int c = c_first + tid; c < c_full; c += kFmtThreads) dst[c] = src[c];
+            if (tid < 2) {                                              // the two boundary chunks shared with the neighbouring tiles
+                const int c = tid ? c_full : 0;
+                if ((tid == 0 && c_first) || (tid == 1 && c_full < nchunk && (c_full > 0 || !c_first))) {
+                    const int lo = c << 4, a = lo > shift ? lo : shift, b = lo + 16 < end ? lo + 16 : end;
                     for (int x = a; x < b; ++x) base[x] = (char)st[x];
                 }
             }

@@ -88,6 +88,8 @@ struct SimParams {
     uint64_t thr_genomic, thr_hap0;
     int32_t  isize_lo, isize_n;
     int32_t  qdelta_lo, qdelta_n;
+    int32_t  q_wrap;                           // the quality sum can leave the int8 range (emulate the reference's char arithmetic)
+    uint32_t inv_name_chunks;                  // 2^32 / (name_cap / 16) + 1
     int32_t  fixed_quality, out_bwa, out_bfast;
     int32_t  prefix_len;                       // strlen(read_prefix)+1 ("pfx_"), 0 if none
     int32_t  flow_order_len;
@@ -100,7 +102,7 @@ struct SimParams {
     int32_t  rec_cap[3];                       // upper bound of a pair's bytes per output stream
     // device tables
     const uint32_t *isize_cdf, *qdelta_cdf;
-    const uint32_t *qguide;                    // [2048] one-load guide into qdelta_cdf (see qdelta_rank)
+    const uint32_t *qguide;                    // [1024][2] one-load guide into qdelta_cdf (see qdelta_rank)
     const uint16_t *isize_guide, *gap_guide[2]; // [1025] the same for isize_cdf and err_gap[end] (first len[end] entries)
     const uint32_t *err_gap[2], *err_acc[2];   // substitution errors by thinning (DESIGN.md "RNG addressing")
     const uint8_t  *qbase[2];
