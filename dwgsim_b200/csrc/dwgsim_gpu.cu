@@ -302,7 +302,7 @@ int upload_tables(dwgsim_gpu *h)
     s.out_bwa = p.reads_output_type != 2; s.out_bfast = p.reads_output_type != 1;
     s.prefix_len = (int32_t)h->prefix_s.size();
     s.flow_order_len = p.flow_order_len;
-    s.tile_pairs = 32;
+    s.tile_pairs = 4;
     s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide;
     s.isize_guide = h->dt.isize_guide; s.gap_guide[0] = h->dt.gap_guide[0]; s.gap_guide[1] = h->dt.gap_guide[1];
     s.inv_nw = (uint32_t)(4294967296.0 / std::max(s.nw[0] + s.nw[1], 1)) + 1u;
@@ -453,13 +453,11 @@ int update_caps(dwgsim_gpu *h)
     h->sp.name_cap = (int32_t)((name_cap_of(h) + 15) & ~15ull);
     h->sp.inv_name_chunks = (uint32_t)(4294967296.0 / std::max(h->sp.name_cap >> 4, 1)) + 1u;
     for (int k = 0; k < 3; ++k) h->sp.rec_cap[k] = (int32_t)cap[k];
-    // tile of the format kernel: as many pairs as fit ~110 KB of shared memory (two CTAs per SM), at most 32
-    // tile of the format kernel: 32 pairs (measured best for 2x150: 56 KB of staging, 4 CTAs per SM), halved for long
-    // reads until at least two CTAs fit an SM; DWGSIM_TILE_PAIRS overrides it for experiments
-    h->sp.tile_pairs = 32;
+    // mini-tile of the format kernel: pairs per warp, as many as keep two 16-warp CTAs on an SM (<= 113 KB each), at most 4
+    // (2x150: 4 pairs = 152 eight-base groups = 4.75 rounds of the warp); DWGSIM_TILE_PAIRS overrides it for experiments
+    h->sp.tile_pairs = 4;
     if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(32, atoi(e)));
-    else while (h->sp.tile_pairs > 24 && format_smem_layout(h->sp).total > 56 * 1024) --h->sp.tile_pairs;   // 4 CTAs per SM
-    while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 110 * 1024) h->sp.tile_pairs >>= 1;
+    while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 113 * 1024) --h->sp.tile_pairs;
     const FormatSmem L = format_smem_layout(h->sp);
     if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
     CUDA_TRY(h, cudaFuncSetAttribute(format_kernel_of(h->sp), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -685,7 +683,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
-    const int ntiles = (n + sp.tile_pairs - 1) / sp.tile_pairs;
+    const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + kFmtWarps - 1) / kFmtWarps;    // CTAs that have a mini-tile per warp
     int occ_f = 1;
     const format_kernel_t fmt = format_kernel_of(sp);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fmt, kFmtThreads, smem_b);

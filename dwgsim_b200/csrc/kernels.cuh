@@ -1349,48 +1349,47 @@ layout_offsets_kernel(int n, const unsigned long long *__restrict__ blk_len_excl
 }
 
 // ---- kernel B: format ------------------------------------------------------------------------------------
-// A CTA formats a tile of consecutive pairs.  The records of consecutive pairs are contiguous in each output
-// stream, so the tile owns ONE contiguous byte range per stream: it is assembled in shared memory at the same
-// offset modulo 16 as its destination and copied out with aligned 16-byte stores (byte stores only in the two
-// boundary chunks shared with the neighbouring tiles).  Work inside the tile is flattened over the threads:
-//   phase 0  one thread per pair: load the pair's record, serial, stream offsets and name lengths (the names
-//            themselves, src/dwgsim.c:923-929, were written by layout_lengths_kernel)
-//   phase 1  one thread per (pair, end, 8-base group), consecutive lanes = consecutive groups: 8 bases -> ASCII
-//            with two PRMTs, 8 qualities from two Philox blocks (src/dwgsim.c:899-918), written into the bwa and
-//            bfast records (src/dwgsim.c:920-980)
-//   phase 2  one thread per record: name, "/1", separators
-//   phase 3  all threads: 16-byte copy-out
+// Every WARP formats its own mini-tiles of P.tile_pairs consecutive pairs, independently of the other warps of the CTA
+// (no CTA barrier after the prologue; the warps only share the read-only sampling tables).  The records of consecutive
+// pairs are contiguous in each output stream, so a mini-tile owns ONE contiguous byte range per stream: it is
+// assembled in the warp's shared-memory region at the same offset modulo 16 as its destination and copied out with
+// aligned 16-byte stores (byte stores only in the two boundary chunks shared with the neighbouring mini-tiles).
+//   step 0  lanes 0..np: the pair's record, stream offsets and name lengths, prefetched one mini-tile ahead (the names
+//           themselves, src/dwgsim.c:923-929, were written by layout_lengths_kernel)
+//   step 1  one lane per (pair, end, 8-base group), consecutive lanes = consecutive groups: 8 bases -> ASCII with two
+//           PRMTs, 8 qualities from two Philox blocks (src/dwgsim.c:899-918), written into the bwa and bfast records
+//           (src/dwgsim.c:920-980)
+//   step 2  one lane per record and 16-byte name chunk; "/1", separators
+//   step 3  16-byte copy-out
 
-constexpr int kFmtThreads = 256;
+constexpr int kFmtThreads = 512;
+constexpr int kFmtWarps = kFmtThreads / 32;
 
-
-struct TileMeta {                      // per pair, in shared memory
-    PairRec rec;
-    unsigned long long serial;
-    const char *cname;
-    uint32_t so[3];                    // start of the pair's bytes in each stream's staging buffer
-    uint32_t cname_len;
-    uint32_t lo, hi;                   // Philox counter words of the pair
+struct PairMeta {                      // per pair of the warp's mini-tile, in shared memory (32 bytes)
+    uint32_t so[3];                    // start of the pair's bytes in each stream's staging area
+    uint16_t len[2];                   // read lengths
     uint16_t nfull, nbwa;              // name lengths: bfast (full counts) and bwa variant
-    uint32_t pad;
+    uint32_t attempt;
+    uint32_t pad[2];
 };
 
 struct FormatSmem {
-    int guide_off, cdf_off, qbase_off[2], meta_off, names_off, stage_off[3], name_cap, total;
+    int guide_off, cdf_off, qbase_off[2], warp_off, warp_stride, meta_off, stage_off[3], total;   // meta/stage: inside a warp's region
 };
 __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
 {
     FormatSmem L;
-    const int TP = P.tile_pairs;
+    const int WP = P.tile_pairs;
     int o = 0;
     L.guide_off = o; o += 1024 * 8;
     L.cdf_off = o; o += ((P.qdelta_n > 0 && P.qdelta_n <= 512 ? P.qdelta_n : 0) * 4 + 15) & ~15;
     for (int e = 0; e < 2; ++e) { L.qbase_off[e] = o; o += (P.cap[e] + 16) & ~15; }
-    L.meta_off = o; o += (TP * (int)sizeof(TileMeta) + 15) & ~15;
-    L.name_cap = P.name_cap;
-    L.names_off = o;
-    for (int k = 0; k < 3; ++k) { L.stage_off[k] = o; o += (TP * P.rec_cap[k] + 32 + 15) & ~15; }
-    L.total = o;
+    L.warp_off = o;
+    int w = 0;
+    L.meta_off = w; w += WP * (int)sizeof(PairMeta);
+    for (int k = 0; k < 3; ++k) { L.stage_off[k] = w; w += (WP * P.rec_cap[k] + 32 + 15) & ~15; }
+    L.warp_stride = w;
+    L.total = o + kFmtWarps * w;
     return L;
 }
 
@@ -1402,29 +1401,39 @@ __device__ __forceinline__ uint2 lds64(uint32_t a)
 {
     uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 template <int kOff>
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOff) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// a value the compiler must keep in an ordinary register (uniform registers do not survive the divergent code around
+// the table lookups, and rebuilding a shared-window address costs four instructions each time)
+__device__ __forceinline__ uint32_t in_register(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 
 // quality noise: inverse CDF through a 1024-bucket guide.  An entry {t, r} holds the rank r at the bucket's lower bound
 // and, when exactly one threshold c lies inside the 2^22-wide bucket, t = c - 1 (no threshold: t = 2^32 - 1): one 8-byte
 // shared-memory load and one compare.  r < 0 marks buckets with several thresholds (the tails), t = their number: the
 // scan starts from the side of the bucket where the probability mass is (top of a lower-tail bucket, bottom of an upper).
-__device__ __forceinline__ int qdelta_rank(uint32_t guide_addr, const uint32_t *cdf, uint32_t u)
+__device__ __noinline__ int qdelta_rank_tail(uint2 ent, const uint32_t *cdf, uint32_t u)
 {
-    const uint2 ent = lds64(guide_addr + ((u >> 22) << 3));
-    int j = (int)ent.y;
-    if (j < 0) {
-        const int r = j & 0x7fffffff, top = r + (int)ent.x;
-        if (!(u >> 31)) { j = top; while (j > r && u < cdf[j - 1]) --j; }
-        else { j = r; while (j < top && u >= cdf[j]) ++j; }
-        return j;
-    }
-    return j + (u > ent.x ? 1 : 0);
+    const int r = (int)(ent.y & 0x7fffffffu), top = r + (int)ent.x;
+    int j;
+    if (!(u >> 31)) { j = top; while (j > r && u < cdf[j - 1]) --j; }
+    else { j = r; while (j < top && u >= cdf[j]) ++j; }
+    return j;
 }
 
+struct FmtPrefetch {                   // step 0 of a mini-tile, held in registers by lane j for pair j (lane np: end offsets)
+    uint32_t lens, tail;               // PairRec words 2 (len[0] | len[1] << 16) and 7 (n_err_first, flags, attempt << 16)
+    uint32_t off[3];                   // byte offset of the pair's records in each stream (lane np: end of the mini-tile)
+    uint32_t nl;                       // name lengths: nfull | nbwa << 16
+};
+
 template <bool kSolid, bool kWrap>
-__global__ void __launch_bounds__(kFmtThreads)
+__global__ void __launch_bounds__(kFmtThreads, 2)
 format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
                     const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
                     const unsigned long long *__restrict__ serial, const uint32_t *__restrict__ offs /* [3][n] */,
@@ -1434,99 +1443,127 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const FormatSmem L = format_smem_layout(P);
-    const int TP = P.tile_pairs, tid = threadIdx.x;
+    const int WP = P.tile_pairs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool cdf_in_smem = P.qdelta_n > 0 && P.qdelta_n <= 512;
-    uint32_t *cdf_s = reinterpret_cast<uint32_t *>(smem + L.cdf_off);
-    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + L.meta_off);
-    const uint32_t a_base = smem_addr(smem);
-    const uint32_t a_guide = a_base + L.guide_off, a_qb0 = a_base + L.qbase_off[0], a_qb1 = a_base + L.qbase_off[1];
-    const uint32_t a_st0 = a_base + L.stage_off[0], a_st1 = a_base + L.stage_off[1], a_st2 = a_base + L.stage_off[2];
-    __shared__ int s_shift[3], s_total[3];
-
+    const uint32_t *cdf = cdf_in_smem ? reinterpret_cast<const uint32_t *>(smem + L.cdf_off) : P.qdelta_cdf;   // tails only
     {
         uint2 *guide = reinterpret_cast<uint2 *>(smem + L.guide_off);
         for (int j = tid; j < 1024; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? reinterpret_cast<const uint2 *>(P.qguide)[j] : make_uint2(0u, 0u);
-        if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) cdf_s[j] = P.qdelta_cdf[j];
+        if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) reinterpret_cast<uint32_t *>(smem + L.cdf_off)[j] = P.qdelta_cdf[j];
         for (int j = tid; j < P.cap[0]; j += kFmtThreads) smem[L.qbase_off[0] + j] = P.qbase[0][j];
         for (int j = tid; j < P.cap[1]; j += kFmtThreads) smem[L.qbase_off[1] + j] = P.qbase[1][j];
     }
-    __syncthreads();
+    __syncthreads();                                                 // the only CTA-wide barrier
+    const uint32_t a_base = in_register(smem_addr(smem));
+    const uint32_t a_guide = a_base + L.guide_off, a_qb0 = a_base + L.qbase_off[0], a_qb1 = a_base + L.qbase_off[1];
+    const uint32_t a_warp = a_base + L.warp_off + warp * L.warp_stride;
+    const uint32_t a_meta = a_warp + L.meta_off;
+    const uint32_t a_st0 = a_warp + L.stage_off[0], a_st1 = a_warp + L.stage_off[1], a_st2 = a_warp + L.stage_off[2];
+    PairMeta *meta = reinterpret_cast<PairMeta *>(smem + L.warp_off + warp * L.warp_stride + L.meta_off);
+    (void)a_meta; (void)blob; (void)serial;
 
     constexpr bool solid = kSolid;
     constexpr int from = kSolid ? 1 : 0;                            // bwa drops the first colour (src/dwgsim.c:949-953)
     const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
-    const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
     const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
     const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1, NW = P.nw[0] + P.nw[1];
-    const int ntiles = (n + TP - 1) / TP;
+    const int ntiles = (n + WP - 1) / WP;
+    const int tstride = gridDim.x * kFmtWarps;
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int p0 = tile * TP, np = min(TP, n - p0);
-        // ---- phase 0a: per-pair record, serial, offsets -------------------------------------------------
-        if (tid < 3) {
-            const int k = tid;
-            const bool on = k == 2 ? on2 : on0;
+    auto prefetch = [&](int tile) {
+        FmtPrefetch f;
+        f.lens = f.tail = 0; f.off[0] = f.off[1] = f.off[2] = 0; f.nl = 0;
+        if (tile >= ntiles) return f;
+        const int p0 = tile * WP, np = min(WP, n - p0), p = p0 + lane;
+        if (lane < np) {
+            const uint32_t *r = reinterpret_cast<const uint32_t *>(recs + p);
+            f.lens = __ldg(r + 2); f.tail = __ldg(r + 7);
+            f.nl = __ldg(reinterpret_cast<const uint32_t *>(gname_len) + p);
+        }
+        if (lane <= np) {
+            if (on0) { f.off[0] = p < n ? __ldg(offs + p) : (uint32_t)totals[0]; f.off[1] = p < n ? __ldg(offs + (size_t)n + p) : (uint32_t)totals[1]; }
+            if (on2) f.off[2] = p < n ? __ldg(offs + (size_t)2 * n + p) : (uint32_t)totals[2];
+        }
+        return f;
+    };
+
+    int tile = blockIdx.x * kFmtWarps + warp;
+    FmtPrefetch cur = prefetch(tile);
+    for (; tile < ntiles; tile += tstride) {
+        const FmtPrefetch nxt = prefetch(tile + tstride);
+        const int p0 = tile * WP, np = min(WP, n - p0);
+        // ---- step 0: geometry of the mini-tile ---------------------------------------------------------------
+        uint32_t begin[3], shift[3], total[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            begin[k] = __shfl_sync(0xffffffffu, cur.off[k], 0);
+            total[k] = __shfl_sync(0xffffffffu, cur.off[k], np) - begin[k];
             char *outk = k == 0 ? out0 : (k == 1 ? out1 : out2);
-            const uint32_t begin = on ? offs[(size_t)k * n + p0] : 0u;
-            const unsigned long long end = !on ? 0ull : (p0 + np < n ? (unsigned long long)offs[(size_t)k * n + p0 + np] : totals[k]);
-            s_shift[k] = (int)(reinterpret_cast<uintptr_t>(outk + begin) & 15u);
-            s_total[k] = on ? (int)(end - begin) : 0;
+            shift[k] = (uint32_t)(reinterpret_cast<uintptr_t>(outk + begin[k]) & 15u);
         }
-        __syncthreads();
-        if (tid < np) {
-            const int p = p0 + tid;
-            const int64_t q = first + p;
-            int ci;
-            const ContigDesc *cd = find_contig(blob, q, &ci);
-            const uint64_t gidx = (uint64_t)(gidx_origin + q);
-            TileMeta &m = meta[tid];
-            m.rec = recs[p];
-            m.serial = serial[p];
-            m.cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
-            m.cname_len = cd->name_len;
-            m.so[0] = on0 ? offs[p] - offs[p0] + (uint32_t)s_shift[0] : 0u;
-            m.so[1] = on0 ? offs[(size_t)n + p] - offs[(size_t)n + p0] + (uint32_t)s_shift[1] : 0u;
-            m.so[2] = on2 ? offs[(size_t)2 * n + p] - offs[(size_t)2 * n + p0] + (uint32_t)s_shift[2] : 0u;
-            m.lo = (uint32_t)gidx; m.hi = (uint32_t)(gidx >> 32);
-            m.nfull = gname_len[(size_t)p * 2]; m.nbwa = gname_len[(size_t)p * 2 + 1];
+        if (lane < np) {
+            PairMeta m;
+            m.len[0] = (uint16_t)(cur.lens & 0xFFFFu); m.len[1] = (uint16_t)(cur.lens >> 16); m.attempt = cur.tail >> 16;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) m.so[k] = cur.off[k] - begin[k] + shift[k];
+            m.nfull = (uint16_t)(cur.nl & 0xFFFFu); m.nbwa = (uint16_t)(cur.nl >> 16);
+            m.pad[0] = m.pad[1] = 0;
+            meta[lane] = m;
         }
-        __syncthreads();
-        // ---- phase 1: bases and qualities, one thread per (pair, end, 8-base group) -------------------------
-        for (int it = tid; it < np * G; it += kFmtThreads) {
+        __syncwarp();
+        // ---- step 1: bases and qualities, one lane per (pair, end, 8-base group) ----------------------------------
+        for (int it = lane; it < np * G; it += 32) {
             const int t = (int)__umulhi((uint32_t)it, P.inv_groups), gi = it - t * G;
             const int e = gi < g0 ? 0 : 1, g = gi - (e ? g0 : 0);
-            const TileMeta &m = meta[t];
-            const int Le = m.rec.len[e], k0 = g << 3;
+            const PairMeta &m = meta[t];
+            const int Le = m.len[e], k0 = g << 3;
             if (k0 >= Le) continue;
             const int cnt = min(8, Le - k0);
             const uint32_t codes = __ldg(seqw + (size_t)(p0 + t) * NW + (e ? P.nw[0] : 0) + g);
-            // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
-            const uint32_t a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu), a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
-            uint32_t d_lo = a_lo, d_hi = a_hi;
-            if (solid) { d_lo = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d_hi = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
             // qualities, src/dwgsim.c:899-918 (char arithmetic there; emulated with an int8 wrap where it can matter)
             uint32_t q_lo = 0, q_hi = 0;
             if (P.fixed_quality) { q_lo = q_hi = 0x01010101u * (uint32_t)P.fixed_quality; }
             else {
-                const PairKey key{P.seed, m.lo, m.hi, (uint32_t)m.rec.attempt};
+                const uint64_t gidx = (uint64_t)(gidx_origin + first + p0 + t);
+                const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), m.attempt};
                 uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
                 if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); if (cnt > 4) b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
                 const uint2 qb8 = lds64((e ? a_qb1 : a_qb0) + k0);           // k0 is a multiple of 8
-                const int qk = 33 + P.qdelta_lo;
-                const uint32_t *cdf = cdf_in_smem ? cdf_s : P.qdelta_cdf;     // only the tail buckets look at it
+                int qc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qc[i] = 33 + (int)__byte_perm(i < 4 ? qb8.x : qb8.y, 0u, 0x4440 + (i & 3));
+                if (P.qdelta_n > 0) {
+                    uint32_t tails = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {                           // straight-line code: eight loads, eight compares
+                        const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
+                        const uint2 ent = lds64(a_guide + ((u >> 22) << 3));
+                        qc[i] += P.qdelta_lo + (int)ent.y + (u > ent.x ? 1 : 0);
+                        tails |= ent.y;
+                    }
+                    if ((int)tails < 0) {                                   // some draw fell into a tail bucket (rare): redo those
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
+                            const uint2 ent = lds64(a_guide + ((u >> 22) << 3));
+                            if ((int)ent.y < 0) qc[i] += qdelta_rank_tail(ent, cdf, u) - (int)ent.y - (u > ent.x ? 1 : 0);
+                        }
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    int qc = (int)__byte_perm(i < 4 ? qb8.x : qb8.y, 0u, 0x4440 + (i & 3));
-                    if (P.qdelta_n > 0) {
-                        qc += qk + qdelta_rank(a_guide, cdf, word_of(i < 4 ? b0 : b1, i & 3));
-                        if (kWrap) qc = (int)(signed char)(qc & 0xFF);
-                    } else qc += 33;
-                    qc = max(33, min(73, qc));
-                    if (i < 4) q_lo |= (uint32_t)qc << (8 * i); else q_hi |= (uint32_t)qc << (8 * (i - 4));
+                    int v = qc[i];
+                    if (kWrap) v = (int)(signed char)(v & 0xFF);
+                    v = max(33, min(73, v));
+                    if (i < 4) q_lo |= (uint32_t)v << (8 * i); else q_hi |= (uint32_t)v << (8 * (i - 4));
                 }
             }
+            // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
+            const uint32_t a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu), a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
+            uint32_t d_lo = a_lo, d_hi = a_hi;
+            if (solid) { d_lo = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d_hi = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
             // write into the records: predicated byte stores at fixed offsets from four section pointers
-            const int len0 = m.rec.len[0];
+            const int len0 = m.len[0];
             const int rec0 = (on2 && len0 > 0) ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
             const uint32_t sb = (e ? a_st1 : a_st0) + m.so[e];
             const uint32_t sf = a_st2 + m.so[2] + (e ? rec0 : 0);
@@ -1537,40 +1574,40 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t ch = (i < 4 ? a_lo : a_hi) >> (8 * (i & 3)), dg = (i < 4 ? d_lo : d_hi) >> (8 * (i & 3));
-                const uint32_t qc = (i < 4 ? q_lo : q_hi) >> (8 * (i & 3));
+                const uint32_t qv = (i < 4 ? q_lo : q_hi) >> (8 * (i & 3));
                 const bool in = i < cnt;
                 if (on0 && in && !(i == 0 && skip0)) {
                     switch (i) {      // the offset is part of the instruction
-                        case 0: sts8<0>(ps_b, ch); sts8<0>(pq_b, qc); break; case 1: sts8<1>(ps_b, ch); sts8<1>(pq_b, qc); break;
-                        case 2: sts8<2>(ps_b, ch); sts8<2>(pq_b, qc); break; case 3: sts8<3>(ps_b, ch); sts8<3>(pq_b, qc); break;
-                        case 4: sts8<4>(ps_b, ch); sts8<4>(pq_b, qc); break; case 5: sts8<5>(ps_b, ch); sts8<5>(pq_b, qc); break;
-                        case 6: sts8<6>(ps_b, ch); sts8<6>(pq_b, qc); break; default: sts8<7>(ps_b, ch); sts8<7>(pq_b, qc); break;
+                        case 0: sts8<0>(ps_b, ch); sts8<0>(pq_b, qv); break; case 1: sts8<1>(ps_b, ch); sts8<1>(pq_b, qv); break;
+                        case 2: sts8<2>(ps_b, ch); sts8<2>(pq_b, qv); break; case 3: sts8<3>(ps_b, ch); sts8<3>(pq_b, qv); break;
+                        case 4: sts8<4>(ps_b, ch); sts8<4>(pq_b, qv); break; case 5: sts8<5>(ps_b, ch); sts8<5>(pq_b, qv); break;
+                        case 6: sts8<6>(ps_b, ch); sts8<6>(pq_b, qv); break; default: sts8<7>(ps_b, ch); sts8<7>(pq_b, qv); break;
                     }
                 }
                 if (on2 && in) {
                     switch (i) {
-                        case 0: sts8<0>(ps_f, dg); sts8<0>(pq_f, qc); break; case 1: sts8<1>(ps_f, dg); sts8<1>(pq_f, qc); break;
-                        case 2: sts8<2>(ps_f, dg); sts8<2>(pq_f, qc); break; case 3: sts8<3>(ps_f, dg); sts8<3>(pq_f, qc); break;
-                        case 4: sts8<4>(ps_f, dg); sts8<4>(pq_f, qc); break; case 5: sts8<5>(ps_f, dg); sts8<5>(pq_f, qc); break;
-                        case 6: sts8<6>(ps_f, dg); sts8<6>(pq_f, qc); break; default: sts8<7>(ps_f, dg); sts8<7>(pq_f, qc); break;
+                        case 0: sts8<0>(ps_f, dg); sts8<0>(pq_f, qv); break; case 1: sts8<1>(ps_f, dg); sts8<1>(pq_f, qv); break;
+                        case 2: sts8<2>(ps_f, dg); sts8<2>(pq_f, qv); break; case 3: sts8<3>(ps_f, dg); sts8<3>(pq_f, qv); break;
+                        case 4: sts8<4>(ps_f, dg); sts8<4>(pq_f, qv); break; case 5: sts8<5>(ps_f, dg); sts8<5>(pq_f, qv); break;
+                        case 6: sts8<6>(ps_f, dg); sts8<6>(pq_f, qv); break; default: sts8<7>(ps_f, dg); sts8<7>(pq_f, qv); break;
                     }
                 }
             }
         }
-        // ---- phase 2: names (one thread per record and 16-byte chunk), suffixes and separators -----------------
+        // ---- step 2: names (one lane per record and 16-byte chunk), suffixes and separators ----------------------
         {
-            const int nchunks = L.name_cap >> 4;
-            for (int it = tid; it < np * 4 * nchunks; it += kFmtThreads) {
+            const int nchunks = P.name_cap >> 4;
+            for (int it = lane; it < np * 4 * nchunks; it += 32) {
                 const int rc = (int)__umulhi((uint32_t)it, P.inv_name_chunks), c = it - rc * nchunks, t = rc >> 2, rr = rc & 3, e = rr & 1, bf = rr >> 1;
-                const TileMeta &m = meta[t];
-                const int Le = m.rec.len[e];
+                const PairMeta &m = meta[t];
+                const int Le = m.len[e];
                 if (Le <= 0 || (bf ? !on2 : !on0)) continue;
                 const int nn = bf ? m.nfull : m.nbwa, x0 = c << 4;
                 if (x0 >= nn) continue;
-                const int len0 = m.rec.len[0];
+                const int len0 = m.len[0];
                 const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
                 const uint32_t d = (bf ? a_st2 + m.so[2] + (e ? rec0 : 0) : (e ? a_st1 : a_st0) + m.so[e]) + x0;
-                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (bf ? 0 : nvar - 1)) * L.name_cap;
+                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (bf ? 0 : nvar - 1)) * P.name_cap;
                 const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nm + x0));
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                 const int left = nn - x0;
@@ -1583,10 +1620,10 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                     if (4 * b4 + 3 < left) sts8(d + 4 * b4 + 3, x >> 24);
                 }
             }
-            for (int it = tid; it < np * 4; it += kFmtThreads) {
+            for (int it = lane; it < np * 4; it += 32) {
                 const int t = it >> 2, rr = it & 3, e = rr & 1, bf = rr >> 1;
-                const TileMeta &m = meta[t];
-                const int Le = m.rec.len[e];
+                const PairMeta &m = meta[t];
+                const int Le = m.len[e];
                 if (Le <= 0) continue;
                 if (!bf) {
                     if (!on0) continue;
@@ -1597,7 +1634,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                     sts8(sb + 3 + me + 3 + me, '\n');
                 } else {
                     if (!on2) continue;
-                    const int len0 = m.rec.len[0];
+                    const int len0 = m.len[0];
                     const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
                     uint32_t sf = a_st2 + m.so[2] + (e ? rec0 : 0) + m.nfull;
                     sts8(sf, '\n');
@@ -1608,30 +1645,26 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 }
             }
         }
-        __syncthreads();
-        // ---- phase 3: copy-out ------------------------------------------------------------------------------
+        __syncwarp();
+        // ---- step 3: copy-out ------------------------------------------------------------------------------------
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const int total = s_total[k];
-            if (total <= 0) continue;
-            const int shift = s_shift[k];
-            const uint32_t begin = offs[(size_t)k * n + p0];
-            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin - shift;   // 16-byte aligned
-            const uint8_t *st = smem + L.stage_off[k];
-            const int end = shift + total, nchunk = (end + 15) >> 4;
-            const int c_first = shift ? 1 : 0, c_full = end >> 4;       // chunks [c_first, c_full) lie wholly inside the tile's range
-            const uint4 *src = reinterpret_cast<const uint4 *>(st);
+            if (total[k] == 0) continue;
+            const uint32_t a_st = k == 0 ? a_st0 : (k == 1 ? a_st1 : a_st2);
+            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin[k] - shift[k];   // 16-byte aligned
+            const int sh = (int)shift[k], end = sh + (int)total[k], nchunk = (end + 15) >> 4;
+            const int c_first = sh ? 1 : 0, c_full = end >> 4;           // chunks [c_first, c_full) lie wholly inside the range
             uint4 *dst = reinterpret_cast<uint4 *>(base);
-            for (int c = c_first + tid; c < c_full; c += kFmtThreads) dst[c] = src[c];
-            if (tid < 2) {                                              // the two boundary chunks shared with the neighbouring tiles
-                const int c = tid ? c_full : 0;
-                if ((tid == 0 && c_first) || (tid == 1 && c_full < nchunk && (c_full > 0 || !c_first))) {
-                    const int lo = c << 4, a = lo > shift ? lo : shift, b = lo + 16 < end ? lo + 16 : end;
-                    for (int x = a; x < b; ++x) base[x] = (char)st[x];
-                }
+            for (int c = c_first + lane; c < c_full; c += 32) dst[c] = lds128(a_st + (c << 4));
+            // the two boundary chunks are shared with the neighbouring mini-tiles: lanes 0-15 / 16-31 store their bytes
+            {
+                const int c = lane < 16 ? 0 : c_full, x = (c << 4) + (lane & 15);
+                const bool mine = lane < 16 ? c_first != 0 : (c_full < nchunk && (c_full > 0 || !c_first));
+                if (mine && x >= sh && x < end) base[x] = (char)lds8(a_st + x);
             }
         }
-        __syncthreads();
+        __syncwarp();
+        cur = nxt;
     }
 }
 

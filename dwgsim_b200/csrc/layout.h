@@ -71,6 +71,7 @@ struct PairRec {                               // 32 bytes
     uint8_t  flags;                            // see below
     uint16_t attempt;                          // attempt index that succeeded (keys the quality draws)
 };
+static_assert(sizeof(PairRec) == 32, "the format kernel reads words 2 and 7 of a PairRec");
 constexpr uint8_t kRecRandom = 1, kRecStrand0 = 2, kRecStrand1 = 4, kRecHap1 = 8, kRecFailed = 0x80;
 
 // ---- Philox addressing (DESIGN.md "RNG addressing"; oracle/dwgsim_oracle.c restates it) ---------
