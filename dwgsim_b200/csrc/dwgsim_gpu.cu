@@ -73,7 +73,8 @@ struct Workspace {
     unsigned long long *blk_rand = nullptr;   // [nblk]
     unsigned long long *blk_len = nullptr;    // [3][nblk]
     unsigned long long *totals = nullptr;     // [8]: 0 n_random, 1..3 stream bytes
-    unsigned long long *status = nullptr;     // [2]: error bits, failed attempts
+    unsigned long long *status = nullptr;     // [4]: error bits, failed attempts, sizes of the job lists F1, R1
+    uint2 *jobs = nullptr;                    // [2][cap]: retry and random job lists of the simulate passes
     char *out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint64_t out_cap[3] = {0, 0, 0};
     unsigned long long *h_totals = nullptr;   // pinned [8 + 2]
@@ -545,7 +546,7 @@ void free_workspace(dwgsim_gpu *h)
 {
     Workspace &w = h->ws;
     cudaFree(w.recs); cudaFree(w.seqs); cudaFree(w.serial); cudaFree(w.lens); cudaFree(w.names); cudaFree(w.name_len);
-    cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status);
+    cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status); cudaFree(w.jobs);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(w.out[s][k]);
     for (int k = 0; k < 3; ++k) { cudaFree(w.gz_slots[k]); cudaFree(w.gz_out[0][k]); cudaFree(w.gz_out[1][k]); }
     cudaFree(w.gz_sizes); cudaFree(w.gz_offs); cudaFree(w.gz_totals); cudaFree(w.gz_hist);
@@ -570,8 +571,9 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_rand, (size_t)nblk * 8));
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_len, (size_t)nblk * 24));
         CUDA_TRY(h, cudaMalloc((void **)&w.totals, 64));
-        CUDA_TRY(h, cudaMalloc((void **)&w.status, 16));
-        CUDA_TRY(h, cudaMemset(w.status, 0, 16));
+        CUDA_TRY(h, cudaMalloc((void **)&w.status, 48));
+        CUDA_TRY(h, cudaMemset(w.status, 0, 48));
+        CUDA_TRY(h, cudaMalloc((void **)&w.jobs, (size_t)n * 2 * sizeof(uint2)));
         CUDA_TRY(h, cudaMallocHost((void **)&w.h_totals, 128));
         uint64_t cap[3];
         record_caps(h, cap);
@@ -629,7 +631,8 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
     const int flr = (sp.flow_order_len + 15) & ~15;
     const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
     cudaStream_t st = h->s_compute;
-    CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 16, st));
+    int extra_launches = 0;
+    CUDA_TRY(h, cudaMemsetAsync(w.status, 0, 48, st));
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[0], st));
     if (h->ion_warp_kernel)
         simulate_pairs_kernel<<<grid, kThreads, smem_a, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
@@ -640,17 +643,23 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         if (sp.data_type == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<true>, kTpThreads, smem_tp);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<false>, kTpThreads, smem_tp);
         const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::max(occ_tp, 1));
-        if (sp.data_type == 2)
-            simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
-        else
-            simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.status);
+        JobLists J;
+        J.retry = w.jobs; J.random = w.jobs + (size_t)w.cap_pairs; J.count = w.status + 2;
+        // two passes (kernels.cuh "Job lists"): fresh pairs, then the retries and random pairs they left behind
+        for (int pass = 0; pass < 2; ++pass) {
+            if (sp.data_type == 2)
+                simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);
+            else
+                simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);
+        }
+        extra_launches = 1;
     }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
     layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_rand, nblk, 1, w.totals);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[5], st));
     CUDA_TRY(h, cudaGetLastError());
-    *launches = 3;
+    *launches = 3 + extra_launches;
     return DWGSIM_GPU_OK;
 }
 

@@ -565,15 +565,94 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
     }
 }
 
+// ---- explicit shared-memory accesses (32-bit shared-window addresses; the staging areas are selected at run time, and a
+// generic pointer there would turn every byte store into a 64-bit generic ST) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+template <int kOff>
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOff) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// a value the compiler must keep in an ordinary register (uniform registers do not survive the divergent code around
+// the table lookups, and rebuilding a shared-window address costs four instructions each time)
+__device__ __forceinline__ uint32_t in_register(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+
 // ---- kernel A (Illumina / SOLiD): one thread per pair ------------------------------------------------------
+// The walk reads the 2-bit reference through a per-thread ring of four 8-byte words (4 x 32 bases) in shared memory that
+// is filled by cp.async: the copies are issued 64-96 bases before their use and land without occupying a register, so
+// no lane waits on a dependent reference load.  The rings of both ends are primed before the first walk starts.  The N
+// mask is looked at only when the read's neighbourhood holds an N at all (RefRing::has_n, decided by a few 16-byte
+// loads before the walk).  Word indices just outside a contig's section are inside the blob (sections are 256-byte
+// aligned and never last), and the bases read from there are never emitted.
+constexpr int kRingSlotStride = 128 * 8;   // [4 slots][kTpThreads] x 8 bytes: lanes of a warp hit consecutive 8-byte words
+struct RefRing {
+    uint32_t base;                     // shared-window address of this thread's slot 0
+    int q;                             // the ring holds words q..q+3 (forward) / q-2..q+1 (backward)
+    bool has_n, fresh;
+};
+constexpr int kNCheckSlack = 64;       // the N pre-check covers the read plus this many positions in walk direction
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void ring_issue(const ContigView &c, uint32_t base, int idx)
+{
+    cp_async8(base + (uint32_t)(idx & 3) * kRingSlotStride, reinterpret_cast<const uint2 *>(c.ref2) + idx);
+}
+// start the copies of the four words around the first position of a walk
+__device__ __forceinline__ void ring_prime(const ContigView &c, RefRing &R, int start, int dir)
+{
+    R.q = start >> 5; R.fresh = true;
+    const int first = dir > 0 ? R.q : R.q - 2;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ring_issue(c, R.base, first + t);
+    cp_async_commit();
+}
+// the N pre-check of a read of s bases starting at `start`: OR of the N bits of the 128-base-aligned blocks around
+// [start, start +- (s + kNCheckSlack)]; the walk switches the mask loads on when it strays further (long deletions)
+__device__ __forceinline__ uint32_t n_precheck(const ContigView &c, int start, int dir, int s)
+{
+    int lo = dir > 0 ? start : start - s - kNCheckSlack, hi = dir > 0 ? start + s + kNCheckSlack : start;
+    lo = lo < 0 ? 0 : lo; hi = hi >= c.len ? c.len - 1 : hi;
+    uint32_t any = 0;
+    const uint4 *m4 = reinterpret_cast<const uint4 *>(c.nmask);
+    for (int b = lo >> 7; b <= (hi >> 7); ++b) { const uint4 v = __ldg(m4 + b); any |= v.x | v.y | v.z | v.w; }
+    return any;
+}
 // 8 consecutive bases of the 2-bit reference -> 8 nibble codes (0-3, 4 = N), optionally reversed + complemented
-__device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, int i, int dir, int m)
+__device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, RefRing &R, int i, int dir, int m)
 {
     const int j = dir > 0 ? i : i - m + 1;                    // lowest position of the group
-    const uint32_t w0 = __ldg(c.ref2 + (j >> 4)), w1 = __ldg(c.ref2 + (j >> 4) + 1);
-    const uint32_t n0 = __ldg(c.nmask + (j >> 5)), n1 = __ldg(c.nmask + (j >> 5) + 1);
-    uint32_t x = __funnelshift_r(w0, w1, (j & 15) << 1) & ((1u << (2 * m)) - 1u);
-    uint32_t y = __funnelshift_r(n0, n1, j & 31) & ((1u << m) - 1u);
+    const int jq = j >> 5;
+    if (R.fresh) { cp_async_wait<0>(); R.fresh = false; }     // first use: the primed words (issued long ago)
+    if (jq != R.q) {
+        if (dir > 0 && jq == R.q + 1) { ring_issue(c, R.base, jq + 3); cp_async_commit(); cp_async_wait<2>(); }
+        else if (dir < 0 && jq == R.q - 1) { ring_issue(c, R.base, jq - 2); cp_async_commit(); cp_async_wait<2>(); }
+        else {                                                 // a jump (leading events, a long deletion): start over
+            const int first = dir > 0 ? jq : jq - 2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ring_issue(c, R.base, first + t);
+            cp_async_commit(); cp_async_wait<0>();
+        }
+        R.q = jq;
+    }
+    const uint2 lo = lds64(R.base + (uint32_t)(jq & 3) * kRingSlotStride), hi = lds64(R.base + (uint32_t)((jq + 1) & 3) * kRingSlotStride);
+    const int pos = j & 31;
+    const uint32_t wa = pos < 16 ? lo.x : lo.y, wb = pos < 16 ? lo.y : hi.x;
+    uint32_t x = __funnelshift_r(wa, wb, (pos << 1) & 31) & ((1u << (2 * m)) - 1u);
+    uint32_t y = 0;
+    if (R.has_n) {
+        const uint32_t n0 = __ldg(c.nmask + (j >> 5)), n1 = __ldg(c.nmask + (j >> 5) + 1);
+        y = __funnelshift_r(n0, n1, j & 31) & ((1u << m) - 1u);
+    }
     // minus strand: reverse the order of the m bases and complement them (computed for every lane, then selected)
     uint32_t xr = __brev(x) >> (32 - 2 * m);
     xr = (((xr >> 1) & 0x5555u) | ((xr & 0x5555u) << 1)) ^ ((1u << (2 * m)) - 1u);
@@ -654,7 +733,8 @@ __device__ __forceinline__ int walk_hint(const ContigView &c, int h, int start, 
     if (start < 0 || start >= c.len) return 0;
     return (int)__ldg(c.blk[h] + (start >> kBlkShift) + (strand ? 1 : 0));
 }
-__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w, int hint)
+__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w, int hint,
+                                            RefRing &C)
 {
     const int dir = strand ? -1 : 1;
     const Event *ev = c.ev[h];
@@ -683,6 +763,8 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
     }
     int ext = i - (strand ? s - 1 : 0);
     if (ext < 0) return false;
+    int strayed = dir > 0 ? i - start : start - i;                 // positions beyond the N pre-check's plain reach
+    if (strayed > kNCheckSlack - 2) C.has_n = true;
     const uint32_t comp = strand ? 3u : 0u;                       // base b < 4 -> b ^ comp
     int k = 0;
     int ins_left = 0, ins_at = 0;                                  // insertion being emitted: bases left, next index
@@ -714,7 +796,7 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
         if (run > s - k) run = s - k;
         if (run > 0) {                                             // plain reference bases up to the next event
             const int m = run < 8 ? run : 8;
-            emit_group(E, fetch_codes(c, i, dir, m), m);
+            emit_group(E, fetch_codes(c, C, i, dir, m), m);
             i += dir * m; k += m;
             continue;
         }
@@ -733,6 +815,7 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
             ins_ref_pending = false;
         } else if (t == kEvDelete) {
             ++w.n_indel;
+            if (++strayed > kNCheckSlack - 2) C.has_n = true;
             if (strand && --ext < 0) { ok = false; break; }
         } else {
             emit_group(E, base, 1); ++k;
@@ -879,40 +962,61 @@ __device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int ca
 }
 
 constexpr int kTpThreads = 128;
-constexpr int kTpMinBlocks = 6;        // <= 80 registers per thread: 24 warps per SM
-constexpr int kTpQueueCap = 2 * kTpThreads;
+constexpr int kTpWarps = kTpThreads / 32;
+#ifndef DWG_TP_MIN_BLOCKS
+#define DWG_TP_MIN_BLOCKS 5
+#endif
+constexpr int kTpMinBlocks = DWG_TP_MIN_BLOCKS;   // 5: <= 102 registers per thread, 20 warps per SM
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// the sectors of the packed reference and of the N mask that a read of s bases starting at `start` will touch
+// the sectors of the packed reference that a read of s bases starting at `start` will touch
 __device__ __forceinline__ void prefetch_read(const ContigView &c, int start, int strand, int s)
 {
     int lo = strand ? start - s + 1 : start, hi = strand ? start : start + s - 1;
     lo = lo < 0 ? 0 : lo; hi = hi >= c.len ? c.len - 1 : hi;
     if (lo > hi) return;
     prefetch_l2(c.ref2 + (lo >> 4)); prefetch_l2(c.ref2 + (hi >> 4));
-    prefetch_l2(c.nmask + (lo >> 5)); prefetch_l2(c.nmask + (hi >> 5));
 }
 
-// One CTA works through its share of the batch in ROUNDS of kTpThreads jobs, one job per thread.  A job is one
-// attempt at one pair (src/dwgsim.c:649-843) or the generation of one random pair (:983-1001).  Fresh pairs start
-// with attempt 0; an attempt that is rejected (N filter, contig end, -x miss) re-enters through the CTA's retry
-// queue with the next attempt number, and a pair whose gate draw says "random" goes to the random queue, so every
-// round runs ONE code path on all of its lanes: retries and random pairs are batched into (nearly) full rounds of
-// their own instead of keeping 31 finished lanes of a warp waiting.  The draws of a pair are addressed by (pair,
-// attempt), so the result does not depend on which round executes a job.
+// Job lists of the simulate passes (DESIGN.md "Kernels"): an attempt that is rejected (N filter, contig end, -x miss)
+// and a pair whose gate draw says "random" are not finished by the lane that found out -- 31 finished lanes would wait
+// for it -- but appended to a list in HBM and executed by the next pass with full warps:
+//   pass 0  one attempt 0 at every pair of the batch          -> lists F1 (retry, attempt 1) and R1 (random pairs)
+//   pass 1  F1 and R1; every lane loops until its pair is done (2 % of the retries are rejected again)
+// The draws of a pair are addressed by (pair, attempt), so the result does not depend on which pass executes a job.
+struct JobLists {
+    uint2 *retry, *random;             // (pair index in the batch, attempt | failed << 16)
+    unsigned long long *count;         // [2]: |F1|, |R1|
+};
+// append the items of the lanes with `push` set (warp-converged call): one atomic per warp
+__device__ __forceinline__ void list_push(uint2 *list, unsigned long long *count, bool push, uint2 item, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, push);
+    if (!m) return;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (push) list[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
 template <bool kIon>
 __global__ void __launch_bounds__(kTpThreads, kTpMinBlocks)
-simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n,
-                         PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
+simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n, int pass,
+                         JobLists J, PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
 {
-    // staging tile: one row of nw0+nw1 words per thread, odd row stride => conflict-free; flushed to HBM (pair-major)
-    // by the whole CTA with coalesced stores
+    // the jobs of this pass: fresh pairs, or the two lists of the previous pass back to back
+    const int n_f = pass == 0 ? 0 : (int)J.count[0], n_r = pass == 0 ? 0 : (int)J.count[1];
+    const int n_jobs = pass == 0 ? n : n_f + n_r;
+    if ((int)(blockIdx.x * kTpThreads) >= n_jobs) return;
+    // staging tile: one row of nw0+nw1 words per thread, odd row stride => conflict-free; every warp flushes its own 32
+    // rows to HBM (pair-major) with coalesced stores
     extern __shared__ __align__(16) uint32_t tile[];
-    __shared__ uint2 q_retry[kTpQueueCap], q_random[kTpQueueCap];     // (pair index in the batch, attempt | failed << 16)
-    __shared__ int row_pair[kTpThreads];                              // destination pair of each staged row, -1 = none
-    __shared__ int n_retry, n_random;
+    __shared__ __align__(16) uint2 ring_mem[2 * 4 * kTpThreads];          // reference rings of both ends, [end][slot][thread]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NW = P.nw[0] + P.nw[1], RS = NW | 1;
     uint32_t *row = tile + (size_t)threadIdx.x * RS;
+    uint32_t *wtile = tile + (size_t)warp * 32 * RS;
     // sampling tables behind the tile: insert-size CDF + guide, per end: gap CDF (len entries) + guide, accept thresholds
     TpTables T;
     {
@@ -940,48 +1044,37 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             T.flow_order = fo;
             T.flow_mask = reinterpret_cast<uint32_t *>(fo + ((P.flow_order_len + 15) & ~15)) + (size_t)threadIdx.x * ((P.flow_order_len + 31) >> 5);
         }
-        if (threadIdx.x == 0) { n_retry = 0; n_random = 0; }
-        __syncthreads();
+        __syncthreads();                                                 // the only CTA-wide barrier
     }
     constexpr bool ion = kIon;
     const int solid = P.data_type == 1;
     const int s0 = P.len[0], s1 = P.len[1];
     uint32_t *dst0 = row, *dst1 = row + P.nw[0];
+    const uint32_t ring_base = smem_addr(ring_mem) + threadIdx.x * 8;
     unsigned failed_total = 0;
-    const int n_round = (n + kTpThreads - 1) / kTpThreads * kTpThreads;
-    int pbase = blockIdx.x * kTpThreads;
 
-    for (;;) {
-        // ---- pick the round (uniform over the CTA): full queue rounds first, then fresh pairs, then the leftovers ----
-        const int cr = n_retry, cq = n_random;
-        int kind;                                           // 0 fresh, 1 retry, 2 random
-        if (cq >= kTpThreads) kind = 2;
-        else if (cr >= kTpThreads) kind = 1;
-        else if (pbase < n_round) kind = 0;
-        else if (cr > 0) kind = 1;
-        else if (cq > 0) kind = 2;
-        else break;
-        int p = -1; uint32_t attempt = 0, failed_flag = 0;
-        if (kind == 0) { p = pbase + threadIdx.x; if (p >= n) p = -1; pbase += gridDim.x * kTpThreads; }
-        else {
-            const int cnt = kind == 1 ? cr : cq, take = cnt < kTpThreads ? cnt : kTpThreads;
-            if ((int)threadIdx.x < take) {
-                const uint2 it = (kind == 1 ? q_retry : q_random)[cnt - take + threadIdx.x];
+    for (int jbase = (blockIdx.x * kTpWarps + warp) * 32; jbase < n_jobs; jbase += gridDim.x * kTpThreads) {
+        const int job = jbase + lane;
+        int p = -1, kind = 0;                                            // kind 0: an attempt, 1: a random pair
+        uint32_t attempt = 0, failed_flag = 0;
+        if (job < n_jobs) {
+            if (pass == 0) p = job;
+            else {
+                const uint2 it = job < n_f ? J.retry[job] : J.random[job - n_f];
+                kind = job < n_f ? 0 : 1;
                 p = (int)it.x; attempt = it.y & 0xFFFFu; failed_flag = it.y >> 16;
             }
-            __syncthreads();                                // every item is read before the counter moves
-            if (threadIdx.x == 0) { if (kind == 1) n_retry = cnt - take; else n_random = cnt - take; }
         }
-        __syncthreads();
         int staged = -1;
-        if (p >= 0) {
+        bool push_retry = false, push_random = false;
+        while (p >= 0) {                                                 // one trip in pass 0
             const int64_t q = first + p;
             const uint64_t gidx = (uint64_t)(gidx_origin + q);
             PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), attempt};
             PairRec rec;
             rec.attempt = (uint16_t)attempt;
             rec.n_err_first = 0;
-            if (kind == 2) {                                              // random pair, src/dwgsim.c:983-1001
+            if (kind == 1) {                                             // random pair, src/dwgsim.c:983-1001
                 rec.flags = (uint8_t)(kRecRandom | (failed_flag ? kRecFailed : 0));
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -1011,111 +1104,128 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 }
                 recs[p] = rec;
                 staged = p;
-            } else {
-                const uint4 b0 = draw_block(key, kStPair, 0, 0);
-                if ((uint64_t)b0.x < P.thr_genomic) {                         // src/dwgsim.c:649
-                    q_random[atomicAdd(&n_random, 1)] = make_uint2((uint32_t)p, attempt);
-                } else {
-                    int contig_index;
-                    const ContigDesc *cd = find_contig(blob, q, &contig_index);
-                    const ContigView cv = view_of(blob, cd);
-                    int d, pos;
-                    bool ok = true;
-                    if (P.amplicons) { pos = 0; d = cv.len; }
-                    else {
-                        const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
-                        if (s1 > 0) {
-                            d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
-                            const int min_dist = s0 + s1;
-                            if (d < min_dist) d = min_dist;
-                            if (d > slen) d = slen;
-                        } else d = 0;
-                        const uint64_t range = (uint64_t)((int64_t)slen - d + 1);
-                        pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
-                        if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) ok = false;
+                break;
+            }
+            const uint4 b0 = draw_block(key, kStPair, 0, 0);
+            if ((uint64_t)b0.x < P.thr_genomic) {                             // src/dwgsim.c:649
+                kind = 1;
+                if (pass == 0) { push_random = true; break; }
+                continue;
+            }
+            int contig_index;
+            const ContigDesc *cd = find_contig(blob, q, &contig_index);
+            const ContigView cv = view_of(blob, cd);
+            int d, pos;
+            bool ok = true;
+            if (P.amplicons) { pos = 0; d = cv.len; }
+            else {
+                const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
+                if (s1 > 0) {
+                    d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
+                    const int min_dist = s0 + s1;
+                    if (d < min_dist) d = min_dist;
+                    if (d > slen) d = slen;
+                } else d = 0;
+                const uint64_t range = (uint64_t)((int64_t)slen - d + 1);
+                pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
+                if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) ok = false;
+            }
+            Walk w0, w1;
+            Emit E0, E1;
+            E0.n_err = E1.n_err = 0; E0.err_first = E1.err_first = 0;
+            w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
+            int strand0 = 0, strand1 = 0, hap = 0;
+            if (ok) {
+                const uint4 b1 = draw_block(key, kStPair, 0, 1);
+                hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
+                strand0 = P.read_one_strand == 0 ? ((b1.y >> 31) ? 0 : 1) : (P.read_one_strand == 1 ? 0 : 1);
+                if (P.strandedness == 0) strand1 = (P.data_type == 0) ? 1 - strand0 : strand0;
+                else strand1 = (P.strandedness == 1) ? strand0 : 1 - strand0;
+                int st0, st1 = 0;
+                const int last = cv.len - 1;
+                if (s1 > 0) {                                             // src/dwgsim.c:745-810
+                    if (strand0 == strand1) {
+                        if (strand0 == 0) { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d - 1 : pos + d - s0); st1 = pos; }
+                        else { st0 = pos + s0 - 1; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
+                    } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
+                    else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
+                } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
+                // start the memory accesses of both ends before walking the first one
+                RefRing R0, R1;
+                R0.base = ring_base; R1.base = ring_base + 4 * kRingSlotStride;
+                int hint1 = -1;
+                uint32_t any1 = 0;
+                const bool in0 = st0 >= 0 && st0 < cv.len, in1 = s1 > 0 && st1 >= 0 && st1 < cv.len;
+                if (in0) ring_prime(cv, R0, st0, strand0 ? -1 : 1); else { R0.q = -0x40000000; R0.fresh = false; }
+                if (in1) ring_prime(cv, R1, st1, strand1 ? -1 : 1); else { R1.q = -0x40000000; R1.fresh = false; }
+                if (s1 > 0) { hint1 = walk_hint(cv, hap, st1, strand1); if (in1) any1 = n_precheck(cv, st1, strand1 ? -1 : 1, s1); }
+                const int hint0 = walk_hint(cv, hap, st0, strand0);
+                const uint32_t any0 = in0 ? n_precheck(cv, st0, strand0 ? -1 : 1, s0) : 0u;
+                R0.has_n = any0 != 0; R1.has_n = any1 != 0;
+                emit_begin(E0, dst0, s0, solid, !ion, T, key, 0);
+                ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0, hint0, R0);
+                if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
+                if (s1 > 0) {
+                    bool ok1 = false;
+                    if (ok) {                                              // a rejected end 0 already rejects the pair
+                        emit_begin(E1, dst1, s1, solid, !ion, T, key, 1);
+                        ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1, R1);
+                        if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
                     }
-                    Walk w0, w1;
-                    Emit E0, E1;
-                    E0.n_err = E1.n_err = 0; E0.err_first = E1.err_first = 0;
-                    w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
-                    int strand0 = 0, strand1 = 0, hap = 0;
-                    if (ok) {
-                        const uint4 b1 = draw_block(key, kStPair, 0, 1);
-                        hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
-                        strand0 = P.read_one_strand == 0 ? ((b1.y >> 31) ? 0 : 1) : (P.read_one_strand == 1 ? 0 : 1);
-                        if (P.strandedness == 0) strand1 = (P.data_type == 0) ? 1 - strand0 : strand0;
-                        else strand1 = (P.strandedness == 1) ? strand0 : 1 - strand0;
-                        int st0, st1 = 0;
-                        const int last = cv.len - 1;
-                        if (s1 > 0) {                                             // src/dwgsim.c:745-810
-                            if (strand0 == strand1) {
-                                if (strand0 == 0) { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d - 1 : pos + d - s0); st1 = pos; }
-                                else { st0 = pos + s0 - 1; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
-                            } else if (strand0 == 0) { st0 = pos; st1 = P.amplicons ? last : (P.is_inner ? pos + s0 + d + s1 - 1 : pos + d - 1); }
-                            else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
-                        } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
-                        // start the DRAM accesses of both ends before walking the first one
-                        prefetch_read(cv, st0, strand0, s0);
-                        int hint1 = -1;
-                        if (s1 > 0) { prefetch_read(cv, st1, strand1, s1); hint1 = walk_hint(cv, hap, st1, strand1); }
-                        const int hint0 = walk_hint(cv, hap, st0, strand0);
-                        emit_begin(E0, dst0, s0, solid, !ion, T, key, 0);
-                        ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0, hint0);
-                        if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
-                        if (s1 > 0) {
-                            bool ok1 = false;
-                            if (ok) {                                              // a rejected end 0 already rejects the pair
-                                emit_begin(E1, dst1, s1, solid, !ion, T, key, 1);
-                                ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1);
-                                if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
-                            }
-                            ok = ok && ok1;
-                        } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; E1.n_err = 0; E1.err_first = 0; }
-                    }
-                    if (!ok) {                                                    // src/dwgsim.c:833-842
-                        ++failed_total;
-                        if (attempt >= (uint32_t)kMaxTrials) {                    // 10001 rejected attempts: the host reports it
-                            atomicOr(status, 1ull);
-                            q_random[atomicAdd(&n_random, 1)] = make_uint2((uint32_t)p, attempt | (1u << 16));
-                        } else q_retry[atomicAdd(&n_retry, 1)] = make_uint2((uint32_t)p, attempt + 1u);
-                    } else {
-                        rec.flags = (uint8_t)((strand0 ? kRecStrand0 : 0) | (strand1 ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0));
-                        rec.pos[0] = (uint32_t)(w0.ext + 1); rec.pos[1] = (uint32_t)(w1.ext + 1);
-                        rec.len[0] = (uint16_t)s0; rec.len[1] = (uint16_t)s1;
-                        rec.n_sub[0] = (uint16_t)w0.n_sub; rec.n_sub[1] = (uint16_t)w1.n_sub;
-                        rec.n_indel[0] = (uint16_t)w0.n_indel; rec.n_indel[1] = (uint16_t)w1.n_indel;
-                        rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
-                        rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
-                        rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
-                        if constexpr (kIon) {                                       // flow-space errors, src/dwgsim.c:861-864
+                    ok = ok && ok1;
+                } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; E1.n_err = 0; E1.err_first = 0; }
+            }
+            if (!ok) {                                                    // src/dwgsim.c:833-842
+                ++failed_total;
+                if (attempt >= (uint32_t)kMaxTrials) {                    // 10001 rejected attempts: the host reports it
+                    atomicOr(status, 1ull);
+                    kind = 1; failed_flag = 1;
+                    if (pass == 0) { push_random = true; break; }
+                    continue;
+                }
+                ++attempt;
+                if (pass == 0) { push_retry = true; break; }
+                continue;
+            }
+            rec.flags = (uint8_t)((strand0 ? kRecStrand0 : 0) | (strand1 ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0));
+            rec.pos[0] = (uint32_t)(w0.ext + 1); rec.pos[1] = (uint32_t)(w1.ext + 1);
+            rec.len[0] = (uint16_t)s0; rec.len[1] = (uint16_t)s1;
+            rec.n_sub[0] = (uint16_t)w0.n_sub; rec.n_sub[1] = (uint16_t)w1.n_sub;
+            rec.n_indel[0] = (uint16_t)w0.n_indel; rec.n_indel[1] = (uint16_t)w1.n_indel;
+            rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
+            rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
+            rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
+            if constexpr (kIon) {                                       // flow-space errors, src/dwgsim.c:861-864
 #pragma unroll 1
-                            for (int j = 0; j < 2; ++j) {
-                                const int s = j ? s1 : s0;
-                                if (s <= 0) continue;
-                                int nerr = 0, ovf = 0;
-                                FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
-                                const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_thr[j], T.flow_order,
-                                                                  P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
-                                if (ovf) atomicOr(status, 2ull);
-                                rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);
-                                rec.n_err[j] = (uint16_t)nerr;
-                            }
-                        }
-                        recs[p] = rec;
-                        staged = p;
-                    }
+                for (int j = 0; j < 2; ++j) {
+                    const int s = j ? s1 : s0;
+                    if (s <= 0) continue;
+                    int nerr = 0, ovf = 0;
+                    FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
+                    const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_thr[j], T.flow_order,
+                                                      P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
+                    if (ovf) atomicOr(status, 2ull);
+                    rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);
+                    rec.n_err[j] = (uint16_t)nerr;
                 }
             }
+            recs[p] = rec;
+            staged = p;
+            break;
         }
-        row_pair[threadIdx.x] = staged;
-        // flush the staged rows (pair-major in HBM, NW words per pair); rows of one fresh round are contiguous there
-        __syncthreads();
+        __syncwarp();
+        if (pass == 0) {
+            const uint2 item = make_uint2((uint32_t)p, attempt | (failed_flag << 16));
+            list_push(J.retry, J.count, push_retry, item, lane);
+            list_push(J.random, J.count + 1, push_random, item, lane);
+        }
+        // flush the warp's staged rows (pair-major in HBM, NW words per pair); the rows of a pass-0 round are contiguous there
         // tile index of linear word x is x + (x / NW) * (RS - NW); x / NW by a multiply-high with P.inv_nw = 2^32/NW + 1
-        for (int x = threadIdx.x; x < kTpThreads * NW; x += kTpThreads) {
-            const int r = (int)__umulhi((uint32_t)x, P.inv_nw), dp = row_pair[r];
-            if (dp >= 0) seqw[(size_t)dp * NW + (x - r * NW)] = tile[x + r * (RS - NW)];
+        for (int x = lane; x < 32 * NW; x += 32) {
+            const int r = (int)__umulhi((uint32_t)x, P.inv_nw), dp = __shfl_sync(0xffffffffu, staged, r);
+            if (dp >= 0) seqw[(size_t)dp * NW + (x - r * NW)] = wtile[x + r * (RS - NW)];
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
 }
@@ -1392,26 +1502,6 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     L.total = o + kFmtWarps * w;
     return L;
 }
-
-// ---- explicit shared-memory accesses (32-bit shared-window addresses; the staging areas are selected at run time, and a
-// generic pointer there would turn every byte store into a 64-bit generic ST) ---------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t a)
-{
-    uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t a)
-{
-    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-template <int kOff>
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOff) : "memory"); }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-// a value the compiler must keep in an ordinary register (uniform registers do not survive the divergent code around
-// the table lookups, and rebuilding a shared-window address costs four instructions each time)
-__device__ __forceinline__ uint32_t in_register(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 
 // quality noise: inverse CDF through a 1024-bucket guide.  An entry {t, r} holds the rank r at the bucket's lower bound
 // and, when exactly one threshold c lies inside the 2^22-wide bucket, t = c - 1 (no threshold: t = 2^32 - 1): one 8-byte
