@@ -669,29 +669,16 @@ struct Emit {                          // emission state of one read
     uint64_t acc; int na, w;           // pending nibbles, their count, next word index
     int k, nN;                         // symbols emitted, N bases seen (src/dwgsim.c:823-831)
     int solid; uint32_t prev;          // colour space: previous base, adaptor = 0 (src/dwgsim.c:845-858)
-    int next_err, n_err, err_first;    // substitution errors (src/dwgsim.c:233-244) by thinning
-    uint32_t cand; uint4 cur;
-    const uint32_t *gap, *accp; const uint16_t *gguide; int s; PairKey key; uint32_t end;
 };
-__device__ __forceinline__ void err_next(Emit &E)
-{
-    E.cur = draw_block(E.key, kStErr, E.end, E.cand);
-    E.next_err += 1 + guided_rank(E.gap, E.gguide, E.cur.x);
-}
 struct TpTables {                     // shared-memory copies of the sampling tables of the thread-per-pair kernel
     const uint32_t *isize_cdf; const uint16_t *isize_guide;
     const uint32_t *gap[2], *acc[2]; const uint16_t *gap_guide[2];
     const int8_t *flow_order; uint32_t *flow_mask;
 };
-__device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int s, int solid, bool errors,
-                                           const TpTables &T, const PairKey &key, int end)
+__device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int solid)
 {
     E.dst = dst; E.acc = 0; E.na = 0; E.w = 0; E.k = 0; E.nN = 0;
-    E.solid = solid; E.prev = 0; E.n_err = 0; E.err_first = 0; E.cand = 0; E.s = s;
-    E.gap = T.gap[end]; E.accp = T.acc[end]; E.gguide = T.gap_guide[end]; E.key = key; E.end = (uint32_t)end;
-    E.cur = make_uint4(0, 0, 0, 0);
-    E.next_err = -1;
-    if (errors) err_next(E); else E.next_err = 0x7fffffff;
+    E.solid = solid; E.prev = 0;
 }
 // append m <= 8 base codes (nibbles in the low bits of `codes`, zero above)
 __device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
@@ -702,18 +689,6 @@ __device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
         E.prev = (codes >> (4 * (m - 1))) & 15u;
         const uint32_t x = (codes ^ prevs) & 0x33333333u, nf = (codes | prevs) & 0x44444444u;
         codes = ((x & ~((nf >> 2) * 3u)) | nf) & (m == 8 ? 0xFFFFFFFFu : ((1u << (4 * m)) - 1u));
-    }
-    while (E.next_err < E.k + m) {
-        const int sh = (E.next_err - E.k) << 2;
-        uint32_t c = (codes >> sh) & 15u;
-        if (c < 4 && E.cur.y < E.accp[E.next_err]) {
-            c = (c + 1u + __umulhi(E.cur.z, 3u)) & 3u;
-            codes = (codes & ~(15u << sh)) | (c << sh);
-            ++E.n_err;
-            if (E.next_err == 0) E.err_first = 1;
-        }
-        ++E.cand;
-        err_next(E);
     }
     E.acc |= (uint64_t)codes << (4 * E.na);
     E.na += m; E.k += m;
@@ -961,10 +936,34 @@ __device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int ca
     return len;
 }
 
+// Substitution errors (__gen_errors_mismatches, src/dwgsim.c:233-244) by thinning (DESIGN.md "RNG addressing"), applied to
+// the read's staged row after the walk: candidate n of a read sits 1 + rank(gap table, x_n) symbols after candidate
+// n - 1 and is kept when the symbol is not N and y_n is below the cycle's acceptance threshold.  Running this after the
+// walk lets the lanes of a warp draw their candidates in lockstep (one Philox block per candidate) instead of each
+// lane drawing inside its own group of the walk loop.
+__device__ __forceinline__ void apply_errors(uint32_t *row, int s, const TpTables &T, const PairKey &key, int end, int &n_err, int &err_first)
+{
+    const uint32_t *gap = T.gap[end], *accp = T.acc[end];
+    const uint16_t *gguide = T.gap_guide[end];
+    int pos = -1;
+    n_err = 0; err_first = 0;
+    for (uint32_t cand = 0;; ++cand) {
+        const uint4 cur = draw_block(key, kStErr, (uint32_t)end, cand);
+        pos += 1 + guided_rank(gap, gguide, cur.x);
+        if (pos >= s) break;
+        const uint32_t c = nib_get(row, pos);
+        if (c < 4 && cur.y < accp[pos]) {
+            nib_set(row, pos, (c + 1u + __umulhi(cur.z, 3u)) & 3u);
+            ++n_err;
+            if (pos == 0) err_first = 1;
+        }
+    }
+}
+
 constexpr int kTpThreads = 128;
 constexpr int kTpWarps = kTpThreads / 32;
 #ifndef DWG_TP_MIN_BLOCKS
-#define DWG_TP_MIN_BLOCKS 5
+#define DWG_TP_MIN_BLOCKS 6
 #endif
 constexpr int kTpMinBlocks = DWG_TP_MIN_BLOCKS;   // 5: <= 102 registers per thread, 20 warps per SM
 
@@ -1083,7 +1082,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
                     if (s <= 0) continue;
                     Emit E;
-                    emit_begin(E, j ? dst1 : dst0, s, solid, false, T, key, j);
+                    emit_begin(E, j ? dst1 : dst0, solid);
                     for (int k = 0; k < s; k += 64) {
                         const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
 #pragma unroll
@@ -1132,7 +1131,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             }
             Walk w0, w1;
             Emit E0, E1;
-            E0.n_err = E1.n_err = 0; E0.err_first = E1.err_first = 0;
+            int n_err0 = 0, n_err1 = 0, err_first0 = 0, err_first1 = 0;
             w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
             int strand0 = 0, strand1 = 0, hap = 0;
             if (ok) {
@@ -1162,18 +1161,18 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 const int hint0 = walk_hint(cv, hap, st0, strand0);
                 const uint32_t any0 = in0 ? n_precheck(cv, st0, strand0 ? -1 : 1, s0) : 0u;
                 R0.has_n = any0 != 0; R1.has_n = any1 != 0;
-                emit_begin(E0, dst0, s0, solid, !ion, T, key, 0);
+                emit_begin(E0, dst0, solid);
                 ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0, hint0, R0);
                 if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
                 if (s1 > 0) {
                     bool ok1 = false;
                     if (ok) {                                              // a rejected end 0 already rejects the pair
-                        emit_begin(E1, dst1, s1, solid, !ion, T, key, 1);
+                        emit_begin(E1, dst1, solid);
                         ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1, R1);
                         if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
                     }
                     ok = ok && ok1;
-                } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; E1.n_err = 0; E1.err_first = 0; }
+                } else { w1.ext = 0; w1.n_sub = w1.n_indel = w1.n_indel_first = 0; }
             }
             if (!ok) {                                                    // src/dwgsim.c:833-842
                 ++failed_total;
@@ -1187,14 +1186,18 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 if (pass == 0) { push_retry = true; break; }
                 continue;
             }
+            if (!ion) {                                                   // src/dwgsim.c:866-881
+                apply_errors(dst0, s0, T, key, 0, n_err0, err_first0);
+                if (s1 > 0) apply_errors(dst1, s1, T, key, 1, n_err1, err_first1);
+            }
             rec.flags = (uint8_t)((strand0 ? kRecStrand0 : 0) | (strand1 ? kRecStrand1 : 0) | (hap ? kRecHap1 : 0));
             rec.pos[0] = (uint32_t)(w0.ext + 1); rec.pos[1] = (uint32_t)(w1.ext + 1);
             rec.len[0] = (uint16_t)s0; rec.len[1] = (uint16_t)s1;
             rec.n_sub[0] = (uint16_t)w0.n_sub; rec.n_sub[1] = (uint16_t)w1.n_sub;
             rec.n_indel[0] = (uint16_t)w0.n_indel; rec.n_indel[1] = (uint16_t)w1.n_indel;
             rec.n_indel_first[0] = (uint16_t)w0.n_indel_first; rec.n_indel_first[1] = (uint16_t)w1.n_indel_first;
-            rec.n_err[0] = (uint16_t)E0.n_err; rec.n_err[1] = (uint16_t)(s1 > 0 ? E1.n_err : 0);
-            rec.n_err_first = (uint8_t)((E0.err_first ? 1 : 0) | ((s1 > 0 && E1.err_first) ? 2 : 0));
+            rec.n_err[0] = (uint16_t)n_err0; rec.n_err[1] = (uint16_t)(s1 > 0 ? n_err1 : 0);
+            rec.n_err_first = (uint8_t)((err_first0 ? 1 : 0) | ((s1 > 0 && err_first1) ? 2 : 0));
             if constexpr (kIon) {                                       // flow-space errors, src/dwgsim.c:861-864
 #pragma unroll 1
                 for (int j = 0; j < 2; ++j) {
