@@ -586,16 +586,19 @@ __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.
 __device__ __forceinline__ uint32_t in_register(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 
 // ---- kernel A (Illumina / SOLiD): one thread per pair ------------------------------------------------------
-// The walk reads the 2-bit reference through a per-thread ring of four 8-byte words (4 x 32 bases) in shared memory that
-// is filled by cp.async: the copies are issued 64-96 bases before their use and land without occupying a register, so
-// no lane waits on a dependent reference load.  The rings of both ends are primed before the first walk starts.  The N
-// mask is looked at only when the read's neighbourhood holds an N at all (RefRing::has_n, decided by a few 16-byte
-// loads before the walk).  Word indices just outside a contig's section are inside the blob (sections are 256-byte
-// aligned and never last), and the bases read from there are never emitted.
-constexpr int kRingSlotStride = 128 * 8;   // [4 slots][kTpThreads] x 8 bytes: lanes of a warp hit consecutive 8-byte words
-struct RefRing {
+// The walk reads the 2-bit reference from a per-thread window in shared memory that cp.async fills before the walk
+// starts: the 8-byte words (32 bases each) that cover the read plus kWindowSlack positions in walk direction.  The
+// copies land without occupying a register and the walk never waits on a dependent reference load; a walk that strays
+// outside its window (long deletions) falls back to direct loads.  The N mask is looked at only when the read's
+// neighbourhood holds an N at all (RefWindow::has_n, decided by a few 16-byte loads before the walk).  Word indices just
+// outside a contig's section are inside the blob (sections are 256-byte aligned and never last), and the bases read
+// from there are never emitted.
+constexpr int kWindowSlotStride = 128 * 8; // [slots][kTpThreads] x 8 bytes: lanes of a warp hit consecutive 8-byte words
+constexpr int kWindowSlack = 32;
+__host__ __device__ inline int window_slots(int len) { return (len + kWindowSlack + 31) / 32 + 1; }
+struct RefWindow {
     uint32_t base;                     // shared-window address of this thread's slot 0
-    int q;                             // the ring holds words q..q+3 (forward) / q-2..q+1 (backward)
+    int first, slots;                  // the window holds words first .. first + slots - 1
     bool has_n, fresh;
 };
 constexpr int kNCheckSlack = 64;       // the N pre-check covers the read plus this many positions in walk direction
@@ -603,18 +606,16 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm v
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
-__device__ __forceinline__ void ring_issue(const ContigView &c, uint32_t base, int idx)
+// start the copies of the words a walk of s bases from `start` will read
+__device__ __forceinline__ void window_prime(const ContigView &c, RefWindow &R, int start, int dir, int s)
 {
-    cp_async8(base + (uint32_t)(idx & 3) * kRingSlotStride, reinterpret_cast<const uint2 *>(c.ref2) + idx);
-}
-// start the copies of the four words around the first position of a walk
-__device__ __forceinline__ void ring_prime(const ContigView &c, RefRing &R, int start, int dir)
-{
-    R.q = start >> 5; R.fresh = true;
-    const int first = dir > 0 ? R.q : R.q - 2;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) ring_issue(c, R.base, first + t);
+    cp_async_wait<0>();                                                    // copies of a window that was never read
+    R.slots = window_slots(s);
+    R.first = dir > 0 ? (start >> 5) : ((start >> 5) - R.slots + 2);        // backward: the group at `start` may need word (start >> 5) + 1
+    const uint2 *src = reinterpret_cast<const uint2 *>(c.ref2) + R.first;
+    for (int t = 0; t < R.slots; ++t) cp_async8(R.base + (uint32_t)t * kWindowSlotStride, src + t);
     cp_async_commit();
+    R.fresh = true;
 }
 // the N pre-check of a read of s bases starting at `start`: OR of the N bits of the 128-base-aligned blocks around
 // [start, start +- (s + kNCheckSlack)]; the walk switches the mask loads on when it strays further (long deletions)
@@ -628,23 +629,14 @@ __device__ __forceinline__ uint32_t n_precheck(const ContigView &c, int start, i
     return any;
 }
 // 8 consecutive bases of the 2-bit reference -> 8 nibble codes (0-3, 4 = N), optionally reversed + complemented
-__device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, RefRing &R, int i, int dir, int m)
+__device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, RefWindow &R, int i, int dir, int m)
 {
     const int j = dir > 0 ? i : i - m + 1;                    // lowest position of the group
-    const int jq = j >> 5;
-    if (R.fresh) { cp_async_wait<0>(); R.fresh = false; }     // first use: the primed words (issued long ago)
-    if (jq != R.q) {
-        if (dir > 0 && jq == R.q + 1) { ring_issue(c, R.base, jq + 3); cp_async_commit(); cp_async_wait<2>(); }
-        else if (dir < 0 && jq == R.q - 1) { ring_issue(c, R.base, jq - 2); cp_async_commit(); cp_async_wait<2>(); }
-        else {                                                 // a jump (leading events, a long deletion): start over
-            const int first = dir > 0 ? jq : jq - 2;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) ring_issue(c, R.base, first + t);
-            cp_async_commit(); cp_async_wait<0>();
-        }
-        R.q = jq;
-    }
-    const uint2 lo = lds64(R.base + (uint32_t)(jq & 3) * kRingSlotStride), hi = lds64(R.base + (uint32_t)((jq + 1) & 3) * kRingSlotStride);
+    const int t = (j >> 5) - R.first;
+    if (R.fresh) { cp_async_wait<0>(); R.fresh = false; }     // first use of the window
+    uint2 lo, hi;
+    if (t >= 0 && t + 1 < R.slots) { lo = lds64(R.base + (uint32_t)t * kWindowSlotStride); hi = lds64(R.base + (uint32_t)(t + 1) * kWindowSlotStride); }
+    else { const uint2 *src = reinterpret_cast<const uint2 *>(c.ref2) + (j >> 5); lo = __ldg(src); hi = __ldg(src + 1); }
     const int pos = j & 31;
     const uint32_t wa = pos < 16 ? lo.x : lo.y, wb = pos < 16 ? lo.y : hi.x;
     uint32_t x = __funnelshift_r(wa, wb, (pos << 1) & 31) & ((1u << (2 * m)) - 1u);
@@ -709,7 +701,7 @@ __device__ __forceinline__ int walk_hint(const ContigView &c, int h, int start, 
     return (int)__ldg(c.blk[h] + (start >> kBlkShift) + (strand ? 1 : 0));
 }
 __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w, int hint,
-                                            RefRing &C)
+                                            RefWindow &C)
 {
     const int dir = strand ? -1 : 1;
     const Event *ev = c.ev[h];
@@ -968,13 +960,13 @@ constexpr int kTpWarps = kTpThreads / 32;
 constexpr int kTpMinBlocks = DWG_TP_MIN_BLOCKS;   // 5: <= 102 registers per thread, 20 warps per SM
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// the sectors of the packed reference that a read of s bases starting at `start` will touch
+// the sectors of the packed reference that the window of a read of s bases starting at `start` will touch
 __device__ __forceinline__ void prefetch_read(const ContigView &c, int start, int strand, int s)
 {
-    int lo = strand ? start - s + 1 : start, hi = strand ? start : start + s - 1;
+    int lo = strand ? start - s - kWindowSlack : start, hi = strand ? start + 32 : start + s + kWindowSlack;
     lo = lo < 0 ? 0 : lo; hi = hi >= c.len ? c.len - 1 : hi;
-    if (lo > hi) return;
-    prefetch_l2(c.ref2 + (lo >> 4)); prefetch_l2(c.ref2 + (hi >> 4));
+    for (int w = lo >> 4; w <= (hi >> 4); w += 8) prefetch_l2(c.ref2 + w);      // one per 32-byte sector
+    prefetch_l2(c.ref2 + (hi >> 4));
 }
 
 // Job lists of the simulate passes (DESIGN.md "Kernels"): an attempt that is rejected (N filter, contig end, -x miss)
@@ -1011,15 +1003,16 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     // staging tile: one row of nw0+nw1 words per thread, odd row stride => conflict-free; every warp flushes its own 32
     // rows to HBM (pair-major) with coalesced stores
     extern __shared__ __align__(16) uint32_t tile[];
-    __shared__ __align__(16) uint2 ring_mem[2 * 4 * kTpThreads];          // reference rings of both ends, [end][slot][thread]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NW = P.nw[0] + P.nw[1], RS = NW | 1;
     uint32_t *row = tile + (size_t)threadIdx.x * RS;
     uint32_t *wtile = tile + (size_t)warp * 32 * RS;
     // sampling tables behind the tile: insert-size CDF + guide, per end: gap CDF (len entries) + guide, accept thresholds
+    // then the reference window, [slot][thread] x 8 bytes
+    uint2 *const win_mem = reinterpret_cast<uint2 *>(tile + (((size_t)kTpThreads * RS + 1) & ~(size_t)1));
     TpTables T;
     {
-        uint32_t *p32 = tile + (size_t)kTpThreads * RS;
+        uint32_t *p32 = reinterpret_cast<uint32_t *>(win_mem + (size_t)max(window_slots(P.len[0]), window_slots(P.len[1])) * kTpThreads);
         const bool isz_smem = P.isize_n <= 8192;          // wider insert-size tables (-s > ~500) stay in HBM / L2
         uint32_t *isz = p32; p32 += isz_smem ? ((P.isize_n + 1) & ~1) : 0;
         uint32_t *gp[2], *ac[2];
@@ -1049,7 +1042,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     const int solid = P.data_type == 1;
     const int s0 = P.len[0], s1 = P.len[1];
     uint32_t *dst0 = row, *dst1 = row + P.nw[0];
-    const uint32_t ring_base = smem_addr(ring_mem) + threadIdx.x * 8;
+    const uint32_t ring_base = smem_addr(win_mem) + threadIdx.x * 8;
     unsigned failed_total = 0;
 
     for (int jbase = (blockIdx.x * kTpWarps + warp) * 32; jbase < n_jobs; jbase += gridDim.x * kTpThreads) {
@@ -1150,25 +1143,28 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     else { st0 = P.amplicons ? last : (P.is_inner ? pos + s1 + d + s0 - 1 : pos + d - 1); st1 = pos; }
                 } else st0 = strand0 == 0 ? pos : (P.amplicons ? last : pos + s0 - 1);
                 // start the memory accesses of both ends before walking the first one
-                RefRing R0, R1;
-                R0.base = ring_base; R1.base = ring_base + 4 * kRingSlotStride;
+                RefWindow R;
+                R.base = ring_base; R.slots = 0; R.first = 0; R.fresh = false;
                 int hint1 = -1;
                 uint32_t any1 = 0;
                 const bool in0 = st0 >= 0 && st0 < cv.len, in1 = s1 > 0 && st1 >= 0 && st1 < cv.len;
-                if (in0) ring_prime(cv, R0, st0, strand0 ? -1 : 1); else { R0.q = -0x40000000; R0.fresh = false; }
-                if (in1) ring_prime(cv, R1, st1, strand1 ? -1 : 1); else { R1.q = -0x40000000; R1.fresh = false; }
+                if (in0) window_prime(cv, R, st0, strand0 ? -1 : 1, s0);
+                if (in1) prefetch_read(cv, st1, strand1, s1);                // end 1's window is primed after walk 0: have it in L2 by then
                 if (s1 > 0) { hint1 = walk_hint(cv, hap, st1, strand1); if (in1) any1 = n_precheck(cv, st1, strand1 ? -1 : 1, s1); }
                 const int hint0 = walk_hint(cv, hap, st0, strand0);
                 const uint32_t any0 = in0 ? n_precheck(cv, st0, strand0 ? -1 : 1, s0) : 0u;
-                R0.has_n = any0 != 0; R1.has_n = any1 != 0;
+                R.has_n = any0 != 0;
                 emit_begin(E0, dst0, solid);
-                ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0, hint0, R0);
+                ok = walk_thread(cv, hap, st0, strand0, s0, E0, w0, hint0, R);
                 if (ok) { emit_end(E0); ok = E0.nN <= P.max_n; }
                 if (s1 > 0) {
                     bool ok1 = false;
                     if (ok) {                                              // a rejected end 0 already rejects the pair
                         emit_begin(E1, dst1, solid);
-                        ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1, R1);
+                        R.slots = 0; R.fresh = false;
+                        if (in1) window_prime(cv, R, st1, strand1 ? -1 : 1, s1);
+                        R.has_n = any1 != 0;
+                        ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1, R);
                         if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
                     }
                     ok = ok && ok1;
