@@ -157,7 +157,7 @@ format_kernel_t format_kernel_of(const SimParams &sp)
 // dynamic shared memory of simulate_pairs_tp_kernel: staging tile + sampling tables (see the kernel prologue)
 size_t tp_smem_bytes(const SimParams &sp)
 {
-    size_t words = (((size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) + 1) & ~(size_t)1) + (sp.isize_n <= 8192 ? ((sp.isize_n + 1) & ~1) : 0);
+    size_t words = (((size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) + 1) & ~(size_t)1) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
     words += 2 * (size_t)std::max(window_slots(sp.len[0]), window_slots(sp.len[1])) * kTpThreads;     // the reference window
     for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);
     const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4;

@@ -954,6 +954,10 @@ __device__ __forceinline__ void apply_errors(uint32_t *row, int s, const TpTable
 
 constexpr int kTpThreads = 128;
 constexpr int kTpWarps = kTpThreads / 32;
+#ifndef DWG_ISIZE_SMEM_MAX
+#define DWG_ISIZE_SMEM_MAX 8192
+#endif
+constexpr int kIsizeSmemMax = DWG_ISIZE_SMEM_MAX;  // insert-size CDFs up to this many entries are copied to shared memory
 #ifndef DWG_TP_MIN_BLOCKS
 #define DWG_TP_MIN_BLOCKS 6
 #endif
@@ -1013,7 +1017,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     TpTables T;
     {
         uint32_t *p32 = reinterpret_cast<uint32_t *>(win_mem + (size_t)max(window_slots(P.len[0]), window_slots(P.len[1])) * kTpThreads);
-        const bool isz_smem = P.isize_n <= 8192;          // wider insert-size tables (-s > ~500) stay in HBM / L2
+        const bool isz_smem = P.isize_n <= kIsizeSmemMax;  // wider insert-size tables stay in HBM / L2 (one lookup per pair)
         uint32_t *isz = p32; p32 += isz_smem ? ((P.isize_n + 1) & ~1) : 0;
         uint32_t *gp[2], *ac[2];
         for (int e = 0; e < 2; ++e) { gp[e] = p32; p32 += (P.len[e] + 1) & ~1; ac[e] = p32; p32 += (P.len[e] + 1) & ~1; }
@@ -1284,6 +1288,7 @@ __device__ __forceinline__ void record_lengths(const SimParams &P, const PairRec
 
 __device__ __forceinline__ int put_dec(char *p, uint32_t v)      // writes v in decimal, returns the digit count
 {
+    if (v < 10u) { p[0] = (char)('0' + v); return 1; }              // strands, flags and most counts are one digit
     const int nd = ndigits10(v);
     for (int d = nd - 1; d >= 0; --d) { p[d] = (char)('0' + v % 10u); v /= 10u; }
     return nd;
@@ -1383,27 +1388,25 @@ layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const
     __shared__ uint32_t sw[kWarpsPerBlock];
     __shared__ unsigned long long sw64[kWarpsPerBlock];
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    PairRec r[kScanItems];
     uint32_t c = 0;
 #pragma unroll
-    for (int t = 0; t < kScanItems; ++t) {
-        if (base + t < n) { r[t] = recs[base + t]; c += (r[t].flags & kRecRandom) ? 1u : 0u; }
-        else r[t].flags = 0;
-    }
+    for (int t = 0; t < kScanItems; ++t) if (base + t < n) c += (recs[base + t].flags & kRecRandom) ? 1u : 0u;
     uint32_t tot;
     uint32_t ex = block_exclusive_scan<uint32_t>(c, &tot, sw);
     unsigned long long rs = rand_base + blk_rand_excl[blockIdx.x] + ex;
     unsigned long long sum[3] = {0, 0, 0};
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t < kScanItems; ++t) {
         if (base + t >= n) break;
         const int64_t q = first + base + t;
         int ci;
         const ContigDesc *cd = find_contig(blob, q, &ci);
+        const PairRec rt = recs[base + t];                    // (L1 hit: read above for the random-pair count)
         unsigned long long ser;
-        if (r[t].flags & kRecRandom) ser = rs++;
+        if (rt.flags & kRecRandom) ser = rs++;
         else ser = (unsigned long long)(q - cd->pair_base);
         serial[base + t] = ser;
+        int nl_v[2] = {0, 0};
         {   // the read name(s), written once here and copied by the format kernel
             const BlobHeader *hd = reinterpret_cast<const BlobHeader *>(blob);
             const char *cname = reinterpret_cast<const char *>(blob + hd->names_off + cd->name_off);
@@ -1413,15 +1416,27 @@ layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const
                 int nl;
                 if (P.name_cap <= 256) {               // assemble locally, store 16 bytes at a time
                     __align__(16) char tmp[256];
-                    nl = write_name(P, r[t], ser, cname, (int)cd->name_len, v, tmp);
+                    nl = write_name(P, rt, ser, cname, (int)cd->name_len, v, tmp);
                     for (int x = 0; x < nl; x += 16) *reinterpret_cast<uint4 *>(dst + x) = *reinterpret_cast<const uint4 *>(tmp + x);
-                } else nl = write_name(P, r[t], ser, cname, (int)cd->name_len, v, dst);
-                name_len[(size_t)(base + t) * 2 + v] = (uint16_t)nl;
+                } else nl = write_name(P, rt, ser, cname, (int)cd->name_len, v, dst);
+                nl_v[v] = nl;
             }
-            if (nvar == 1) name_len[(size_t)(base + t) * 2 + 1] = name_len[(size_t)(base + t) * 2];
+            if (nvar == 1) nl_v[1] = nl_v[0];
+            *reinterpret_cast<uint32_t *>(name_len + (size_t)(base + t) * 2) = (uint32_t)nl_v[0] | ((uint32_t)nl_v[1] << 16);
         }
-        uint32_t len[3];
-        record_lengths(P, r[t], ser, (int)cd->name_len, len);
+        // bytes of the pair's records in the three streams (src/dwgsim.c:920-980), from the name lengths just written
+        uint32_t len[3] = {0, 0, 0};
+        {
+            const bool solid = P.data_type == 1;
+            const int name_full = nl_v[0], name_bwa = nl_v[1];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int L = rt.len[j];
+                if (L <= 0) continue;
+                if (P.out_bwa) len[j] = (uint32_t)(name_bwa + 3 + (solid ? 2 * (L - 1) : 2 * L) + 4);
+                if (P.out_bfast) len[2] += (uint32_t)(name_full + 1 + 2 * L + 4 + (solid ? 1 : 0));
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) { lens[(size_t)k * n + base + t] = len[k]; sum[k] += len[k]; }
     }
