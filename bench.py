@@ -37,9 +37,9 @@ MUT_RATE, INDEL_FRAC, N_FRAC = 0.001, 0.1, 0.01
 PAIRS_PER_STEP = 1 << 20
 ALGO_BYTES_PER_PAIR = 1524.0      # 118 B read (2-bit ref + N mask + mutation table) + 1,406 B FASTQ written
 E2E_CONTIG_LEN = 8 << 20          # contig handed over per e2e step (dense host arrays: 17 B/base)
-# dram__bytes_read.sum + dram__bytes_write.sum of the three main kernels of one 2^20-pair step, from the ncu --set full
-# capture profiles/r01_ncu_key_metrics_final.txt (simulate 0.525 GB + layout_lengths 0.124 GB + format 1.768 GB)
-NCU_DRAM_BYTES_PER_STEP = 2.417e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the eight launches of one 2^20-pair step, from the ncu --set full
+# capture profiles/r01b_ncu_key_metrics.txt (simulate passes 0.525 GB + layout kernels 0.181 GB + format 1.750 GB)
+NCU_DRAM_BYTES_PER_STEP = 2.456e9
 
 
 def peak_hbm():
@@ -376,86 +376,71 @@ def main():
     kern_ms = sum(ms) / args.steps
     achieved = ALGO_BYTES_PER_PAIR * B / (kern_ms * 1e-3) / 1e9
     dom = max(range(3), key=lambda i: ms[i])
-    names = ["simulate_pairs_kernel", "layout_* (5 scan kernels)", "format_fastq_kernel"]
+    names = ["simulate_pairs_tp_kernel (2 passes)", "layout_* (5 scan kernels)", "format_fastq_kernel"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_STEP if B == PAIRS_PER_STEP else None,
-                "traffic_source": "ncu --set full capture of the same step (profiles/r01_ncu_key_metrics_final.txt), bytes per step",
+                "traffic_source": "ncu --set full capture of the same step (profiles/r01b_ncu_key_metrics.txt), bytes per step",
                 "peak_source": peak_src,
-                "kernel": "whole step = simulate + layout + format (7 launches); dominant: %s" % names[dom],
+                "kernel": "whole step = simulate (2 passes) + layout + format (8 launches); dominant: %s" % names[dom],
                 "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "fastq_bytes_per_pair": out_bytes / (B * args.steps),
                 "ms_per_step_by_kernel": {n: m / args.steps for n, m in zip(names, ms)}}
 
     # ---- e2e: the C ABI with host buffers (dense arrays in, FASTQ bytes out to host memory) ----
+    # Headline leg: the drop-in's default output, .fastq.gz bytes (what the reference writes to its gzFiles,
+    # src/dwgsim.c:1151-1157), compressed on the GPU before the device->host copy.  Second leg: plain FASTQ text.
     e2e = None
     if not args.no_e2e:
         seq, hap = dense_contig(E2E_CONTIG_LEN, 7 + rank)
         n_pairs_c = int(E2E_CONTIG_LEN * COVERAGE / 300.0 / 0.95 + 0.5)
-        g2 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
-        g2.set_batch(1 << 18, 3)
-
-        def e2e_step(i):
-            g2.add_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,
-                          None, 0, None, 0, n_pairs_c)
-            return g2.run_count()
-
-        # warm-up: the first steps allocate the pinned ring and first-touch its pages (100+ ms stalls on a fresh box)
-        n_warm = 6
-        for i in range(n_warm):
-            e2e_step(i)
+        n_warm = 6       # the first steps allocate the pinned ring and first-touch its pages (100+ ms stalls on a fresh box)
         n_e2e = max(5, min(args.steps, 20))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        te = time.perf_counter()
-        h2d = d2h = 0
-        pack_ms = 0.0
-        for i in range(n_e2e):
-            st = e2e_step(n_warm + i)
-            h2d += st.h2d_bytes; d2h += st.d2h_bytes; pack_ms += st.ms_pack
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - te
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": world * n_pairs_c * n_e2e / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d // n_e2e,
-               "d2h_bytes_per_step": d2h // n_e2e, "steps": n_e2e, "pairs_per_step": n_pairs_c,
-               "host_pack_ms_per_step": pack_ms / n_e2e,
-               "what": "per step: dwgsim_gpu_add_contig(%d Mbp contig as dense seq_t + 2 x mut_t[len] host arrays) + "
-                       "dwgsim_gpu_run -> FASTQ bytes of all three files delivered in pair order to host memory "
-                       "(library counting sink)" % (E2E_CONTIG_LEN >> 20)}
-        g2.close()
-        # the same with the device gzip writer: the sink receives .fastq.gz bytes (what the reference writes to its gzFiles)
-        try:
-            g3 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
-            g3.set_batch(1 << 18, 3)
-            g3.set_compression(1)
 
-            def gz_step(i):
-                g3.add_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,
+        def e2e_leg(compress):
+            g2 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
+            g2.set_batch(1 << 18, 3)
+            if compress:
+                g2.set_compression(1)
+
+            def one(i):
+                g2.add_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,
                               None, 0, None, 0, n_pairs_c)
-                return g3.run_count()
+                return g2.run_count()
 
             for i in range(n_warm):
-                gz_step(i)
-            torch.cuda.synchronize()
-            tg = time.perf_counter()
-            gz_d2h = gz_raw = 0
-            for i in range(n_e2e):
-                st = gz_step(n_warm + i)
-                gz_d2h += st.d2h_bytes; gz_raw += sum(st.raw_bytes)
-            torch.cuda.synchronize()
-            gz_s = time.perf_counter() - tg
+                one(i)
             if world > 1:
-                t = torch.tensor([gz_s], dtype=torch.float64, device="cuda")
+                dist.barrier()
+            torch.cuda.synchronize()
+            te = time.perf_counter()
+            h2d = d2h = raw = 0
+            pack_ms = 0.0
+            for i in range(n_e2e):
+                st = one(n_warm + i)
+                h2d += st.h2d_bytes; d2h += st.d2h_bytes; pack_ms += st.ms_pack; raw += sum(st.raw_bytes)
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - te
+            if world > 1:
+                t = torch.tensor([secs], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                gz_s = float(t.item())
-            e2e["gzip_sink"] = {"value": world * n_pairs_c * n_e2e / gz_s, "unit": "pairs/s", "d2h_bytes_per_step": gz_d2h // n_e2e,
-                                "compression_ratio": gz_d2h / max(gz_raw, 1),
-                                "what": "same steps with dwgsim_gpu_set_compression(1): gzip members written on the GPU, "
-                                        ".fastq.gz bytes delivered to host memory"}
-            g3.close()
-        except Exception as ex:  # keep the headline if the optional leg fails
+                secs = float(t.item())
+            g2.close()
+            return {"value": world * n_pairs_c * n_e2e / secs, "unit": "pairs/s", "h2d_bytes_per_step": h2d // n_e2e,
+                    "d2h_bytes_per_step": d2h // n_e2e, "steps": n_e2e, "pairs_per_step": n_pairs_c,
+                    "host_pack_ms_per_step": pack_ms / n_e2e, "fastq_bytes_per_step": raw // n_e2e}
+
+        what = ("per step: dwgsim_gpu_add_contig(%d Mbp contig as dense seq_t + 2 x mut_t[len] host arrays, packed on the host, "
+                "copied to the device) + dwgsim_gpu_run -> %s of all three files delivered in pair order to host memory "
+                "(library counting sink)")
+        raw_leg = e2e_leg(False)
+        raw_leg["what"] = what % (E2E_CONTIG_LEN >> 20, "FASTQ text")
+        try:
+            e2e = e2e_leg(True)
+            e2e["compression_ratio"] = e2e["d2h_bytes_per_step"] / max(e2e["fastq_bytes_per_step"], 1)
+            e2e["what"] = what % (E2E_CONTIG_LEN >> 20, ".fastq.gz bytes (gzip members written on the GPU, "
+                                                         "dwgsim_gpu_set_compression(1), the host shell's default)")
+            e2e["raw_sink"] = raw_leg
+        except Exception as ex:  # keep a headline if the compressed leg fails
+            e2e = raw_leg
             e2e["gzip_sink"] = {"error": str(ex)}
 
     cpu_baseline = None

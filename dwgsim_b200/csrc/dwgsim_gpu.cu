@@ -120,6 +120,8 @@ struct dwgsim_gpu {
     uint8_t *blob = nullptr;
     uint64_t blob_bytes = 0;
     bool blob_owned = true;
+    uint8_t *blob_spare = nullptr;            // the allocation of the previous run's genome, reused when large enough
+    uint64_t blob_spare_cap = 0;
     int64_t blob_pairs = 0;
     int max_name_len = 4;
     double ms_pack = 0;
@@ -468,7 +470,12 @@ int update_caps(dwgsim_gpu *h)
 
 void free_blob(dwgsim_gpu *h)
 {
-    if (h->blob && h->blob_owned) cudaFree(h->blob);
+    if (h->blob && h->blob_owned) {                            // per-contig runs allocate the same few MB again and again
+        if (h->blob_bytes > h->blob_spare_cap && h->blob_bytes <= (256ull << 20)) {
+            cudaFree(h->blob_spare);
+            h->blob_spare = h->blob; h->blob_spare_cap = h->blob_bytes;
+        } else cudaFree(h->blob);
+    }
     h->blob = nullptr; h->blob_bytes = 0; h->blob_pairs = 0; h->blob_owned = true;
     h->sp.regions = 0;
 }
@@ -515,7 +522,8 @@ int finalize_genome(dwgsim_gpu *h)
         d.reg_off = off; off = align_up(off + c.regions.size() * sizeof(Region), 256);
     }
     hd.n_bytes = off; hd.total_pairs = pair_base; hd.total_len = total_len;
-    CUDA_TRY(h, cudaMalloc((void **)&h->blob, off));
+    if (h->blob_spare && h->blob_spare_cap >= off) { h->blob = h->blob_spare; h->blob_spare = nullptr; h->blob_spare_cap = 0; }
+    else CUDA_TRY(h, cudaMalloc((void **)&h->blob, off));
     h->blob_owned = true; h->blob_bytes = off; h->blob_pairs = pair_base;
     h->sp.regions = (int32_t)(hd.flags & 1u);
     auto put = [&](uint64_t at, const void *src, size_t n) -> cudaError_t {
@@ -907,6 +915,7 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     cudaSetDevice(h->device);
     free_workspace(h);
     free_blob(h);
+    cudaFree(h->blob_spare);
     cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
     for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
     cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
