@@ -65,6 +65,8 @@ typedef struct {
     int32_t amplicons;
     int32_t finalized;
     char    fn_regions_bed[1024];           /* -x: BED of regions to cover ("" = none)              */
+    int32_t muts_input_type;                /* -1 none, 0 = -b BED, 1 = -m TXT, 2 = -v VCF (src/mut_input.h:33-37) */
+    char    fn_muts_input[1024];            /* the file of mutations to replay                      */
 } orc_opt_t;
 
 /* tables the Philox backend (and the GPU) samples from instead of calling log/sqrt per draw */

@@ -28,6 +28,7 @@ class OrcOpt(C.Structure):
         ("has_read_prefix", C.c_int32), ("read_prefix", C.c_char * 256),
         ("reads_output_type", C.c_int32), ("output_type", C.c_int32), ("amplicons", C.c_int32),
         ("finalized", C.c_int32), ("fn_regions_bed", C.c_char * 1024),
+        ("muts_input_type", C.c_int32), ("fn_muts_input", C.c_char * 1024),
     ]
 
 
@@ -151,6 +152,9 @@ def make_opt(**kw):
             o.fixed_quality = ord(v) if isinstance(v, str) else int(v)
         elif k == "fn_regions_bed":
             o.fn_regions_bed = v.encode() if isinstance(v, str) else v
+        elif k in ("fn_muts_txt", "fn_muts_bed", "fn_muts_vcf"):        # -m / -b / -v
+            o.fn_muts_input = v.encode() if isinstance(v, str) else v
+            o.muts_input_type = {"fn_muts_bed": 0, "fn_muts_txt": 1, "fn_muts_vcf": 2}[k]
         else:
             if not hasattr(o, k):
                 raise KeyError(k)
@@ -205,7 +209,8 @@ def opt_to_ref_argv(**kw):
          "indel_frac": "-R", "indel_extend": "-X", "indel_min": "-I", "rand_read": "-y", "max_n": "-n",
          "data_type": "-c", "strandedness": "-S", "read_one_strand": "-A", "seed": "-z",
          "quality_std": "-Q", "reads_output_type": "-o", "output_type": "-M", "flow_order": "-f",
-         "read_prefix": "-P", "fixed_quality": "-q", "e": "-e", "E": "-E", "fn_regions_bed": "-x"}
+         "read_prefix": "-P", "fixed_quality": "-q", "e": "-e", "E": "-E", "fn_regions_bed": "-x",
+         "fn_muts_txt": "-m", "fn_muts_bed": "-b", "fn_muts_vcf": "-v"}
     argv = []
     for k, v in kw.items():
         if k == "length":

@@ -18,7 +18,8 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle import pyoracle as po  # noqa: E402
 
@@ -96,7 +97,16 @@ MATRIX = {
                                                                         ("hp", 1, 2000), ("hp", 2000, 2600)]),
     "regions_skip_n": dict(seed=33, C=3, length=(80, 80), dist=300, std_dev=20,
                            regions=[("chrA", 5010, 5590), ("chrB", 1000, 11000), ("hp", 500, 7500)]),
+    # -m / -v / -b: mutations replayed from a file (fixtures next to this script; the .txt and .vcf are what the
+    # reference itself wrote for `-z 40 -r 0.01 -R 0.3 -X 0.6 -M 2`, the .vcf with two untagged records appended,
+    # the .bed is hand-written: explicit and random bases, an overlap that is ignored, an N, a 26-base insertion)
+    "replay_txt": dict(seed=41, N=2000, muts_txt="replay_muts.txt"),
+    "replay_vcf": dict(seed=42, N=2000, muts_vcf="replay_muts.vcf"),
+    "replay_bed": dict(seed=43, N=2000, length=(100, 100), muts_bed="replay_muts.bed"),
+    "replay_bed_hap_C": dict(seed=44, C=2, is_hap=1, muts_bed="replay_muts.bed"),
 }
+REPLAY_SOURCE = dict(seed=40, output_type=2, mut_rate=0.01, indel_frac=0.3, indel_extend=0.6)
+REPLAY_VCF_EXTRA = "hp\t7996\t.\tA\tC\t.\t.\tnote=untagged\nhp\t7998\t.\tAC\tGT\t.\t.\tnote=untagged_again\n"
 
 
 def materialize(opts, outdir):
@@ -108,6 +118,9 @@ def materialize(opts, outdir):
             for name, a, b in opts.pop("regions"):
                 f.write("%s\t%d\t%d\n" % (name, a, b))
         opts["fn_regions_bed"] = path
+    for k in ("muts_txt", "muts_bed", "muts_vcf"):
+        if k in opts:
+            opts["fn_" + k] = os.path.join(HERE, opts.pop(k))
     return opts
 
 
@@ -138,6 +151,15 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         fasta = synth_fasta(os.path.join(td, "synth.fa"))
         res["_fasta_md5"] = md5_of(fasta)
+        # the replay fixtures: the reference's own mutation files of one run
+        sub = os.path.join(td, "replay_src")
+        os.makedirs(sub)
+        subprocess.run([po.ref_binary()] + po.opt_to_ref_argv(**REPLAY_SOURCE) + [fasta, os.path.join(sub, "src")], check=True,
+                       stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
+        with open(os.path.join(sub, "src.mutations.txt")) as f, open(os.path.join(HERE, "replay_muts.txt"), "w") as g:
+            g.write(f.read())
+        with open(os.path.join(sub, "src.mutations.vcf")) as f, open(os.path.join(HERE, "replay_muts.vcf"), "w") as g:
+            g.write(f.read() + REPLAY_VCF_EXTRA)
         for name, opts in MATRIX.items():
             res[name] = run_ref(fasta, opts, td)
             print(name, res[name])
