@@ -21,6 +21,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -115,7 +116,9 @@ int usage(const Options &o)
     fprintf(stderr, "         -H            haploid mode\n");
     fprintf(stderr, "         -z INT        random seed (-1 uses the current time) [%d]\n", o.seed);
     fprintf(stderr, "         -M INT        output 0: reads and mutations, 1: reads only, 2: mutations only [%d]\n", o.output_type);
-    fprintf(stderr, "         -m/-b/-v FILE replay mutations from txt / bed / vcf (not supported by this build)\n");
+    fprintf(stderr, "         -m FILE       the mutations txt file to re-create [%s]\n", o.muts_input_type != 0 ? "not using" : o.fn_muts_input.c_str());
+    fprintf(stderr, "         -b FILE       the bed-like file set of candidate mutations [%s]\n", o.muts_input_type != 1 ? "not using" : o.fn_muts_input.c_str());
+    fprintf(stderr, "         -v FILE       the vcf file set of candidate mutations (use pl tag for strand) [%s]\n", o.muts_input_type != 2 ? "not using" : o.fn_muts_input.c_str());
     fprintf(stderr, "         -x FILE       the bed of regions to cover [%s]\n", o.fn_regions_bed.empty() ? "not using" : o.fn_regions_bed.c_str());
     fprintf(stderr, "         -P STRING     a read prefix to prepend to each read name\n");
     fprintf(stderr, "         -q STRING     a fixed base quality to apply (single character)\n");
@@ -396,16 +399,27 @@ bool get_ins(const Hap &h, int64_t i, uint64_t *n, uint64_t *ins)
 }
 
 // mut_add_ins with random bases, src/mut.c:282-377
-void add_insertion(const Options &o, Hap &h1, Hap &h2, int64_t i, uint64_t c)
+// mut_add_ins, src/mut.c:282-377.  hap < 0: draw the ploidy; bases == nullptr: random bases (num == 0: draw the length too);
+// bases given: their length counts and N / unknown letters become random bases
+void add_insertion(const Options &o, Hap &h1, Hap &h2, int64_t i, uint64_t c, int hap = -1, const char *bases = nullptr, uint64_t num = 0)
 {
-    uint64_t num = 0, ins = 0;
-    int hap;
-    do { num++; } while (num < INS_LONG_MAX && ((long long)num < o.indel_min || g_rng.next() < o.indel_extend));
-    if (o.is_hap || g_rng.next() < 0.333333) hap = 3;
-    else if (g_rng.next() < 0.5) hap = 1;
-    else hap = 2;
+    uint64_t ins = 0;
+    if (!bases) {
+        if (num == 0) do { num++; } while (num < INS_LONG_MAX && ((long long)num < o.indel_min || g_rng.next() < o.indel_extend));
+    } else num = strlen(bases);
+    if (INS_LONG_MAX < num) num = INS_LONG_MAX;
+    if (hap < 0) {
+        if (o.is_hap || g_rng.next() < 0.333333) hap = 3;
+        else if (g_rng.next() < 0.5) hap = 1;
+        else hap = 2;
+    }
     if (num <= INS_SHORT_MAX) {
-        for (uint64_t j = 0; j < num; j++) ins = (ins << 2) | (uint64_t)(g_rng.next() * 4.0);
+        if (!bases) for (uint64_t j = 0; j < num; j++) ins = (ins << 2) | (uint64_t)(g_rng.next() * 4.0);
+        else for (int64_t j = (int64_t)num - 1; 0 <= j; --j) {
+            int base = g_nt4[(unsigned char)bases[j]];
+            if (base >= 4) base = (int)(g_rng.next() * 4.0);
+            ins = (ins << 2) | (uint64_t)base;
+        }
         const uint64_t v = (num << INS_LEN_SHIFT) | (ins << INS_SHIFT) | T_INSERT | c;
         if (hap & 1) h1.s[i] = v;
         if (hap & 2) h2.s[i] = v;
@@ -420,7 +434,10 @@ void add_insertion(const Options &o, Hap &h1, Hap &h2, int64_t i, uint64_t c)
     }
     int byte_i = 0, bit_i = 0;
     for (uint64_t left = num; left > 0; left--) {
-        const uint8_t b = (uint8_t)((int)(g_rng.next() * 4.0) << (bit_i << 1));
+        int base;
+        if (!bases) base = (int)(g_rng.next() * 4.0);
+        else { base = g_nt4[(unsigned char)bases[left - 1]]; if (base >= 4) base = (int)(g_rng.next() * 4.0); }
+        const uint8_t b = (uint8_t)(base << (bit_i << 1));
         if (pl[0]) pl[0][byte_i] |= b;
         if (pl[1]) pl[1][byte_i] |= b;
         if (++bit_i == 4) { bit_i = 0; byte_i++; }
@@ -547,6 +564,198 @@ void diref(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2)
             else { deleting = g_rng.next() < 0.5 ? 1 : 2; ret[deleting - 1]->s[i] = T_DELETE | c; }
             del_len = 1;
         } else add_insertion(o, h1, h2, i, c);
+    }
+    left_justify(seq, h1, h2);
+}
+
+// ---- mutations to replay: -m TXT (src/mut_txt.c), -b BED (src/mut_bed.c), -v VCF (src/mut_vcf.c) ------------------------
+struct ContigList { std::vector<std::string> name; std::vector<uint32_t> len; };
+struct MutRec {
+    int32_t contig; uint32_t start, end;      // BED: zero-based start, end; TXT / VCF: start = one-based position
+    int type, is_hap;                         // T_SUBST / T_INSERT / T_DELETE; TXT / VCF: haplotype bits
+    std::string bases; bool has_bases_ptr;    // (VCF deletions carry no bases)
+};
+struct MutsInput {
+    int kind = -1;                            // 0 TXT, 1 BED, 2 VCF (the order of the -m / -b / -v switches)
+    std::vector<MutRec> recs;
+};
+[[noreturn]] void die(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    exit(1);
+}
+char iupac_to_mut(char iupac, char base)                                     // src/dwgsim.c:202-213
+{
+    static const char *codes = "XACMGRSVTWYHKDBN";
+    const int b = g_nt4[(unsigned char)base];
+    for (int i = 0; i < 4; i++) if (codes[(1 << (b & 3)) | (1 << (i & 3))] == iupac) return "ACGTN"[i];
+    return 'X';
+}
+int muttype_of(char *str)                                                    // src/dwgsim.c:183-200
+{
+    for (char *p = str; *p; ++p) *p = (char)tolower((unsigned char)*p);
+    const std::string t = str;
+    if (t == "snp" || t == "substitute" || t == "sub" || t == "s") return (int)T_SUBST;
+    if (t == "insertion" || t == "insert" || t == "ins" || t == "i") return (int)T_INSERT;
+    if (t == "deletion" || t == "delet" || t == "del" || t == "d") return (int)T_DELETE;
+    return -1;
+}
+void read_muts_txt(FILE *fp, const ContigList &c, MutsInput &M)              // src/mut_txt.c:39-128
+{
+    char name[1024], mut[1024], ref;
+    uint32_t pos, prev_pos = 0, is_hap;
+    size_t i = 0;
+    while (0 < fscanf(fp, "%1023s\t%u\t%c\t%1023s\t%d", name, &pos, &ref, mut, &is_hap)) {
+        while (i < c.name.size() && c.name[i] != name) { i++; prev_pos = 0; }
+        if (i == c.name.size()) die("Error: mutation contig not found or out of order [%s]\n", name);
+        if (pos <= 0 || c.len[i] < pos) die("Error: start out of range [%s,%u]\n", name, pos);
+        if (pos < prev_pos) die("Error: out of order [%s,%u]\n", name, pos);
+        MutRec r{(int32_t)i, pos, 0, 0, (int)is_hap, mut, true};
+        if ('-' == ref && '-' != mut[0]) r.type = (int)T_INSERT;
+        else if ('-' != ref && '-' == mut[0]) r.type = (int)T_DELETE;
+        else if ('-' != ref && '-' != mut[0]) {
+            r.type = (int)T_SUBST;
+            if (is_hap < 3) {                                                 // heterozygous: IUPAC code of reference + alternative
+                if (g_nt4[(unsigned char)r.bases[0]] < 4) die("Error: heterozygous bases must be in IUPAC form\n");
+                const char b = iupac_to_mut(r.bases[0], ref);
+                if ('X' == b) die("Error: out of range\n");
+                r.bases.assign(1, b);
+            }
+        } else die("Error: out of range\n");
+        M.recs.push_back(r);
+    }
+}
+void read_muts_bed(FILE *fp, const ContigList &c, MutsInput &M)              // src/mut_bed.c:37-137
+{
+    char name[1024], type[1024], bases[1024];
+    uint32_t start, end, prev_contig = 0, max_end = 0;
+    size_t i = 0;
+    while (0 < fscanf(fp, "%1023s\t%u\t%u\t%1023s\t%1023s", name, &start, &end, bases, type)) {
+        while (i < c.name.size() && c.name[i] != name) i++;
+        if (i == c.name.size()) die("Error: contig not found [%s]\n", name);
+        if (c.len[i] <= start) die("Error: start out of range [%s,%u]\n", name, start);
+        if (c.len[i] < end) die("Error: end out of range [%s,%u]\n", name, end);
+        if (end <= start) die("Error: end <= start [%s,%u,%u]\n", name, start, end);
+        if (0 != strcmp("*", bases) && (end - start) != strlen(bases)) die("Error: bases did not match start and end [%s,%u,%u,%s]\n", name, start, end, bases);
+        if (prev_contig == (uint32_t)i && start + 1 <= max_end) {
+            fprintf(stderr, "Warning: overlapping entries, ignoring entry [%s\t%u\t%u\t%s\t%s]\n", name, start, end, bases, type);
+            continue;
+        }
+        if (prev_contig != (uint32_t)i || max_end < end) { prev_contig = (uint32_t)i; max_end = end; }
+        const std::string type_in = type;
+        const int t = muttype_of(type);
+        if (t == (int)T_INSERT && INS_SHORT_MAX < end - start)
+            die("Error: insertion of length %d exceeded the maximum supported length of %d\n", (int)(end - start), (int)INS_SHORT_MAX);
+        if (t < 0) die("Error: mutation type unrecognized [%s]\n", type);
+        M.recs.push_back(MutRec{(int32_t)i, start, end, t, 0, bases, true});
+    }
+}
+void read_muts_vcf(FILE *fp, const ContigList &c, MutsInput &M)              // src/mut_vcf.c:42-278, line by line
+{
+    static int warned = 0;
+    std::string line;
+    char name[1024] = "", id[1024] = "", ref[1024] = "", alt[1025] = "";
+    uint32_t pos = 0, prev_pos = 0;
+    size_t i = 0;
+    int ch;
+    do {
+        line.clear();
+        while (EOF != (ch = fgetc(fp)) && ch != '\n' && ch != '\r') line.push_back((char)ch);
+        if (line.empty() || line[0] == '#') continue;
+        if (EOF == sscanf(line.c_str(), "%1023s\t%u\t%1023s\t%1023s\t%1024s", name, &pos, id, ref, alt)) die("Error: VCF parsing error\n");
+        uint32_t is_hap = 4;
+        for (size_t s = 0; s + 4 < line.size(); s++)                         // [\t;]pl=[1-3]
+            if (('\t' == line[s] || ';' == line[s]) && 'p' == line[s + 1] && 'l' == line[s + 2] && '=' == line[s + 3]) {
+                switch (line[s + 4]) {
+                    case '1': is_hap = 1; break;
+                    case '2': is_hap = 2; break;
+                    case '3': is_hap = 3; break;
+                    default: die("Error: Could not determine the strand of the mutation from the 'pl' tag.\n");
+                }
+                break;
+            }
+        if (4 == is_hap && 0 == warned) {                                     // NB: later untagged records keep is_hap = 4 (no haplotype)
+            fprintf(stderr, "Warning: strand of the mutation not found; please use the 'pl' tag.\n");
+            warned = 1; is_hap = 3;
+        }
+        while (i < c.name.size() && c.name[i] != name) { i++; prev_pos = 0; }
+        if (i == c.name.size()) die("Error: contig not found [%s]\n", name);
+        if (pos <= 0 || c.len[i] < pos) die("Error: start out of range [%s,%u]\n", name, pos);
+        if (pos < prev_pos) die("Error: out of order [%s,%u]\n", name, pos);
+        int ref_l = (int)strlen(ref), alt_l = (int)strlen(alt), j;
+        if (1 == ref_l && ref[0] == '.') { ref[0] = 0; ref_l = 0; }
+        if (1 == alt_l && alt[0] == '.') { alt[0] = 0; alt_l = 0; }
+        if (0 == alt_l && 0 == ref_l) die("Error: empty alleles\n");
+        for (j = 0; j < alt_l; j++) if (',' == alt[j]) die("Error: multiple alleles are not supported\n");
+        for (j = 0; j < ref_l; j++) { ref[j] = "ACGTN"[std::min<int>(g_nt4[(unsigned char)ref[j]], 4)]; if ('N' == ref[j]) die("Error: non-ACGT base found\n"); }
+        for (j = 0; j < alt_l; j++) { alt[j] = "ACGTN"[std::min<int>(g_nt4[(unsigned char)alt[j]], 4)]; if ('N' == alt[j]) die("Error: non-ACGT base found\n"); }
+        if (ref_l == alt_l) {
+            for (j = 0; j < ref_l; j++) M.recs.push_back(MutRec{(int32_t)i, pos + (uint32_t)j, 0, (int)T_SUBST, (int)is_hap, std::string(1, alt[j]), true});
+        } else if (ref_l < alt_l) {
+            for (j = 0; j < ref_l; j++, pos++) if (ref[j] != alt[j]) break;
+            M.recs.push_back(MutRec{(int32_t)i, pos, 0, (int)T_INSERT, (int)is_hap, alt + j, true});
+        } else {
+            for (j = 0; j < alt_l; j++, pos++) if (ref[j] != alt[j]) break;
+            if (j == ref_l) die("Error: no deleted bases\n");
+            for (; j < ref_l; j++, pos++) M.recs.push_back(MutRec{(int32_t)i, pos, 0, (int)T_DELETE, (int)is_hap, "", false});
+        }
+        prev_pos = pos;
+    } while (ch != EOF);
+}
+
+void left_justify(const std::vector<uint8_t> &seq, Hap &h1, Hap &h2);
+// mut_diref, replay branches, src/mut.c:644-745, then :752-757
+void diref_replay(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, int contig_i, const MutsInput &M)
+{
+    const int64_t l = (int64_t)seq.size();
+    h1.reset((size_t)l); h2.reset((size_t)l);
+    Hap *ret[2] = {&h1, &h2};
+    for (int64_t j = 0; j < l; ++j) h1.s[j] = h2.s[j] = (uint64_t)g_nt4[seq[j]];
+    if (M.kind == 1) {
+        for (const MutRec &r : M.recs) {
+            if (r.contig == contig_i) {
+                const bool has_bases = r.bases != "*";
+                bool is_hom = false;
+                int hap, which_hap = 0;
+                if (o.is_hap || g_rng.next() < 0.333333) { is_hom = true; hap = 3; }
+                else { which_hap = g_rng.next() < 0.5 ? 0 : 1; hap = 1 << which_hap; }
+                if (r.type == (int)T_SUBST) {
+                    for (uint32_t j = r.start; j < r.end; ++j) {
+                        uint64_t c = (uint64_t)g_nt4[seq[j]];
+                        if (!has_bases) { const double x = g_rng.next(); c = (c + (uint64_t)(x * 3.0 + 1)) & 3; }
+                        else c = (uint64_t)g_nt4[(unsigned char)r.bases[j - r.start]];
+                        if (is_hom) h1.s[j] = h2.s[j] = T_SUBST | c;
+                        else ret[which_hap]->s[j] = T_SUBST | c;
+                    }
+                } else if (r.type == (int)T_DELETE) {
+                    for (uint32_t j = r.start; j < r.end; ++j) {
+                        const uint64_t c = (uint64_t)g_nt4[seq[j]];
+                        if (is_hom) h1.s[j] = h2.s[j] = T_DELETE | c;
+                        else ret[which_hap]->s[j] = T_DELETE | c;
+                    }
+                } else if (r.type == (int)T_INSERT) {
+                    const uint64_t c = (uint64_t)g_nt4[seq[r.start]];
+                    if (!has_bases) add_insertion(o, h1, h2, r.start, c, hap, nullptr, r.end - r.start);
+                    else add_insertion(o, h1, h2, r.start, c, hap, r.bases.c_str(), 0);
+                }
+            } else if (contig_i < r.contig) break;
+        }
+    } else {
+        for (const MutRec &r : M.recs) {
+            if (r.contig != contig_i) continue;
+            const uint32_t pos = r.start;
+            const uint64_t c = (uint64_t)g_nt4[seq[pos - 1]];
+            if (r.type == (int)T_DELETE) {
+                if (r.is_hap & 1) h1.s[pos - 1] |= T_DELETE | c;
+                if (r.is_hap & 2) h2.s[pos - 1] |= T_DELETE | c;
+            } else if (r.type == (int)T_SUBST) {
+                if (r.is_hap & 1) h1.s[pos - 1] = T_SUBST | g_nt4[(unsigned char)r.bases[0]];
+                if (r.is_hap & 2) h2.s[pos - 1] = T_SUBST | g_nt4[(unsigned char)r.bases[0]];
+            } else if (r.type == (int)T_INSERT) add_insertion(o, h1, h2, pos - 1, c, r.is_hap, r.bases.c_str(), 0);
+        }
     }
     left_justify(seq, h1, h2);
 }
@@ -686,7 +895,6 @@ FILE *xopen(const std::string &fn, const char *mode)
 }
 
 // ---- -x regions (src/regions_bed.c) ------------------------------------------------------------------------------------
-struct ContigList { std::vector<std::string> name; std::vector<uint32_t> len; };
 struct Regions {
     std::vector<uint32_t> contig, start, end;
     // regions_bed_init, src/regions_bed.c:43-115: contigs in FASTA order, starts sorted, overlapping regions merged
@@ -724,10 +932,6 @@ int main(int argc, char **argv)
     Options o;
     int first = 0;
     if (!parse_options(o, argc, argv, &first)) return usage(o);
-    if (o.muts_input_type >= 0) {
-        fprintf(stderr, "[dwgsim_core] Error: -m/-b/-v are not supported by this build\n");
-        return 1;
-    }
     const std::string fn_fa = argv[first], prefix = argv[first + 1];
     Fasta fa;
     if (!fa.open(fn_fa.c_str())) { fprintf(stderr, "[main] fail to open file '%s'. Abort!\n", fn_fa.c_str()); return 1; }
@@ -797,6 +1001,15 @@ int main(int argc, char **argv)
         fprintf(fp_vcf, "##INFO=<ID=mt,Number=1,Type=String,Description=\"Variant Type: SUBSTITUTE/INSERT/DELETE\">\n");
         fprintf(fp_vcf, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n");
     }
+    MutsInput muts;
+    if (o.muts_input_type >= 0) {                                        // src/dwgsim.c:494-497
+        FILE *fp = xopen(o.fn_muts_input, "r");
+        muts.kind = o.muts_input_type;
+        if (muts.kind == 0) read_muts_txt(fp, contigs, muts);
+        else if (muts.kind == 1) read_muts_bed(fp, contigs, muts);
+        else read_muts_vcf(fp, contigs, muts);
+        fclose(fp);
+    }
     Regions regions;
     const bool use_regions = !o.fn_regions_bed.empty();
     if (use_regions) {                                                   // src/dwgsim.c:499-506
@@ -856,7 +1069,8 @@ int main(int argc, char **argv)
             prev_skip = 0;
         }
         double t0 = now();
-        diref(o, seq, h1, h2);
+        if (muts.kind >= 0) diref_replay(o, seq, h1, h2, contig_i, muts);
+        else diref(o, seq, h1, h2);
         t_mut += now() - t0; t0 = now();
         if (o.output_type != 1) print_mutations(name.c_str(), seq, h1, h2, fp_txt, fp_vcf);
         t_print += now() - t0;

@@ -57,6 +57,11 @@ MUT_CASES = {
     "ion_base_error_calibration": (dict(seed=28, data_type=2, length=(100, 0), e=0.02, flow_order=FLOW, use_base_error=1), "synth"),
     "skips_short_contig_paired": (dict(seed=9, dist=3000, std_dev=2000, mut_rate=0.01), "synth"),
     "regions_skip_rules": (dict(make_golden.MATRIX["regions_skip_n"], mut_rate=0.01), "synth"),
+    # -m / -v / -b: mutations replayed from a file (src/mut.c:644-745); the oracle is pinned on these by test_oracle_matrix.py
+    "replay_txt": (make_golden.MATRIX["replay_txt"], "synth"),
+    "replay_vcf": (make_golden.MATRIX["replay_vcf"], "synth"),
+    "replay_bed": (make_golden.MATRIX["replay_bed"], "synth"),
+    "replay_bed_haploid": (make_golden.MATRIX["replay_bed_hap_C"], "synth"),
 }
 
 
@@ -82,10 +87,31 @@ def test_option_surface(cli, synth_fa, tmp_path):
     assert r.returncode == 1 and b"-c was out of range" in r.stderr
     r = run(cli, ["-c", "2", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
     assert r.returncode == 1 and b"-f is required" in r.stderr
-    r = run(cli, ["-m", "muts.txt", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
+    r = run(cli, ["-m", "no_such_muts.txt", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
+    assert r.returncode == 1
+    r = run(cli, ["-m", "a.txt", "-b", "b.bed", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)   # one input at most
     assert r.returncode == 1
     r = run(cli, ["-d", "abc", "-C", "0", synth_fa, str(tmp_path / "x")], check=False)
     assert r.returncode == 1 and b"is not a number" in r.stderr
+
+
+def test_replayed_txt_reproduces_itself(cli, synth_fa, tmp_path):
+    """-m with the reference's own .mutations.txt gives that file back (the purpose of the option), and rejected
+    inputs end like the reference's parsers do (src/mut_txt.c:58-69, src/mut_bed.c:57-80)"""
+    src = os.path.join(HERE, "golden", "replay_muts.txt")
+    run(cli, ["-M", "2", "-z", "3", "-m", src, synth_fa, str(tmp_path / "x")])     # -M 2 like the run that wrote it (no contig skipped)
+    assert open(str(tmp_path / "x.mutations.txt")).read() == open(src).read()
+    bad = tmp_path / "bad.txt"
+    bad.write_text("chrA\t500\tA\tC\t3\nchrA\t100\tA\tG\t3\nchrZ\t5\tA\tG\t3\n")
+    r = run(cli, ["-C", "0", "-m", str(bad), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"mutation contig not found or out of order [chrZ]" in r.stderr
+    bad.write_text("chrA\t500\tA\tC\t1\n")                       # heterozygous substitutions must be IUPAC codes
+    r = run(cli, ["-C", "0", "-m", str(bad), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"heterozygous bases must be in IUPAC form" in r.stderr
+    bed = tmp_path / "bad.bed"
+    bed.write_text("chrA\t10\t40\t*\tins\n")
+    r = run(cli, ["-C", "0", "-b", str(bed), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"exceeded the maximum supported length of 26" in r.stderr
 
 
 def test_reference_stderr_lines(cli, synth_fa, tmp_path):
@@ -120,6 +146,8 @@ GPU_CASES = {
     "ion_plain": (dict(seed=25, N=1200, data_type=2, length=(200, 0), e=0.02, flow_order=FLOW), ["--uncompressed"]),
     "regions_N": (make_golden.MATRIX["regions_N"], ["--uncompressed"]),
     "regions_skip_n_gz": (make_golden.MATRIX["regions_skip_n"], []),
+    "replay_bed_gz": (make_golden.MATRIX["replay_bed"], []),
+    "replay_vcf_plain": (make_golden.MATRIX["replay_vcf"], ["--uncompressed"]),
 }
 
 
