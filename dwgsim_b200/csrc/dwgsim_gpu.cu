@@ -160,7 +160,7 @@ format_kernel_t format_kernel_of(const SimParams &sp)
 size_t tp_smem_bytes(const SimParams &sp)
 {
     size_t words = (((size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) + 1) & ~(size_t)1) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
-    words += 2 * (size_t)std::max(window_slots(sp.len[0]), window_slots(sp.len[1])) * kTpThreads;     // the reference window
+    words += 2 * (size_t)sp.win_slots * kTpThreads;                                                 // the reference window
     for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);
     const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4;
     return words * 4 + 3 * 1026 * 2 + flow + 32;
@@ -457,10 +457,14 @@ int update_caps(dwgsim_gpu *h)
     h->sp.name_cap = (int32_t)((name_cap_of(h) + 15) & ~15ull);
     h->sp.inv_name_chunks = (uint32_t)(4294967296.0 / std::max(h->sp.name_cap >> 4, 1)) + 1u;
     for (int k = 0; k < 3; ++k) h->sp.rec_cap[k] = (int32_t)cap[k];
-    // mini-tile of the format kernel: pairs per warp, as many as keep two 16-warp CTAs on an SM (<= 113 KB each), at most 4
-    // (2x150: 4 pairs = 152 eight-base groups = 4.75 rounds of the warp); DWGSIM_TILE_PAIRS overrides it for experiments
-    h->sp.tile_pairs = 4;
-    if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(32, atoi(e)));
+    // mini-tile of the format kernel: pairs per warp, about 150 eight-base groups (2x150: 4 pairs = 152 groups = 4.75 rounds
+    // of the warp; 2x50: 11 pairs), fewer while two 16-warp CTAs do not fit an SM (<= 113 KB each); at most 31 (one lane
+    // per pair + one in step 0); DWGSIM_TILE_PAIRS overrides it for experiments
+    {
+        const int groups = std::max((h->sp.cap[0] + 7) / 8 + (h->sp.cap[1] + 7) / 8, 1);
+        h->sp.tile_pairs = std::max(1, std::min(31, (152 + groups - 1) / groups));       // ~150 groups of 8 bases per warp
+    }
+    if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(31, atoi(e)));
     while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 113 * 1024) --h->sp.tile_pairs;
     const FormatSmem L = format_smem_layout(h->sp);
     if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
@@ -655,13 +659,14 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         JobLists J;
         J.retry = w.jobs; J.random = w.jobs + (size_t)w.cap_pairs; J.count = w.status + 2;
         // two passes (kernels.cuh "Job lists"): fresh pairs, then the retries and random pairs they left behind
-        for (int pass = 0; pass < 2; ++pass) {
+        const int n_pass = 2;
+        for (int pass = 0; pass < n_pass; ++pass) {
             if (sp.data_type == 2)
                 simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);
             else
                 simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);
         }
-        extra_launches = 1;
+        extra_launches = n_pass - 1;
     }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[1], st));
     layout_count_random_kernel<<<nblk, kThreads, 0, st>>>(w.recs, n, w.blk_rand);
@@ -888,6 +893,17 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         const SimParams &sp = h->sp;
         const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15, flr = (sp.flow_order_len + 15) & ~15;
         const size_t smem_a = (size_t)kWarpsPerBlock * (cap0 + cap1 + flr) + flr;
+        // the reference window of the thread-per-pair kernel costs shared memory: keep it when at least four CTAs (16 warps)
+        // still fit an SM or when it does not cost a CTA (long Ion Torrent rows leave room for two or three CTAs only)
+        {
+            auto ctas = [&](size_t bytes) { return (int)std::min<size_t>(6, (227 * 1024) / (bytes + 1024)); };
+            h->sp.win_slots = 0;
+            const int without = ctas(tp_smem_bytes(h->sp));
+            h->sp.win_slots = std::max(window_slots(sp.len[0]), window_slots(sp.len[1]));
+            const int with = ctas(tp_smem_bytes(h->sp));
+            if (const char *e = getenv("DWGSIM_WINDOW")) { if (atoi(e) == 0) h->sp.win_slots = 0; }
+            else if (with < 4 && with < without) h->sp.win_slots = 0;
+        }
         const size_t smem_tp = tp_smem_bytes(sp);
         // one staging row per thread in shared memory bounds the combined read length (about 3,400 symbols); Ion Torrent
         // rows hold 2*len+64 symbols and longer ones fall back to the warp-per-pair kernel

@@ -607,10 +607,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 // start the copies of the words a walk of s bases from `start` will read
-__device__ __forceinline__ void window_prime(const ContigView &c, RefWindow &R, int start, int dir, int s)
+__device__ __forceinline__ void window_prime(const ContigView &c, RefWindow &R, int start, int dir, int s, int max_slots)
 {
+    if (max_slots <= 0) return;                                            // no window: every group reads HBM / L2 directly
     cp_async_wait<0>();                                                    // copies of a window that was never read
-    R.slots = window_slots(s);
+    R.slots = min(window_slots(s), max_slots);
     R.first = dir > 0 ? (start >> 5) : ((start >> 5) - R.slots + 2);        // backward: the group at `start` may need word (start >> 5) + 1
     const uint2 *src = reinterpret_cast<const uint2 *>(c.ref2) + R.first;
     for (int t = 0; t < R.slots; ++t) cp_async8(R.base + (uint32_t)t * kWindowSlotStride, src + t);
@@ -1016,7 +1017,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     uint2 *const win_mem = reinterpret_cast<uint2 *>(tile + (((size_t)kTpThreads * RS + 1) & ~(size_t)1));
     TpTables T;
     {
-        uint32_t *p32 = reinterpret_cast<uint32_t *>(win_mem + (size_t)max(window_slots(P.len[0]), window_slots(P.len[1])) * kTpThreads);
+        uint32_t *p32 = reinterpret_cast<uint32_t *>(win_mem + (size_t)P.win_slots * kTpThreads);
         const bool isz_smem = P.isize_n <= kIsizeSmemMax;  // wider insert-size tables stay in HBM / L2 (one lookup per pair)
         uint32_t *isz = p32; p32 += isz_smem ? ((P.isize_n + 1) & ~1) : 0;
         uint32_t *gp[2], *ac[2];
@@ -1043,6 +1044,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         __syncthreads();                                                 // the only CTA-wide barrier
     }
     constexpr bool ion = kIon;
+    const bool defer = pass == 0;
     const int solid = P.data_type == 1;
     const int s0 = P.len[0], s1 = P.len[1];
     uint32_t *dst0 = row, *dst1 = row + P.nw[0];
@@ -1063,7 +1065,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         }
         int staged = -1;
         bool push_retry = false, push_random = false;
-        while (p >= 0) {                                                 // one trip in pass 0
+        while (p >= 0) {                                                 // one trip when retries are deferred
             const int64_t q = first + p;
             const uint64_t gidx = (uint64_t)(gidx_origin + q);
             PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), attempt};
@@ -1105,7 +1107,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             const uint4 b0 = draw_block(key, kStPair, 0, 0);
             if ((uint64_t)b0.x < P.thr_genomic) {                             // src/dwgsim.c:649
                 kind = 1;
-                if (pass == 0) { push_random = true; break; }
+                if (defer) { push_random = true; break; }
                 continue;
             }
             int contig_index;
@@ -1152,7 +1154,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 int hint1 = -1;
                 uint32_t any1 = 0;
                 const bool in0 = st0 >= 0 && st0 < cv.len, in1 = s1 > 0 && st1 >= 0 && st1 < cv.len;
-                if (in0) window_prime(cv, R, st0, strand0 ? -1 : 1, s0);
+                if (in0) window_prime(cv, R, st0, strand0 ? -1 : 1, s0, P.win_slots);
                 if (in1) prefetch_read(cv, st1, strand1, s1);                // end 1's window is primed after walk 0: have it in L2 by then
                 if (s1 > 0) { hint1 = walk_hint(cv, hap, st1, strand1); if (in1) any1 = n_precheck(cv, st1, strand1 ? -1 : 1, s1); }
                 const int hint0 = walk_hint(cv, hap, st0, strand0);
@@ -1166,7 +1168,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     if (ok) {                                              // a rejected end 0 already rejects the pair
                         emit_begin(E1, dst1, solid);
                         R.slots = 0; R.fresh = false;
-                        if (in1) window_prime(cv, R, st1, strand1 ? -1 : 1, s1);
+                        if (in1) window_prime(cv, R, st1, strand1 ? -1 : 1, s1, P.win_slots);
                         R.has_n = any1 != 0;
                         ok1 = walk_thread(cv, hap, st1, strand1, s1, E1, w1, hint1, R);
                         if (ok1) { emit_end(E1); ok1 = E1.nN <= P.max_n; }
@@ -1179,11 +1181,11 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 if (attempt >= (uint32_t)kMaxTrials) {                    // 10001 rejected attempts: the host reports it
                     atomicOr(status, 1ull);
                     kind = 1; failed_flag = 1;
-                    if (pass == 0) { push_random = true; break; }
+                    if (defer) { push_random = true; break; }
                     continue;
                 }
                 ++attempt;
-                if (pass == 0) { push_retry = true; break; }
+                if (defer) { push_retry = true; break; }
                 continue;
             }
             if (!ion) {                                                   // src/dwgsim.c:866-881
@@ -1217,7 +1219,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             break;
         }
         __syncwarp();
-        if (pass == 0) {
+        if (defer) {
             const uint2 item = make_uint2((uint32_t)p, attempt | (failed_flag << 16));
             list_push(J.retry, J.count, push_retry, item, lane);
             list_push(J.random, J.count + 1, push_random, item, lane);
@@ -1643,14 +1645,14 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                         const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
                         const uint2 ent = lds64(a_guide + ((u >> 22) << 3));
                         qc[i] += P.qdelta_lo + (int)ent.y + (u > ent.x ? 1 : 0);
-                        tails |= ent.y;
+                        if (i < cnt) tails |= ent.y;                        // (draws past the end of the read are not used)
                     }
                     if ((int)tails < 0) {                                   // some draw fell into a tail bucket (rare): redo those
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
                             const uint2 ent = lds64(a_guide + ((u >> 22) << 3));
-                            if ((int)ent.y < 0) qc[i] += qdelta_rank_tail(ent, cdf, u) - (int)ent.y - (u > ent.x ? 1 : 0);
+                            if (i < cnt && (int)ent.y < 0) qc[i] += qdelta_rank_tail(ent, cdf, u) - (int)ent.y - (u > ent.x ? 1 : 0);
                         }
                     }
                 }
