@@ -320,21 +320,25 @@ def main():
     stream = torch.cuda.ExternalStream(gpu.cuda_stream(), device=torch.device("cuda", local_rank))
     rand_base = 0
 
-    exchange = None
+    # N > 1: the one exchange of the path -- random-pair counts of the round, so that rand_ii in the names stays the
+    # global running count (src/dwgsim.c:1096) -- as an NCCL all-gather of device counters enqueued on the library's
+    # stream between the simulate passes and the layout kernels: no host round trip inside a step
     if world > 1:
-        from dwgsim_b200 import shard
-        exchange = shard.make_exchange()
+        allc = torch.zeros(world, dtype=torch.int64, device="cuda")
+        base_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+        running_t = torch.zeros(1, dtype=torch.int64, device="cuda")
 
     def step(k):
         nonlocal rand_base
         first = ((k % n_steps_avail) * world + rank) * B
         if world > 1:
-            # the one exchange of the path: random-pair counts of the round (all-gather over NCCL), so that rand_ii
-            # in the names stays the global running count (src/dwgsim.c:1096)
-            cnt = gpu.resident_begin(first, B, True)
-            before, tot = exchange(k, cnt)
-            b = gpu.resident_finish(rand_base + before)
-            rand_base += tot
+            gpu.resident_begin(first, B, False)
+            cnt = torch.as_tensor(_CudaArray(gpu.resident_count_ptr(), 8), device="cuda").view(torch.int64)
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(allc, cnt)
+                torch.add(running_t, allc[:rank].sum(), out=base_t)
+                b = gpu.resident_finish_dev(base_t.data_ptr())
+                running_t.add_(allc.sum())
         else:
             b = gpu.simulate_resident(first, B, rand_base)
             rand_base += b.n_random

@@ -230,6 +230,17 @@ class DwgsimGpu:
         self._check(self._L.dwgsim_gpu_resident_finish(self._h, rand_serial_base, C.byref(b)))
         return b
 
+    def resident_count_ptr(self):
+        """device address of the uint64 random-pair count of the batch begun last"""
+        p = C.c_uint64()
+        self._check(self._L.dwgsim_gpu_resident_count_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def resident_finish_dev(self, rand_serial_base_device_ptr):
+        b = Batch()
+        self._check(self._L.dwgsim_gpu_resident_finish_dev(self._h, rand_serial_base_device_ptr, C.byref(b)))
+        return b
+
     def copy_stream(self, file_id, n_bytes):
         buf = C.create_string_buffer(max(int(n_bytes), 1))
         self._check(self._L.dwgsim_gpu_copy_stream(self._h, file_id, buf, n_bytes))

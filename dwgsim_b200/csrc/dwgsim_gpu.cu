@@ -688,7 +688,8 @@ int read_random_count(dwgsim_gpu *h, int64_t *n_random)
 }
 
 // phase 2: record lengths -> offsets -> FASTQ text; results land in ws.h_totals after a sync
-int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slot, bool timed, int *launches)
+int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int slot, bool timed, int *launches,
+                  const unsigned long long *rand_base_dev = nullptr)
 {
     Workspace &w = h->ws;
     const SimParams &sp = h->sp;
@@ -701,7 +702,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     (void)cap0; (void)cap1;
     cudaStream_t st = h->s_compute;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[4], st));
-    layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, w.blk_rand,
+    layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, rand_base_dev, w.blk_rand,
                                                      w.serial, w.lens, w.blk_len, w.names, w.name_len);
     layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
@@ -1093,7 +1094,8 @@ int dwgsim_gpu_resident_begin(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t
     return DWGSIM_GPU_OK;
 }
 
-int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
+namespace {
+int resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, const unsigned long long *rand_base_dev, dwgsim_gpu_batch_t *out)
 {
     if (!h || !out || h->pending_first < 0) return DWGSIM_GPU_ESTATE;
     cudaSetDevice(h->device);
@@ -1101,7 +1103,7 @@ int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim
     const int64_t first = h->pending_first;
     const int n = h->pending_n;
     h->pending_first = -1;
-    if ((rc = launch_format(h, first, n, rand_serial_base, 0, true, &launches))) return rc;
+    if ((rc = launch_format(h, first, n, rand_serial_base, 0, true, &launches, rand_base_dev))) return rc;
     BatchResult r;
     rc = collect_batch(h, true, &r);
     memset(out, 0, sizeof *out);
@@ -1109,8 +1111,27 @@ int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim
     h->last_slot = 0;
     out->n_pairs = n; out->n_random = r.n_random; out->n_failed_attempts = r.n_failed;
     out->ms_simulate = r.ms[0]; out->ms_layout = r.ms[1]; out->ms_format = r.ms[2];
-    out->n_launches = launches + 3;
+    out->n_launches = launches + 3 + (h->ion_warp_kernel ? 0 : 1);
     return rc;
+}
+}  // namespace
+
+int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
+{
+    return resident_finish(h, rand_serial_base, nullptr, out);
+}
+
+int dwgsim_gpu_resident_count_ptr(dwgsim_gpu_t *h, uint64_t *count_device_ptr)
+{
+    if (!h || !count_device_ptr || !h->ws.totals) return DWGSIM_GPU_ESTATE;
+    *count_device_ptr = (uint64_t)(uintptr_t)h->ws.totals;        // totals[0]: written by the scan that follows the simulate passes
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_resident_finish_dev(dwgsim_gpu_t *h, uint64_t rand_serial_base_device_ptr, dwgsim_gpu_batch_t *out)
+{
+    if (!rand_serial_base_device_ptr) return DWGSIM_GPU_EINVAL;
+    return resident_finish(h, 0, reinterpret_cast<const unsigned long long *>((uintptr_t)rand_serial_base_device_ptr), out);
 }
 
 int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)

@@ -1382,7 +1382,8 @@ layout_scan_blocks_kernel(unsigned long long *__restrict__ v, int m, int n_array
 // serial (ii or rand_ii) + record lengths per pair, block sums of the lengths
 __global__ void __launch_bounds__(kThreads)
 layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const PairRec *__restrict__ recs, int n,
-                      int64_t first, unsigned long long rand_base, const unsigned long long *__restrict__ blk_rand_excl,
+                      int64_t first, unsigned long long rand_base, const unsigned long long *__restrict__ rand_base_dev,
+                      const unsigned long long *__restrict__ blk_rand_excl,
                       unsigned long long *__restrict__ serial, uint32_t *__restrict__ lens /* [3][n] */,
                       unsigned long long *__restrict__ blk_len /* [3][nblk] */,
                       char *__restrict__ names /* [n][nvar][name_cap] */, uint16_t *__restrict__ name_len /* [n][2] */)
@@ -1395,7 +1396,7 @@ layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const
     for (int t = 0; t < kScanItems; ++t) if (base + t < n) c += (recs[base + t].flags & kRecRandom) ? 1u : 0u;
     uint32_t tot;
     uint32_t ex = block_exclusive_scan<uint32_t>(c, &tot, sw);
-    unsigned long long rs = rand_base + blk_rand_excl[blockIdx.x] + ex;
+    unsigned long long rs = rand_base + (rand_base_dev ? *rand_base_dev : 0ull) + blk_rand_excl[blockIdx.x] + ex;
     unsigned long long sum[3] = {0, 0, 0};
 #pragma unroll 1
     for (int t = 0; t < kScanItems; ++t) {

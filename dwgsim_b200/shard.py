@@ -34,11 +34,23 @@ def make_exchange(device=None, group=None):
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
+    # one collective and ONE device->host read per round (a list all_gather plus an .item() per rank costs a
+    # synchronising copy per rank: 0.4 ms per round at 8 GPUs)
+    mine = torch.zeros(1, dtype=torch.int64, device=device)
+    allc = torch.zeros(world, dtype=torch.int64, device=device)
+    state = {"flat": hasattr(dist, "all_gather_into_tensor")}
+
     def exchange(rnd, my_random):
-        mine = torch.tensor([int(my_random)], dtype=torch.int64, device=device)
-        allc = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allc, mine, group=group)
-        return prefix_of([int(x.item()) for x in allc], rank)
+        mine.fill_(int(my_random))
+        if state["flat"]:
+            try:
+                dist.all_gather_into_tensor(allc, mine, group=group)
+                return prefix_of(allc.tolist(), rank)
+            except (RuntimeError, NotImplementedError):
+                state["flat"] = False
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        return prefix_of([int(x.item()) for x in parts], rank)
 
     return exchange
 

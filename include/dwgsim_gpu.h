@@ -168,6 +168,12 @@ int dwgsim_gpu_simulate_resident(dwgsim_gpu_t *h, int64_t first, int64_t n, int6
  * count (pass NULL to skip the host sync), finish() lays the records out from rand_serial_base */
 int dwgsim_gpu_resident_begin(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t *n_random);
 int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim_gpu_batch_t *out);
+/* The same exchange without a host round trip (sharded runs over NCCL): after begin(.., NULL) the batch's random-pair
+ * count sits in device memory at *count_device_ptr (one uint64, valid in the order of dwgsim_gpu_cuda_stream), and
+ * finish_dev() reads rand_serial_base (one uint64) from device memory when its kernels run.  The caller enqueues the
+ * collective and the prefix arithmetic between the two calls on that stream. */
+int dwgsim_gpu_resident_count_ptr(dwgsim_gpu_t *h, uint64_t *count_device_ptr);
+int dwgsim_gpu_resident_finish_dev(dwgsim_gpu_t *h, uint64_t rand_serial_base_device_ptr, dwgsim_gpu_batch_t *out);
 /* copy one stream of the last resident batch to host memory (tests) */
 int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap);
 /* Queue a synthetic genome built procedurally inside the library (benchmarks only; no dense

@@ -64,3 +64,33 @@ def test_two_ranks_reproduce_unsharded_bytes(oracle, synth_fa, tmp_path):
     for fid, name in enumerate(gh.FILE_NAMES):
         merged = shard.interleave([parts[0][0][fid], parts[1][0][fid]])
         assert merged == want[fid], "%s: %s" % (name, gh.first_diff(want[fid], merged))
+
+
+def test_device_side_rand_base_equals_host_path():
+    """resident_begin + resident_finish_dev (rand_serial_base read from device memory, the NCCL path of bench.py) writes the
+    bytes of simulate_resident with the same base on the host, and the device counter holds the batch's random pairs"""
+    import torch
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    with DwgsimGpu(params_from_options(seed=5, length=(100, 100), rand_read=0.1)) as gpu:
+        gpu.genome_synthetic([300000, 200000], 11, 0.002, 0.2, 0.01, 10.0)
+        gpu.genome_finalize()
+        n, base = 20000, 123456789
+        b0 = gpu.simulate_resident(1000, n, base)
+        want = [gpu.copy_stream(k, b0.n_bytes[k]) for k in range(3)]
+        gpu.resident_begin(1000, n, False)
+        stream = torch.cuda.ExternalStream(gpu.cuda_stream())
+
+        class Arr:
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        cnt = torch.as_tensor(Arr(gpu.resident_count_ptr(), 8), device="cuda").view(torch.int64)
+        base_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            base_t.fill_(base)
+            b1 = gpu.resident_finish_dev(base_t.data_ptr())
+            seen = int(cnt.item())
+        assert seen == b1.n_random == b0.n_random and b0.n_random > 0
+        assert [gpu.copy_stream(k, b1.n_bytes[k]) for k in range(3)] == want
+        assert b"rand_0_0_0_0_1_1_0:0:0_0:0:0_%x" % base in want[0]          # the first random pair carries the base as rand_ii
