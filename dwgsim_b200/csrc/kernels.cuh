@@ -26,7 +26,10 @@ namespace dwg {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kScanItems = 4;
+#ifndef DWG_SCAN_ITEMS
+#define DWG_SCAN_ITEMS 1
+#endif
+constexpr int kScanItems = DWG_SCAN_ITEMS;       // pairs per thread of the layout kernels (1: most threads in flight; the kernels wait on loads)
 constexpr int kScanTile = kThreads * kScanItems;   // pairs per layout block
 constexpr int kMaxTrials = 10000;                  // src/dwgsim.c:837
 
