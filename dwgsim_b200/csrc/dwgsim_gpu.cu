@@ -659,7 +659,7 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         JobLists J;
         J.retry = w.jobs; J.random = w.jobs + (size_t)w.cap_pairs; J.count = w.status + 2;
         // two passes (kernels.cuh "Job lists"): fresh pairs, then the retries and random pairs they left behind
-        const int n_pass = 2;
+        const int n_pass = sp.data_type == 2 ? 1 : 2;          // (Ion Torrent lanes finish their own retries)
         for (int pass = 0; pass < n_pass; ++pass) {
             if (sp.data_type == 2)
                 simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);

@@ -1047,7 +1047,9 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         __syncthreads();                                                 // the only CTA-wide barrier
     }
     constexpr bool ion = kIon;
-    const bool defer = pass == 0;
+    // Ion Torrent rounds are long (the flow model runs per read): a second pass of a few warps costs more than repeating
+    // a walk inside the lane, so there every lane finishes its own pair
+    const bool defer = pass == 0 && !kIon;
     const int solid = P.data_type == 1;
     const int s0 = P.len[0], s1 = P.len[1];
     uint32_t *dst0 = row, *dst1 = row + P.nw[0];
@@ -1067,15 +1069,18 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             }
         }
         int staged = -1;
-        bool push_retry = false, push_random = false;
+        bool push_retry = false, push_random = false, walked = false;    // walked: both ends of an accepted attempt are staged
+        Walk w0, w1;
+        int strand0 = 0, strand1 = 0, hap = 0;
+        w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
         while (p >= 0) {                                                 // one trip when retries are deferred
             const int64_t q = first + p;
             const uint64_t gidx = (uint64_t)(gidx_origin + q);
             PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), attempt};
-            PairRec rec;
-            rec.attempt = (uint16_t)attempt;
-            rec.n_err_first = 0;
-            if (kind == 1) {                                             // random pair, src/dwgsim.c:983-1001
+            if (kind == 1) {
+                PairRec rec;
+                rec.attempt = (uint16_t)attempt;
+                rec.n_err_first = 0;                                             // random pair, src/dwgsim.c:983-1001
                 rec.flags = (uint8_t)(kRecRandom | (failed_flag ? kRecFailed : 0));
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -1131,11 +1136,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
                 if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) ok = false;
             }
-            Walk w0, w1;
             Emit E0, E1;
-            int n_err0 = 0, n_err1 = 0, err_first0 = 0, err_first1 = 0;
-            w0.ext = w1.ext = 0; w0.n_sub = w0.n_indel = w0.n_indel_first = w1.n_sub = w1.n_indel = w1.n_indel_first = 0;
-            int strand0 = 0, strand1 = 0, hap = 0;
             if (ok) {
                 const uint4 b1 = draw_block(key, kStPair, 0, 1);
                 hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
@@ -1191,6 +1192,18 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 if (defer) { push_retry = true; break; }
                 continue;
             }
+            walked = true;
+            break;
+        }
+        // the accepted attempt's epilogue runs after the loop, where the lanes of the warp are together again (inside it,
+        // a lane that retries would send the others through the error models a second time)
+        if (kIon) __syncwarp();                                          // (without it the lanes arrive here in the groups they left the loop in)
+        if (walked) {
+            const uint64_t gidx = (uint64_t)(gidx_origin + first + p);
+            const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), attempt};
+            PairRec rec;
+            rec.attempt = (uint16_t)attempt;
+            int n_err0 = 0, n_err1 = 0, err_first0 = 0, err_first1 = 0;
             if (!ion) {                                                   // src/dwgsim.c:866-881
                 apply_errors(dst0, s0, T, key, 0, n_err0, err_first0);
                 if (s1 > 0) apply_errors(dst1, s1, T, key, 1, n_err1, err_first1);
@@ -1219,7 +1232,6 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             }
             recs[p] = rec;
             staged = p;
-            break;
         }
         __syncwarp();
         if (defer) {
