@@ -159,7 +159,7 @@ format_kernel_t format_kernel_of(const SimParams &sp)
 // dynamic shared memory of simulate_pairs_tp_kernel: staging tile + sampling tables (see the kernel prologue)
 size_t tp_smem_bytes(const SimParams &sp)
 {
-    size_t words = (((size_t)kTpThreads * ((sp.nw[0] + sp.nw[1]) | 1) + 1) & ~(size_t)1) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
+    size_t words = (((size_t)kTpThreads * sp.row_stride + 3) & ~(size_t)3) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
     words += 2 * (size_t)sp.win_slots * kTpThreads;                                                 // the reference window
     for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);
     const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4;
@@ -310,6 +310,12 @@ int upload_tables(dwgsim_gpu *h)
     s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide;
     s.isize_guide = h->dt.isize_guide; s.gap_guide[0] = h->dt.gap_guide[0]; s.gap_guide[1] = h->dt.gap_guide[1];
     s.inv_nw = (uint32_t)(4294967296.0 / std::max(s.nw[0] + s.nw[1], 1)) + 1u;
+    {   // staged rows: unpadded when lanes then collide two ways at most (stride = 2 mod 4 words); Ion Torrent rows are edited
+        // in place word by word and keep the conflict-free odd stride
+        const int nw = s.nw[0] + s.nw[1];
+        s.row_stride = (p.data_type != 2 && (nw & 3) == 2) ? nw : (nw | 1);
+        if (const char *e = getenv("DWGSIM_ROW_PAD")) if (atoi(e)) s.row_stride = nw | 1;
+    }
     s.inv_groups = (uint32_t)(4294967296.0 / std::max((s.cap[0] + 7) / 8 + (s.cap[1] + 7) / 8, 1)) + 1u;
     s.flow_order = h->dt.flow_order; s.prefix = h->dt.prefix;
     return DWGSIM_GPU_OK;

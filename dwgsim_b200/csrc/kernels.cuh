@@ -644,20 +644,20 @@ __device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, RefWindow &
     const int pos = j & 31;
     const uint32_t wa = pos < 16 ? lo.x : lo.y, wb = pos < 16 ? lo.y : hi.x;
     uint32_t x = __funnelshift_r(wa, wb, (pos << 1) & 31) & ((1u << (2 * m)) - 1u);
-    uint32_t y = 0;
-    if (R.has_n) {
-        const uint32_t n0 = __ldg(c.nmask + (j >> 5)), n1 = __ldg(c.nmask + (j >> 5) + 1);
-        y = __funnelshift_r(n0, n1, j & 31) & ((1u << m) - 1u);
-    }
     // minus strand: reverse the order of the m bases and complement them (computed for every lane, then selected)
     uint32_t xr = __brev(x) >> (32 - 2 * m);
     xr = (((xr >> 1) & 0x5555u) | ((xr & 0x5555u) << 1)) ^ ((1u << (2 * m)) - 1u);
-    const uint32_t yr = __brev(y) >> (32 - m);
     x = dir < 0 ? xr : x;
-    y = dir < 0 ? yr : y;
     x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u;
-    y = (y | (y << 12)) & 0x000F000Fu; y = (y | (y << 6)) & 0x03030303u; y = (y | (y << 3)) & 0x11111111u;
-    return (x & ~(y * 3u)) | (y << 2);
+    if (R.has_n) {                                            // the N mask of the group, same treatment, merged as code 4
+        const uint32_t n0 = __ldg(c.nmask + (j >> 5)), n1 = __ldg(c.nmask + (j >> 5) + 1);
+        uint32_t y = __funnelshift_r(n0, n1, j & 31) & ((1u << m) - 1u);
+        const uint32_t yr = __brev(y) >> (32 - m);
+        y = dir < 0 ? yr : y;
+        y = (y | (y << 12)) & 0x000F000Fu; y = (y | (y << 6)) & 0x03030303u; y = (y | (y << 3)) & 0x11111111u;
+        x = (x & ~(y * 3u)) | (y << 2);
+    }
+    return x;
 }
 
 struct Emit {                          // emission state of one read
@@ -1012,12 +1012,12 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     // rows to HBM (pair-major) with coalesced stores
     extern __shared__ __align__(16) uint32_t tile[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int NW = P.nw[0] + P.nw[1], RS = NW | 1;
+    const int NW = P.nw[0] + P.nw[1], RS = P.row_stride;
     uint32_t *row = tile + (size_t)threadIdx.x * RS;
     uint32_t *wtile = tile + (size_t)warp * 32 * RS;
     // sampling tables behind the tile: insert-size CDF + guide, per end: gap CDF (len entries) + guide, accept thresholds
     // then the reference window, [slot][thread] x 8 bytes
-    uint2 *const win_mem = reinterpret_cast<uint2 *>(tile + (((size_t)kTpThreads * RS + 1) & ~(size_t)1));
+    uint2 *const win_mem = reinterpret_cast<uint2 *>(tile + (((size_t)kTpThreads * RS + 3) & ~(size_t)3));
     TpTables T;
     {
         uint32_t *p32 = reinterpret_cast<uint32_t *>(win_mem + (size_t)P.win_slots * kTpThreads);
@@ -1239,11 +1239,19 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             list_push(J.retry, J.count, push_retry, item, lane);
             list_push(J.random, J.count + 1, push_random, item, lane);
         }
-        // flush the warp's staged rows (pair-major in HBM, NW words per pair); the rows of a pass-0 round are contiguous there
-        // tile index of linear word x is x + (x / NW) * (RS - NW); x / NW by a multiply-high with P.inv_nw = 2^32/NW + 1
-        for (int x = lane; x < 32 * NW; x += 32) {
-            const int r = (int)__umulhi((uint32_t)x, P.inv_nw), dp = __shfl_sync(0xffffffffu, staged, r);
-            if (dp >= 0) seqw[(size_t)dp * NW + (x - r * NW)] = wtile[x + r * (RS - NW)];
+        // flush the warp's staged rows (pair-major in HBM, NW words per pair).  The rows of a pass-0 round are contiguous in
+        // HBM; without row padding they are contiguous in shared memory too and leave as 16-byte vectors (rows of deferred
+        // pairs go along and are overwritten by pass 1)
+        if (RS == NW && pass == 0 && jbase + 32 <= n_jobs) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(wtile);
+            uint4 *dst = reinterpret_cast<uint4 *>(seqw + (size_t)jbase * NW);
+            for (int x = lane; x < 8 * NW; x += 32) dst[x] = src[x];
+        } else {
+            // tile index of linear word x is x + (x / NW) * (RS - NW); x / NW by a multiply-high with P.inv_nw = 2^32/NW + 1
+            for (int x = lane; x < 32 * NW; x += 32) {
+                const int r = (int)__umulhi((uint32_t)x, P.inv_nw), dp = __shfl_sync(0xffffffffu, staged, r);
+                if (dp >= 0) seqw[(size_t)dp * NW + (x - r * NW)] = wtile[x + r * (RS - NW)];
+            }
         }
         __syncwarp();
     }

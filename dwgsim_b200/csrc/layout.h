@@ -97,6 +97,8 @@ struct SimParams {
     uint32_t flow_thr[2];
     int32_t  nw[2];                            // 32-bit words of nibble-packed read codes per end (8 codes per word);
                                                // stored word-major: word w of pair p at seqw[(w0[end] + w) * n + p]
+    int32_t  row_stride;                       // words between the staged rows of two threads in the simulate kernel: nw0+nw1 when
+                                               // that keeps shared-memory conflicts at two ways (vector flush), else padded to odd
     int32_t  win_slots;                        // 8-byte words of the simulate kernel's shared-memory reference window per thread
                                                // (0: reads go straight to HBM / L2; chosen on the host by occupancy)
     int32_t  tile_pairs;                       // pairs per warp mini-tile of the format kernel
