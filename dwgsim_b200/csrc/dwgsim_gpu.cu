@@ -710,7 +710,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[4], st));
     layout_lengths_kernel<<<nblk, kThreads, 0, st>>>(sp, h->blob, w.recs, n, first, (unsigned long long)rand_base, rand_base_dev, w.blk_rand,
                                                      w.serial, w.lens, w.blk_len, w.names, w.name_len);
-    layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
+    layout_scan_blocks_kernel<<<3, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
     const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + kFmtWarps - 1) / kFmtWarps;    // CTAs that have a mini-tile per warp

@@ -1371,33 +1371,33 @@ layout_count_random_kernel(const PairRec *__restrict__ recs, int n, unsigned lon
     if (threadIdx.x == 0) blk_rand[blockIdx.x] = tot;
 }
 
-// single-block exclusive scan of m 64-bit block sums (m <= a few thousand), in place; totals[slot] = sum
+// exclusive scan of m 64-bit block sums per array (m <= a few thousand; one CTA per array), in place; totals[a] = sum
 __global__ void __launch_bounds__(1024)
 layout_scan_blocks_kernel(unsigned long long *__restrict__ v, int m, int n_arrays, unsigned long long *__restrict__ totals)
 {
     __shared__ unsigned long long sw[32];
-    __shared__ unsigned long long carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int a = 0; a < n_arrays; ++a) {
+    const int per = (m + 1023) / 1024;                                // consecutive elements per thread: one pass over the array
+    for (int a = blockIdx.x; a < n_arrays; a += gridDim.x) {          // one CTA per array
         unsigned long long *x = v + (size_t)a * m;
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        for (int base = 0; base < m; base += 1024) {
-            const int i = base + threadIdx.x;
-            unsigned long long val = i < m ? x[i] : 0ull, inc = val;
+        const int i0 = threadIdx.x * per, i1 = min(i0 + per, m);
+        unsigned long long mine = 0;
+        for (int i = i0; i < i1; ++i) mine += x[i];
+        unsigned long long inc = mine;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            if (lane == 31) sw[warp] = inc;
-            __syncthreads();
-            unsigned long long wb = 0, tot = 0;
-            for (int j = 0; j < 32; ++j) { unsigned long long t = sw[j]; if (j < warp) wb += t; tot += t; }
-            const unsigned long long c = carry;
-            if (i < m) x[i] = c + wb + inc - val;
-            __syncthreads();
-            if (threadIdx.x == 0) carry = c + tot;
-            __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sw[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {                                              // scan of the 32 warp sums
+            unsigned long long w = sw[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            sw[lane] = winc - w;
+            if (lane == 31) totals[a] = winc;
         }
-        if (threadIdx.x == 0) totals[a] = carry;
+        __syncthreads();
+        unsigned long long run = sw[warp] + inc - mine;               // exclusive prefix of this thread's first element
+        for (int i = i0; i < i1; ++i) { const unsigned long long t = x[i]; x[i] = run; run += t; }
         __syncthreads();
     }
 }
