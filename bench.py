@@ -38,8 +38,8 @@ PAIRS_PER_STEP = 1 << 20
 ALGO_BYTES_PER_PAIR = 1524.0      # 118 B read (2-bit ref + N mask + mutation table) + 1,406 B FASTQ written
 E2E_CONTIG_LEN = 8 << 20          # contig handed over per e2e step (dense host arrays: 17 B/base)
 # dram__bytes_read.sum + dram__bytes_write.sum of the eight launches of one 2^20-pair step, from the ncu --set full
-# capture profiles/r01b_ncu_key_metrics.txt (simulate passes 0.525 GB + layout kernels 0.181 GB + format 1.750 GB)
-NCU_DRAM_BYTES_PER_STEP = 2.456e9
+# capture profiles/r01c_ncu_key_metrics.txt (reads 0.743 GB + writes 1.685 GB)
+NCU_DRAM_BYTES_PER_STEP = 2.427e9
 
 
 def peak_hbm():
@@ -383,7 +383,7 @@ def main():
     names = ["simulate_pairs_tp_kernel (2 passes)", "layout_* (5 scan kernels)", "format_fastq_kernel"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_STEP if B == PAIRS_PER_STEP else None,
-                "traffic_source": "ncu --set full capture of the same step (profiles/r01b_ncu_key_metrics.txt), bytes per step",
+                "traffic_source": "ncu --set full capture of the same step (profiles/r01c_ncu_key_metrics.txt), bytes per step",
                 "peak_source": peak_src,
                 "kernel": "whole step = simulate (2 passes) + layout + format (8 launches); dominant: %s" % names[dom],
                 "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "fastq_bytes_per_pair": out_bytes / (B * args.steps),
