@@ -12,6 +12,9 @@
 // New long options only (the short-option surface is the reference's): --uncompressed, --host-gzip, --threads N,
 // --device D, --batch PAIRS.
 #include <getopt.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -28,6 +31,7 @@
 #include <ctime>
 #include <chrono>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -338,25 +342,40 @@ int parse_options(Options &o, int argc, char **argv, int *first_arg)
 }
 
 // ---- FASTA (seq_read_fasta, src/mut.c:49-87) over an in-memory file ------------------------------------------------
-struct Fasta {
-    std::vector<char> buf;
-    size_t pos = 0;
+struct Fasta {                                 // seq_read_fasta, src/mut.c:49-87, over a read-only mapping of the file
+    const char *buf = nullptr;
+    size_t n = 0, pos = 0;
+    bool mapped = false;
+    std::vector<char> owned;
+    uint8_t keep[256];
+    ~Fasta() { if (mapped) munmap((void *)buf, n); }
     bool open(const char *path)
     {
-        FILE *fp = fopen(path, "rb");
-        if (!fp) return false;
-        fseek(fp, 0, SEEK_END);
-        const long sz = ftell(fp);
-        fseek(fp, 0, SEEK_SET);
-        buf.resize((size_t)sz);
-        const bool ok = fread(buf.data(), 1, buf.size(), fp) == buf.size();
+        for (int c = 0; c < 256; c++) keep[c] = (isalpha(c) || c == '-' || c == '.') ? 1 : 0;     // src/mut.c:75
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                buf = (const char *)m; n = (size_t)st.st_size; mapped = true;
+                ::close(fd);
+                return true;
+            }
+        }
+        FILE *fp = fdopen(fd, "rb");                               // pipes and empty files: read it all
+        if (!fp) { ::close(fd); return false; }
+        char tmp[1 << 16];
+        size_t got;
+        while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) owned.insert(owned.end(), tmp, tmp + got);
         fclose(fp);
-        return ok;
+        buf = owned.data(); n = owned.size();
+        return true;
     }
-    // next contig into seq (symbols kept as in the file); returns length or -1
-    int64_t next(std::vector<uint8_t> &seq, std::string &name)
+    // next contig: its symbols (kept as in the file) into seq unless count_only; returns the length or -1
+    int64_t next(std::vector<uint8_t> &seq, std::string &name, bool count_only = false)
     {
-        const size_t n = buf.size();
         while (pos < n && buf[pos] != '>') pos++;
         if (pos >= n) return -1;
         pos++;
@@ -364,9 +383,23 @@ struct Fasta {
         int c = 0;
         while (pos < n) { c = (unsigned char)buf[pos++]; if (c == ' ' || c == '\t' || c == '\n') break; if (c != '\r') name.push_back((char)c); }
         if (c != '\n') while (pos < n && buf[pos++] != '\n') {}
-        seq.clear();
-        while (pos < n && (c = (unsigned char)buf[pos]) != '>') { pos++; if (isalpha(c) || c == '-' || c == '.') seq.push_back((uint8_t)c); }
-        return (int64_t)seq.size();
+        // the record ends at the next '>' (anywhere, like the reference's fgetc loop)
+        const char *beg = buf + pos;
+        const char *end = (const char *)memchr(beg, '>', n - pos);
+        if (!end) end = buf + n;
+        const size_t span = (size_t)(end - beg);
+        pos += span;
+        int64_t len = 0;
+        if (count_only) {
+            for (size_t i = 0; i < span; i++) len += keep[(unsigned char)beg[i]];
+            return len;
+        }
+        seq.resize(span + 1);
+        uint8_t *out = seq.data();
+        for (size_t i = 0; i < span; i++) { const unsigned char ch = (unsigned char)beg[i]; *out = ch; out += keep[ch]; }   // branch-free filter
+        len = (int64_t)(out - seq.data());
+        seq.resize((size_t)len);
+        return len;
     }
 };
 
@@ -375,7 +408,8 @@ struct Hap {
     std::vector<uint64_t> s;
     std::vector<uint8_t *> ins;
     ~Hap() { for (auto p : ins) free(p); }
-    void reset(size_t l) { for (auto p : ins) free(p); ins.clear(); s.assign(l + 2, 0); }
+    // every s[i], i < l, is written by mut_diref before it is read: no zero fill (a recycled vector keeps its pages)
+    void reset(size_t l) { for (auto p : ins) free(p); ins.clear(); s.resize(l + 2); s[l] = s[l + 1] = 0; }
 };
 int long_ins_bytes(uint64_t n) { return 1 + (n <= 0xFF ? 1 : (n <= 0xFFFF ? 2 : 4)) + (int)((n + 3) >> 2); }
 uint8_t *long_ins_payload(uint8_t *rec, uint32_t *n)
@@ -986,7 +1020,7 @@ int main(int argc, char **argv)
         fclose(fp_fai);
     } else {
         int64_t l;
-        while ((l = fa.next(seq, name)) >= 0) {
+        while ((l = fa.next(seq, name, true)) >= 0) {
             fprintf(stderr, "[dwgsim_core] %s length: %lld\n", name.c_str(), (long long)l);
             tot_len += (uint64_t)l; ++n_ref;
             contigs.name.push_back(name); contigs.len.push_back((uint32_t)l);
@@ -1023,77 +1057,155 @@ int main(int argc, char **argv)
     double t_mut = 0, t_print = 0, t_gpu = 0, t_pack = 0, t_kernels = 0;
     const double t_begin = now();
     long long bytes_out = 0, bases_in = 0;
-    Hap h1, h2;
     long long n_sim = 0;
     unsigned long long ctr = 0;
-    int contig_i = 0, prev_skip = 0, rc_exit = 0;
+    int rc_exit = 0;
     const int maxlen = std::max(o.length[0], o.length[1]);
-    int64_t l64;
-    while ((l64 = fa.next(seq, name)) >= 0) {                             // src/dwgsim.c:519-1106
-        const int seq_l = (int)l64;
-        int l = seq_l;                                                    // with -x: the total length of the contig's regions
+
+    // One contig's prologue (src/dwgsim.c:519-632): budget, skip rules, mut_diref.  With reads to simulate it runs on a
+    // producer thread, one contig ahead of the consumer below (mutation files, packing, GPU read loop), so the host's
+    // serial part -- the drand48 stream of mut_diref must be replayed in contig order -- overlaps the rest.
+    struct Job {
+        std::string name;
+        std::vector<uint8_t> seq;
+        Hap h1, h2;
+        int seq_l = 0, l = 0, contig_i = 0;
         long long n_pairs = 0;
         std::vector<uint32_t> reg_start, reg_end;
-        n_ref--;
-        if (o.output_type == 2) fprintf(stderr, "\r[dwgsim_core] Currently on: %s", name.c_str());
-        else {
-            if (use_regions)
-                for (size_t i = 0; i < regions.start.size(); i++)
-                    if ((uint32_t)contig_i == regions.contig[i]) { reg_start.push_back(regions.start[i]); reg_end.push_back(regions.end[i]); }
-            if (0 == n_ref && o.C < 0) n_pairs = o.N - n_sim;             // NB: the last contig keeps its full length, also with -x
-            else if (use_regions && [&]() {                               // src/dwgsim.c:539-581
-                     int m = 0, num_n = 0;
-                     for (size_t i = 0; i < reg_start.size(); i++) m += (int)(reg_end[i] - reg_start[i]);
-                     if (0 == m) { fprintf(stderr, "[dwgsim_core] #0 skip sequence '%s' as it is not in the targeted region\n", name.c_str()); return true; }
-                     l = m;
-                     for (size_t i = 0; i < reg_start.size(); i++)
-                         for (uint32_t q = reg_start[i]; q <= reg_end[i]; q++) {     // the reference reads seq[q-1] for q in [start, end]
-                             const int ch = q >= 1 ? seq[q - 1] : 'N';
-                             switch (ch) { case 'a': case 'A': case 'c': case 'C': case 'g': case 'G': case 't': case 'T': break; default: num_n++; }
-                         }
-                     if (0.95 < num_n / (double)l) { fprintf(stderr, "[dwgsim_core] #1 skip sequence '%s' as %d out of %d bases are non-ACGT\n", name.c_str(), num_n, l); return true; }
-                     return false;
-                 }()) { contig_i++; continue; }
-            else if (0 < o.N) {
-                n_pairs = (long long)(uint64_t)((long double)l / tot_len * o.N + 0.5);
-                if (o.N - n_sim < n_pairs) n_pairs = o.N - n_sim;
-            } else n_pairs = (long long)(uint64_t)(l * o.C / ((long double)(o.length[0] + o.length[1])) / (1.0 - o.rand_read) + 0.5);
-            auto skip = [&](const char *fmt_done) { (void)fmt_done; if (0 == prev_skip) fprintf(stderr, "\n"); prev_skip = 1; };
-            if (o.amplicons == 1) {
-                if (l < maxlen) { skip(""); fprintf(stderr, "[dwgsim_core] #2 skip sequence '%s' as it is shorter than the read length %d < %d!\n", name.c_str(), l, maxlen); contig_i++; continue; }
-            } else if (0 < o.length[1] && l < o.dist + 3 * o.std_dev) {
-                skip(""); fprintf(stderr, "[dwgsim_core] #3 skip sequence '%s' as it is shorter than %f!\n", name.c_str(), o.dist + 3 * o.std_dev); contig_i++; continue;
-            } else if (l < o.length[0] || (0 < o.length[1] && l < o.length[1])) {
-                skip(""); fprintf(stderr, "[dwgsim_core] #4 skip sequence '%s' as it is shorter than %d!\n", name.c_str(), l < o.length[0] ? o.length[0] : o.length[1]); contig_i++; continue;
-            } else if (n_pairs < 0) { fprintf(stderr, "[dwgsim_core] #5 skip sequence '%s' as not enough pairs found\n", name.c_str()); continue; }
-            prev_skip = 0;
+        double t_mut = 0;
+    };
+    struct Producer {
+        int contig_i = 0, prev_skip = 0, n_ref = 0;
+        long long n_sim = 0;                      // pairs budgeted so far (what the consumer's n_sim will be)
+    } P;
+    P.n_ref = n_ref;
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Job>> pool;         // finished jobs: their vectors keep capacity (and mapped pages) for the next contig
+    auto recycle = [&](std::unique_ptr<Job> j) { std::lock_guard<std::mutex> g(pool_mu); pool.push_back(std::move(j)); };
+    auto produce = [&]() -> std::unique_ptr<Job> {   // next simulated contig, or null at the end of the FASTA
+        std::unique_ptr<Job> j;
+        {
+            std::lock_guard<std::mutex> g(pool_mu);
+            if (!pool.empty()) { j = std::move(pool.back()); pool.pop_back(); }
         }
+        if (!j) j.reset(new Job);
+        int64_t l64;
+        while ((l64 = fa.next(j->seq, j->name)) >= 0) {                   // src/dwgsim.c:519-1106
+            const std::string &name = j->name;
+            const std::vector<uint8_t> &seq = j->seq;
+            const int seq_l = (int)l64;
+            int l = seq_l;                                                // with -x: the total length of the contig's regions
+            long long n_pairs = 0;
+            std::vector<uint32_t> &reg_start = j->reg_start, &reg_end = j->reg_end;
+            reg_start.clear(); reg_end.clear();
+            const int contig_i = P.contig_i;
+            P.n_ref--;
+            if (o.output_type == 2) fprintf(stderr, "\r[dwgsim_core] Currently on: %s", name.c_str());
+            else {
+                if (use_regions)
+                    for (size_t i = 0; i < regions.start.size(); i++)
+                        if ((uint32_t)contig_i == regions.contig[i]) { reg_start.push_back(regions.start[i]); reg_end.push_back(regions.end[i]); }
+                if (0 == P.n_ref && o.C < 0) n_pairs = o.N - P.n_sim;     // NB: the last contig keeps its full length, also with -x
+                else if (use_regions && [&]() {                           // src/dwgsim.c:539-581
+                         int m = 0, num_n = 0;
+                         for (size_t i = 0; i < reg_start.size(); i++) m += (int)(reg_end[i] - reg_start[i]);
+                         if (0 == m) { fprintf(stderr, "[dwgsim_core] #0 skip sequence '%s' as it is not in the targeted region\n", name.c_str()); return true; }
+                         l = m;
+                         for (size_t i = 0; i < reg_start.size(); i++)
+                             for (uint32_t q = reg_start[i]; q <= reg_end[i]; q++) {     // the reference reads seq[q-1] for q in [start, end]
+                                 const int ch = q >= 1 ? seq[q - 1] : 'N';
+                                 switch (ch) { case 'a': case 'A': case 'c': case 'C': case 'g': case 'G': case 't': case 'T': break; default: num_n++; }
+                             }
+                         if (0.95 < num_n / (double)l) { fprintf(stderr, "[dwgsim_core] #1 skip sequence '%s' as %d out of %d bases are non-ACGT\n", name.c_str(), num_n, l); return true; }
+                         return false;
+                     }()) { P.contig_i++; continue; }
+                else if (0 < o.N) {
+                    n_pairs = (long long)(uint64_t)((long double)l / tot_len * o.N + 0.5);
+                    if (o.N - P.n_sim < n_pairs) n_pairs = o.N - P.n_sim;
+                } else n_pairs = (long long)(uint64_t)(l * o.C / ((long double)(o.length[0] + o.length[1])) / (1.0 - o.rand_read) + 0.5);
+                auto skip = [&]() { if (0 == P.prev_skip) fprintf(stderr, "\n"); P.prev_skip = 1; };
+                if (o.amplicons == 1) {
+                    if (l < maxlen) { skip(); fprintf(stderr, "[dwgsim_core] #2 skip sequence '%s' as it is shorter than the read length %d < %d!\n", name.c_str(), l, maxlen); P.contig_i++; continue; }
+                } else if (0 < o.length[1] && l < o.dist + 3 * o.std_dev) {
+                    skip(); fprintf(stderr, "[dwgsim_core] #3 skip sequence '%s' as it is shorter than %f!\n", name.c_str(), o.dist + 3 * o.std_dev); P.contig_i++; continue;
+                } else if (l < o.length[0] || (0 < o.length[1] && l < o.length[1])) {
+                    skip(); fprintf(stderr, "[dwgsim_core] #4 skip sequence '%s' as it is shorter than %d!\n", name.c_str(), l < o.length[0] ? o.length[0] : o.length[1]); P.contig_i++; continue;
+                } else if (n_pairs < 0) { fprintf(stderr, "[dwgsim_core] #5 skip sequence '%s' as not enough pairs found\n", name.c_str()); continue; }
+                P.prev_skip = 0;
+            }
+            const double t0 = now();
+            if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, contig_i, muts);
+            else diref(o, j->seq, j->h1, j->h2);
+            j->t_mut = now() - t0;
+            j->seq_l = seq_l; j->l = l; j->contig_i = contig_i; j->n_pairs = n_pairs;
+            if (o.output_type != 2 && n_pairs > 0) P.n_sim += n_pairs;
+            P.contig_i++;
+            return j;
+        }
+        return nullptr;
+    };
+    auto consume = [&](Job &j) -> bool {                                 // false: stop (the GPU path reported an error)
         double t0 = now();
-        if (muts.kind >= 0) diref_replay(o, seq, h1, h2, contig_i, muts);
-        else diref(o, seq, h1, h2);
-        t_mut += now() - t0; t0 = now();
-        if (o.output_type != 1) print_mutations(name.c_str(), seq, h1, h2, fp_txt, fp_vcf);
+        t_mut += j.t_mut;
+        if (o.output_type != 1) print_mutations(j.name.c_str(), j.seq, j.h1, j.h2, fp_txt, fp_vcf);
         t_print += now() - t0;
-        bases_in += seq_l;
-        if (o.output_type != 2 && n_pairs > 0) {
+        bases_in += j.seq_l;
+        if (o.output_type != 2 && j.n_pairs > 0) {
             if (!gpu) gpu_open();
             t0 = now();
-            int rc = dwgsim_gpu_add_contig(gpu, contig_i, name.c_str(), seq.data(), seq_l, h1.s.data(), h2.s.data(), h1.ins.data(),
-                                           (int32_t)h1.ins.size(), h2.ins.data(), (int32_t)h2.ins.size(), n_pairs);
-            if (rc == DWGSIM_GPU_OK && use_regions) rc = dwgsim_gpu_set_regions(gpu, reg_start.data(), reg_end.data(), (int32_t)reg_start.size(), l);
+            int rc = dwgsim_gpu_add_contig(gpu, j.contig_i, j.name.c_str(), j.seq.data(), j.seq_l, j.h1.s.data(), j.h2.s.data(), j.h1.ins.data(),
+                                           (int32_t)j.h1.ins.size(), j.h2.ins.data(), (int32_t)j.h2.ins.size(), j.n_pairs);
+            if (rc == DWGSIM_GPU_OK && use_regions) rc = dwgsim_gpu_set_regions(gpu, j.reg_start.data(), j.reg_end.data(), (int32_t)j.reg_start.size(), j.l);
             dwgsim_gpu_stats_t st;
             if (rc == DWGSIM_GPU_OK) rc = dwgsim_gpu_run(gpu, sink_cb, &wr, &st);
             if (rc != DWGSIM_GPU_OK) {
                 fprintf(stderr, "\r[dwgsim_core] %s%s%s\n", dwgsim_gpu_strerror(rc), *dwgsim_gpu_last_error(gpu) ? ": " : "", dwgsim_gpu_last_error(gpu));
                 rc_exit = 1;
-                break;
+                return false;
             }
             t_gpu += now() - t0; t_pack += st.ms_pack * 1e-3; t_kernels += (st.ms_simulate + st.ms_layout + st.ms_format) * 1e-3;
             bytes_out += st.bytes[0] + st.bytes[1] + st.bytes[2];
-            ctr += (unsigned long long)n_pairs; n_sim += n_pairs;
+            ctr += (unsigned long long)j.n_pairs; n_sim += j.n_pairs;
             fprintf(stderr, "\r[dwgsim_core] %llu", ctr);
         }
-        contig_i++;
+        return true;
+    };
+    // The prologue is memory-bound (17 B/base of dense arrays): a second thread only pays when there is GPU work to hide
+    // behind it.  DWGSIM_PIPELINE=0/1 overrides.
+    const char *pipe_env = getenv("DWGSIM_PIPELINE");
+    const bool pipelined = pipe_env ? atoi(pipe_env) != 0 : (o.output_type != 2 && (o.N > 0 || o.C > 0));
+    if (!pipelined) {
+        for (;;) { std::unique_ptr<Job> j = produce(); if (!j || !consume(*j)) break; recycle(std::move(j)); }
+    } else {
+        // bounded hand-over: at most one finished contig waits while the next is being prepared (three contigs in memory)
+        std::mutex mu;
+        std::condition_variable cv;
+        std::unique_ptr<Job> slot;
+        bool slot_full = false, done = false, stop = false;
+        std::thread producer([&]() {
+            for (;;) {
+                std::unique_ptr<Job> j = produce();
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&]() { return !slot_full || stop; });
+                if (stop) return;
+                if (!j) { done = true; cv.notify_all(); return; }
+                slot = std::move(j); slot_full = true;
+                cv.notify_all();
+            }
+        });
+        for (;;) {
+            std::unique_ptr<Job> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&]() { return slot_full || done; });
+                if (!slot_full) break;
+                j = std::move(slot); slot_full = false;
+                cv.notify_all();
+            }
+            if (!consume(*j)) { std::unique_lock<std::mutex> lk(mu); stop = true; cv.notify_all(); break; }
+            recycle(std::move(j));
+        }
+        producer.join();
     }
     if (!rc_exit) fprintf(stderr, "\n[dwgsim_core] Complete!\n");
     if (getenv("DWGSIM_STATS")) {
