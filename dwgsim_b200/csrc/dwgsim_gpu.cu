@@ -471,7 +471,9 @@ int update_caps(dwgsim_gpu *h)
         h->sp.tile_pairs = std::max(1, std::min(31, (152 + groups - 1) / groups));       // ~150 groups of 8 bases per warp
     }
     if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(31, atoi(e)));
+    h->sp.fmt_warps = kFmtWarps;
     while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 113 * 1024) --h->sp.tile_pairs;
+    while (h->sp.fmt_warps > 1 && format_smem_layout(h->sp).total > 227 * 1024) h->sp.fmt_warps >>= 1;   // long reads: fewer warps per CTA
     const FormatSmem L = format_smem_layout(h->sp);
     if (L.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
     CUDA_TRY(h, cudaFuncSetAttribute(format_kernel_of(h->sp), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -713,13 +715,14 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     layout_scan_blocks_kernel<<<3, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
-    const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + kFmtWarps - 1) / kFmtWarps;    // CTAs that have a mini-tile per warp
+    const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmtWarps, fmt_threads = 32 * fmt_warps;
+    const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;    // CTAs that have a mini-tile per warp
     int occ_f = 1;
     const format_kernel_t fmt = format_kernel_of(sp);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fmt, kFmtThreads, smem_b);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fmt, fmt_threads, smem_b);
     const int grid_f = std::min(ntiles, sm_count * std::max(occ_f, 1));
     (void)grid;
-    fmt<<<grid_f, kFmtThreads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
+    fmt<<<grid_f, fmt_threads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
                                                              w.totals + 1, w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());

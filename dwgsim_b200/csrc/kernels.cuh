@@ -1539,7 +1539,7 @@ __host__ __device__ inline FormatSmem format_smem_layout(const SimParams &P)
     L.meta_off = w; w += WP * (int)sizeof(PairMeta);
     for (int k = 0; k < 3; ++k) { L.stage_off[k] = w; w += (WP * P.rec_cap[k] + 32 + 15) & ~15; }
     L.warp_stride = w;
-    L.total = o + kFmtWarps * w;
+    L.total = o + (P.fmt_warps > 0 ? P.fmt_warps : kFmtWarps) * w;
     return L;
 }
 
@@ -1578,10 +1578,10 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
     const uint32_t *cdf = cdf_in_smem ? reinterpret_cast<const uint32_t *>(smem + L.cdf_off) : P.qdelta_cdf;   // tails only
     {
         uint2 *guide = reinterpret_cast<uint2 *>(smem + L.guide_off);
-        for (int j = tid; j < 1024; j += kFmtThreads) guide[j] = P.qdelta_n > 0 ? reinterpret_cast<const uint2 *>(P.qguide)[j] : make_uint2(0u, 0u);
-        if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += kFmtThreads) reinterpret_cast<uint32_t *>(smem + L.cdf_off)[j] = P.qdelta_cdf[j];
-        for (int j = tid; j < P.cap[0]; j += kFmtThreads) smem[L.qbase_off[0] + j] = P.qbase[0][j];
-        for (int j = tid; j < P.cap[1]; j += kFmtThreads) smem[L.qbase_off[1] + j] = P.qbase[1][j];
+        for (int j = tid; j < 1024; j += (int)blockDim.x) guide[j] = P.qdelta_n > 0 ? reinterpret_cast<const uint2 *>(P.qguide)[j] : make_uint2(0u, 0u);
+        if (cdf_in_smem) for (int j = tid; j < P.qdelta_n; j += (int)blockDim.x) reinterpret_cast<uint32_t *>(smem + L.cdf_off)[j] = P.qdelta_cdf[j];
+        for (int j = tid; j < P.cap[0]; j += (int)blockDim.x) smem[L.qbase_off[0] + j] = P.qbase[0][j];
+        for (int j = tid; j < P.cap[1]; j += (int)blockDim.x) smem[L.qbase_off[1] + j] = P.qbase[1][j];
     }
     __syncthreads();                                                 // the only CTA-wide barrier
     const uint32_t a_base = in_register(smem_addr(smem));
@@ -1598,7 +1598,8 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
     const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
     const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1, NW = P.nw[0] + P.nw[1];
     const int ntiles = (n + WP - 1) / WP;
-    const int tstride = gridDim.x * kFmtWarps;
+    const int n_warps = (int)blockDim.x >> 5;
+    const int tstride = gridDim.x * n_warps;
 
     auto prefetch = [&](int tile) {
         FmtPrefetch f;
@@ -1617,7 +1618,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
         return f;
     };
 
-    int tile = blockIdx.x * kFmtWarps + warp;
+    int tile = blockIdx.x * n_warps + warp;
     FmtPrefetch cur = prefetch(tile);
     for (; tile < ntiles; tile += tstride) {
         const FmtPrefetch nxt = prefetch(tile + tstride);

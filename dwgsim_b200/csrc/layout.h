@@ -102,6 +102,7 @@ struct SimParams {
     int32_t  win_slots;                        // 8-byte words of the simulate kernel's shared-memory reference window per thread
                                                // (0: reads go straight to HBM / L2; chosen on the host by occupancy)
     int32_t  tile_pairs;                       // pairs per warp mini-tile of the format kernel
+    int32_t  fmt_warps;                        // warps per CTA of the format kernel (16; fewer when long reads need the shared memory)
     uint32_t inv_nw, inv_groups;               // 2^32 / (nw0+nw1) + 1 and 2^32 / (groups per pair) + 1: divisions by multiply-high
     int32_t  name_cap;                         // bytes reserved per read name in shared memory
     int32_t  rec_cap[3];                       // upper bound of a pair's bytes per output stream

@@ -70,6 +70,13 @@ def test_ion_torrent_warp_kernel_fallback(oracle, synth_fa, tmp_path, monkeypatc
                        mut_rate=0.01, indel_frac=0.4), synth_fa, tmp_path)
 
 
+def test_long_paired_reads_shrink_the_format_cta(oracle, synth_fa, tmp_path):
+    """2 x 1,200-base Ion Torrent reads: a pair's records need ~20 KB of staging per warp, so the format kernel runs with
+    fewer warps per CTA (and the simulate kernel falls back to warp-per-pair)"""
+    check(oracle, dict(seed=28, N=200, data_type=2, length=(1200, 1200), dist=3000, std_dev=100, e=0.01, E=0.01,
+                       flow_order=make_golden.FLOW), synth_fa, tmp_path)
+
+
 def test_ion_torrent_long_reads_use_fallback(oracle, synth_fa, tmp_path):
     check(oracle, dict(seed=27, N=300, data_type=2, length=(1500, 0), e=0.01, flow_order=make_golden.FLOW), synth_fa, tmp_path)
 
