@@ -763,8 +763,27 @@ void read_muts_vcf(FILE *fp, const ContigList &c, MutsInput &M)              // 
 }
 
 void left_justify(const std::vector<uint8_t> &seq, Hap &h1, Hap &h2);
+// The substitution checks of mut_debug (src/mut.c:379-425; the reference calls it before and after mut_left_justify and
+// aborts on an `assert`).  Randomly generated mutations always pass; a replayed file can name a substitution that
+// does not change the base, or two different heterozygous substitutions at one position.  Here: a message and exit 1.
+void check_replayed(const char *contig, const std::vector<uint8_t> &seq, const Hap &h1, const Hap &h2)
+{
+    const int64_t l = (int64_t)seq.size();
+    for (int64_t i = 0; i < l; ++i) {
+        const uint64_t c0 = g_nt4[seq[i]], c1 = h1.s[i], c2 = h2.s[i];
+        if (c0 >= 4 || ((c1 & TYPE_MASK) == T_NOCHANGE && (c2 & TYPE_MASK) == T_NOCHANGE)) continue;
+        bool ok = true;
+        if ((c1 & BASE_TYPE_MASK) == (c2 & BASE_TYPE_MASK)) {
+            if ((c1 & TYPE_MASK) == T_SUBST) ok = (c0 & 3) != (c1 & 3);
+        } else if ((c1 & TYPE_MASK) == T_SUBST || (c2 & TYPE_MASK) == T_SUBST) {
+            ok = (c1 & 3) != (c2 & 3) && ((c0 & 3) == (c1 & 3) || (c0 & 3) == (c2 & 3));
+        }
+        if (!ok) die("[dwgsim_core] Error: inconsistent substitution at %s:%lld in the mutations to replay (it must change the "
+                     "base, and two alleles need separate positions); the reference aborts here in mut_debug\n", contig, (long long)i + 1);
+    }
+}
 // mut_diref, replay branches, src/mut.c:644-745, then :752-757
-void diref_replay(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, int contig_i, const MutsInput &M)
+void diref_replay(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, int contig_i, const MutsInput &M, const char *contig)
 {
     const int64_t l = (int64_t)seq.size();
     h1.reset((size_t)l); h2.reset((size_t)l);
@@ -813,7 +832,9 @@ void diref_replay(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Ha
             } else if (r.type == (int)T_INSERT) add_insertion(o, h1, h2, pos - 1, c, r.is_hap, r.bases.c_str(), 0);
         }
     }
+    check_replayed(contig, seq, h1, h2);
     left_justify(seq, h1, h2);
+    check_replayed(contig, seq, h1, h2);
 }
 
 void print_ins(FILE *fp, const Hap &h, int64_t i)                        // src/mut.c:249-279
@@ -1065,6 +1086,9 @@ int main(int argc, char **argv)
         else if (muts.kind == 1) read_muts_bed(fp, contigs, muts);
         else read_muts_vcf(fp, contigs, muts);
         fclose(fp);
+        // the reference shrinks its record array to the number of records read; with none, realloc(p, 0) returns NULL
+        // and it exits with this message (src/mut_txt.c:117-125, src/mut_bed.c:126-134, src/mut_vcf.c:267-275)
+        if (muts.recs.empty()) die("Error: memory allocation failed in muts_%s_init\n", muts.kind == 0 ? "txt" : (muts.kind == 1 ? "bed" : "vcf"));
     }
     Regions regions;
     const bool use_regions = !o.fn_regions_bed.empty();
@@ -1156,7 +1180,7 @@ int main(int argc, char **argv)
                 P.prev_skip = 0;
             }
             const double t0 = now();
-            if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, contig_i, muts);
+            if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, contig_i, muts, j->name.c_str());
             else diref(o, j->seq, j->h1, j->h2);
             j->t_mut = now() - t0;
             j->seq_l = seq_l; j->l = l; j->contig_i = contig_i; j->n_pairs = n_pairs;

@@ -108,6 +108,14 @@ def test_replayed_txt_reproduces_itself(cli, synth_fa, tmp_path):
     bad.write_text("chrA\t500\tA\tC\t1\n")                       # heterozygous substitutions must be IUPAC codes
     r = run(cli, ["-C", "0", "-m", str(bad), synth_fa, str(tmp_path / "y")], check=False)
     assert r.returncode == 1 and b"heterozygous bases must be in IUPAC form" in r.stderr
+    (tmp_path / "empty.txt").write_text("")                        # the reference cannot hold zero records (realloc(p, 0))
+    r = run(cli, ["-C", "0", "-m", str(tmp_path / "empty.txt"), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"memory allocation failed in muts_txt_init" in r.stderr
+    same = tmp_path / "same.bed"                                     # a substitution that keeps the base: the reference aborts in mut_debug
+    seq = "".join(l.strip() for l in open(synth_fa).read().split(">")[1].split("\n")[1:])
+    same.write_text("chrA\t100\t101\t%s\tsnp\n" % seq[100].upper())
+    r = run(cli, ["-C", "0", "-H", "-b", str(same), synth_fa, str(tmp_path / "y")], check=False)
+    assert r.returncode == 1 and b"inconsistent substitution at chrA:101" in r.stderr
     bed = tmp_path / "bad.bed"
     bed.write_text("chrA\t10\t40\t*\tins\n")
     r = run(cli, ["-C", "0", "-b", str(bed), synth_fa, str(tmp_path / "y")], check=False)
