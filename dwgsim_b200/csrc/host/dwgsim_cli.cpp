@@ -503,7 +503,7 @@ void add_insertion(const Options &o, Hap &h1, Hap &h2, int64_t i, uint64_t c, in
 }
 
 // mut_left_justify_ins, src/mut.c:427-478
-void left_justify_ins(Hap &h, int64_t i)
+void left_justify_ins(Hap &h, int64_t i, std::vector<int64_t> *touched = nullptr)
 {
     uint64_t n, ins;
     int64_t j = i;
@@ -515,6 +515,7 @@ void left_justify_ins(Hap &h, int64_t i)
             j--;
         }
         h.s[j] = (n << INS_LEN_SHIFT) | (ins << INS_SHIFT) | T_INSERT | (h.s[j] & 3);
+        if (touched && j != i) touched->push_back(j);
         return;
     }
     uint32_t num;
@@ -527,81 +528,136 @@ void left_justify_ins(Hap &h, int64_t i)
         j--;
     }
     h.s[j] = (ins << INS_SHIFT) | T_INSERT | (h.s[j] & 3);
+    if (touched && j != i) touched->push_back(j);
 }
 
-void shift_del(Hap &h, int64_t i, int del)                              // src/mut.c:540-553
+void shift_del(Hap &h, int64_t i, int del, std::vector<int64_t> *touched = nullptr)   // src/mut.c:540-553
 {
     for (int64_t j = i - 1; j >= 0; j--) {
         if ((h.s[j] & TYPE_MASK) == T_NOCHANGE && (h.s[j] & 3) == (h.s[j + del] & 3)) {
             const uint64_t t = h.s[j];
             h.s[j] = h.s[j + del];
             h.s[j + del] = (t | TYPE_MASK) ^ TYPE_MASK;
+            if (touched) touched->push_back(j);
         } else break;
     }
 }
 
 // mut_left_justify, src/mut.c:481-589
-void left_justify(const std::vector<uint8_t> &seq, Hap &h1, Hap &h2)
+// mut_left_justify, src/mut.c:482-589.  `events` (optional): the ascending positions that are not NOCHANGE in either
+// haplotype when mut_diref's loop ends.  The reference visits every base; all it does at a NOCHANGE position with an
+// A/C/G/T base is to clear prev_del, so visiting the events (and looking into a gap only while prev_del is set) is the
+// same pass.  `touched` collects the positions the pass writes mutations to (they lie left of the visited event).
+void left_justify(const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, const std::vector<int64_t> *events = nullptr,
+                  std::vector<int64_t> *touched = nullptr)
 {
     const int64_t l = (int64_t)seq.size();
     int prev_del[2] = {0, 0};
-    for (int64_t i = 0; i < l; ++i) {
+    auto step = [&](int64_t i) {
         const uint64_t c0 = g_nt4[seq[i]], c1 = h1.s[i], c2 = h2.s[i];
-        if (c0 >= 4) continue;
+        if (c0 >= 4) return;
         const uint64_t t1 = c1 & TYPE_MASK, t2 = c2 & TYPE_MASK;
-        if (t1 == T_NOCHANGE && t2 == T_NOCHANGE) { prev_del[0] = prev_del[1] = 0; continue; }
+        if (t1 == T_NOCHANGE && t2 == T_NOCHANGE) { prev_del[0] = prev_del[1] = 0; return; }
         int64_t j;
         int del;
         if ((c1 & BASE_TYPE_MASK) == (c2 & BASE_TYPE_MASK)) {
             if (t1 == T_SUBST) prev_del[0] = prev_del[1] = 0;
             else if (t1 == T_DELETE) {
-                if (prev_del[0] == 1 || prev_del[1] == 1) continue;
+                if (prev_del[0] == 1 || prev_del[1] == 1) return;
                 prev_del[0] = prev_del[1] = 1;
                 for (j = i + 1, del = 1; j < l && (h1.s[j] & TYPE_MASK) == T_DELETE; j++) del++;
-                if (l <= i + del || i == 0) continue;
+                if (l <= i + del || i == 0) return;
                 for (j = i - 1; j >= 0; j--) {
                     if ((h1.s[j] & TYPE_MASK) != T_INSERT && (h2.s[j] & TYPE_MASK) != T_INSERT && (h1.s[j] & TYPE_MASK) != T_DELETE &&
                         (h2.s[j] & TYPE_MASK) != T_DELETE && (h1.s[j] & 3) == (h1.s[j + del] & 3) && (h2.s[j] & 3) == (h2.s[j + del] & 3)) {
                         uint64_t t = h1.s[j]; h1.s[j] = h1.s[j + del]; h1.s[j + del] = (t | TYPE_MASK) ^ TYPE_MASK;
                         t = h2.s[j]; h2.s[j] = h2.s[j + del]; h2.s[j + del] = (t | TYPE_MASK) ^ TYPE_MASK;
+                        if (touched) touched->push_back(j);
                     } else break;
                 }
-            } else { prev_del[0] = prev_del[1] = 0; left_justify_ins(h1, i); left_justify_ins(h2, i); }
+            } else { prev_del[0] = prev_del[1] = 0; left_justify_ins(h1, i, touched); left_justify_ins(h2, i, touched); }
         } else {
             if (t1 == T_SUBST || t2 == T_SUBST) prev_del[0] = prev_del[1] = 0;
             else if (t1 == T_DELETE) {
-                if (prev_del[0] == 1) continue;
+                if (prev_del[0] == 1) return;
                 prev_del[0] = 1;
                 for (j = i + 1, del = 1; j < l && (h1.s[j] & TYPE_MASK) == T_DELETE; j++) del++;
-                if (l <= i + del || i == 0) continue;
-                shift_del(h1, i, del);
+                if (l <= i + del || i == 0) return;
+                shift_del(h1, i, del, touched);
             } else if (t2 == T_DELETE) {
-                if (prev_del[1] == 1) continue;
+                if (prev_del[1] == 1) return;
                 prev_del[1] = 1;
                 for (j = i + 1, del = 1; j < l && (h2.s[j] & TYPE_MASK) == T_DELETE; j++) del++;
-                if (l <= i + del || i == 0) continue;
-                shift_del(h2, i, del);
-            } else if (t1 == T_INSERT) { prev_del[0] = prev_del[1] = 0; left_justify_ins(h1, i); }
-            else if (t2 == T_INSERT) { prev_del[0] = prev_del[1] = 0; left_justify_ins(h2, i); }
+                if (l <= i + del || i == 0) return;
+                shift_del(h2, i, del, touched);
+            } else if (t1 == T_INSERT) { prev_del[0] = prev_del[1] = 0; left_justify_ins(h1, i, touched); }
+            else if (t2 == T_INSERT) { prev_del[0] = prev_del[1] = 0; left_justify_ins(h2, i, touched); }
         }
+    };
+    if (!events) { for (int64_t i = 0; i < l; ++i) step(i); return; }
+    int64_t last = -1;
+    for (const int64_t i : *events) {
+        if ((prev_del[0] | prev_del[1]) && i != last + 1)            // the NOCHANGE bases in between: an A/C/G/T one clears prev_del
+            for (int64_t j = last + 1; j < i; ++j) if (g_nt4[seq[j]] < 4) { prev_del[0] = prev_del[1] = 0; break; }
+        step(i);
+        last = i;
     }
 }
 
 // mut_diref, random branch, src/mut.c:591-643 + :752-757.  The common case (no mutation at this base) is one LCG
 // step and one integer compare: drand48() < r  <=>  X < ceil(r * 2^48) for the 48-bit state X.
-void diref(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2)
+// LCG jump-ahead: x_{n+k} = kJumpA[k] x_n + kJumpC[k] (mod 2^48) for the drand48 recurrence
+struct LcgJump {
+    uint64_t a[9], c[9];
+    LcgJump()
+    {
+        a[0] = 1; c[0] = 0;
+        for (int k = 1; k <= 8; k++) { a[k] = (a[k - 1] * 0x5DEECE66Dull) & 0xFFFFFFFFFFFFull; c[k] = (c[k - 1] * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull; }
+    }
+};
+const LcgJump kJump;
+
+// mut_diref, random branch (src/mut.c:606-643), then mut_left_justify.  `events` receives the ascending positions that
+// end up mutated (every base of a deletion), `touched` the positions mut_left_justify moved mutations to.
+void diref(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, std::vector<int64_t> *events = nullptr,
+           std::vector<int64_t> *touched = nullptr)
 {
     const int64_t l = (int64_t)seq.size();
     h1.reset((size_t)l); h2.reset((size_t)l);
     Hap *ret[2] = {&h1, &h2};
     const uint64_t thr = (uint64_t)std::ceil(std::ldexp(o.mut_rate, 48));
     int deleting = 0, del_len = 0;
+    std::vector<int64_t> local;
+    std::vector<int64_t> &ev = events ? *events : local;
+    ev.clear();
+    if (touched) touched->clear();
+    const uint8_t *sq = seq.data();
+    uint64_t *s1 = h1.s.data(), *s2 = h2.s.data();
     for (int64_t i = 0; i < l; ++i) {
-        uint64_t c = h1.s[i] = h2.s[i] = (uint64_t)g_nt4[seq[i]];
+        if (!deleting && i + 8 <= l) {
+            // eight A/C/G/T bases none of whose draws (one each: `drand48() < mut_rate`) comes out below the rate: the
+            // common case, decided with eight independent jump-ahead steps instead of a chain of eight
+            uint64_t c8[8];
+            uint64_t bad = 0;
+            for (int k = 0; k < 8; k++) { c8[k] = g_nt4[sq[i + k]]; bad |= c8[k]; }
+            if (bad < 4) {
+                const uint64_t x = g_rng.x;
+                uint64_t hit = 0;
+                for (int k = 1; k <= 8; k++) hit |= (uint64_t)(((kJump.a[k] * x + kJump.c[k]) & 0xFFFFFFFFFFFFull) < thr);
+                if (!hit) {
+                    for (int k = 0; k < 8; k++) { s1[i + k] = c8[k]; s2[i + k] = c8[k]; }
+                    g_rng.x = (kJump.a[8] * x + kJump.c[8]) & 0xFFFFFFFFFFFFull;
+                    i += 7;
+                    continue;
+                }
+            }
+        }
+        uint64_t c = s1[i] = s2[i] = (uint64_t)g_nt4[sq[i]];
         if (deleting) {
             if (del_len < o.indel_min || g_rng.next() < o.indel_extend) {
-                if (deleting & 1) h1.s[i] |= T_DELETE | c;
-                if (deleting & 2) h2.s[i] |= T_DELETE | c;
+                if (deleting & 1) s1[i] |= T_DELETE | c;
+                if (deleting & 2) s2[i] |= T_DELETE | c;
+                ev.push_back(i);
                 del_len++;
                 continue;
             }
@@ -610,18 +666,24 @@ void diref(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2)
         if (c >= 4) continue;
         g_rng.x = (g_rng.x * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull;
         if (g_rng.x >= thr) continue;                                      // drand48() < mut_rate is false
+        ev.push_back(i);
         if (g_rng.next() >= o.indel_frac) {
             const double r = g_rng.next();
             c = (c + (uint64_t)(r * 3.0 + 1)) & 3;
-            if (o.is_hap || g_rng.next() < 0.333333) h1.s[i] = h2.s[i] = T_SUBST | c;
+            if (o.is_hap || g_rng.next() < 0.333333) s1[i] = s2[i] = T_SUBST | c;
             else ret[g_rng.next() < 0.5 ? 0 : 1]->s[i] = T_SUBST | c;
         } else if (g_rng.next() < 0.5) {
-            if (o.is_hap || g_rng.next() < 0.3333333) { h1.s[i] = h2.s[i] = T_DELETE | c; deleting = 3; }
+            if (o.is_hap || g_rng.next() < 0.3333333) { s1[i] = s2[i] = T_DELETE | c; deleting = 3; }
             else { deleting = g_rng.next() < 0.5 ? 1 : 2; ret[deleting - 1]->s[i] = T_DELETE | c; }
             del_len = 1;
         } else add_insertion(o, h1, h2, i, c);
     }
-    left_justify(seq, h1, h2);
+    left_justify(seq, h1, h2, events ? &ev : nullptr, touched);         // (without a caller's list: the reference's full pass)
+    if (events && touched && !touched->empty()) {                        // candidates for the writers: events + touched, ascending
+        ev.insert(ev.end(), touched->begin(), touched->end());
+        std::sort(ev.begin(), ev.end());
+        ev.erase(std::unique(ev.begin(), ev.end()), ev.end());
+    }
 }
 
 // ---- mutations to replay: -m TXT (src/mut_txt.c), -b BED (src/mut_bed.c), -v VCF (src/mut_vcf.c) ------------------------
@@ -762,7 +824,6 @@ void read_muts_vcf(FILE *fp, const ContigList &c, MutsInput &M)              // 
     } while (ch != EOF);
 }
 
-void left_justify(const std::vector<uint8_t> &seq, Hap &h1, Hap &h2);
 // The substitution checks of mut_debug (src/mut.c:379-425; the reference calls it before and after mut_left_justify and
 // aborts on an `assert`).  Randomly generated mutations always pass; a replayed file can name a substitution that
 // does not change the base, or two different heterozygous substitutions at one position.  Here: a message and exit 1.
@@ -864,11 +925,19 @@ void print_del_vcf(FILE *vcf, const char *name, const std::vector<uint8_t> &seq,
     fprintf(vcf, "\t100\tPASS\tAF=%s;pl=%d;mt=DELETE\n", which == 3 ? "1.0" : "0.5", which);
 }
 // mut_print, src/mut.c:781-893
-void print_mutations(const char *name, const std::vector<uint8_t> &seq, const Hap &h1, const Hap &h2, FILE *txt, FILE *vcf)
+// `candidates` (optional): ascending positions that contain every mutated position; the bases in between are NOCHANGE in
+// both haplotypes, where the reference's loop only clears `prev`
+void print_mutations(const char *name, const std::vector<uint8_t> &seq, const Hap &h1, const Hap &h2, FILE *txt, FILE *vcf,
+                     const std::vector<int64_t> *candidates = nullptr)
 {
     const int64_t l = (int64_t)seq.size();
     int prev[2] = {0, 0};
-    for (int64_t i = 0; i < l; ++i) {
+    const int64_t n_it = candidates ? (int64_t)candidates->size() : l;
+    int64_t last = -1;
+    for (int64_t it = 0; it < n_it; ++it) {
+        const int64_t i = candidates ? (*candidates)[(size_t)it] : it;
+        if (i != last + 1) prev[0] = prev[1] = 0;
+        last = i;
         const uint64_t c0 = g_nt4[seq[i]], c1 = h1.s[i], c2 = h2.s[i], t1 = c1 & TYPE_MASK, t2 = c2 & TYPE_MASK;
         if (t1 == T_NOCHANGE && t2 == T_NOCHANGE) { prev[0] = prev[1] = 0; continue; }
         if (c0 < 4) {
@@ -1118,6 +1187,8 @@ int main(int argc, char **argv)
         int seq_l = 0, l = 0, contig_i = 0;
         long long n_pairs = 0;
         std::vector<uint32_t> reg_start, reg_end;
+        std::vector<int64_t> events, touched;     // mutated positions (random mut_diref only): the writers need not scan the contig
+        bool have_events = false;
         double t_mut = 0;
     };
     struct Producer {
@@ -1180,7 +1251,9 @@ int main(int argc, char **argv)
                 P.prev_skip = 0;
             }
             const double t0 = now();
+            j->have_events = muts.kind < 0 && !getenv("DWGSIM_FULL_SCAN");
             if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, contig_i, muts, j->name.c_str());
+            else if (j->have_events) diref(o, j->seq, j->h1, j->h2, &j->events, &j->touched);
             else diref(o, j->seq, j->h1, j->h2);
             j->t_mut = now() - t0;
             j->seq_l = seq_l; j->l = l; j->contig_i = contig_i; j->n_pairs = n_pairs;
@@ -1193,7 +1266,7 @@ int main(int argc, char **argv)
     auto consume = [&](Job &j) -> bool {                                 // false: stop (the GPU path reported an error)
         double t0 = now();
         t_mut += j.t_mut;
-        if (o.output_type != 1) print_mutations(j.name.c_str(), j.seq, j.h1, j.h2, fp_txt, fp_vcf);
+        if (o.output_type != 1) print_mutations(j.name.c_str(), j.seq, j.h1, j.h2, fp_txt, fp_vcf, j.have_events ? &j.events : nullptr);
         t_print += now() - t0;
         bases_in += j.seq_l;
         if (o.output_type != 2 && j.n_pairs > 0) {
