@@ -134,7 +134,7 @@ struct dwgsim_gpu {
     int shard_rank = 0, shard_world = 1;
     dwgsim_gpu_exchange_fn exchange = nullptr;
     void *exchange_user = nullptr;
-    int64_t pending_first = -1; int pending_n = 0;
+    int64_t pending_first = -1; int pending_n = 0, pending_launches = 0;
     Workspace ws;
     char *pinned[8][3] = {};
     uint64_t pinned_cap[3] = {0, 0, 0};
@@ -1098,7 +1098,7 @@ int dwgsim_gpu_resident_begin(dwgsim_gpu_t *h, int64_t first, int64_t n, int64_t
     if ((rc = ensure_workspace(h, std::max<int64_t>(n, h->ws.cap_pairs), false))) return rc;
     int launches = 0;
     if ((rc = launch_simulate(h, first, (int)n, true, &launches))) return rc;
-    h->pending_first = first; h->pending_n = (int)n;
+    h->pending_first = first; h->pending_n = (int)n; h->pending_launches = launches;
     if (n_random) return read_random_count(h, n_random);
     return DWGSIM_GPU_OK;
 }
@@ -1120,7 +1120,7 @@ int resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, const unsigned lo
     h->last_slot = 0;
     out->n_pairs = n; out->n_random = r.n_random; out->n_failed_attempts = r.n_failed;
     out->ms_simulate = r.ms[0]; out->ms_layout = r.ms[1]; out->ms_format = r.ms[2];
-    out->n_launches = launches + 3 + (h->ion_warp_kernel ? 0 : 1);
+    out->n_launches = launches + h->pending_launches;
     return rc;
 }
 }  // namespace
