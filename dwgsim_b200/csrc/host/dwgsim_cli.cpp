@@ -703,7 +703,8 @@ struct MutsInput {
     va_start(ap, fmt);
     vfprintf(stderr, fmt, ap);
     va_end(ap);
-    exit(1);
+    fflush(nullptr);
+    _exit(1);                                  // (may run on the producer thread: no static destructors under the consumer's feet)
 }
 char iupac_to_mut(char iupac, char base)                                     // src/dwgsim.c:202-213
 {
