@@ -31,6 +31,7 @@
 #include <ctime>
 #include <chrono>
 #include <functional>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -988,10 +989,22 @@ struct Writer {
     bool gz_file = true;            // the files are .gz (bytes arrive compressed when gz is false)
     int threads = 1;
     static constexpr size_t kBlock = 1 << 20;
+    // Bytes that need no compression here are written by one helper thread per file, so the three files of a batch go out
+    // side by side (copying into the page cache was the read loop's longest part).  The buffer must stay valid until the
+    // write has been joined: by the next write to the same file, or by flush() -- the host shell calls it after every
+    // dwgsim_gpu_run, before the library can reuse its pinned slots.
+    std::future<bool> pending[3];
+    bool join(int id) { return pending[id].valid() ? pending[id].get() : true; }
+    bool flush() { bool ok = true; for (int k = 0; k < 3; k++) ok = join(k) && ok; return ok; }
     bool write(int id, const char *buf, size_t n)
     {
         if (!fp[id] || n == 0) return true;
-        if (!gz) return fwrite(buf, 1, n, fp[id]) == n;
+        if (!gz) {
+            if (!join(id)) return false;
+            FILE *f = fp[id];
+            pending[id] = std::async(std::launch::async, [f, buf, n]() { return fwrite(buf, 1, n, f) == n; });
+            return true;
+        }
         const size_t nblk = (n + kBlock - 1) / kBlock;
         std::vector<std::vector<uint8_t>> out(nblk);
         std::atomic<size_t> next{0};
@@ -1023,6 +1036,7 @@ struct Writer {
     }
     void close_all()
     {
+        flush();
         for (auto &f : fp) if (f) {
             if (gz_file && ftell(f) == 0) {      // an empty gzip member, like gzclose on an untouched gzFile
                 gzFile g = gzdopen(dup(fileno(f)), "wb");
@@ -1278,6 +1292,7 @@ int main(int argc, char **argv)
             if (rc == DWGSIM_GPU_OK && use_regions) rc = dwgsim_gpu_set_regions(gpu, j.reg_start.data(), j.reg_end.data(), (int32_t)j.reg_start.size(), j.l);
             dwgsim_gpu_stats_t st;
             if (rc == DWGSIM_GPU_OK) rc = dwgsim_gpu_run(gpu, sink_cb, &wr, &st);
+            if (!wr.flush() && rc == DWGSIM_GPU_OK) { fprintf(stderr, "\r[dwgsim_core] Error: writing the FASTQ files failed\n"); rc_exit = 1; return false; }
             if (rc != DWGSIM_GPU_OK) {
                 fprintf(stderr, "\r[dwgsim_core] %s%s%s\n", dwgsim_gpu_strerror(rc), *dwgsim_gpu_last_error(gpu) ? ": " : "", dwgsim_gpu_last_error(gpu));
                 rc_exit = 1;
