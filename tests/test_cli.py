@@ -122,6 +122,19 @@ def test_replayed_txt_reproduces_itself(cli, synth_fa, tmp_path):
     assert r.returncode == 1 and b"exceeded the maximum supported length of 26" in r.stderr
 
 
+def test_prologue_variants_write_the_same_mutation_files(cli, synth_fa, tmp_path):
+    """the producer thread (DWGSIM_PIPELINE=1) and the event-list driven left-justification / writers against the inline,
+    every-base forms (DWGSIM_PIPELINE=0, DWGSIM_FULL_SCAN=1): same .mutations.txt/.vcf"""
+    args = ["-C", "0", "-z", "77", "-r", "0.02", "-R", "0.5", "-X", "0.8", "-I", "2"]
+    outs = []
+    for k, env in enumerate(({"DWGSIM_PIPELINE": "1"}, {"DWGSIM_PIPELINE": "0"}, {"DWGSIM_PIPELINE": "0", "DWGSIM_FULL_SCAN": "1"})):
+        prefix = str(tmp_path / ("v%d" % k))
+        subprocess.run([cli] + args + [synth_fa, prefix], capture_output=True, check=True, env=dict(os.environ, **env))
+        outs.append((md5(prefix + ".mutations.txt"), md5(prefix + ".mutations.vcf")))
+    assert outs[0] == outs[1] == outs[2]
+    assert os.path.getsize(str(tmp_path / "v0.mutations.txt")) > 10000
+
+
 def test_reference_stderr_lines(cli, synth_fa, tmp_path):
     r = run(cli, ["-C", "0", "-z", "1", synth_fa, str(tmp_path / "x")])
     err = r.stderr.decode()
