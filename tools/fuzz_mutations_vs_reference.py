@@ -9,6 +9,13 @@ from oracle import pyoracle as po
 ref=po.ref_binary(); cli=os.path.join(ROOT,'dwgsim_b200','bin','dwgsim')
 WD='/tmp/dwgsim_fuzz'; os.makedirs(WD,exist_ok=True)
 fa=WD+'/synth.fa'; mg.synth_fasta(fa)
+if len(sys.argv)>3 and sys.argv[3]=='random-fasta':
+    sys.path.insert(0,os.path.join(ROOT,'tools'))
+    import importlib.util
+    spec=importlib.util.spec_from_file_location('fo',os.path.join(ROOT,'tools','fuzz_oracle_vs_reference.py'))
+    src=open(os.path.join(ROOT,'tools','fuzz_oracle_vs_reference.py')).read()
+    ns={}; exec(src[src.index('def random_fasta'):src.index('fa = mg.synth_fasta')],ns)
+    fa=ns['random_fasta'](WD+'/rand_m.fa',int(sys.argv[1]))
 def md5(p): return hashlib.md5(open(p,'rb').read()).hexdigest() if os.path.exists(p) else None
 def run(binary, args, prefix):
     for e in ('.mutations.txt','.mutations.vcf'):

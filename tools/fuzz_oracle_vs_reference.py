@@ -1,6 +1,6 @@
 """Differential fuzz (build container only: needs oracle/_ref/dwgsim_ref): random option sets through the compiled reference and the
 oracle's drand48 backend; all five output files must be byte-identical.
-    python tools/fuzz_oracle_vs_reference.py SEED N"""
+    python tools/fuzz_oracle_vs_reference.py SEED N [random-fasta]"""
 import gzip, hashlib, os, random, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
@@ -8,7 +8,32 @@ import make_golden as mg
 from oracle import pyoracle as po
 
 WD = "/tmp/dwgsim_fuzz"; os.makedirs(WD, exist_ok=True)
+def random_fasta(path, seed):
+    """contigs of assorted lengths around the skip thresholds, N runs, lowercase, IUPAC codes, Windows line ends now and then"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    with open(path, "wb") as f:
+        for k in range(int(rng.integers(1, 7))):
+            n = int(rng.choice([60, 200, 500, 700, 1500, 5000, 20000]))
+            s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+            for _ in range(int(rng.integers(0, 3))):
+                a = int(rng.integers(0, n)); s[a:a + int(rng.integers(1, max(2, n // 4)))] = ord("N")
+            if rng.random() < 0.3:
+                a = int(rng.integers(0, n)); s[a:a + 50] += 32
+            if rng.random() < 0.3:
+                s[int(rng.integers(0, n))] = ord(rng.choice(list("RYKMSWBDHV")))
+            f.write((">c%d %s\n" % (k, "desc" if rng.random() < 0.5 else "")).encode())
+            w = int(rng.choice([50, 60, 70, 1000000]))
+            eol = b"\r\n" if rng.random() < 0.15 else b"\n"
+            b = s.tobytes()
+            for i in range(0, len(b), w):
+                f.write(b[i:i + w] + eol)
+    return path
+
+
 fa = mg.synth_fasta(os.path.join(WD, "synth.fa"))
+if len(sys.argv) > 3 and sys.argv[3] == "random-fasta":
+    fa = random_fasta(os.path.join(WD, "rand.fa"), int(sys.argv[1]))
 FLOW = mg.FLOW
 
 
@@ -20,7 +45,7 @@ def md5(p):
         return hashlib.md5(f.read()).hexdigest()
 
 
-rnd = random.Random(int(sys.argv[1])); bad = 0
+rnd = random.Random(int(sys.argv[1])); bad = 0; compared = 0
 for it in range(int(sys.argv[2])):
     o = dict(seed=rnd.randint(0, 10 ** 6))
     dt = rnd.choice([0, 0, 0, 1, 2])
@@ -67,9 +92,10 @@ for it in range(int(sys.argv[2])):
         if (r.returncode != 0) != (err != 0):
             bad += 1; print("EXIT MISMATCH", it, o, r.returncode, err, r.stderr.decode(errors="ignore")[-150:])
         continue
+    compared += 1
     for f in mg.FILES:
         a = md5(os.path.join(sub, "ref." + f + (".gz" if f.endswith("fastq") else ""))); b = md5(os.path.join(sub, "orc." + f))
         if a != b:
             bad += 1; print("MISMATCH", it, f, o); break
     if bad > 4: break
-print("done, mismatches", bad)
+print("done: %d cases compared file by file, mismatches %d" % (compared, bad))
