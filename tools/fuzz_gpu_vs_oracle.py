@@ -1,6 +1,6 @@
 """Parity fuzz on the GPU (run under gpurun): random option sets through the oracle's Philox backend and through the C ABI
 (tests/gpu_harness.py plays the reference host); the three FASTQ streams must be byte-identical.
-    python tools/fuzz_gpu_vs_oracle.py SEED N"""
+    python tools/fuzz_gpu_vs_oracle.py SEED N [random-fasta]"""
 import os, random, shutil, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
@@ -10,8 +10,15 @@ from oracle import pyoracle as po
 
 WD = "/tmp/dwgsim_fuzz_gpu"; os.makedirs(WD, exist_ok=True)
 fa = mg.synth_fasta(os.path.join(WD, "synth.fa"))
+RANDOM_FASTA = len(sys.argv) > 3 and sys.argv[3] == "random-fasta"
+if RANDOM_FASTA:                    # a new FASTA every 10 cases (tools/fuzz_oracle_vs_reference.py: random_fasta)
+    src = open(os.path.join(ROOT, "tools", "fuzz_oracle_vs_reference.py")).read()
+    ns = {}
+    exec(src[src.index("def random_fasta"):src.index("fa = mg.synth_fasta")], ns)
 rnd = random.Random(int(sys.argv[1])); bad = 0; done = 0; t0 = time.time()
 for it in range(int(sys.argv[2])):
+    if RANDOM_FASTA and it % 10 == 0:
+        fa = ns["random_fasta"](os.path.join(WD, "rand.fa"), int(sys.argv[1]) * 100000 + it)
     o = dict(seed=rnd.randint(0, 10 ** 6))
     dt = rnd.choice([0, 0, 0, 1, 1, 2])
     o["data_type"] = dt
