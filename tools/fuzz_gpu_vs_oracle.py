@@ -57,7 +57,7 @@ for it in range(int(sys.argv[2])):
     except ValueError:
         continue
     try:
-        if sess.stats.error != 0:
+        if sess.stats.error != 0 or sess.n_contigs == 0:        # nothing to hand to the C ABI (every contig skipped)
             continue
         try:
             got, stats = gh.gpu_actual(sess, o, orc_opt=sess.opt, **kw)
