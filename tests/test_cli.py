@@ -135,6 +135,31 @@ def test_prologue_variants_write_the_same_mutation_files(cli, synth_fa, tmp_path
     assert os.path.getsize(str(tmp_path / "v0.mutations.txt")) > 10000
 
 
+def test_fai_census(cli, oracle, synth_fa, tmp_path):
+    """with <ref.fa>.fai next to the FASTA the census pass reads names and lengths from it (src/dwgsim.c:467-478)"""
+    fa = str(tmp_path / "s.fa")
+    data = open(synth_fa, "rb").read()
+    open(fa, "wb").write(data)
+    recs, name, n = [], None, 0
+    for line in data.split(b"\n"):
+        if line.startswith(b">"):
+            if name is not None:
+                recs.append((name, n))
+            name, n = line[1:].split()[0].decode(), 0
+        else:
+            n += len(line)
+    recs.append((name, n))
+    open(fa + ".fai", "w").write("".join("%s\t%d\t0\t60\t61\n" % r for r in recs))
+    opts = dict(seed=6, C=0, mut_rate=0.02, indel_frac=0.4)
+    a, b = str(tmp_path / "cli"), str(tmp_path / "orc")
+    r = run(cli, oracle.opt_to_ref_argv(**opts) + [fa, a])
+    assert b"[dwgsim_core] hp length: 8000" in r.stderr
+    with oracle.Session(oracle.make_opt(**opts), fa, b) as s:
+        assert s.stats.error == 0
+    for f in ("mutations.txt", "mutations.vcf"):
+        assert md5(a + "." + f) == md5(b + "." + f), f
+
+
 def test_reference_stderr_lines(cli, synth_fa, tmp_path):
     r = run(cli, ["-C", "0", "-z", "1", synth_fa, str(tmp_path / "x")])
     err = r.stderr.decode()
