@@ -57,6 +57,7 @@ struct DeviceTables {
     uint32_t *isize_cdf = nullptr, *qdelta_cdf = nullptr, *err_gap[2] = {nullptr, nullptr}, *err_acc[2] = {nullptr, nullptr};
     uint16_t *isize_guide = nullptr, *gap_guide[2] = {nullptr, nullptr};
     uint32_t *qguide = nullptr;
+    uint8_t *qtab = nullptr;
     uint8_t *qbase[2] = {nullptr, nullptr};
     int8_t *flow_order = nullptr;
     char *prefix = nullptr;
@@ -100,6 +101,7 @@ struct dwgsim_gpu {
     std::vector<uint32_t> isize_cdf, qdelta_cdf, err_gap[2], err_acc[2];
     std::vector<uint16_t> isize_guide, gap_guide[2];
     std::vector<uint32_t> qguide;
+    std::vector<uint8_t> qtab;
     bool ion_warp_kernel = false;
     // device gzip writer: mode, per-stream tables in HBM
     int gz_mode = 0;
@@ -231,6 +233,18 @@ void derive_tables(dwgsim_gpu *h)
         h->qguide[2 * g] = inside == 1 ? cdf[j] - 1u : (inside > 1 ? (uint32_t)inside : 0xFFFFFFFFu);
         h->qguide[2 * g + 1] = (uint32_t)j | (inside > 1 ? 0x80000000u : 0u);
     }
+    // format_fastq2_kernel: rank by the upper kQTabBits of a draw; cells that hold a threshold are marked (bit 7) and
+    // decided from the whole 32-bit draw
+    h->qtab.assign((size_t)1 << kQTabBits, 0);
+    if (!h->qdelta_cdf.empty() && h->qdelta_cdf.size() < 128) {
+        const std::vector<uint32_t> &cdf = h->qdelta_cdf;
+        for (uint32_t c = 0; c < (1u << kQTabBits); ++c) {
+            const uint32_t lo = c << (32 - kQTabBits), hi = lo + ((1u << (32 - kQTabBits)) - 1u);
+            const size_t r_lo = (size_t)(std::upper_bound(cdf.begin(), cdf.end(), lo) - cdf.begin());
+            const size_t r_hi = (size_t)(std::upper_bound(cdf.begin(), cdf.end(), hi) - cdf.begin());
+            h->qtab[c] = r_lo == r_hi ? (uint8_t)r_lo : (uint8_t)0x80;
+        }
+    }
     auto make_guide = [](const uint32_t *cdf, size_t n, std::vector<uint16_t> &g) {     // g[b] = rank of (b << 22), b = 0..1024
         g.assign(1025, 0);
         for (uint32_t b = 0; b < 1024; ++b) g[b] = (uint16_t)(std::upper_bound(cdf, cdf + n, b << 22) - cdf);
@@ -274,6 +288,7 @@ int upload_tables(dwgsim_gpu *h)
     if ((rc = upload(h, &h->dt.isize_cdf, h->isize_cdf.data(), h->isize_cdf.size()))) return rc;
     if ((rc = upload(h, &h->dt.qdelta_cdf, h->qdelta_cdf.data(), h->qdelta_cdf.size()))) return rc;
     if ((rc = upload(h, &h->dt.qguide, h->qguide.data(), h->qguide.size()))) return rc;
+    if ((rc = upload(h, &h->dt.qtab, h->qtab.data(), h->qtab.size()))) return rc;
     if ((rc = upload(h, &h->dt.isize_guide, h->isize_guide.data(), h->isize_guide.size()))) return rc;
     for (int e = 0; e < 2; ++e) if ((rc = upload(h, &h->dt.gap_guide[e], h->gap_guide[e].data(), h->gap_guide[e].size()))) return rc;
     for (int e = 0; e < 2; ++e) {
@@ -307,7 +322,9 @@ int upload_tables(dwgsim_gpu *h)
     s.prefix_len = (int32_t)h->prefix_s.size();
     s.flow_order_len = p.flow_order_len;
     s.tile_pairs = 4;
-    s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide;
+    s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide; s.qtab = h->dt.qtab;
+    s.fmt_v2 = (!s.q_wrap && h->qdelta_cdf.size() < 128) ? 1 : 0;
+    if (const char *e = getenv("DWGSIM_FORMAT_V1")) if (atoi(e)) s.fmt_v2 = 0;
     s.isize_guide = h->dt.isize_guide; s.gap_guide[0] = h->dt.gap_guide[0]; s.gap_guide[1] = h->dt.gap_guide[1];
     s.inv_nw = (uint32_t)(4294967296.0 / std::max(s.nw[0] + s.nw[1], 1)) + 1u;
     {   // staged rows: unpadded when lanes then collide two ways at most (stride = 2 mod 4 words); Ion Torrent rows are edited
@@ -471,6 +488,18 @@ int update_caps(dwgsim_gpu *h)
         h->sp.tile_pairs = std::max(1, std::min(31, (152 + groups - 1) / groups));       // ~150 groups of 8 bases per warp
     }
     if (const char *e = getenv("DWGSIM_TILE_PAIRS")) h->sp.tile_pairs = std::max(1, std::min(31, atoi(e)));
+    if (h->sp.fmt_v2) {
+        // one CTA per SM (the noise table takes 64 KB of its shared memory): as many warps as fit with the mini-tile wanted
+        h->sp.fmt_warps = kFmt2WarpsMax;
+        if (const char *e = getenv("DWGSIM_FMT_WARPS")) h->sp.fmt_warps = std::max(1, std::min(kFmt2WarpsMax, atoi(e)));
+        while (h->sp.tile_pairs > 1 && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.tile_pairs;
+        while (h->sp.fmt_warps > 1 && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.fmt_warps;
+        const Format2Smem L2 = format2_smem_layout(h->sp);
+        if (L2.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
+        if (h->sp.data_type == 1) CUDA_TRY(h, cudaFuncSetAttribute(format_fastq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+        else CUDA_TRY(h, cudaFuncSetAttribute(format_fastq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+        return DWGSIM_GPU_OK;
+    }
     h->sp.fmt_warps = kFmtWarps;
     while (h->sp.tile_pairs > 1 && format_smem_layout(h->sp).total > 113 * 1024) --h->sp.tile_pairs;
     while (h->sp.fmt_warps > 1 && format_smem_layout(h->sp).total > 227 * 1024) h->sp.fmt_warps >>= 1;   // long reads: fewer warps per CTA
@@ -706,7 +735,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
     const int grid = std::min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count * 8);
     const int cap0 = (sp.cap[0] + 15) & ~15, cap1 = (sp.cap[1] + 15) & ~15;
-    const size_t smem_b = (size_t)format_smem_layout(sp).total;
+    const size_t smem_b = sp.fmt_v2 ? 0 : (size_t)format_smem_layout(sp).total;
     (void)cap0; (void)cap1;
     cudaStream_t st = h->s_compute;
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[4], st));
@@ -715,15 +744,27 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     layout_scan_blocks_kernel<<<3, 1024, 0, st>>>(w.blk_len, nblk, 3, w.totals + 1);
     layout_offsets_kernel<<<nblk, kThreads, 0, st>>>(n, w.blk_len, w.lens);
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
-    const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmtWarps, fmt_threads = 32 * fmt_warps;
-    const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;    // CTAs that have a mini-tile per warp
-    int occ_f = 1;
-    const format_kernel_t fmt = format_kernel_of(sp);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fmt, fmt_threads, smem_b);
-    const int grid_f = std::min(ntiles, sm_count * std::max(occ_f, 1));
-    (void)grid;
-    fmt<<<grid_f, fmt_threads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
-                                                             w.totals + 1, w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+    if (sp.fmt_v2) {
+        const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmt2WarpsMax, fmt_threads = 32 * fmt_warps;
+        const size_t smem_2 = (size_t)format2_smem_layout(sp).total;
+        const int ctas = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;  // CTAs that have a mini-tile per warp
+        const int grid_f = std::min(ctas, sm_count);
+        if (sp.data_type == 1)
+            format_fastq2_kernel<true><<<grid_f, fmt_threads, smem_2, st>>>(sp, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
+                                                                            w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+        else
+            format_fastq2_kernel<false><<<grid_f, fmt_threads, smem_2, st>>>(sp, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
+                                                                             w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+    } else {
+        const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmtWarps, fmt_threads = 32 * fmt_warps;
+        const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;    // CTAs that have a mini-tile per warp
+        int occ_f = 1;
+        const format_kernel_t fmt = format_kernel_of(sp);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fmt, fmt_threads, smem_b);
+        const int grid_f = std::min(ntiles, sm_count * std::max(occ_f, 1));
+        fmt<<<grid_f, fmt_threads, smem_b, st>>>(sp, h->blob, first, h->gidx_origin, n, w.recs, w.seqs, w.serial, w.lens,
+                                                 w.totals + 1, w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+    }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 32, cudaMemcpyDeviceToHost, st));
@@ -942,7 +983,7 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     free_workspace(h);
     free_blob(h);
     cudaFree(h->blob_spare);
-    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
+    cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.qtab); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
     for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
     cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
     for (int k = 0; k < 3; ++k) { cudaFree(h->gz_code[k]); cudaFree(h->gz_prefix[k]); }

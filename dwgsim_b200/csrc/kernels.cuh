@@ -1556,6 +1556,14 @@ __device__ __noinline__ int qdelta_rank_tail(uint2 ent, const uint32_t *cdf, uin
     return j;
 }
 
+// QUAL draw of base i of an 8-base group: upper 16 bits from field i of the group's first Philox block, lower 16 bits
+// from the same field of its second block (field f = half f&1 of word f>>1); oracle: draw_qual_delta
+__device__ __forceinline__ uint32_t qual_draw32(const uint4 &b0, const uint4 &b1, int i)
+{
+    const uint32_t h = word_of(b0, (uint32_t)i >> 1), l = word_of(b1, (uint32_t)i >> 1);
+    return (i & 1) ? ((h & 0xFFFF0000u) | (l >> 16)) : ((h << 16) | (l & 0xFFFFu));
+}
+
 struct FmtPrefetch {                   // step 0 of a mini-tile, held in registers by lane j for pair j (lane np: end offsets)
     uint32_t lens, tail;               // PairRec words 2 (len[0] | len[1] << 16) and 7 (n_err_first, flags, attempt << 16)
     uint32_t off[3];                   // byte offset of the pair's records in each stream (lane np: end of the mini-tile)
@@ -1658,7 +1666,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                 const uint64_t gidx = (uint64_t)(gidx_origin + first + p0 + t);
                 const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), m.attempt};
                 uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
-                if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); if (cnt > 4) b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
+                if (P.qdelta_n > 0) { b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g)); b1 = draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)); }
                 const uint2 qb8 = lds64((e ? a_qb1 : a_qb0) + k0);           // k0 is a multiple of 8
                 int qc[8];
 #pragma unroll
@@ -1667,7 +1675,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                     uint32_t tails = 0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {                           // straight-line code: eight loads, eight compares
-                        const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
+                        const uint32_t u = qual_draw32(b0, b1, i);
                         const uint2 ent = lds64(a_guide + ((u >> 22) << 3));
                         qc[i] += P.qdelta_lo + (int)ent.y + (u > ent.x ? 1 : 0);
                         if (i < cnt) tails |= ent.y;                        // (draws past the end of the read are not used)
@@ -1675,7 +1683,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
                     if ((int)tails < 0) {                                   // some draw fell into a tail bucket (rare): redo those
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const uint32_t u = word_of(i < 4 ? b0 : b1, i & 3);
+                            const uint32_t u = qual_draw32(b0, b1, i);
                             const uint2 ent = lds64(a_guide + ((u >> 22) << 3));
                             if (i < cnt && (int)ent.y < 0) qc[i] += qdelta_rank_tail(ent, cdf, u) - (int)ent.y - (u > ent.x ? 1 : 0);
                         }
@@ -1797,6 +1805,341 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
         __syncwarp();
         cur = nxt;
     }
+}
+
+
+// ---- kernel B2: format, word-granular -----------------------------------------------------------------------
+// Same mini-tile organisation, inputs and output bytes as format_fastq_kernel above, rebuilt around three changes:
+//   * qualities: the 8 QUAL draws of a group are the eight 16-bit fields of ONE Philox block; a byte table indexed by the
+//     16-bit draw gives the noise rank directly (P.qtab, 2^kQTabBits entries in shared memory), bit 7 marks the draws whose
+//     table cell contains a CDF threshold: only those (about 5e-4 of the draws) take their lower 16 bits from the group's
+//     second block and search the CDF.  Base + noise + clamp run two qualities per instruction (VIADDMNMX.S16x2.RELU)
+//   * bases and qualities of a group are assembled in two registers each and leave as aligned 32-bit words after a byte
+//     funnel shift against the previous lane's last word (SHFL + PRMT); no predicated byte stores.  A field's first and
+//     last word spill at most three bytes over its ends: exactly the "\n+\n" between bases and qualities, the "/1\n" /
+//     name tail before the bases and the "\n" + next name after the qualities, all of which step 2 writes afterwards
+//   * the 16-byte aligned interior of every stream range leaves with one cp.async.bulk.global.shared::cta per stream
+//     (UBLKCP) while the warp goes on with its next mini-tile; the staging area is reused after wait_group.read
+// Specialisation: colour space.  Configurations whose quality sum can wrap in int8 or whose noise table has 128 or
+// more steps (quality_std >= 7.8) stay on format_fastq_kernel.
+#ifndef DWG_QTAB_BITS
+#define DWG_QTAB_BITS 16
+#endif
+constexpr int kQTabBits = DWG_QTAB_BITS;
+constexpr int kFmt2WarpsMax = 24;
+constexpr int kFmt2ThreadsMax = kFmt2WarpsMax * 32;
+
+struct Format2Smem {
+    int qtab_off, cdf_off, qb_off[2], warp_off, warp_stride, meta_off, stage_off[3], total;
+};
+__host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
+{
+    Format2Smem L;
+    const int WP = P.tile_pairs;
+    const bool noise = P.qdelta_n > 0 && !P.fixed_quality;
+    int o = 0;
+    L.qtab_off = o; o += noise ? (1 << kQTabBits) : 0;
+    L.cdf_off = o; o += ((noise ? P.qdelta_n : 0) * 4 + 15) & ~15;
+    for (int e = 0; e < 2; ++e) { L.qb_off[e] = o; o += (((P.cap[e] + 7) & ~7) * 2 + 16) & ~15; }
+    L.warp_off = o;
+    int w = 0;
+    L.meta_off = w; w += WP * (int)sizeof(PairMeta);
+    for (int k = 0; k < 3; ++k) { L.stage_off[k] = w; w += (WP * P.rec_cap[k] + 32 + 15) & ~15; }
+    L.warp_stride = w;
+    L.total = o + (P.fmt_warps > 0 ? P.fmt_warps : kFmt2WarpsMax) * w;
+    return L;
+}
+
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t viaddmin_relu_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
+
+// one field (bases or qualities of one record): the lane's 8 bytes {lo, hi} belong at byte address p; `prev` is the last
+// word of the previous group of the same read (anything for the first group)
+// `skip1`: the lane's first byte is not part of the field (first colour of a SOLiD bwa record): when it is the last byte
+// of its word that word holds nothing of the field, and writing it would reach four bytes back
+__device__ __forceinline__ void store_field(uint32_t p, uint32_t prev, uint32_t lo, uint32_t hi, bool tail, int cnt, bool skip1 = false)
+{
+    const uint32_t bs = p & 3u, w = p - bs, sel = 0x7654u - 0x1111u * bs;       // bytes [4 - bs, 8 - bs) of {first, second}
+    const int v = (int)bs + cnt;                                                 // end of the lane's bytes in its 12-byte window
+    if (!(skip1 && bs == 3u)) sts32(w, __byte_perm(prev, lo, sel));
+    if (!tail || v > 4) sts32(w + 4, __byte_perm(lo, hi, sel));
+    if (tail && v > 8) sts32(w + 8, __byte_perm(hi, 0u, sel));
+}
+
+// the draws of a group whose table cell holds a CDF threshold: full 32-bit draw, rank by binary search
+__device__ __noinline__ uint4 qual_ranks_slow(uint4 r, const uint4 b0, const uint4 b1, const uint32_t *cdf, int n)
+{
+    uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t sh = 16u * (i & 1);
+        if (!((rr[i >> 1] >> sh) & 0x80u)) continue;
+        const uint32_t u = qual_draw32(b0, b1, i);
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (u >= cdf[mid]) lo = mid + 1; else hi = mid; }
+        rr[i >> 1] = (rr[i >> 1] & ~(0xFFFFu << sh)) | ((uint32_t)lo << sh);
+    }
+    return make_uint4(rr[0], rr[1], rr[2], rr[3]);
+}
+
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool kSolid>
+__global__ void __launch_bounds__(kFmt2ThreadsMax, 1)
+format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int n,
+                     const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
+                     const uint32_t *__restrict__ offs /* [3][n] */,
+                     const unsigned long long *__restrict__ totals /* bytes of the batch per stream */,
+                     const char *__restrict__ gnames, const uint16_t *__restrict__ gname_len,
+                     char *__restrict__ out0, char *__restrict__ out1, char *__restrict__ out2)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const Format2Smem L = format2_smem_layout(P);
+    const int WP = P.tile_pairs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qmode = P.fixed_quality ? 2 : (P.qdelta_n > 0 ? 1 : 0);          // 0: no noise, 1: noise table, 2: fixed character
+    {
+        if (qmode == 1) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.qtab);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem + L.qtab_off);
+            for (int j = tid; j < (1 << kQTabBits) / 16; j += (int)blockDim.x) dst[j] = __ldg(src + j);
+            for (int j = tid; j < P.qdelta_n; j += (int)blockDim.x) reinterpret_cast<uint32_t *>(smem + L.cdf_off)[j] = P.qdelta_cdf[j];
+        }
+        for (int e = 0; e < 2; ++e) {
+            int16_t *qb = reinterpret_cast<int16_t *>(smem + L.qb_off[e]);
+            const int padded = (P.cap[e] + 7) & ~7;
+            for (int j = tid; j < padded; j += (int)blockDim.x) qb[j] = (int16_t)((j < P.cap[e] ? (int)P.qbase[e][j] : 0) + (qmode == 1 ? P.qdelta_lo : 0));
+        }
+    }
+    __syncthreads();                                                 // the only CTA-wide barrier
+    const uint32_t a_base = in_register(smem_addr(smem));
+    const uint32_t a_qtab = a_base + L.qtab_off, a_qb0 = a_base + L.qb_off[0], a_qb1 = a_base + L.qb_off[1];
+    const uint32_t a_warp = a_base + L.warp_off + warp * L.warp_stride;
+    const uint32_t a_st0 = a_warp + L.stage_off[0], a_st1 = a_warp + L.stage_off[1], a_st2 = a_warp + L.stage_off[2];
+    PairMeta *meta = reinterpret_cast<PairMeta *>(smem + L.warp_off + warp * L.warp_stride + L.meta_off);
+    const uint32_t *cdf = reinterpret_cast<const uint32_t *>(smem + L.cdf_off);
+
+    constexpr bool solid = kSolid;
+    constexpr int from = kSolid ? 1 : 0;                            // bwa drops the first colour (src/dwgsim.c:949-953)
+    const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
+    const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
+    const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1, NW = P.nw[0] + P.nw[1];
+    const int ntiles = (n + WP - 1) / WP;
+    const int n_warps = (int)blockDim.x >> 5;
+    const int tstride = gridDim.x * n_warps;
+    constexpr uint32_t full = 0xffffffffu;
+
+    auto prefetch = [&](int tile) {
+        FmtPrefetch f;
+        f.lens = f.tail = 0; f.off[0] = f.off[1] = f.off[2] = 0; f.nl = 0;
+        if (tile >= ntiles) return f;
+        const int p0 = tile * WP, np = min(WP, n - p0), p = p0 + lane;
+        if (lane < np) {
+            const uint32_t *r = reinterpret_cast<const uint32_t *>(recs + p);
+            f.lens = __ldg(r + 2); f.tail = __ldg(r + 7);
+            f.nl = __ldg(reinterpret_cast<const uint32_t *>(gname_len) + p);
+        }
+        if (lane <= np) {
+            if (on0) { f.off[0] = p < n ? __ldg(offs + p) : (uint32_t)totals[0]; f.off[1] = p < n ? __ldg(offs + (size_t)n + p) : (uint32_t)totals[1]; }
+            if (on2) f.off[2] = p < n ? __ldg(offs + (size_t)2 * n + p) : (uint32_t)totals[2];
+        }
+        return f;
+    };
+
+    int tile = blockIdx.x * n_warps + warp;
+    FmtPrefetch cur = prefetch(tile);
+    bool bulk_pending = false;                                       // (lanes 0-2) a bulk store of the previous mini-tile may still read the staging area
+    for (; tile < ntiles; tile += tstride) {
+        const FmtPrefetch nxt = prefetch(tile + tstride);
+        const int p0 = tile * WP, np = min(WP, n - p0);
+        {   // the read codes of this mini-tile towards L1, those of the next one towards L2
+            const uintptr_t c0 = reinterpret_cast<uintptr_t>(seqw + (size_t)p0 * NW), a0 = c0 & ~(uintptr_t)127;
+            if (a0 + ((uintptr_t)lane << 7) < c0 + (size_t)np * NW * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + ((uintptr_t)lane << 7)));
+            const int pn = (tile + tstride) * WP;
+            if (pn < n) {
+                const uintptr_t c1 = reinterpret_cast<uintptr_t>(seqw + (size_t)pn * NW), a1 = c1 & ~(uintptr_t)127;
+                if (a1 + ((uintptr_t)lane << 7) < c1 + (size_t)min(WP, n - pn) * NW * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(a1 + ((uintptr_t)lane << 7)));
+            }
+        }
+        // ---- step 0: geometry of the mini-tile ---------------------------------------------------------------
+        uint32_t begin[3], shift[3], total[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            begin[k] = __shfl_sync(full, cur.off[k], 0);
+            total[k] = __shfl_sync(full, cur.off[k], np) - begin[k];
+            char *outk = k == 0 ? out0 : (k == 1 ? out1 : out2);
+            shift[k] = (uint32_t)(reinterpret_cast<uintptr_t>(outk + begin[k]) & 15u);
+        }
+        if (lane < np) {
+            PairMeta m;
+            m.len[0] = (uint16_t)(cur.lens & 0xFFFFu); m.len[1] = (uint16_t)(cur.lens >> 16); m.attempt = cur.tail >> 16;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) m.so[k] = cur.off[k] - begin[k] + shift[k];
+            m.nfull = (uint16_t)(cur.nl & 0xFFFFu); m.nbwa = (uint16_t)(cur.nl >> 16);
+            m.pad[0] = m.pad[1] = 0;
+            meta[lane] = m;
+        }
+        if (bulk_pending) { bulk_wait_read(); bulk_pending = false; }   // the staging area is free again
+        __syncwarp();
+        // ---- step 1: bases and qualities, one lane per (pair, end, 8-base group), aligned word stores -------------
+        const int items = np * G, n_iter = (items + 31) >> 5;
+        uint32_t carry_a = 0, carry_d = 0, carry_q = 0;
+        for (int iter = 0; iter < n_iter; ++iter) {
+            const int it = (iter << 5) + lane;
+            bool active = it < items;
+            int t = 0, e = 0, g = 0, Le = 0, k0 = 0;
+            if (active) {
+                t = (int)__umulhi((uint32_t)it, P.inv_groups);
+                const int gi = it - t * G;
+                e = gi < g0 ? 0 : 1; g = gi - (e ? g0 : 0);
+                Le = meta[t].len[e]; k0 = g << 3;
+                active = k0 < Le;
+            }
+            uint32_t a_lo = 0, a_hi = 0, d_lo = 0, d_hi = 0, q_lo = 0, q_hi = 0;
+            if (active) {
+                const PairMeta &m = meta[t];
+                const uint32_t codes = __ldg(seqw + (size_t)(p0 + t) * NW + (e ? P.nw[0] : 0) + g);
+                // qualities, src/dwgsim.c:899-918
+                if (qmode == 2) q_lo = q_hi = 0x01010101u * (uint32_t)P.fixed_quality;
+                else {
+                    const uint4 qb = lds128((e ? a_qb1 : a_qb0) + (k0 << 1));      // 8 x int16: Phred base (+ lowest noise step)
+                    uint4 r = make_uint4(0, 0, 0, 0);
+                    if (qmode == 1) {
+                        const uint64_t gidx = (uint64_t)(gidx_origin + first + p0 + t);
+                        const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), m.attempt};
+                        const uint4 b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g));
+                        constexpr int dsh = 16 - kQTabBits;
+#define DWG_LK(word, half) lds8(a_qtab + ((half) ? ((word) >> (16 + dsh)) : (((word) & 0xFFFFu) >> dsh)))
+                        r.x = DWG_LK(b0.x, 0) | (DWG_LK(b0.x, 1) << 16);
+                        r.y = DWG_LK(b0.y, 0) | (DWG_LK(b0.y, 1) << 16);
+                        r.z = DWG_LK(b0.z, 0) | (DWG_LK(b0.z, 1) << 16);
+                        r.w = DWG_LK(b0.w, 0) | (DWG_LK(b0.w, 1) << 16);
+#undef DWG_LK
+                        if ((r.x | r.y | r.z | r.w) & 0x00800080u)
+                            r = qual_ranks_slow(r, b0, draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)), cdf, P.qdelta_n);
+                    }
+                    // 33 + clamp(base + noise, 0, 40), two qualities per instruction
+                    const uint32_t v0 = viaddmin_relu_s16x2(r.x, qb.x, 0x00280028u), v1 = viaddmin_relu_s16x2(r.y, qb.y, 0x00280028u);
+                    const uint32_t v2 = viaddmin_relu_s16x2(r.z, qb.z, 0x00280028u), v3 = viaddmin_relu_s16x2(r.w, qb.w, 0x00280028u);
+                    q_lo = __byte_perm(v0, v1, 0x6420) + 0x21212121u;
+                    q_hi = __byte_perm(v2, v3, 0x6420) + 0x21212121u;
+                }
+                // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
+                a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu); a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
+                d_lo = a_lo; d_hi = a_hi;
+                if (solid) { d_lo = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d_hi = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
+            }
+            // the last word of the previous group (previous lane; lane 0: last lane of the previous round)
+            uint32_t pa = __shfl_up_sync(full, a_hi, 1), pq = __shfl_up_sync(full, q_hi, 1), pd = pa;
+            if (solid) pd = __shfl_up_sync(full, d_hi, 1);
+            if (lane == 0) { pa = carry_a; pq = carry_q; pd = carry_d; }
+            carry_a = __shfl_sync(full, a_hi, 31); carry_q = __shfl_sync(full, q_hi, 31);
+            carry_d = solid ? __shfl_sync(full, d_hi, 31) : carry_a;
+            if (active) {
+                const PairMeta &m = meta[t];
+                const int cnt = min(8, Le - k0);
+                const bool tail = k0 + 8 >= Le;
+                const int len0 = m.len[0];
+                const int me = Le - from;
+                if (on0) {
+                    const uint32_t ps_b = (e ? a_st1 : a_st0) + m.so[e] + m.nbwa + 3 - from + k0;    // bwa: bases, then qualities
+                    store_field(ps_b, pa, a_lo, a_hi, tail, cnt, solid && g == 0);
+                    store_field(ps_b + me + 3, pq, q_lo, q_hi, tail, cnt, solid && g == 0);
+                }
+                if (on2) {
+                    const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
+                    const uint32_t ps_f = a_st2 + m.so[2] + (e ? rec0 : 0) + m.nfull + 1 + (solid ? 1 : 0) + k0;   // bfast
+                    store_field(ps_f, pd, d_lo, d_hi, tail, cnt);
+                    store_field(ps_f + Le + 3, pq, q_lo, q_hi, tail, cnt);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- step 2: names (one lane per record and 16-byte chunk), suffixes and separators, byte-exact --------------
+        {
+            const int nchunks = P.name_cap >> 4;
+            for (int it = lane; it < np * 4 * nchunks; it += 32) {
+                const int rc = (int)__umulhi((uint32_t)it, P.inv_name_chunks), c = it - rc * nchunks, t = rc >> 2, rr = rc & 3, e = rr & 1, bf = rr >> 1;
+                const PairMeta &m = meta[t];
+                const int Le = m.len[e];
+                if (Le <= 0 || (bf ? !on2 : !on0)) continue;
+                const int nn = bf ? m.nfull : m.nbwa, x0 = c << 4;
+                if (x0 >= nn) continue;
+                const int len0 = m.len[0];
+                const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
+                const uint32_t d = (bf ? a_st2 + m.so[2] + (e ? rec0 : 0) : (e ? a_st1 : a_st0) + m.so[e]) + x0;
+                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (bf ? 0 : nvar - 1)) * P.name_cap;
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nm + x0));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                const int left = nn - x0;
+#pragma unroll
+                for (int b4 = 0; b4 < 4; ++b4) {
+                    const uint32_t x = w[b4];
+                    if (4 * b4 + 0 < left) sts8(d + 4 * b4, x);
+                    if (4 * b4 + 1 < left) sts8(d + 4 * b4 + 1, x >> 8);
+                    if (4 * b4 + 2 < left) sts8(d + 4 * b4 + 2, x >> 16);
+                    if (4 * b4 + 3 < left) sts8(d + 4 * b4 + 3, x >> 24);
+                }
+            }
+            for (int it = lane; it < np * 4; it += 32) {
+                const int t = it >> 2, rr = it & 3, e = rr & 1, bf = rr >> 1;
+                const PairMeta &m = meta[t];
+                const int Le = m.len[e];
+                if (Le <= 0) continue;
+                if (!bf) {
+                    if (!on0) continue;
+                    const uint32_t sb = (e ? a_st1 : a_st0) + m.so[e] + m.nbwa;
+                    const int me = Le - from;
+                    sts8(sb, '/'); sts8(sb + 1, solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sts8(sb + 2, '\n');
+                    sts8(sb + 3 + me, '\n'); sts8(sb + 3 + me + 1, '+'); sts8(sb + 3 + me + 2, '\n');
+                    sts8(sb + 3 + me + 3 + me, '\n');
+                } else {
+                    if (!on2) continue;
+                    const int len0 = m.len[0];
+                    const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
+                    uint32_t sf = a_st2 + m.so[2] + (e ? rec0 : 0) + m.nfull;
+                    sts8(sf, '\n');
+                    sf += 1;
+                    if (solid) { sts8(sf, 'A'); sf += 1; }
+                    sts8(sf + Le, '\n'); sts8(sf + Le + 1, '+'); sts8(sf + Le + 2, '\n');
+                    sts8(sf + Le + 3 + Le, '\n');
+                }
+            }
+        }
+        fence_async_smem();                                          // the bulk engine reads what the lanes wrote
+        __syncwarp();
+        // ---- step 3: copy-out: lane k < 3 sends the 16-byte aligned interior of stream k as one bulk store -----------
+        {
+            const int k = lane < 3 ? lane : 0;
+            const uint32_t a_st = k == 0 ? a_st0 : (k == 1 ? a_st1 : a_st2);
+            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin[k] - shift[k];   // 16-byte aligned
+            const int sh = (int)shift[k], end = sh + (int)total[k];
+            const int c_first = sh ? 1 : 0, c_full = end >> 4;          // chunks [c_first, c_full) lie wholly inside the range
+            if (lane < 3 && total[k] != 0 && c_full > c_first) {
+                bulk_store(base + (c_first << 4), a_st + (c_first << 4), (uint32_t)(c_full - c_first) << 4);
+                bulk_commit();
+                bulk_pending = true;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                                // the two boundary chunks are shared with the neighbouring mini-tiles
+            if (total[k] == 0) continue;
+            const uint32_t a_st = k == 0 ? a_st0 : (k == 1 ? a_st1 : a_st2);
+            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin[k] - shift[k];
+            const int sh = (int)shift[k], end = sh + (int)total[k], nchunk = (end + 15) >> 4;
+            const int c_first = sh ? 1 : 0, c_full = end >> 4;
+            const int c = lane < 16 ? 0 : c_full, x = (c << 4) + (lane & 15);
+            const bool mine = lane < 16 ? c_first != 0 : (c_full < nchunk && (c_full > 0 || !c_first));
+            if (mine && x >= sh && x < end) base[x] = (char)lds8(a_st + x);
+        }
+        cur = nxt;
+    }
+    if (bulk_pending) bulk_wait_read();
 }
 
 }  // namespace dwg
