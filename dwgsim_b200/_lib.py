@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libdwgsim_b200.so")
+SO = os.environ.get("DWGSIM_LIB") or os.path.join(HERE, "libdwgsim_b200.so")   # (DWGSIM_LIB: kernel-variant experiments)
 
 
 class Params(C.Structure):

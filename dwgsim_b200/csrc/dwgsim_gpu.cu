@@ -78,6 +78,8 @@ struct Workspace {
     uint2 *jobs = nullptr;                    // [2][cap]: retry and random job lists of the simulate passes
     char *out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint64_t out_cap[3] = {0, 0, 0};
+    int32_t name_cap = 0;                     // the name / record bounds the buffers were sized with (update_caps raises them
+    uint64_t rec_cap[3] = {0, 0, 0};          //   when a later contig has a longer name)
     unsigned long long *h_totals = nullptr;   // pinned [8 + 2]
     // device gzip writer
     uint8_t *gz_slots[3] = {nullptr, nullptr, nullptr};
@@ -323,8 +325,9 @@ int upload_tables(dwgsim_gpu *h)
     s.flow_order_len = p.flow_order_len;
     s.tile_pairs = 4;
     s.isize_cdf = h->dt.isize_cdf; s.qdelta_cdf = h->dt.qdelta_cdf; s.qguide = h->dt.qguide; s.qtab = h->dt.qtab;
+    for (int r = 0; r < 10; ++r) s.qkey[r] = s.seed + (uint32_t)r * 0x9E3779B9u;
     s.fmt_v2 = (!s.q_wrap && h->qdelta_cdf.size() < 128) ? 1 : 0;
-    if (const char *e = getenv("DWGSIM_FORMAT_V1")) if (atoi(e)) s.fmt_v2 = 0;
+    if (const char *e = getenv("DWGSIM_FORMAT")) if (atoi(e) == 1) s.fmt_v2 = 0;                  // 1: the byte-granular kernel everywhere
     s.isize_guide = h->dt.isize_guide; s.gap_guide[0] = h->dt.gap_guide[0]; s.gap_guide[1] = h->dt.gap_guide[1];
     s.inv_nw = (uint32_t)(4294967296.0 / std::max(s.nw[0] + s.nw[1], 1)) + 1u;
     {   // staged rows: unpadded when lanes then collide two ways at most (stride = 2 mod 4 words); Ion Torrent rows are edited
@@ -334,6 +337,8 @@ int upload_tables(dwgsim_gpu *h)
         if (const char *e = getenv("DWGSIM_ROW_PAD")) if (atoi(e)) s.row_stride = nw | 1;
     }
     s.inv_groups = (uint32_t)(4294967296.0 / std::max((s.cap[0] + 7) / 8 + (s.cap[1] + 7) / 8, 1)) + 1u;
+    if (s.fmt_v2)                                              // format_fastq2_kernel: 16 bases per lane
+        s.inv_groups = (uint32_t)(4294967296.0 / std::max(((s.cap[0] + 7) / 8 + 1) / 2 + ((s.cap[1] + 7) / 8 + 1) / 2, 1)) + 1u;
     s.flow_order = h->dt.flow_order; s.prefix = h->dt.prefix;
     return DWGSIM_GPU_OK;
 }
@@ -492,6 +497,8 @@ int update_caps(dwgsim_gpu *h)
         // one CTA per SM (the noise table takes 64 KB of its shared memory): as many warps as fit with the mini-tile wanted
         h->sp.fmt_warps = kFmt2WarpsMax;
         if (const char *e = getenv("DWGSIM_FMT_WARPS")) h->sp.fmt_warps = std::max(1, std::min(kFmt2WarpsMax, atoi(e)));
+        const int warps_floor = getenv("DWGSIM_TILE_PAIRS") ? 1 : std::min(h->sp.fmt_warps, 20);
+        while (h->sp.fmt_warps > warps_floor && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.fmt_warps;
         while (h->sp.tile_pairs > 1 && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.tile_pairs;
         while (h->sp.fmt_warps > 1 && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.fmt_warps;
         const Format2Smem L2 = format2_smem_layout(h->sp);
@@ -609,8 +616,17 @@ void free_workspace(dwgsim_gpu *h)
 int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
 {
     Workspace &w = h->ws;
-    if (w.cap_pairs < n) {
+    uint64_t cap_now[3];
+    record_caps(h, cap_now);
+    // the names buffer, the output streams and the pinned ring are sized from the longest contig name seen so far: a later,
+    // longer name (add_contig / genome_import after a run) needs them again
+    const bool grown = w.cap_pairs > 0 && (h->sp.name_cap > w.name_cap || cap_now[0] > w.rec_cap[0] || cap_now[1] > w.rec_cap[1] ||
+                                           cap_now[2] > w.rec_cap[2]);
+    if (w.cap_pairs < n || grown) {
+        n = std::max<int64_t>(n, w.cap_pairs);
         free_workspace(h);
+        w.name_cap = h->sp.name_cap;
+        for (int k = 0; k < 3; ++k) w.rec_cap[k] = cap_now[k];
         const int64_t nblk = (n + kScanTile - 1) / kScanTile;
         CUDA_TRY(h, cudaMalloc((void **)&w.recs, (size_t)n * sizeof(PairRec)));
         CUDA_TRY(h, cudaMalloc((void **)&w.seqs, (size_t)n * 4 * (size_t)(h->sp.nw[0] + h->sp.nw[1] + 1)));

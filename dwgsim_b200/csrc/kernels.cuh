@@ -1127,7 +1127,8 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
             else {
                 const int slen = P.regions ? region_sample_len(blob, q) : cv.len;
                 if (s1 > 0) {
-                    d = P.isize_lo + guided_rank(T.isize_cdf, T.isize_guide, b0.y);
+                    // (the guide holds 16-bit ranks: tables past 65,535 steps, -s above about 4,000, are searched whole)
+                    d = P.isize_lo + (P.isize_n <= 65535 ? guided_rank(T.isize_cdf, T.isize_guide, b0.y) : table_rank(P.isize_cdf, P.isize_n, b0.y));
                     const int min_dist = s0 + s1;
                     if (d < min_dist) d = min_dist;
                     if (d > slen) d = slen;
@@ -1814,23 +1815,41 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
 //     16-bit draw gives the noise rank directly (P.qtab, 2^kQTabBits entries in shared memory), bit 7 marks the draws whose
 //     table cell contains a CDF threshold: only those (about 5e-4 of the draws) take their lower 16 bits from the group's
 //     second block and search the CDF.  Base + noise + clamp run two qualities per instruction (VIADDMNMX.S16x2.RELU)
-//   * bases and qualities of a group are assembled in two registers each and leave as aligned 32-bit words after a byte
-//     funnel shift against the previous lane's last word (SHFL + PRMT); no predicated byte stores.  A field's first and
-//     last word spill at most three bytes over its ends: exactly the "\n+\n" between bases and qualities, the "/1\n" /
-//     name tail before the bases and the "\n" + next name after the qualities, all of which step 2 writes afterwards
+//   * everything is assembled in registers and leaves as aligned 32-bit words after a byte funnel shift against the
+//     previous lane's last word (SHFL + PRMT); no predicated byte stores in the bulk of the work.  Such a field spills
+//     at most three bytes over each of its ends, so the order of the passes makes every spill land on bytes a later pass
+//     writes: names first (their spill: the previous record's last bytes and the suffix / first bases), then bases and
+//     qualities (spill: the 3-byte "\n+\n" between them, the suffix and up to two name bytes before the bases, the "\n"
+//     and up to two name bytes after the qualities), then one lane per record rewrites exactly those bytes
 //   * the 16-byte aligned interior of every stream range leaves with one cp.async.bulk.global.shared::cta per stream
 //     (UBLKCP) while the warp goes on with its next mini-tile; the staging area is reused after wait_group.read
 // Specialisation: colour space.  Configurations whose quality sum can wrap in int8 or whose noise table has 128 or
 // more steps (quality_std >= 7.8) stay on format_fastq_kernel.
 #ifndef DWG_QTAB_BITS
-#define DWG_QTAB_BITS 16
+#define DWG_QTAB_BITS 15
 #endif
 constexpr int kQTabBits = DWG_QTAB_BITS;
-constexpr int kFmt2WarpsMax = 24;
+#ifndef DWG_FMT2_WARPS
+#define DWG_FMT2_WARPS 24
+#endif
+constexpr int kFmt2WarpsMax = DWG_FMT2_WARPS;
 constexpr int kFmt2ThreadsMax = kFmt2WarpsMax * 32;
 
+struct ReadMeta {                      // per (pair, end) of the warp's mini-tile, in shared memory (32 bytes)
+    uint32_t ps_b, pq_b, ps_f, pq_f;   // shared-window byte address of base / quality 0 in the bwa and the bfast record
+    uint32_t len;                      // read length
+    uint32_t c2;                       // Philox counter word 2 of the QUAL stream: attempt | stream << 16 | end << 24
+    uint32_t g_lo, g_hi;               // global pair index (Philox counter words 0, 1)
+};
+struct NameMeta {                      // per record (pair, end, bwa | bfast), 16 bytes; dst == 0: no such record
+    uint32_t dst;                      // shared-window byte address of the '@'
+    uint32_t nn;                       // name length
+    uint32_t src;                      // byte offset of the name text in gnames
+    uint32_t len;                      // read length (bytes of bases in the record: len - from for bwa)
+};
+
 struct Format2Smem {
-    int qtab_off, cdf_off, qb_off[2], warp_off, warp_stride, meta_off, stage_off[3], total;
+    int qtab_off, cdf_off, qb_off[2], warp_off, warp_stride, meta_off, rmeta_off, nmeta_off, stage_off[3], total;
 };
 __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
 {
@@ -1844,6 +1863,8 @@ __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
     L.warp_off = o;
     int w = 0;
     L.meta_off = w; w += WP * (int)sizeof(PairMeta);
+    L.rmeta_off = w; w += 2 * WP * (int)sizeof(ReadMeta);
+    L.nmeta_off = w; w += 4 * WP * (int)sizeof(NameMeta);
     for (int k = 0; k < 3; ++k) { L.stage_off[k] = w; w += (WP * P.rec_cap[k] + 32 + 15) & ~15; }
     L.warp_stride = w;
     L.total = o + (P.fmt_warps > 0 ? P.fmt_warps : kFmt2WarpsMax) * w;
@@ -1851,10 +1872,27 @@ __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
 }
 
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t viaddmin_relu_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Philox4x32-10 with the first key word's round keys taken from the kernel parameters (P.qkey[r] = seed + r * 0x9E3779B9:
+// constant-bank operands of the XORs) and the second key word's folded into immediates
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SimParams &P)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ P.qkey[r], n2 = h0 ^ c3 ^ (kPhiloxKey1 + (uint32_t)r * 0xBB67AE85u);
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 
 // one field (bases or qualities of one record): the lane's 8 bytes {lo, hi} belong at byte address p; `prev` is the last
-// word of the previous group of the same read (anything for the first group)
+// word of the previous group of the same read (anything for the first group).
 // `skip1`: the lane's first byte is not part of the field (first colour of a SOLiD bwa record): when it is the last byte
 // of its word that word holds nothing of the field, and writing it would reach four bytes back
 __device__ __forceinline__ void store_field(uint32_t p, uint32_t prev, uint32_t lo, uint32_t hi, bool tail, int cnt, bool skip1 = false)
@@ -1864,6 +1902,18 @@ __device__ __forceinline__ void store_field(uint32_t p, uint32_t prev, uint32_t 
     if (!(skip1 && bs == 3u)) sts32(w, __byte_perm(prev, lo, sel));
     if (!tail || v > 4) sts32(w + 4, __byte_perm(lo, hi, sel));
     if (tail && v > 8) sts32(w + 8, __byte_perm(hi, 0u, sel));
+}
+
+// the same for a lane that holds 16 bytes x[0..3]
+__device__ __forceinline__ void store_field16(uint32_t p, uint32_t prev, const uint32_t (&x)[4], bool tail, int cnt, bool skip1)
+{
+    const uint32_t bs = p & 3u, w = p - bs, sel = 0x7654u - 0x1111u * bs;
+    const int v = (int)bs + cnt;                                                 // end of the lane's bytes in its 20-byte window
+    if (!(skip1 && bs == 3u)) sts32(w, __byte_perm(prev, x[0], sel));
+    if (!tail || v > 4) sts32(w + 4, __byte_perm(x[0], x[1], sel));
+    if (!tail || v > 8) sts32(w + 8, __byte_perm(x[1], x[2], sel));
+    if (!tail || v > 12) sts32(w + 12, __byte_perm(x[2], x[3], sel));
+    if (tail && v > 16) sts32(w + 16, __byte_perm(x[3], 0u, sel));
 }
 
 // the draws of a group whose table cell holds a CDF threshold: full 32-bit draw, rank by binary search
@@ -1900,10 +1950,12 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
                      char *__restrict__ out0, char *__restrict__ out1, char *__restrict__ out2)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const Format2Smem L = format2_smem_layout(P);
     const int WP = P.tile_pairs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qmode = P.fixed_quality ? 2 : (P.qdelta_n > 0 ? 1 : 0);          // 0: no noise, 1: noise table, 2: fixed character
+    uint32_t a_qtab, a_qb0, a_qb1, a_meta, a_rm, a_nm, a_st0, a_st1, a_st2;
+    const uint32_t *cdf;
     {
+        const Format2Smem L = format2_smem_layout(P);
         if (qmode == 1) {
             const uint4 *src = reinterpret_cast<const uint4 *>(P.qtab);
             uint4 *dst = reinterpret_cast<uint4 *>(smem + L.qtab_off);
@@ -1915,20 +1967,22 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
             const int padded = (P.cap[e] + 7) & ~7;
             for (int j = tid; j < padded; j += (int)blockDim.x) qb[j] = (int16_t)((j < P.cap[e] ? (int)P.qbase[e][j] : 0) + (qmode == 1 ? P.qdelta_lo : 0));
         }
+        const uint32_t a_base = smem_addr(smem);
+        a_qtab = in_register(a_base + L.qtab_off); a_qb0 = a_base + L.qb_off[0]; a_qb1 = a_base + L.qb_off[1];
+        const uint32_t a_warp = a_base + L.warp_off + warp * L.warp_stride;
+        a_meta = a_warp + L.meta_off; a_rm = in_register(a_warp + L.rmeta_off); a_nm = in_register(a_warp + L.nmeta_off);
+        a_st0 = a_warp + L.stage_off[0]; a_st1 = a_warp + L.stage_off[1]; a_st2 = a_warp + L.stage_off[2];
+        cdf = reinterpret_cast<const uint32_t *>(smem + L.cdf_off);
     }
     __syncthreads();                                                 // the only CTA-wide barrier
-    const uint32_t a_base = in_register(smem_addr(smem));
-    const uint32_t a_qtab = a_base + L.qtab_off, a_qb0 = a_base + L.qb_off[0], a_qb1 = a_base + L.qb_off[1];
-    const uint32_t a_warp = a_base + L.warp_off + warp * L.warp_stride;
-    const uint32_t a_st0 = a_warp + L.stage_off[0], a_st1 = a_warp + L.stage_off[1], a_st2 = a_warp + L.stage_off[2];
-    PairMeta *meta = reinterpret_cast<PairMeta *>(smem + L.warp_off + warp * L.warp_stride + L.meta_off);
-    const uint32_t *cdf = reinterpret_cast<const uint32_t *>(smem + L.cdf_off);
 
     constexpr bool solid = kSolid;
     constexpr int from = kSolid ? 1 : 0;                            // bwa drops the first colour (src/dwgsim.c:949-953)
+    constexpr int sfx_f = kSolid ? 2 : 1;                           // bytes between a bfast name and its first base: "\n" ("\nA")
     const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
     const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
-    const int g0 = (P.cap[0] + 7) >> 3, g1 = (P.cap[1] + 7) >> 3, G = g0 + g1, NW = P.nw[0] + P.nw[1];
+    const int g0 = (P.cap[0] + 7) >> 3, G = P.nw[0] + P.nw[1];      // 8-base groups (= code words) per pair; end 0 owns the first g0
+    const int h0 = (g0 + 1) >> 1, G2 = h0 + ((G - g0 + 1) >> 1);    // 16-base lane items per pair (P.inv_groups = 2^32 / G2 + 1)
     const int ntiles = (n + WP - 1) / WP;
     const int n_warps = (int)blockDim.x >> 5;
     const int tstride = gridDim.x * n_warps;
@@ -1957,16 +2011,21 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
     for (; tile < ntiles; tile += tstride) {
         const FmtPrefetch nxt = prefetch(tile + tstride);
         const int p0 = tile * WP, np = min(WP, n - p0);
+        const uint32_t *seqw_tile = seqw + (size_t)p0 * G;            // code word of item `it` of this mini-tile: seqw_tile[it]
+        const char *gnames_tile = gnames + (size_t)p0 * nvar * P.name_cap;
         {   // the read codes of this mini-tile towards L1, those of the next one towards L2
-            const uintptr_t c0 = reinterpret_cast<uintptr_t>(seqw + (size_t)p0 * NW), a0 = c0 & ~(uintptr_t)127;
-            if (a0 + ((uintptr_t)lane << 7) < c0 + (size_t)np * NW * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + ((uintptr_t)lane << 7)));
+            const uintptr_t c0 = reinterpret_cast<uintptr_t>(seqw_tile), a0 = c0 & ~(uintptr_t)127;
+            if (a0 + ((uintptr_t)lane << 7) < c0 + (size_t)np * G * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + ((uintptr_t)lane << 7)));
+            // the names of this mini-tile (np * nvar rows of name_cap bytes, 128-byte lines) towards L1 as well
+            const uintptr_t n0 = reinterpret_cast<uintptr_t>(gnames) + (size_t)p0 * nvar * P.name_cap, na = n0 & ~(uintptr_t)127;
+            if (na + ((uintptr_t)lane << 7) < n0 + (size_t)np * nvar * P.name_cap) asm volatile("prefetch.global.L1 [%0];" ::"l"(na + ((uintptr_t)lane << 7)));
             const int pn = (tile + tstride) * WP;
             if (pn < n) {
-                const uintptr_t c1 = reinterpret_cast<uintptr_t>(seqw + (size_t)pn * NW), a1 = c1 & ~(uintptr_t)127;
-                if (a1 + ((uintptr_t)lane << 7) < c1 + (size_t)min(WP, n - pn) * NW * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(a1 + ((uintptr_t)lane << 7)));
+                const uintptr_t c1 = reinterpret_cast<uintptr_t>(seqw + (size_t)pn * G), a1 = c1 & ~(uintptr_t)127;
+                if (a1 + ((uintptr_t)lane << 7) < c1 + (size_t)min(WP, n - pn) * G * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(a1 + ((uintptr_t)lane << 7)));
             }
         }
-        // ---- step 0: geometry of the mini-tile ---------------------------------------------------------------
+        // ---- step 0: geometry of the mini-tile: per-pair, then per-read and per-record metadata ----------------------
         uint32_t begin[3], shift[3], total[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1976,43 +2035,90 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
             shift[k] = (uint32_t)(reinterpret_cast<uintptr_t>(outk + begin[k]) & 15u);
         }
         if (lane < np) {
-            PairMeta m;
-            m.len[0] = (uint16_t)(cur.lens & 0xFFFFu); m.len[1] = (uint16_t)(cur.lens >> 16); m.attempt = cur.tail >> 16;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) m.so[k] = cur.off[k] - begin[k] + shift[k];
-            m.nfull = (uint16_t)(cur.nl & 0xFFFFu); m.nbwa = (uint16_t)(cur.nl >> 16);
-            m.pad[0] = m.pad[1] = 0;
-            meta[lane] = m;
+            uint4 m0, m1;                                            // PairMeta
+            m0.x = cur.off[0] - begin[0] + shift[0]; m0.y = cur.off[1] - begin[1] + shift[1]; m0.z = cur.off[2] - begin[2] + shift[2];
+            m0.w = cur.lens; m1.x = cur.nl; m1.y = cur.tail >> 16; m1.z = m1.w = 0;
+            sts128(a_meta + lane * 32, m0); sts128(a_meta + lane * 32 + 16, m1);
         }
         if (bulk_pending) { bulk_wait_read(); bulk_pending = false; }   // the staging area is free again
         __syncwarp();
-        // ---- step 1: bases and qualities, one lane per (pair, end, 8-base group), aligned word stores -------------
-        const int items = np * G, n_iter = (items + 31) >> 5;
+        int max_nn = 0;
+        for (int rd = lane; rd < 2 * np; rd += 32) {                  // ReadMeta + the read's two NameMeta
+            const int t = rd >> 1, e = rd & 1;
+            const uint4 m0 = lds128(a_meta + t * 32);
+            const uint2 m1 = lds64(a_meta + t * 32 + 16);
+            const int len0 = (int)(m0.w & 0xFFFFu), Le = e ? (int)(m0.w >> 16) : len0;
+            const int nfull = (int)(m1.x & 0xFFFFu), nbwa = (int)(m1.x >> 16);
+            const uint32_t rec_b = (e ? a_st1 + m0.y : a_st0 + m0.x);
+            const int rec0 = len0 > 0 ? nfull + sfx_f + 2 * len0 + 4 : 0;
+            const uint32_t rec_f = a_st2 + m0.z + (e ? rec0 : 0);
+            const uint64_t gidx = (uint64_t)(gidx_origin + first + p0 + t);
+            uint4 r0, r1;
+            r0.x = rec_b + nbwa + 3 - from; r0.y = r0.x + (Le - from) + 3;
+            r0.z = rec_f + nfull + sfx_f; r0.w = r0.z + Le + 3;
+            r1.x = (uint32_t)Le; r1.y = (m1.y & 0xFFFFu) | (kStQual << 16) | ((uint32_t)e << 24);
+            r1.z = (uint32_t)gidx; r1.w = (uint32_t)(gidx >> 32);
+            sts128(a_rm + rd * 32, r0); sts128(a_rm + rd * 32 + 16, r1);
+            const bool has = Le > 0;
+            const uint32_t src = (uint32_t)t * (uint32_t)nvar * (uint32_t)P.name_cap;   // relative to gnames_tile
+            sts128(a_nm + (rd * 2) * 16, make_uint4(has && on0 ? rec_b : 0u, (uint32_t)nbwa, src + (uint32_t)(nvar - 1) * P.name_cap, (uint32_t)(Le - from)));
+            sts128(a_nm + (rd * 2 + 1) * 16, make_uint4(has && on2 ? rec_f : 0u, (uint32_t)nfull, src, (uint32_t)Le));
+            if (has) max_nn = max(max_nn, max(on0 ? nbwa : 0, on2 ? nfull : 0));
+        }
+        max_nn = __reduce_max_sync(full, max_nn);
+        __syncwarp();
+        // ---- step 1: names, one lane per (record, 16-byte chunk); aligned words, spills allowed (see the kernel comment) ---
+        for (int c0 = 0; c0 < max_nn; c0 += 64)
+            for (int rb = 0; rb < 4 * np; rb += 8) {
+                const int rc = rb + (lane >> 2), x0 = c0 + ((lane & 3) << 4);
+                uint4 nm = make_uint4(0, 0, 0, 0);
+                if (rc < 4 * np) nm = lds128(a_nm + rc * 16);
+                const bool act = nm.x != 0 && x0 < (int)nm.y;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (act) v = __ldg(reinterpret_cast<const uint4 *>(gnames_tile + nm.z + x0));
+                uint32_t pw = __shfl_up_sync(full, v.w, 1);               // last word of the previous chunk of the same name
+                if ((lane & 3) == 0) pw = c0 ? __ldg(reinterpret_cast<const uint32_t *>(gnames_tile + nm.z + x0 - 4)) : 0u;
+                if (act) {
+                    const uint32_t d = nm.x + x0, bs = d & 3u, w = d - bs, sel = 0x7654u - 0x1111u * bs;
+                    const int left = (int)nm.y - x0 + (int)bs;             // name bytes from w on
+                    sts32(w, __byte_perm(pw, v.x, sel));
+                    if (left > 4) sts32(w + 4, __byte_perm(v.x, v.y, sel));
+                    if (left > 8) sts32(w + 8, __byte_perm(v.y, v.z, sel));
+                    if (left > 12) sts32(w + 12, __byte_perm(v.z, v.w, sel));
+                    if (left > 16 && (int)nm.y - x0 <= 16) sts32(w + 16, __byte_perm(v.w, 0u, sel));   // (the next chunk's first word otherwise)
+                }
+            }
+        __syncwarp();
+        // ---- step 2: bases and qualities, one lane per (pair, end, 16 bases = two 8-base groups), aligned word stores ----
+        const int items = np * G2, n_iter = (items + 31) >> 5;
         uint32_t carry_a = 0, carry_d = 0, carry_q = 0;
         for (int iter = 0; iter < n_iter; ++iter) {
             const int it = (iter << 5) + lane;
-            bool active = it < items;
-            int t = 0, e = 0, g = 0, Le = 0, k0 = 0;
-            if (active) {
-                t = (int)__umulhi((uint32_t)it, P.inv_groups);
-                const int gi = it - t * G;
-                e = gi < g0 ? 0 : 1; g = gi - (e ? g0 : 0);
-                Le = meta[t].len[e]; k0 = g << 3;
-                active = k0 < Le;
+            const int t = (int)__umulhi((uint32_t)it, P.inv_groups), gi = it - t * G2;
+            const int e = gi < h0 ? 0 : 1, j = gi - (e ? h0 : 0), rd = 2 * t + e, k0 = j << 4;
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            if (it < items) { r0 = lds128(a_rm + rd * 32); r1 = lds128(a_rm + rd * 32 + 16); }
+            const int Le = (int)r1.x;
+            const bool active = k0 < Le, active_b = k0 + 8 < Le;       // (Le == 0 beyond the mini-tile)
+            uint32_t cw[2] = {0, 0};
+            {
+                const uint32_t *src = seqw_tile + t * G + (e ? g0 : 0) + 2 * j;
+                if (active) cw[0] = __ldg(src);
+                if (active_b) cw[1] = __ldg(src + 1);
             }
-            uint32_t a_lo = 0, a_hi = 0, d_lo = 0, d_hi = 0, q_lo = 0, q_hi = 0;
-            if (active) {
-                const PairMeta &m = meta[t];
-                const uint32_t codes = __ldg(seqw + (size_t)(p0 + t) * NW + (e ? P.nw[0] : 0) + g);
+            uint32_t a[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};   // 16 bases (bwa), 16 bases (bfast), 16 qualities
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                if (!(sub ? active_b : active)) continue;
+                const uint32_t codes = cw[sub];
                 // qualities, src/dwgsim.c:899-918
-                if (qmode == 2) q_lo = q_hi = 0x01010101u * (uint32_t)P.fixed_quality;
+                if (qmode == 2) q[2 * sub] = q[2 * sub + 1] = 0x01010101u * (uint32_t)P.fixed_quality;
                 else {
-                    const uint4 qb = lds128((e ? a_qb1 : a_qb0) + (k0 << 1));      // 8 x int16: Phred base (+ lowest noise step)
+                    const uint4 qb = lds128((e ? a_qb1 : a_qb0) + ((k0 + 8 * sub) << 1));    // 8 x int16: Phred base (+ lowest noise step)
                     uint4 r = make_uint4(0, 0, 0, 0);
                     if (qmode == 1) {
-                        const uint64_t gidx = (uint64_t)(gidx_origin + first + p0 + t);
-                        const PairKey key{P.seed, (uint32_t)gidx, (uint32_t)(gidx >> 32), m.attempt};
-                        const uint4 b0 = draw_block(key, kStQual, e, (uint32_t)(2 * g));
+                        const uint32_t blk = (uint32_t)(4 * j + 2 * sub);                       // the group's first QUAL block
+                        const uint4 b0 = philox4x32_10_rk(r1.z, r1.w, r1.y, blk, P);
                         constexpr int dsh = 16 - kQTabBits;
 #define DWG_LK(word, half) lds8(a_qtab + ((half) ? ((word) >> (16 + dsh)) : (((word) & 0xFFFFu) >> dsh)))
                         r.x = DWG_LK(b0.x, 0) | (DWG_LK(b0.x, 1) << 16);
@@ -2021,99 +2127,56 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
                         r.w = DWG_LK(b0.w, 0) | (DWG_LK(b0.w, 1) << 16);
 #undef DWG_LK
                         if ((r.x | r.y | r.z | r.w) & 0x00800080u)
-                            r = qual_ranks_slow(r, b0, draw_block(key, kStQual, e, (uint32_t)(2 * g + 1)), cdf, P.qdelta_n);
+                            r = qual_ranks_slow(r, b0, philox4x32_10_rk(r1.z, r1.w, r1.y, blk + 1u, P), cdf, P.qdelta_n);
                     }
                     // 33 + clamp(base + noise, 0, 40), two qualities per instruction
-                    const uint32_t v0 = viaddmin_relu_s16x2(r.x, qb.x, 0x00280028u), v1 = viaddmin_relu_s16x2(r.y, qb.y, 0x00280028u);
-                    const uint32_t v2 = viaddmin_relu_s16x2(r.z, qb.z, 0x00280028u), v3 = viaddmin_relu_s16x2(r.w, qb.w, 0x00280028u);
-                    q_lo = __byte_perm(v0, v1, 0x6420) + 0x21212121u;
-                    q_hi = __byte_perm(v2, v3, 0x6420) + 0x21212121u;
+                    const uint32_t v0 = __viaddmin_s16x2_relu(r.x, qb.x, 0x00280028u), v1 = __viaddmin_s16x2_relu(r.y, qb.y, 0x00280028u);
+                    const uint32_t v2 = __viaddmin_s16x2_relu(r.z, qb.z, 0x00280028u), v3 = __viaddmin_s16x2_relu(r.w, qb.w, 0x00280028u);
+                    q[2 * sub] = __byte_perm(v0, v1, 0x6420) + 0x21212121u;
+                    q[2 * sub + 1] = __byte_perm(v2, v3, 0x6420) + 0x21212121u;
                 }
                 // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
-                a_lo = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu); a_hi = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
-                d_lo = a_lo; d_hi = a_hi;
-                if (solid) { d_lo = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d_hi = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
+                a[2 * sub] = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu); a[2 * sub + 1] = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
+                if (solid) { d[2 * sub] = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d[2 * sub + 1] = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
             }
-            // the last word of the previous group (previous lane; lane 0: last lane of the previous round)
-            uint32_t pa = __shfl_up_sync(full, a_hi, 1), pq = __shfl_up_sync(full, q_hi, 1), pd = pa;
-            if (solid) pd = __shfl_up_sync(full, d_hi, 1);
+            // the last word of the previous 16 bases (previous lane; lane 0: last lane of the previous round)
+            uint32_t pa = __shfl_up_sync(full, a[3], 1), pq = __shfl_up_sync(full, q[3], 1), pd = pa;
+            if (solid) pd = __shfl_up_sync(full, d[3], 1);
             if (lane == 0) { pa = carry_a; pq = carry_q; pd = carry_d; }
-            carry_a = __shfl_sync(full, a_hi, 31); carry_q = __shfl_sync(full, q_hi, 31);
-            carry_d = solid ? __shfl_sync(full, d_hi, 31) : carry_a;
+            carry_a = __shfl_sync(full, a[3], 31); carry_q = __shfl_sync(full, q[3], 31);
+            carry_d = solid ? __shfl_sync(full, d[3], 31) : carry_a;
             if (active) {
-                const PairMeta &m = meta[t];
-                const int cnt = min(8, Le - k0);
-                const bool tail = k0 + 8 >= Le;
-                const int len0 = m.len[0];
-                const int me = Le - from;
+                const int cnt = min(16, Le - k0);
+                const bool tail = k0 + 16 >= Le;
                 if (on0) {
-                    const uint32_t ps_b = (e ? a_st1 : a_st0) + m.so[e] + m.nbwa + 3 - from + k0;    // bwa: bases, then qualities
-                    store_field(ps_b, pa, a_lo, a_hi, tail, cnt, solid && g == 0);
-                    store_field(ps_b + me + 3, pq, q_lo, q_hi, tail, cnt, solid && g == 0);
+                    store_field16(r0.x + k0, pa, a, tail, cnt, solid && j == 0);
+                    store_field16(r0.y + k0, pq, q, tail, cnt, solid && j == 0);
                 }
                 if (on2) {
-                    const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-                    const uint32_t ps_f = a_st2 + m.so[2] + (e ? rec0 : 0) + m.nfull + 1 + (solid ? 1 : 0) + k0;   // bfast
-                    store_field(ps_f, pd, d_lo, d_hi, tail, cnt);
-                    store_field(ps_f + Le + 3, pq, q_lo, q_hi, tail, cnt);
+                    store_field16(r0.z + k0, pd, solid ? d : a, tail, cnt, false);
+                    store_field16(r0.w + k0, pq, q, tail, cnt, false);
                 }
             }
         }
         __syncwarp();
-        // ---- step 2: names (one lane per record and 16-byte chunk), suffixes and separators, byte-exact --------------
-        {
-            const int nchunks = P.name_cap >> 4;
-            for (int it = lane; it < np * 4 * nchunks; it += 32) {
-                const int rc = (int)__umulhi((uint32_t)it, P.inv_name_chunks), c = it - rc * nchunks, t = rc >> 2, rr = rc & 3, e = rr & 1, bf = rr >> 1;
-                const PairMeta &m = meta[t];
-                const int Le = m.len[e];
-                if (Le <= 0 || (bf ? !on2 : !on0)) continue;
-                const int nn = bf ? m.nfull : m.nbwa, x0 = c << 4;
-                if (x0 >= nn) continue;
-                const int len0 = m.len[0];
-                const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-                const uint32_t d = (bf ? a_st2 + m.so[2] + (e ? rec0 : 0) : (e ? a_st1 : a_st0) + m.so[e]) + x0;
-                const char *nm = gnames + ((size_t)(p0 + t) * nvar + (bf ? 0 : nvar - 1)) * P.name_cap;
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nm + x0));
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                const int left = nn - x0;
-#pragma unroll
-                for (int b4 = 0; b4 < 4; ++b4) {
-                    const uint32_t x = w[b4];
-                    if (4 * b4 + 0 < left) sts8(d + 4 * b4, x);
-                    if (4 * b4 + 1 < left) sts8(d + 4 * b4 + 1, x >> 8);
-                    if (4 * b4 + 2 < left) sts8(d + 4 * b4 + 2, x >> 16);
-                    if (4 * b4 + 3 < left) sts8(d + 4 * b4 + 3, x >> 24);
-                }
-            }
-            for (int it = lane; it < np * 4; it += 32) {
-                const int t = it >> 2, rr = it & 3, e = rr & 1, bf = rr >> 1;
-                const PairMeta &m = meta[t];
-                const int Le = m.len[e];
-                if (Le <= 0) continue;
-                if (!bf) {
-                    if (!on0) continue;
-                    const uint32_t sb = (e ? a_st1 : a_st0) + m.so[e] + m.nbwa;
-                    const int me = Le - from;
-                    sts8(sb, '/'); sts8(sb + 1, solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sts8(sb + 2, '\n');
-                    sts8(sb + 3 + me, '\n'); sts8(sb + 3 + me + 1, '+'); sts8(sb + 3 + me + 2, '\n');
-                    sts8(sb + 3 + me + 3 + me, '\n');
-                } else {
-                    if (!on2) continue;
-                    const int len0 = m.len[0];
-                    const int rec0 = len0 > 0 ? m.nfull + 1 + (solid ? 1 : 0) + 2 * len0 + 4 : 0;
-                    uint32_t sf = a_st2 + m.so[2] + (e ? rec0 : 0) + m.nfull;
-                    sts8(sf, '\n');
-                    sf += 1;
-                    if (solid) { sts8(sf, 'A'); sf += 1; }
-                    sts8(sf + Le, '\n'); sts8(sf + Le + 1, '+'); sts8(sf + Le + 2, '\n');
-                    sts8(sf + Le + 3 + Le, '\n');
-                }
-            }
+        // ---- step 3: one lane per record rewrites the bytes the spills may have touched: the first and the last two name
+        //      bytes, the suffix, "\n+\n" and the closing "\n" -----------------------------------------------------------
+        for (int rc = lane; rc < 4 * np; rc += 32) {
+            const uint4 nm = lds128(a_nm + rc * 16);
+            if (nm.x == 0) continue;
+            const int bf = rc & 1, e = (rc >> 1) & 1, nn = (int)nm.y, L = (int)nm.w;
+            const uint32_t head = __ldg(reinterpret_cast<const uint32_t *>(gnames_tile + nm.z));
+            sts8(nm.x, head); sts8(nm.x + 1, head >> 8);
+            uint32_t s = nm.x + nn;
+            sts8(s - 2, (uint32_t)(uint8_t)__ldg(gnames_tile + nm.z + nn - 2)); sts8(s - 1, (uint32_t)(uint8_t)__ldg(gnames_tile + nm.z + nn - 1));
+            if (!bf) { sts8(s, '/'); sts8(s + 1, solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sts8(s + 2, '\n'); s += 3; }
+            else { sts8(s, '\n'); s += 1; if (solid) { sts8(s, 'A'); s += 1; } }
+            sts8(s + L, '\n'); sts8(s + L + 1, '+'); sts8(s + L + 2, '\n');
+            sts8(s + L + 3 + L, '\n');
         }
         fence_async_smem();                                          // the bulk engine reads what the lanes wrote
         __syncwarp();
-        // ---- step 3: copy-out: lane k < 3 sends the 16-byte aligned interior of stream k as one bulk store -----------
+        // ---- step 4: copy-out: lane k < 3 sends the 16-byte aligned interior of stream k as one bulk store -----------
         {
             const int k = lane < 3 ? lane : 0;
             const uint32_t a_st = k == 0 ? a_st0 : (k == 1 ? a_st1 : a_st2);
@@ -2141,5 +2204,6 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
     }
     if (bulk_pending) bulk_wait_read();
 }
+
 
 }  // namespace dwg

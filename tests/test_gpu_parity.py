@@ -111,3 +111,30 @@ def test_derived_tables_equal_oracle(oracle):
             assert [g.err_gap[e][i] for i in range(n)] == [t.err_gap[e][i] for i in range(n)]
             assert [g.err_acc[e][i] for i in range(n)] == [t.err_acc[e][i] for i in range(n)]
             assert [g.qbase[e][i] for i in range(n)] == [t.qbase[e][i] for i in range(n)]
+
+
+def test_wide_insert_size_table(oracle, synth_fa, tmp_path):
+    """-s 5000: the insert-size table has more steps than the 16-bit guide can index (searched whole on the device)"""
+    check(oracle, dict(seed=21, N=3000, dist=6000, std_dev=5000), synth_fa, tmp_path)
+
+
+@pytest.fixture(scope="module")
+def growing_names_fa(tmp_path_factory):
+    """three contigs whose names grow from 2 to 70 characters (hg38-style alt contig names after 'c1')"""
+    import numpy as np
+    rng = np.random.default_rng(99)
+    p = str(tmp_path_factory.mktemp("names") / "names.fa")
+    with open(p, "w") as f:
+        for name in ("c1", "chr1_KI270706v1_random", "chrUn_" + "x" * 58 + "_alt_v2"):
+            f.write(">%s\n" % name)
+            b = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 6000)]).decode()
+            for i in range(0, len(b), 60):
+                f.write(b[i:i + 60] + "\n")
+    return p
+
+
+@pytest.mark.parametrize("data_type", [0, 1])
+def test_contig_names_grow_between_runs(oracle, growing_names_fa, tmp_path, data_type):
+    """run() once per contig with ever longer contig names: the name, stream and pinned buffers must grow with them"""
+    opts = dict(seed=8, N=6000, data_type=data_type, length=(50, 50) if data_type else (100, 100))
+    check(oracle, opts, growing_names_fa, tmp_path, per_contig_runs=True, batch=4096)
