@@ -59,6 +59,8 @@ _P = C.c_void_p
 SYMBOLS = {
     "dwgsim_gpu_abi_version": (C.c_int, []),
     "dwgsim_gpu_create": (C.c_int, [C.POINTER(_P), C.POINTER(Params), C.c_int]),
+    "dwgsim_gpu_create_group": (C.c_int, [C.POINTER(_P), C.POINTER(Params), C.POINTER(C.c_int32), C.c_int32]),
+    "dwgsim_gpu_group_size": (C.c_int, [_P]),
     "dwgsim_gpu_destroy": (None, [_P]),
     "dwgsim_gpu_strerror": (C.c_char_p, [C.c_int]),
     "dwgsim_gpu_last_error": (C.c_char_p, [_P]),

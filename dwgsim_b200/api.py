@@ -77,13 +77,17 @@ def params_from_options(**kw):
 
 
 class DwgsimGpu:
-    """one dwgsim_gpu_t handle on one CUDA device"""
+    """one dwgsim_gpu_t handle on one CUDA device, or (devices=[...]) on a group of devices of the box"""
 
-    def __init__(self, params, device=0):
+    def __init__(self, params, device=0, devices=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self._params = params
-        rc = self._L.dwgsim_gpu_create(C.byref(self._h), C.byref(params), device)
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*devices)
+            rc = self._L.dwgsim_gpu_create_group(C.byref(self._h), C.byref(params), arr, len(devices))
+        else:
+            rc = self._L.dwgsim_gpu_create(C.byref(self._h), C.byref(params), device)
         if rc:
             self._h = None
             raise DwgsimGpuError(rc, self._L.dwgsim_gpu_strerror(rc).decode())

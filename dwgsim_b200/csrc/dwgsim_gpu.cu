@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -90,9 +92,58 @@ struct Workspace {
 };
 
 }  // namespace
+struct dwgsim_gpu;
+namespace {
+// Several devices behind one handle (dwgsim_gpu_create_group): the ranks of a run are threads of this process.  They meet
+// twice per round: to add up their random-pair counts (rand_ii is a running count over all pairs, src/dwgsim.c:1096) and
+// to hand their batches to the sink in batch order.
+struct GroupSync {
+    std::mutex mu;
+    std::condition_variable cv;
+    int world = 1;
+    std::vector<int64_t> vals;         // this round's random-pair count of every rank
+    int arrived = 0;
+    int64_t generation = 0;
+    std::vector<int64_t> before;       // results of the last completed exchange
+    int64_t total = 0;
+    int64_t turn = 0;                  // next batch index the sink may see
+    bool failed = false;               // some rank gave up: nobody waits any more
+    dwgsim_gpu *leader = nullptr;
+    void reset(int w) { world = w; vals.assign((size_t)w, 0); before.assign((size_t)w, 0); arrived = 0; total = 0; turn = 0; failed = false; }
+    void fail() { std::lock_guard<std::mutex> g(mu); failed = true; cv.notify_all(); }
+    // all-gather + exclusive prefix of one value per rank; false when the run was abandoned
+    bool exchange(int rank, int64_t mine, int64_t *before_me, int64_t *round_total)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
+        vals[(size_t)rank] = mine;
+        const int64_t gen = generation;
+        if (++arrived == world) {
+            int64_t acc = 0;
+            for (int r = 0; r < world; ++r) { before[(size_t)r] = acc; acc += vals[(size_t)r]; }
+            total = acc; arrived = 0; ++generation;
+            cv.notify_all();
+        } else cv.wait(lk, [&]() { return generation != gen || failed; });
+        if (failed && generation == gen) return false;
+        *before_me = before[(size_t)rank]; *round_total = total;
+        return true;
+    }
+    bool wait_turn(int64_t batch)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return turn == batch || failed; });
+        return !failed;
+    }
+    void pass_turn() { std::lock_guard<std::mutex> g(mu); ++turn; cv.notify_all(); }
+};
+
+}  // namespace
 
 struct dwgsim_gpu {
     dwgsim_gpu_params_t p{};
+    // device group (this handle is the leader, rank 0; peers are ranks 1..)
+    std::vector<dwgsim_gpu *> peers;
+    GroupSync *group = nullptr;               // shared by the leader and its peers while a run is in flight
     std::string prefix_s;                     // "pfx_" or ""
     std::vector<int8_t> flow_order;
     int device = 0;
@@ -109,6 +160,8 @@ struct dwgsim_gpu {
     int gz_mode = 0;
     double ms_gz = 0;
     bool gz_ready = false;
+    uint64_t gz_hist_host[3][256] = {};       // byte histograms the Huffman codes were fitted to (group leader: shared with the peers)
+    bool gz_hist_valid = false;
     uint32_t *gz_code[3] = {nullptr, nullptr, nullptr};
     uint8_t *gz_prefix[3] = {nullptr, nullptr, nullptr};
     uint32_t gz_prefix_bits[3] = {0, 0, 0};
@@ -839,13 +892,23 @@ int gz_calibrate(dwgsim_gpu *h, int dslot, const uint64_t bytes[3])
         int rc = upload(h, &h->gz_crc, v.data(), v.size());
         if (rc) return rc;
     }
+    // the devices of a group all use the code the leader fitted to batch 0, so a group writes the bytes of a single device
+    dwgsim_gpu *const lead = h->group ? h->group->leader : h;
+    if (lead != h) {
+        std::unique_lock<std::mutex> lk(h->group->mu);
+        h->group->cv.wait(lk, [&]() { return lead->gz_hist_valid || h->group->failed; });
+        if (!lead->gz_hist_valid) { h->last_error = "another device of the group failed"; return DWGSIM_GPU_ESTATE; }
+    }
     for (int k = 0; k < 3; ++k) {
-        uint64_t hist[256] = {0};
-        if (bytes[k]) {
-            CUDA_TRY(h, cudaMemsetAsync(w.gz_hist, 0, 256 * 8, h->s_compute));
-            gz_histogram_kernel<<<592, 256, 0, h->s_compute>>>((const uint8_t *)w.out[dslot][k], bytes[k], w.gz_hist);
-            CUDA_TRY(h, cudaMemcpyAsync(hist, w.gz_hist, 256 * 8, cudaMemcpyDeviceToHost, h->s_compute));
-            CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+        uint64_t *hist = lead->gz_hist_host[k];
+        if (lead == h) {
+            memset(hist, 0, 256 * 8);
+            if (bytes[k]) {
+                CUDA_TRY(h, cudaMemsetAsync(w.gz_hist, 0, 256 * 8, h->s_compute));
+                gz_histogram_kernel<<<592, 256, 0, h->s_compute>>>((const uint8_t *)w.out[dslot][k], bytes[k], w.gz_hist);
+                CUDA_TRY(h, cudaMemcpyAsync(hist, w.gz_hist, 256 * 8, cudaMemcpyDeviceToHost, h->s_compute));
+                CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+            }
         }
         const GzTables t = gz_build_tables(hist);
         cudaFree(h->gz_code[k]); cudaFree(h->gz_prefix[k]);
@@ -858,6 +921,10 @@ int gz_calibrate(dwgsim_gpu *h, int dslot, const uint64_t bytes[3])
         h->gz_prefix_bits[k] = t.prefix_bits;
     }
     h->gz_ready = true;
+    if (lead == h) {
+        if (h->group) { std::lock_guard<std::mutex> g(h->group->mu); h->gz_hist_valid = true; h->group->cv.notify_all(); }
+        else h->gz_hist_valid = true;
+    }
     return DWGSIM_GPU_OK;
 }
 
@@ -992,9 +1059,38 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
     return DWGSIM_GPU_OK;
 }
 
+int dwgsim_gpu_create_group(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, const int32_t *devices, int32_t n_devices)
+{
+    if (!out || !p || !devices || n_devices < 1 || n_devices > 64) return DWGSIM_GPU_EINVAL;
+    *out = nullptr;
+    // (a device may appear more than once: its ranks then share it, each with its own streams and buffers)
+    dwgsim_gpu *lead = nullptr;
+    int rc = dwgsim_gpu_create(&lead, p, devices[0]);
+    if (rc) return rc;
+    for (int i = 1; i < n_devices; ++i) {
+        dwgsim_gpu *q = nullptr;
+        if ((rc = dwgsim_gpu_create(&q, p, devices[i]))) { dwgsim_gpu_destroy(lead); return rc; }
+        lead->peers.push_back(q);
+        // direct device-to-device copies of the genome blob (NVLink between the GPUs of one box); without peer access the
+        // runtime stages the copy through the host
+        int can = 0;
+        if (devices[i] != devices[0] && cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) {
+            cudaSetDevice(devices[i]);
+            if (cudaDeviceEnablePeerAccess(devices[0], 0) != cudaSuccess) cudaGetLastError();   // (already enabled: fine)
+        }
+    }
+    cudaSetDevice(devices[0]);
+    *out = lead;
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_group_size(const dwgsim_gpu_t *h) { return h ? 1 + (int)h->peers.size() : 0; }
+
 void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
 {
     if (!h) return;
+    for (dwgsim_gpu *q : h->peers) dwgsim_gpu_destroy(q);
+    h->peers.clear();
     cudaSetDevice(h->device);
     free_workspace(h);
     free_blob(h);
@@ -1057,6 +1153,7 @@ int dwgsim_gpu_set_regions(dwgsim_gpu_t *h, const uint32_t *start, const uint32_
 int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_slots)
 {
     if (!h || pairs_per_batch < 1 || pairs_per_batch > (1 << 24) || ring_slots < 2 || ring_slots > 8) return DWGSIM_GPU_EINVAL;
+    for (dwgsim_gpu *q : h->peers) dwgsim_gpu_set_batch(q, pairs_per_batch, ring_slots);
     cudaSetDevice(h->device);
     free_workspace(h);
     h->batch_pairs = pairs_per_batch; h->ring = ring_slots;
@@ -1066,6 +1163,7 @@ int dwgsim_gpu_set_batch(dwgsim_gpu_t *h, int64_t pairs_per_batch, int32_t ring_
 int dwgsim_gpu_set_compression(dwgsim_gpu_t *h, int32_t mode)
 {
     if (!h || mode < 0 || mode > 1) return DWGSIM_GPU_EINVAL;
+    for (dwgsim_gpu *q : h->peers) dwgsim_gpu_set_compression(q, mode);
     cudaSetDevice(h->device);
     if (mode != h->gz_mode) free_workspace(h);
     h->gz_mode = mode;
@@ -1075,6 +1173,7 @@ int dwgsim_gpu_set_compression(dwgsim_gpu_t *h, int32_t mode)
 int dwgsim_gpu_set_shard(dwgsim_gpu_t *h, int32_t rank, int32_t world)
 {
     if (!h || world < 1 || rank < 0 || rank >= world) return DWGSIM_GPU_EINVAL;
+    if (!h->peers.empty()) { h->last_error = "a device group shards its batches itself"; return DWGSIM_GPU_ESTATE; }
     h->shard_rank = rank; h->shard_world = world;
     return DWGSIM_GPU_OK;
 }
@@ -1083,6 +1182,7 @@ int dwgsim_gpu_set_origin(dwgsim_gpu_t *h, int64_t first_pair_index, int64_t fir
 {
     if (!h || first_pair_index < 0 || first_rand_serial < 0) return DWGSIM_GPU_EINVAL;
     h->gidx_origin = first_pair_index; h->rand_serial = first_rand_serial;
+    for (dwgsim_gpu *q : h->peers) { q->gidx_origin = first_pair_index; q->rand_serial = first_rand_serial; }
     return DWGSIM_GPU_OK;
 }
 
@@ -1224,9 +1324,20 @@ int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap
     return DWGSIM_GPU_OK;
 }
 
+namespace {
+int run_group(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats);
+int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats);
+}  // namespace
+
 int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats)
 {
     if (!h || !sink) return DWGSIM_GPU_EINVAL;
+    return h->peers.empty() ? run_one(h, sink, user, stats) : run_group(h, sink, user, stats);
+}
+
+namespace {
+int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats)
+{
     cudaSetDevice(h->device);
     const double t_start = now_ms();
     dwgsim_gpu_stats_t st;
@@ -1242,15 +1353,18 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
     for (int s = 0; s < h->pinned_slots; ++s) cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming);
     cudaEvent_t computed;
     cudaEventCreateWithFlags(&computed, cudaEventDisableTiming);
-    struct Pending { bool live = false; uint64_t bytes[3] = {0, 0, 0}; int pslot = 0; } pend;
+    struct Pending { bool live = false; uint64_t bytes[3] = {0, 0, 0}; int pslot = 0; int64_t batch = 0; } pend;
+    GroupSync *const grp = h->group;                            // ranks of a device group: the sink sees the batches in order
     auto drain = [&](Pending &pd) -> int {
         if (!pd.live) return DWGSIM_GPU_OK;
         CUDA_TRY(h, cudaEventSynchronize(copied[pd.pslot]));
+        if (grp && !grp->wait_turn(pd.batch)) { h->last_error = "another device of the group failed"; return DWGSIM_GPU_ESTATE; }
         for (int k = 0; k < 3; ++k)
             if (pd.bytes[k]) {
                 if (sink(user, k, h->pinned[pd.pslot][k], (size_t)pd.bytes[k])) { h->last_error = "sink callback failed"; return DWGSIM_GPU_ESINK; }
                 st.bytes[k] += (int64_t)pd.bytes[k];
             }
+        if (grp) grp->pass_turn();
         pd.live = false;
         return DWGSIM_GPU_OK;
     };
@@ -1311,7 +1425,7 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
                 st.d2h_bytes += (int64_t)send[k];
             }
         CUDA_TRY(h, cudaEventRecord(copied[pslot], h->s_copy));
-        pend.live = true; pend.pslot = pslot;
+        pend.live = true; pend.pslot = pslot; pend.batch = bi;
         for (int k = 0; k < 3; ++k) pend.bytes[k] = send[k];
         ++st.n_batches; ++mine;
     }
@@ -1329,6 +1443,79 @@ int dwgsim_gpu_run(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_
     if (stats) *stats = st;
     return rc;
 }
+
+int group_exchange(void *user, int64_t round, int64_t my_random, int64_t *before_me, int64_t *round_total)
+{
+    (void)round;
+    dwgsim_gpu *h = (dwgsim_gpu *)user;
+    return h->group->exchange(h->shard_rank, my_random, before_me, round_total) ? 0 : 1;
+}
+
+// dwgsim_gpu_run of a device group: the leader packs and uploads the genome, the peers receive a copy of the blob device to
+// device (NVLink when the devices are peers), then every device runs its share of the batches (b % world == rank) on its
+// own host thread; the sink sees the batches in order, so the bytes are those of a single-device run.
+int run_group(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_stats_t *stats)
+{
+    const int world = 1 + (int)h->peers.size();
+    cudaSetDevice(h->device);
+    const double t_start = now_ms();
+    int rc = finalize_genome(h);
+    if (rc) return rc;
+    for (dwgsim_gpu *q : h->peers) {                                // the blob, device to device
+        cudaSetDevice(q->device);
+        free_blob(q);
+        uint8_t *dst = nullptr;
+        if (q->blob_spare && q->blob_spare_cap >= h->blob_bytes) { dst = q->blob_spare; q->blob_spare = nullptr; q->blob_spare_cap = 0; }
+        else if (cudaMalloc((void **)&dst, h->blob_bytes) != cudaSuccess) { h->last_error = "out of device memory for the genome copy"; return DWGSIM_GPU_ENOMEM; }
+        cudaError_t e = q->device == h->device ? cudaMemcpyAsync(dst, h->blob, h->blob_bytes, cudaMemcpyDeviceToDevice, q->s_compute)
+                                               : cudaMemcpyPeerAsync(dst, q->device, h->blob, h->device, h->blob_bytes, q->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(q->s_compute);
+        if (e != cudaSuccess) { cudaFree(dst); h->last_error = std::string("peer copy of the genome: ") + cudaGetErrorString(e); return DWGSIM_GPU_ECUDA; }
+        q->max_name_len = std::max(q->max_name_len, h->max_name_len);
+        if ((rc = dwgsim_gpu_genome_import(q, (uint64_t)(uintptr_t)dst, h->blob_bytes, 1))) { h->last_error = q->last_error; return rc; }
+        q->gidx_origin = h->gidx_origin; q->rand_serial = h->rand_serial;
+        q->batch_pairs = h->batch_pairs;
+    }
+    cudaSetDevice(h->device);
+    GroupSync sync;
+    sync.reset(world);
+    sync.leader = h;
+    std::vector<dwgsim_gpu *> ranks{h};
+    ranks.insert(ranks.end(), h->peers.begin(), h->peers.end());
+    std::vector<int> rcs((size_t)world, DWGSIM_GPU_OK);
+    std::vector<dwgsim_gpu_stats_t> sts((size_t)world);
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; ++r) {
+        dwgsim_gpu *q = ranks[(size_t)r];
+        q->group = &sync; q->shard_rank = r; q->shard_world = world;
+        q->exchange = group_exchange; q->exchange_user = q;
+    }
+    for (int r = 1; r < world; ++r)
+        th.emplace_back([&, r]() { rcs[(size_t)r] = run_one(ranks[(size_t)r], sink, user, &sts[(size_t)r]); if (rcs[(size_t)r]) sync.fail(); });
+    rcs[0] = run_one(h, sink, user, &sts[0]);
+    if (rcs[0]) sync.fail();
+    for (auto &t : th) t.join();
+    dwgsim_gpu_stats_t st = sts[0];
+    rc = rcs[0];
+    for (int r = 0; r < world; ++r) {
+        dwgsim_gpu *q = ranks[(size_t)r];
+        q->group = nullptr; q->shard_rank = 0; q->shard_world = 1; q->exchange = nullptr; q->exchange_user = nullptr;
+        if (rcs[(size_t)r] && (rc == DWGSIM_GPU_OK || rc == DWGSIM_GPU_ESTATE)) { rc = rcs[(size_t)r]; h->last_error = q->last_error; }
+        if (r == 0) continue;
+        const dwgsim_gpu_stats_t &s2 = sts[(size_t)r];
+        st.n_pairs += s2.n_pairs; st.n_random += s2.n_random; st.n_failed_attempts += s2.n_failed_attempts;
+        for (int k = 0; k < 3; ++k) { st.bytes[k] += s2.bytes[k]; st.raw_bytes[k] += s2.raw_bytes[k]; }
+        st.d2h_bytes += s2.d2h_bytes; st.n_launches += s2.n_launches; st.n_batches += s2.n_batches;
+        // device time: the slowest device bounds the run
+        st.ms_simulate = std::max(st.ms_simulate, s2.ms_simulate); st.ms_layout = std::max(st.ms_layout, s2.ms_layout);
+        st.ms_format = std::max(st.ms_format, s2.ms_format); st.ms_compress = std::max(st.ms_compress, s2.ms_compress);
+    }
+    cudaSetDevice(h->device);
+    st.ms_total = now_ms() - t_start;
+    if (stats) *stats = st;
+    return rc;
+}
+}  // namespace
 
 // ---- synthetic genome (benchmarks): built procedurally on the host, then packed like any other ---------
 namespace {

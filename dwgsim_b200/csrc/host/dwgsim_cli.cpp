@@ -87,7 +87,7 @@ struct Options {                              // dwgsim_opt_t, src/dwgsim_opt.h:
     int muts_input_type = -1, reads_output_type = 0, output_type = 0, amplicons = 0;
     // this build
     bool uncompressed = false, host_gzip = false;
-    int threads = 0, device = 0;
+    int threads = 0, device = 0, gpus = 0;       // gpus: 0 = $DWGSIM_GPUS or 1; N devices starting at `device`, -1 = all
     long long batch = 0;
 };
 
@@ -135,6 +135,7 @@ int usage(const Options &o)
     fprintf(stderr, "         --host-gzip     compress with zlib on the host (level 6, like the reference) instead of on the GPU\n");
     fprintf(stderr, "         --threads INT   host gzip worker threads [all cores]\n");
     fprintf(stderr, "         --device INT    CUDA device [0]\n");
+    fprintf(stderr, "         --gpus INT      devices to spread the read pairs over, starting at --device; -1: all [$DWGSIM_GPUS or 1]\n");
     fprintf(stderr, "         --batch INT     read pairs per device batch\n\n");
     return 1;
 }
@@ -232,7 +233,7 @@ int parse_options(Options &o, int argc, char **argv, int *first_arg)
 {
     static const struct option longopts[] = {
         {"uncompressed", no_argument, nullptr, 1000}, {"threads", required_argument, nullptr, 1001},
-        {"device", required_argument, nullptr, 1002}, {"batch", required_argument, nullptr, 1003},
+        {"device", required_argument, nullptr, 1002}, {"gpus", required_argument, nullptr, 1006}, {"batch", required_argument, nullptr, 1003},
         {"host-gzip", no_argument, nullptr, 1004}, {nullptr, 0, nullptr, 0}};
     int c, muts = 0;
     while ((c = getopt_long(argc, argv, "id:s:N:C:1:2:e:E:r:F:R:X:I:c:S:A:n:y:BHf:z:M:m:b:v:x:P:q:Q:o:ah", longopts, nullptr)) >= 0) {
@@ -274,6 +275,7 @@ int parse_options(Options &o, int argc, char **argv, int *first_arg)
             case 1000: o.uncompressed = true; break;
             case 1001: o.threads = atoi(optarg); break;
             case 1002: o.device = atoi(optarg); break;
+            case 1006: o.gpus = atoi(optarg); break;
             case 1003: o.batch = atoll(optarg); break;
             case 1004: o.host_gzip = true; break;
             default: fprintf(stderr, "Unrecognized option: -%c\n", c); return 0;
@@ -1121,7 +1123,23 @@ int main(int argc, char **argv)
         p.fixed_quality = o.has_fixed_quality ? (unsigned char)o.fixed_quality[0] : 0;
         p.quality_std = o.quality_std; p.read_prefix = o.has_prefix ? o.read_prefix.c_str() : nullptr;
         p.reads_output_type = o.reads_output_type; p.amplicons = o.amplicons;
-        const int rc = dwgsim_gpu_create(&gpu, &p, o.device);
+        int want = o.gpus;
+        if (want == 0) if (const char *e = getenv("DWGSIM_GPUS")) want = atoi(e);
+        if (want == 0) want = 1;
+        std::vector<int32_t> devs;
+        if (want < 0) want = 64;                                         // all there are
+        for (int d = o.device; (int)devs.size() < want; ++d) devs.push_back(d);
+        if (const char *e = getenv("DWGSIM_DEVICES")) {                  // explicit list "0,1,3" (ids may repeat)
+            devs.clear();
+            for (const char *q = e; *q;) { devs.push_back((int32_t)strtol(q, (char **)&q, 10)); while (*q == ',' || *q == ' ') ++q; }
+            if (devs.empty()) devs.push_back(o.device);
+        }
+        int rc = DWGSIM_GPU_ENODEV;
+        // (-1 / more than the box has: shrink to the devices that exist)
+        for (; !devs.empty(); devs.pop_back()) {
+            rc = devs.size() == 1 ? dwgsim_gpu_create(&gpu, &p, devs[0]) : dwgsim_gpu_create_group(&gpu, &p, devs.data(), (int32_t)devs.size());
+            if (rc != DWGSIM_GPU_ENODEV || (o.gpus > 0 || devs.size() == 1)) break;
+        }
         if (rc != DWGSIM_GPU_OK) { fprintf(stderr, "\n[dwgsim_core] Error: %s\n", dwgsim_gpu_strerror(rc)); exit(1); }
         if (o.batch > 0) dwgsim_gpu_set_batch(gpu, o.batch, 3);
         if (!o.uncompressed && !o.host_gzip) dwgsim_gpu_set_compression(gpu, 1);

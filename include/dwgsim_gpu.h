@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DWGSIM_GPU_ABI_VERSION 1
+#define DWGSIM_GPU_ABI_VERSION 2
 
 enum {
     DWGSIM_GPU_OK = 0,
@@ -91,6 +91,14 @@ typedef int (*dwgsim_gpu_sink_fn)(void *user, int file_id, const char *buf, size
 /* -- lifecycle ------------------------------------------------------------------------------ */
 int  dwgsim_gpu_abi_version(void);
 int  dwgsim_gpu_create(dwgsim_gpu_t **h, const dwgsim_gpu_params_t *p, int device);
+/* One handle over several devices of the box (the loop being sharded: src/dwgsim.c:636; its two running counters: :423,
+ * :1096).  Every entry point below works on the group: add_contig packs once, run() copies the packed genome to the other
+ * devices (device to device: NVLink between peers), splits the pair-index space into batches, gives batch b to device
+ * b % n_devices, and hands the batches to the sink in order -- the bytes are those of a single device.  set_shard /
+ * set_exchange are not available on a group (it is its own set of ranks).  A device id may repeat (its ranks share the
+ * device). */
+int  dwgsim_gpu_create_group(dwgsim_gpu_t **h, const dwgsim_gpu_params_t *p, const int32_t *devices, int32_t n_devices);
+int  dwgsim_gpu_group_size(const dwgsim_gpu_t *h);      /* devices behind the handle (1 for dwgsim_gpu_create) */
 void dwgsim_gpu_destroy(dwgsim_gpu_t *h);
 const char *dwgsim_gpu_strerror(int code);
 const char *dwgsim_gpu_last_error(const dwgsim_gpu_t *h);

@@ -24,7 +24,7 @@ def oracle_expected(oracle, opts, fasta, prefix):
     return sess, want
 
 
-def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None, compression=0):
+def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None, compression=0, devices=None):
     from dwgsim_b200 import DwgsimGpu, params_from_options
     params = params_from_options(**{k: v for k, v in opts.items() if k in GPU_KEYS})
     if orc_opt is not None:
@@ -34,7 +34,7 @@ def gpu_actual(sess, opts, batch=None, per_contig_runs=False, orc_opt=None, comp
             params.e_start[i], params.e_by[i] = orc_opt.e_start[i], orc_opt.e_by[i]
     got = [[], [], []]
     stats = []
-    with DwgsimGpu(params) as gpu:
+    with DwgsimGpu(params, devices=devices) as gpu:
         if batch:
             gpu.set_batch(batch, 2)
         if compression:

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.dwgsim_gpu_abi_version() == 1
+    assert lib.dwgsim_gpu_abi_version() == 2
     assert lib.dwgsim_gpu_strerror(0) == b"ok"
     assert b"10001 trials" in lib.dwgsim_gpu_strerror(-5)      # reference message, src/dwgsim.c:838
 
