@@ -7,10 +7,15 @@
 Workload (BASELINE.json configs[1], SURVEY.md 8d "Config 2"): 3.1 Gbp synthetic reference (24 contigs with
 GRCh38 lengths, i.i.d. ACGT, ~1 % N, SNP+indel events at -r 0.001 -R 0.1), Illumina 2x150,
 -e/-E 0.001-0.01, -d 500 -s 50 -y 0.05, all three FASTQ outputs (-o 0), -C 30 => ~326 M pairs.
-A step = one batch of PAIRS_PER_STEP consecutive pair indices of that job through the whole hot path
-(simulate -> layout -> format), genome resident in HBM, FASTQ bytes left in HBM (`value`).
-`e2e` drives the C ABI the way the reference host would: dense seq_t/mutseq_t host arrays in
-(dwgsim_gpu_add_contig), FASTQ bytes out to host memory in pair order (dwgsim_gpu_run + sink).
+A step = `device_batches_per_step` consecutive device batches of PAIRS_PER_BATCH pair indices of that job through the
+whole hot path (simulate -> layout -> format), genome resident in HBM, FASTQ bytes left in HBM (`value`); the number of
+batches per step is chosen after the warm-up so that the K timed steps last at least MIN_TIMED_S seconds (the whole
+326 M-pair job is well under a second of kernel time, so the timed region walks the job's pair indices more than once).
+`configs` repeats the kernel-path measurement for BASELINE.json configs[2..4] (-R 0.15, SOLiD 2x50, Ion Torrent 400 bp SE).
+`e2e` drives the C ABI the way the reference host would: dense seq_t/mutseq_t host arrays in (dwgsim_gpu_add_contig),
+.fastq.gz bytes out through dwgsim_gpu_run to host memory in pair order; `e2e.file_sink` also writes them to new files
+on tmpfs every step, like the reference arm's gzFiles (bounded by the kernel's page-cache copy, a few GB/s per file).
+`e2e_cli` (1 GPU) is the wall time of the drop-in binary on the full 3.1 Gbp FASTA, prologue included.
 """
 import argparse
 import ctypes as C
@@ -34,12 +39,34 @@ OPTS = dict(length=(150, 150), e="0.001-0.01", E="0.001-0.01", seed=1)       # e
 REF_ARGV = ["-1", "150", "-2", "150", "-e", "0.001-0.01", "-E", "0.001-0.01"]
 COVERAGE = 30.0
 MUT_RATE, INDEL_FRAC, N_FRAC = 0.001, 0.1, 0.01
-PAIRS_PER_STEP = 1 << 20
+PAIRS_PER_BATCH = 1 << 20
+MIN_TIMED_S = 1.25                # the K timed steps of the headline last at least this long (>= 5 clock samples)
+MIN_TIMED_S_OTHER = 0.4           # ... and those of the other configs this long
 ALGO_BYTES_PER_PAIR = 1524.0      # 118 B read (2-bit ref + N mask + mutation table) + 1,406 B FASTQ written
 E2E_CONTIG_LEN = 8 << 20          # contig handed over per e2e step (dense host arrays: 17 B/base)
-# dram__bytes_read.sum + dram__bytes_write.sum of the eight launches of one 2^20-pair step, from the ncu --set full
-# capture profiles/r01c_ncu_key_metrics.txt (reads 0.743 GB + writes 1.685 GB)
-NCU_DRAM_BYTES_PER_STEP = 2.427e9
+FLOW = "TACGTACGTCTGAGCATCGATCGATGTACAGC"
+# BASELINE.json configs[1..4]; algorithmic bytes per unit: packed reference + N mask + mutation-table bytes
+# read (sum over ends of ceil(len/4) * 1.5, + 5) + FASTQ bytes written (measured per run; 1,524 B fixed for the headline)
+WORKLOADS = {
+    "illumina_2x150": dict(opts=OPTS, coverage=30.0, indel_frac=0.1, unit="pairs/s",
+                           label="configs[1]: Illumina 2x150bp, -e/-E 0.001-0.01, -r 0.001 -R 0.1, -C 30 (~326M pairs)"),
+    "illumina_2x150_R0.15": dict(opts=OPTS, coverage=30.0, indel_frac=0.15, unit="pairs/s",
+                                 label="configs[2]: Illumina 2x150bp, -r 0.001 -R 0.15 (SNP+indel), -C 30, pair-index shards"),
+    "solid_2x50": dict(opts=dict(length=(50, 50), data_type=1, seed=1), coverage=30.0, indel_frac=0.1, unit="pairs/s",
+                       label="configs[3]: SOLiD colour space -c 1, 2x50bp, -C 30 (~979M pairs)"),
+    "iontorrent_400se": dict(opts=dict(length=(400, 0), data_type=2, e=0.01, flow_order=FLOW, seed=1), coverage=20.0,
+                             indel_frac=0.1, unit="reads/s",
+                             label="configs[4]: Ion Torrent -c 2 flow model, 400bp single-end, -e 0.01, -C 20 (~163M reads)"),
+}
+
+
+def traffic_record():
+    """DRAM bytes of one 2^20-pair step from the committed ncu --set full capture (tools/ncu_read.py --traffic writes it)"""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def peak_hbm():
@@ -185,7 +212,8 @@ def reference_arm(args, rank):
 def config_dict(n_gpus):
     return {"workload": "configs[1]: 3.1 Gbp synthetic reference (24 contigs, GRCh38 lengths), Illumina 2x150bp, "
                         "-e/-E 0.001-0.01, -r 0.001 -R 0.1, -C 30 (~326M pairs), -o 0 (bwa1+bwa2+bfast)",
-            "pairs_per_step": PAIRS_PER_STEP, "l2": "inputs (1.5 GB genome blob) and outputs (1.5 GB/step) larger than L2",
+            "pairs_per_device_batch": PAIRS_PER_BATCH,
+            "l2": "inputs (1.5 GB genome blob) and outputs (1.5 GB per device batch) larger than L2",
             "parallelism": "pair-index shards x%d" % n_gpus}
 
 
@@ -242,15 +270,367 @@ def emit(line):
     out.flush()
 
 
+class KernelPath:
+    """one workload on the resident synthetic genome: rank 0 builds and packs it, NCCL broadcasts the packed blob"""
+
+    def __init__(self, name, rank, local_rank, world, genome_scale):
+        import torch
+        import torch.distributed as dist
+        from dwgsim_b200 import DwgsimGpu, params_from_options
+        self.torch, self.dist = torch, dist
+        self.name, self.w = name, WORKLOADS[name]
+        self.rank, self.world = rank, world
+        self.gpu = DwgsimGpu(params_from_options(**self.w["opts"]), device=local_rank)
+        lengths = [max(int(x * genome_scale), 200000) for x in GRCH38]
+        t0 = time.perf_counter()
+        self.keep = None
+        self.bcast_s = 0.0
+        if rank == 0:
+            self.gpu.genome_synthetic(lengths, 20261017, MUT_RATE, self.w["indel_frac"], N_FRAC, self.w["coverage"])
+            self.gpu.genome_finalize()
+            ptr, nbytes = self.gpu.genome_blob()
+        if world > 1:
+            meta = torch.zeros(1, dtype=torch.int64, device="cuda")
+            if rank == 0:
+                meta[0] = nbytes
+            dist.broadcast(meta, 0)
+            nbytes = int(meta.item())
+            blob_t = torch.as_tensor(_CudaArray(ptr, nbytes), device="cuda") if rank == 0 else \
+                torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            dist.broadcast(blob_t, 0)
+            torch.cuda.synchronize()
+            self.bcast_s = time.perf_counter() - tb
+            if rank != 0:
+                self.gpu.genome_import(blob_t.data_ptr(), nbytes, take_ownership=False)
+            self.keep = blob_t
+        self.setup_s = time.perf_counter() - t0
+        self.total_pairs = self.gpu.genome_pairs()
+        self.B = PAIRS_PER_BATCH
+        self.n_avail = self.total_pairs // (self.B * world)
+        if self.n_avail < 1:
+            self.B = int(self.total_pairs // world)
+            self.n_avail = 1
+        self.stream = torch.cuda.ExternalStream(self.gpu.cuda_stream(), device=torch.device("cuda", local_rank))
+        self.rand_base = 0
+        self.batch_no = 0
+        # N > 1: the one exchange of the path -- random-pair counts of the round, so that rand_ii in the names stays the
+        # global running count (src/dwgsim.c:1096) -- as an NCCL all-gather of device counters enqueued on the library's
+        # stream between the simulate passes and the layout kernels: no host round trip inside a batch
+        if world > 1:
+            self.allc = torch.zeros(world, dtype=torch.int64, device="cuda")
+            self.base_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+            self.running_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def batch(self):
+        torch, dist, gpu = self.torch, self.dist, self.gpu
+        first = ((self.batch_no % self.n_avail) * self.world + self.rank) * self.B
+        self.batch_no += 1
+        if self.world > 1:
+            gpu.resident_begin(first, self.B, False)
+            cnt = torch.as_tensor(_CudaArray(gpu.resident_count_ptr(), 8), device="cuda").view(torch.int64)
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(self.allc, cnt)
+                torch.add(self.running_t, self.allc[:self.rank].sum(), out=self.base_t)
+                b = gpu.resident_finish_dev(self.base_t.data_ptr())
+                self.running_t.add_(self.allc.sum())
+        else:
+            b = gpu.simulate_resident(first, self.B, self.rand_base)
+            self.rand_base += b.n_random
+        return b
+
+    def measure(self, steps, warmup, min_seconds, sampler=None):
+        """`warmup` untimed steps, then exactly `steps` timed steps of `per_step` device batches each"""
+        torch, dist, world = self.torch, self.dist, self.world
+        # calibration: device batches per step so that the timed region lasts min_seconds
+        for _ in range(3):
+            self.batch()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            self.batch()
+        torch.cuda.synchronize()
+        t_batch = (time.perf_counter() - t0) / 4
+        if world > 1:
+            t = torch.tensor([t_batch], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_batch = float(t.item())
+        per_step = max(1, int(min_seconds / (steps * t_batch) + 0.999))
+        for _ in range(warmup):
+            for _ in range(per_step):
+                self.batch()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.stream)
+        ms = [0.0, 0.0, 0.0]
+        out_bytes = launches = 0
+        t_wall0 = time.perf_counter()
+        for _ in range(steps):
+            for _ in range(per_step):
+                b = self.batch()
+                ms[0] += b.ms_simulate; ms[1] += b.ms_layout; ms[2] += b.ms_format
+                out_bytes += sum(b.n_bytes)
+                launches += b.n_launches
+        ev1.record(self.stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop() if sampler else None
+        elapsed_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+        n_batches = steps * per_step
+        units = world * self.B * n_batches
+        # roofline of the kernels (device time from CUDA events inside the library, per launch group; this rank's)
+        peak, peak_src = peak_hbm()
+        L = self.w["opts"]["length"]
+        read_bytes = sum(((x + 3) // 4) * 1.5 for x in L if x > 0) + 5.0
+        fastq_per_unit = out_bytes / (self.B * n_batches)
+        algo = ALGO_BYTES_PER_PAIR if self.name == "illumina_2x150" else read_bytes + fastq_per_unit
+        kern_ms = sum(ms) / n_batches
+        achieved = algo * self.B / (kern_ms * 1e-3) / 1e9
+        names = ["simulate_pairs_tp_kernel", "layout_* (5 scan kernels)", "format_fastq_kernel"]
+        dom = max(range(3), key=lambda i: ms[i])
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "algorithmic_bytes_per_unit": algo, "fastq_bytes_per_unit": fastq_per_unit,
+                    "kernel": "whole device batch = simulate + layout + format; dominant: %s" % names[dom],
+                    "ms_per_batch_by_kernel": {n: m / n_batches for n, m in zip(names, ms)}}
+        fmt_ms = ms[2] / n_batches
+        if fmt_ms > 0:        # the formatter alone: its algorithmic bytes are the FASTQ text it writes
+            fmt_bytes = out_bytes / n_batches
+            roofline["dominant_kernel" if dom == 2 else "format_kernel"] = {
+                "name": "format_fastq_kernel", "ms": fmt_ms, "algorithmic_bytes": fmt_bytes,
+                "achieved": fmt_bytes / (fmt_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": fmt_bytes / (fmt_ms * 1e-3) / 1e9 / peak}
+        sim_ms = ms[0] / n_batches
+        if dom == 0 and sim_ms > 0:
+            roofline["dominant_kernel"] = {"name": "simulate_pairs_tp_kernel", "ms": sim_ms,
+                                           "algorithmic_bytes": algo * self.B, "achieved": algo * self.B / (sim_ms * 1e-3) / 1e9,
+                                           "unit": "GB/s", "frac": algo * self.B / (sim_ms * 1e-3) / 1e9 / peak,
+                                           "note": "measured against the whole batch's algorithmic bytes"}
+        return {"value": units / (elapsed_ms * 1e-3), "unit": self.w["unit"], "elapsed_ms": elapsed_ms, "ms_per_step": elapsed_ms / steps,
+                "device_batches_per_step": per_step, "pairs_per_step": world * self.B * per_step, "timed_s": elapsed_ms * 1e-3,
+                "wall_s_timed_region": t_wall, "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+
+    def close(self):
+        self.gpu.close()
+        self.keep = None
+
+
+def e2e_legs(args, rank, local_rank, world):
+    """The C ABI with host buffers.  Per step: dwgsim_gpu_add_contig (dense seq_t + 2 x mut_t[len] host arrays, packed on
+    the host, copied to the device) + dwgsim_gpu_run.  Sinks: "memory" = the bytes are delivered in pair order to host
+    (pinned) memory and counted (dwgsim_gpu_sink_count: what a consumer in the same process sees); "files" = they are
+    also written to three NEW files on tmpfs per step (dwgsim_gpu_sink_files, one writer thread per file), removed by a
+    helper thread afterwards -- that leg is bounded by the kernel's page-cache copy (a few GB/s per file)."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    seq, hap = dense_contig(E2E_CONTIG_LEN, 7 + rank)
+    n_pairs_c = int(E2E_CONTIG_LEN * COVERAGE / 300.0 / 0.95 + 0.5)
+    n_warm = 6       # the first steps allocate the pinned ring and first-touch its pages (100+ ms stalls on a fresh box)
+    n_e2e = max(5, min(args.steps, 20))
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+
+    def leg(compress, files):
+        wd = tempfile.mkdtemp(prefix="dwgsim_e2e_r%d_" % rank, dir=base) if files else None
+        g2 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
+        g2.set_batch(1 << 18, 3)
+        if compress:
+            g2.set_compression(1)
+        doomed, lock, stop = [], threading.Lock(), [False]
+
+        def reaper():
+            while True:
+                with lock:
+                    paths = doomed[:]
+                    del doomed[:]
+                for q in paths:
+                    try:
+                        os.unlink(q)
+                    except OSError:
+                        pass
+                if stop[0] and not paths:
+                    return
+                time.sleep(0.002)
+
+        th = threading.Thread(target=reaper, daemon=True)
+        th.start()
+
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(1)
+        g2.set_host_threads(max(1, min(32, (os.cpu_count() or 1) // max(world, 1))))
+
+        def pack(i):           # the host half of add_contig; the next step's runs while this step's batches are on the device
+            return g2.pack_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,
+                                  None, 0, None, 0, n_pairs_c)
+
+        nxt = [pool.submit(pack, 0)]
+
+        def one(i):
+            g2.add_packed(nxt[0].result())
+            nxt[0] = pool.submit(pack, i + 1)
+            if not files:
+                st = g2.run_count()
+                return st, sum(st.bytes)
+            names = [os.path.join(wd, "s%d.%s%s" % (i, f, ".gz" if compress else "")) for f in
+                     ("bwa.read1.fastq", "bwa.read2.fastq", "bfast.fastq")]
+            fds = [os.open(q, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644) for q in names]
+            try:
+                st, offs = g2.run_to_files(fds)
+            finally:
+                for fd in fds:
+                    os.close(fd)
+            with lock:
+                doomed.extend(names)
+            return st, sum(offs)
+
+        try:
+            for i in range(n_warm):
+                one(i)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            te = time.perf_counter()
+            h2d = d2h = raw = delivered = 0
+            pack_ms = 0.0
+            for i in range(n_e2e):
+                st, nb = one(n_warm + i)
+                h2d += st.h2d_bytes; d2h += st.d2h_bytes; pack_ms += st.ms_pack; raw += sum(st.raw_bytes); delivered += nb
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - te
+            if world > 1:
+                t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                secs = float(t.item())
+        finally:
+            stop[0] = True
+            th.join(timeout=30)
+            try:
+                g2._L.dwgsim_gpu_packed_free(nxt[0].result())
+            except Exception:
+                pass
+            pool.shutdown()
+            g2.close()
+            if wd:
+                shutil.rmtree(wd, ignore_errors=True)
+        out = {"value": world * n_pairs_c * n_e2e / secs, "unit": "pairs/s", "h2d_bytes_per_step": h2d // n_e2e,
+               "d2h_bytes_per_step": d2h // n_e2e, "steps": n_e2e, "pairs_per_step": n_pairs_c, "ms_per_step": 1e3 * secs / n_e2e,
+               "host_pack_ms_per_step": pack_ms / n_e2e, "fastq_bytes_per_step": raw // n_e2e, "sink_bytes_per_step": delivered // n_e2e}
+        what = ("dwgsim_gpu_pack_contig + add_packed (%d Mbp contig, dense host arrays; the next step's packing runs on a helper "
+                "thread while this step's batches are on the device) + dwgsim_gpu_run -> %s of all three files in pair order, %s") % (
+            E2E_CONTIG_LEN >> 20,
+            ".fastq.gz bytes (gzip members written on the GPU, dwgsim_gpu_set_compression(1), the host shell's default)" if compress else "FASTQ text",
+            "written to three new files on tmpfs per step (dwgsim_gpu_sink_files, one writer thread per file)" if files else
+            "delivered to host memory (library counting sink)")
+        out["what"] = "per step: " + what
+        return out
+
+    e2e = leg(True, False)                      # headline: the drop-in's default output delivered to host memory
+    e2e["compression_ratio"] = e2e["d2h_bytes_per_step"] / max(e2e["fastq_bytes_per_step"], 1)
+    try:
+        e2e["raw_sink"] = leg(False, False)
+    except Exception as ex:
+        e2e["raw_sink"] = {"error": str(ex)}
+    try:
+        e2e["file_sink"] = leg(True, True)
+    except Exception as ex:
+        e2e["file_sink"] = {"error": str(ex)}
+    return e2e
+
+
+def write_genome_fasta(path, scale=1.0):
+    """the 24-contig synthetic reference of configs[1] as a FASTA + .fai (i.i.d. ACGT, 10 kb telomeres and one long N run)"""
+    import numpy as np
+    rng = np.random.default_rng(20261017)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    total = 0
+    with open(path, "wb") as f, open(path + ".fai", "w") as fai:
+        off = 0
+        for i, full in enumerate(GRCH38):
+            n = max(int(full * scale), 200000)
+            name = "chr%d" % (i + 1)
+            s = acgt[np.frombuffer(rng.bytes(n), dtype=np.uint8) & 3]
+            s[:10000] = ord("N"); s[n - 10000:] = ord("N")
+            s[n // 3:n // 3 + int(n * N_FRAC)] = ord("N")
+            head = (">%s\n" % name).encode()
+            f.write(head)
+            off += len(head)
+            rows = n // 60
+            body = np.empty((rows, 61), dtype=np.uint8)
+            body[:, :60] = s[:rows * 60].reshape(rows, 60)
+            body[:, 60] = 10
+            f.write(body.tobytes())
+            if n % 60:
+                f.write(s[rows * 60:].tobytes() + b"\n")
+            fai.write("%s\t%d\t%d\t60\t61\n" % (name, n, off))
+            off += n + rows + (1 if n % 60 else 0)
+            total += n
+    return total
+
+
+def e2e_cli(args, cpu_baseline):
+    """wall time of the drop-in binary on the whole synthetic reference: FASTA (+ .fai) in, -C 30, the three .fastq.gz streams to
+    /dev/null-backed files (symlinks), the mutation files to tmpfs; host prologue (mut_diref, mutation files, packing) included"""
+    import re
+    from dwgsim_b200 import build
+    exe = build.build_cli()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    wd = tempfile.mkdtemp(prefix="dwgsim_cli_", dir=base)
+    try:
+        fa = os.path.join(wd, "genome.fa")
+        t0 = time.perf_counter()
+        bases = write_genome_fasta(fa, args.genome_scale)
+        t_fa = time.perf_counter() - t0
+        prefix = os.path.join(wd, "out")
+        for f in ("bwa.read1.fastq.gz", "bwa.read2.fastq.gz", "bfast.fastq.gz"):
+            os.symlink("/dev/null", prefix + "." + f)
+        argv = [exe] + REF_ARGV + ["-C", "%g" % COVERAGE, "-z", "1", fa, prefix]
+        env = dict(os.environ, DWGSIM_STATS="1")
+        t0 = time.perf_counter()
+        r = subprocess.run(argv, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": r.stderr[-400:]}
+        m = re.search(r"\[dwgsim_b200\] bases (\d+) pairs (\d+) fastq_bytes (\d+) \| total ([\d.]+) s: mut_diref ([\d.]+) s .*?mut_print ([\d.]+) s, "
+                      r"read loop ([\d.]+) s \(host pack ([\d.]+) s, kernels ([\d.]+) s", r.stderr)
+        out = {"wall_s": wall, "genome_bases": bases, "fasta_write_s": t_fa, "gpus": 1,
+               "what": "dwgsim_b200/bin/dwgsim %s on the 24-contig synthetic reference (FASTA + .fai on tmpfs); .fastq.gz streams "
+                       "(device gzip) to /dev/null-backed files, mutations.txt/.vcf to tmpfs; wall time of the process" % " ".join(argv[1:-2])}
+        if m:
+            pairs = int(m.group(2))
+            out.update(pairs=pairs, pairs_per_s=pairs / wall, fastq_bytes=int(m.group(3)), mut_diref_s=float(m.group(5)),
+                       mut_print_s=float(m.group(6)), read_loop_s=float(m.group(7)), host_pack_s=float(m.group(8)),
+                       kernels_s=float(m.group(9)))
+            if cpu_baseline and cpu_baseline.get("value"):
+                ref_prologue = cpu_baseline.get("prologue_ns_per_base", 0.0) * 1e-9 * bases
+                out["reference_extrapolated_s"] = pairs / cpu_baseline["value"] + ref_prologue
+                out["reference_extrapolation"] = "pairs / (1-core reference rate of cpu_baseline) + measured reference prologue ns/base x bases"
+        return out
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
 def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-cli", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip configs[2..4]")
+    ap.add_argument("--only", default=None, help="measure this workload as the headline (debug / profiling)")
     ap.add_argument("--genome-scale", type=float, default=1.0, help="shrink the synthetic genome (debug only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -264,7 +644,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dwgsim_b200 import DwgsimGpu, params_from_options, build
+    from dwgsim_b200 import build
     if not os.path.exists(build.SO):          # normally prebuilt in-tree and shipped with the snapshot
         if rank == 0:
             build.build()
@@ -280,180 +660,37 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    gpu = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
-    lengths = [max(int(x * args.genome_scale), 200000) for x in GRCH38]
-    # ---- genome: rank 0 builds and packs it; NCCL broadcasts the packed blob to the other ranks ----
-    t0 = time.perf_counter()
-    keep = None
-    if rank == 0:
-        gpu.genome_synthetic(lengths, 20261017, MUT_RATE, INDEL_FRAC, N_FRAC, COVERAGE)
-        gpu.genome_finalize()
-        ptr, nbytes = gpu.genome_blob()
-    if world > 1:
-        meta = torch.zeros(1, dtype=torch.int64, device="cuda")
-        if rank == 0:
-            meta[0] = nbytes
-        dist.broadcast(meta, 0)
-        nbytes = int(meta.item())
-        if rank == 0:
-            blob_t = torch.as_tensor(_CudaArray(ptr, nbytes), device="cuda")
-        else:
-            blob_t = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        torch.cuda.synchronize()
-        tb = time.perf_counter()
-        dist.broadcast(blob_t, 0)
-        torch.cuda.synchronize()
-        bcast_s = time.perf_counter() - tb
-        if rank != 0:
-            gpu.genome_import(blob_t.data_ptr(), nbytes, take_ownership=False)
-        keep = blob_t
-    else:
-        bcast_s = 0.0
-    setup_s = time.perf_counter() - t0
-    total_pairs = gpu.genome_pairs()
-    B = PAIRS_PER_STEP
-    n_steps_avail = total_pairs // (B * world)
-    if n_steps_avail < 1:
-        B = int(total_pairs // world)
-        n_steps_avail = 1
+    # ---- headline: configs[1] on the kernel path -------------------------------------------------------------------
+    head_name = args.only or "illumina_2x150"
+    kp = KernelPath(head_name, rank, local_rank, world, args.genome_scale)
+    head = kp.measure(args.steps, args.warmup, MIN_TIMED_S, ClockSampler(local_rank))
+    setup = {"genome_build_s": kp.setup_s, "nccl_broadcast_s": kp.bcast_s, "genome_pairs": kp.total_pairs,
+             "wall_s_timed_region": head["wall_s_timed_region"], "timed_s": head["timed_s"]}
+    kp.close()
+    tr = traffic_record()
+    roofline = head["roofline"]
+    roofline["traffic"] = tr["dram_bytes_per_batch"] if tr and head_name == "illumina_2x150" else None
+    roofline["traffic_source"] = tr.get("source") if tr else None
 
-    stream = torch.cuda.ExternalStream(gpu.cuda_stream(), device=torch.device("cuda", local_rank))
-    rand_base = 0
+    # ---- configs[2..4] ---------------------------------------------------------------------------------------------------
+    configs = {}
+    if not args.no_configs and not args.only:
+        for name in ("illumina_2x150_R0.15", "solid_2x50", "iontorrent_400se"):
+            try:
+                k2 = KernelPath(name, rank, local_rank, world, args.genome_scale)
+                r = k2.measure(max(5, min(args.steps, 20)), 3, MIN_TIMED_S_OTHER)
+                k2.close()
+                configs[name] = {"workload": WORKLOADS[name]["label"] + ", 3.1 Gbp synthetic reference, -o 0", "value": r["value"],
+                                 "unit": r["unit"], "n_gpus": world, "timed_s": r["timed_s"], "pairs_per_step": r["pairs_per_step"],
+                                 "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "algorithmic_bytes_per_unit",
+                                                                            "fastq_bytes_per_unit", "ms_per_batch_by_kernel")}}
+            except Exception as ex:
+                configs[name] = {"error": str(ex)}
 
-    # N > 1: the one exchange of the path -- random-pair counts of the round, so that rand_ii in the names stays the
-    # global running count (src/dwgsim.c:1096) -- as an NCCL all-gather of device counters enqueued on the library's
-    # stream between the simulate passes and the layout kernels: no host round trip inside a step
-    if world > 1:
-        allc = torch.zeros(world, dtype=torch.int64, device="cuda")
-        base_t = torch.zeros(1, dtype=torch.int64, device="cuda")
-        running_t = torch.zeros(1, dtype=torch.int64, device="cuda")
-
-    def step(k):
-        nonlocal rand_base
-        first = ((k % n_steps_avail) * world + rank) * B
-        if world > 1:
-            gpu.resident_begin(first, B, False)
-            cnt = torch.as_tensor(_CudaArray(gpu.resident_count_ptr(), 8), device="cuda").view(torch.int64)
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(allc, cnt)
-                torch.add(running_t, allc[:rank].sum(), out=base_t)
-                b = gpu.resident_finish_dev(base_t.data_ptr())
-                running_t.add_(allc.sum())
-        else:
-            b = gpu.simulate_resident(first, B, rand_base)
-            rand_base += b.n_random
-        return b
-
-    for k in range(args.warmup):
-        step(k)
-    sampler = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    ms = [0.0, 0.0, 0.0]
-    out_bytes = 0
-    launches = 0
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        b = step(args.warmup + k)
-        ms[0] += b.ms_simulate; ms[1] += b.ms_layout; ms[2] += b.ms_format
-        out_bytes += sum(b.n_bytes)
-        launches += b.n_launches
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
-
-    # ---- roofline of the kernels (device time from CUDA events inside the library, per launch group) ----
-    peak, peak_src = peak_hbm()
-    kern_ms = sum(ms) / args.steps
-    achieved = ALGO_BYTES_PER_PAIR * B / (kern_ms * 1e-3) / 1e9
-    dom = max(range(3), key=lambda i: ms[i])
-    names = ["simulate_pairs_tp_kernel (2 passes)", "layout_* (5 scan kernels)", "format_fastq_kernel"]
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_STEP if B == PAIRS_PER_STEP else None,
-                "traffic_source": "ncu --set full capture of the same step (profiles/r01c_ncu_key_metrics.txt), bytes per step",
-                "peak_source": peak_src,
-                "kernel": "whole step = simulate (2 passes) + layout + format (8 launches); dominant: %s" % names[dom],
-                "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "fastq_bytes_per_pair": out_bytes / (B * args.steps),
-                "ms_per_step_by_kernel": {n: m / args.steps for n, m in zip(names, ms)}}
-    # the dominant kernel on its own: the formatter's algorithmic bytes are the FASTQ text it writes (its inputs are the
-    # intermediate records and codes); achieved = those bytes / its CUDA-event time
-    fmt_ms = ms[2] / args.steps
-    if fmt_ms > 0:
-        fmt_bytes = out_bytes / args.steps
-        roofline["dominant_kernel"] = {"name": "format_fastq_kernel", "ms": fmt_ms, "algorithmic_bytes": fmt_bytes,
-                                       "achieved": fmt_bytes / (fmt_ms * 1e-3) / 1e9, "unit": "GB/s",
-                                       "frac": fmt_bytes / (fmt_ms * 1e-3) / 1e9 / peak}
-
-    # ---- e2e: the C ABI with host buffers (dense arrays in, FASTQ bytes out to host memory) ----
-    # Headline leg: the drop-in's default output, .fastq.gz bytes (what the reference writes to its gzFiles,
-    # src/dwgsim.c:1151-1157), compressed on the GPU before the device->host copy.  Second leg: plain FASTQ text.
+    # ---- e2e: the C ABI with host buffers, output to files on tmpfs -----------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        seq, hap = dense_contig(E2E_CONTIG_LEN, 7 + rank)
-        n_pairs_c = int(E2E_CONTIG_LEN * COVERAGE / 300.0 / 0.95 + 0.5)
-        n_warm = 6       # the first steps allocate the pinned ring and first-touch its pages (100+ ms stalls on a fresh box)
-        n_e2e = max(5, min(args.steps, 20))
-
-        def e2e_leg(compress):
-            g2 = DwgsimGpu(params_from_options(**OPTS), device=local_rank)
-            g2.set_batch(1 << 18, 3)
-            if compress:
-                g2.set_compression(1)
-
-            def one(i):
-                g2.add_contig(i, "chrE%d" % i, seq.ctypes.data, E2E_CONTIG_LEN, hap[0].ctypes.data, hap[1].ctypes.data,
-                              None, 0, None, 0, n_pairs_c)
-                return g2.run_count()
-
-            for i in range(n_warm):
-                one(i)
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            te = time.perf_counter()
-            h2d = d2h = raw = 0
-            pack_ms = 0.0
-            for i in range(n_e2e):
-                st = one(n_warm + i)
-                h2d += st.h2d_bytes; d2h += st.d2h_bytes; pack_ms += st.ms_pack; raw += sum(st.raw_bytes)
-            torch.cuda.synchronize()
-            secs = time.perf_counter() - te
-            if world > 1:
-                t = torch.tensor([secs], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                secs = float(t.item())
-            g2.close()
-            return {"value": world * n_pairs_c * n_e2e / secs, "unit": "pairs/s", "h2d_bytes_per_step": h2d // n_e2e,
-                    "d2h_bytes_per_step": d2h // n_e2e, "steps": n_e2e, "pairs_per_step": n_pairs_c,
-                    "host_pack_ms_per_step": pack_ms / n_e2e, "fastq_bytes_per_step": raw // n_e2e}
-
-        what = ("per step: dwgsim_gpu_add_contig(%d Mbp contig as dense seq_t + 2 x mut_t[len] host arrays, packed on the host, "
-                "copied to the device) + dwgsim_gpu_run -> %s of all three files delivered in pair order to host memory "
-                "(library counting sink)")
-        raw_leg = e2e_leg(False)
-        raw_leg["what"] = what % (E2E_CONTIG_LEN >> 20, "FASTQ text")
-        try:
-            e2e = e2e_leg(True)
-            e2e["compression_ratio"] = e2e["d2h_bytes_per_step"] / max(e2e["fastq_bytes_per_step"], 1)
-            e2e["what"] = what % (E2E_CONTIG_LEN >> 20, ".fastq.gz bytes (gzip members written on the GPU, "
-                                                         "dwgsim_gpu_set_compression(1), the host shell's default)")
-            e2e["raw_sink"] = raw_leg
-        except Exception as ex:  # keep a headline if the compressed leg fails
-            e2e = raw_leg
-            e2e["gzip_sink"] = {"error": str(ex)}
+        e2e = e2e_legs(args, rank, local_rank, world)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and ref_binary():
@@ -461,21 +698,31 @@ def main():
             n = 60000
             r = cpu_reference(1, n, 1, 1)
             cpu_baseline = {"value": r["value"], "unit": "pairs/s", "cores": 1, "kind": "reference",
+                            "prologue_ns_per_base": r["prologue_s"] / 2_000_000 * 1e9,
                             "sample": "oracle/_ref/dwgsim_ref -N %d on a 2 Mbp sample of the synthetic reference, same options, "
                                       "all three .fastq.gz outputs, 1 process; prologue (%.2f s, -C 0) subtracted" % (n, r["prologue_s"])}
         except Exception as e:
             cpu_baseline = {"value": None, "unit": "pairs/s", "cores": 1, "kind": "reference", "sample": "failed: %s" % e}
 
+    cli = None
+    if rank == 0 and world == 1 and not args.no_e2e_cli and not args.only:
+        try:
+            cli = e2e_cli(args, cpu_baseline)
+        except Exception as ex:
+            cli = {"error": str(ex)}
+
     if rank == 0:
-        line = {"metric": "read-pairs/sec (2x150bp, 3.1Gbp ref)", "value": value, "unit": "pairs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "setup": {"genome_build_s": setup_s, "nccl_broadcast_s": bcast_s, "genome_pairs": total_pairs,
-                          "wall_s_timed_region": t_wall}}
+        cfg = config_dict(world)
+        if args.only:
+            cfg["workload"] = WORKLOADS[head_name]["label"]
+        line = {"metric": "read-pairs/sec (2x150bp, 3.1Gbp ref)", "value": head["value"], "unit": head["unit"], "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+                "step": {"device_batches_per_step": head["device_batches_per_step"], "pairs_per_step": head["pairs_per_step"],
+                         "timed_s": head["timed_s"]},
+                "clocks": head["clocks"], "e2e": e2e, "e2e_cli": cli, "gpu_launches": head["gpu_launches"], "roofline": roofline,
+                "configs": configs, "cpu_baseline": cpu_baseline, "setup": setup}
         emit(line)
-    gpu.close()
-    del keep
     if world > 1:
         dist.destroy_process_group()
 

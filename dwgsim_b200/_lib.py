@@ -48,6 +48,7 @@ class Tables(C.Structure):
         ("qdelta_lo", C.c_int32), ("qdelta_n", C.c_int32), ("qdelta_cdf", C.POINTER(C.c_uint32)),
         ("n_cycles", C.c_int32 * 2), ("err_gap", C.POINTER(C.c_uint32) * 2), ("err_acc", C.POINTER(C.c_uint32) * 2),
         ("qbase", C.POINTER(C.c_uint8) * 2), ("flow_thr", C.c_uint32 * 2),
+        ("flow_gap", C.POINTER(C.c_uint32) * 2), ("flow_gap_n", C.c_int32 * 2),
     ]
 
 
@@ -66,6 +67,11 @@ SYMBOLS = {
     "dwgsim_gpu_last_error": (C.c_char_p, [_P]),
     "dwgsim_gpu_add_contig": (C.c_int, [_P, C.c_int32, C.c_char_p, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_int32,
                                         C.c_int64]),
+    "dwgsim_gpu_pack_contig": (C.c_int, [_P, C.c_int32, C.c_char_p, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_int32,
+                                         C.c_int64, C.POINTER(_P)]),
+    "dwgsim_gpu_add_packed": (C.c_int, [_P, _P]),
+    "dwgsim_gpu_packed_free": (None, [_P]),
+    "dwgsim_gpu_set_host_threads": (C.c_int, [_P, C.c_int32]),
     "dwgsim_gpu_set_regions": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.c_int32]),
     "dwgsim_gpu_run": (C.c_int, [_P, SINK_FN, _P, C.POINTER(Stats)]),
     "dwgsim_gpu_set_batch": (C.c_int, [_P, C.c_int64, C.c_int32]),
@@ -89,6 +95,10 @@ SYMBOLS = {
     "dwgsim_gpu_gz_host_encode": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "dwgsim_gpu_sink_count": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "dwgsim_gpu_sink_fd": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "dwgsim_gpu_file_sink_open": (_P, [C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "dwgsim_gpu_sink_files": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "dwgsim_gpu_file_sink_close": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "dwgsim_gpu_pwrite_all": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_int64]),
     "dwgsim_gpu_tables": (C.c_int, [_P, C.POINTER(Tables)]),
 }
 

@@ -122,6 +122,23 @@ class DwgsimGpu:
         self._check(self._L.dwgsim_gpu_add_contig(self._h, contig_i, name, seq, length, hap1, hap2, ins1, ins1_n,
                                                   ins2, ins2_n, n_pairs))
 
+    def pack_contig(self, contig_i, name, seq, length, hap1, hap2, ins1=None, ins1_n=0, ins2=None, ins2_n=0, n_pairs=0):
+        """the host half of add_contig (may run on another thread while run() is in flight); returns an opaque handle"""
+        name = name if isinstance(name, bytes) else name.encode()
+        out = C.c_void_p()
+        rc = self._L.dwgsim_gpu_pack_contig(self._h, contig_i, name, seq, length, hap1, hap2, ins1, ins1_n, ins2, ins2_n,
+                                            n_pairs, C.byref(out))
+        if rc:
+            raise DwgsimGpuError(rc, self._L.dwgsim_gpu_strerror(rc).decode())
+        return out
+
+    def add_packed(self, packed):
+        """queue the result of pack_contig (ownership passes to the handle)"""
+        self._check(self._L.dwgsim_gpu_add_packed(self._h, packed))
+
+    def set_host_threads(self, n):
+        self._check(self._L.dwgsim_gpu_set_host_threads(self._h, n))
+
     def set_regions(self, regions, sample_len):
         """-x for the contig just queued: regions = [(start, end), ...] merged and sorted (BED half-open),
         sample_len = the reference's `l` after src/dwgsim.c:539-553"""
@@ -165,6 +182,20 @@ class DwgsimGpu:
         cb = C.cast(self._L.dwgsim_gpu_sink_fd, _lib.SINK_FN)
         self._check(self._L.dwgsim_gpu_run(self._h, cb, C.cast(arr, C.c_void_p), C.byref(st)))
         return st
+
+    def run_to_files(self, fds, offsets=(0, 0, 0)):
+        """run() through the library's file sink (one background writer per file, positional writes); returns
+        (Stats, end offsets)"""
+        fs = self._L.dwgsim_gpu_file_sink_open((C.c_int32 * 3)(*fds), (C.c_int64 * 3)(*offsets))
+        st = Stats()
+        cb = C.cast(self._L.dwgsim_gpu_sink_files, _lib.SINK_FN)
+        rc = self._L.dwgsim_gpu_run(self._h, cb, fs, C.byref(st))
+        end = (C.c_int64 * 3)()
+        wrc = self._L.dwgsim_gpu_file_sink_close(fs, end)
+        self._check(rc)
+        if wrc:
+            raise DwgsimGpuError(-7, "writing the output files failed")
+        return st, list(end)
 
     def run_collect(self):
         """run() into three bytes objects (tests)"""

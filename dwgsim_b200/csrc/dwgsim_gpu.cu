@@ -2,6 +2,7 @@
 // batch pipeline (compute stream + copy stream + pinned ring) around the kernels in kernels.cuh.
 // There is no CPU fallback: every entry point that needs a device fails with DWGSIM_GPU_ENODEV / ECUDA.
 #include <cuda_runtime.h>
+#include <errno.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -62,6 +63,7 @@ struct DeviceTables {
     uint8_t *qtab = nullptr;
     uint8_t *qbase[2] = {nullptr, nullptr};
     int8_t *flow_order = nullptr;
+    uint32_t *flow_gap[2] = {nullptr, nullptr};
     char *prefix = nullptr;
 };
 
@@ -155,6 +157,7 @@ struct dwgsim_gpu {
     std::vector<uint16_t> isize_guide, gap_guide[2];
     std::vector<uint32_t> qguide;
     std::vector<uint8_t> qtab;
+    std::vector<uint32_t> flow_gap[2];
     bool ion_warp_kernel = false;
     // device gzip writer: mode, per-stream tables in HBM
     int gz_mode = 0;
@@ -181,6 +184,7 @@ struct dwgsim_gpu {
     uint64_t blob_spare_cap = 0;
     int64_t blob_pairs = 0;
     int max_name_len = 4;
+    int host_threads = 0;                     // packer threads (0: min(hardware threads, 32))
     double ms_pack = 0;
     int64_t h2d_bytes = 0;
     // global counters carried across runs (ctr / rand_ii of src/dwgsim.c:423)
@@ -325,6 +329,10 @@ void derive_tables(dwgsim_gpu *h)
         }
         make_guide(h->err_gap[e].data(), (size_t)p.length[e], h->gap_guide[e]);
         h->flow_thr[e] = thr32(p.e_start[e]);
+        // Ion Torrent: the per-flow error coin (src/dwgsim.c:290,372) as the geometric gaps of its Bernoulli process
+        h->flow_gap[e].assign(p.data_type == 2 ? (size_t)kFlowGapN : 1, 0);
+        if (p.data_type == 2 && p.e_start[e] > 0.0)
+            for (int j = 0; j < kFlowGapN; ++j) h->flow_gap[e][j] = thr32(1.0 - pow(1.0 - std::min(p.e_start[e], 1.0), (double)(j + 1)));
     }
 }
 
@@ -352,6 +360,7 @@ int upload_tables(dwgsim_gpu *h)
         if ((rc = upload(h, &h->dt.qbase[e], h->qbase[e].data(), h->qbase[e].size()))) return rc;
     }
     if ((rc = upload(h, &h->dt.flow_order, h->flow_order.data(), h->flow_order.size()))) return rc;
+    for (int e = 0; e < 2; ++e) if ((rc = upload(h, &h->dt.flow_gap[e], h->flow_gap[e].data(), h->flow_gap[e].size()))) return rc;
     if ((rc = upload(h, &h->dt.prefix, h->prefix_s.data(), h->prefix_s.size()))) return rc;
     const dwgsim_gpu_params_t &p = h->p;
     SimParams &s = h->sp;
@@ -393,6 +402,7 @@ int upload_tables(dwgsim_gpu *h)
     if (s.fmt_v2)                                              // format_fastq2_kernel: 16 bases per lane
         s.inv_groups = (uint32_t)(4294967296.0 / std::max(((s.cap[0] + 7) / 8 + 1) / 2 + ((s.cap[1] + 7) / 8 + 1) / 2, 1)) + 1u;
     s.flow_order = h->dt.flow_order; s.prefix = h->dt.prefix;
+    s.flow_gap[0] = h->dt.flow_gap[0]; s.flow_gap[1] = h->dt.flow_gap[1];
     return DWGSIM_GPU_OK;
 }
 
@@ -469,7 +479,7 @@ void pack_range(HostContig &c, const uint8_t *seq, const uint64_t *const hap[2],
     }
 }
 
-int pack_contig(dwgsim_gpu *h, HostContig &c, const uint8_t *seq, const uint64_t *hap[2], uint8_t *const *ins[2],
+int pack_contig(int host_threads, std::string &err, HostContig &c, const uint8_t *seq, const uint64_t *hap[2], uint8_t *const *ins[2],
                 const int32_t ins_n[2])
 {
     const int len = c.len;
@@ -477,7 +487,8 @@ int pack_contig(dwgsim_gpu *h, HostContig &c, const uint8_t *seq, const uint64_t
     c.nmask.assign(((size_t)len + 31) / 32 + 1, 0);
     const int nblk = (len >> kBlkShift) + 2;
     // split into 128-base aligned ranges, one per worker thread
-    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    unsigned nt = host_threads > 0 ? (unsigned)host_threads : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (const char *e = getenv("DWGSIM_HOST_THREADS")) if (atoi(e) > 0 && host_threads <= 0) nt = (unsigned)atoi(e);
     if (len < (1 << 20)) nt = 1;
     const int per = (int)((((int64_t)len + nt - 1) / nt + 127) & ~127ll);
     std::vector<PackPart> parts(nt);
@@ -495,7 +506,7 @@ int pack_contig(dwgsim_gpu *h, HostContig &c, const uint8_t *seq, const uint64_t
         c.ev[hh].clear(); c.ev[hh].reserve(total);
         c.pool[hh].clear();
         for (auto &pt : parts) {
-            if (pt.rc) { h->last_error = pt.err ? pt.err : "pack failed"; return pt.rc; }
+            if (pt.rc) { err = pt.err ? pt.err : "pack failed"; return pt.rc; }
             const uint64_t base_bases = (uint64_t)c.pool[hh].size() * 4;
             for (Event e : pt.ev[hh]) {
                 if ((e.meta & 3u) == kEvInsert && (e.meta >> 5) > kInlineInsMax) e.payload += base_bases;
@@ -521,9 +532,9 @@ uint64_t name_cap_of(const dwgsim_gpu *h)
 {
     return 1 + h->prefix_s.size() + (uint64_t)std::max(h->max_name_len, 4) + 13 + 20 + 4 + 30 + 16;
 }
-void record_caps(const dwgsim_gpu *h, uint64_t cap[3])
+void record_caps(const dwgsim_gpu *h, uint64_t cap[3], uint64_t name_slack = 0)
 {
-    const uint64_t name = name_cap_of(h);
+    const uint64_t name = name_cap_of(h) + name_slack;
     const SimParams &s = h->sp;
     for (int e = 0; e < 2; ++e) cap[e] = s.out_bwa && s.len[e] > 0 ? name + 3 + 2ull * s.cap[e] + 4 : 0;
     cap[2] = 0;
@@ -672,20 +683,23 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
     uint64_t cap_now[3];
     record_caps(h, cap_now);
     // the names buffer, the output streams and the pinned ring are sized from the longest contig name seen so far: a later,
-    // longer name (add_contig / genome_import after a run) needs them again
+    // longer name (add_contig / genome_import after a run) needs them again.  They are allocated with room for names 32
+    // characters longer, so "chr9" -> "chr10" does not cost a reallocation (seconds, with the pinned ring)
     const bool grown = w.cap_pairs > 0 && (h->sp.name_cap > w.name_cap || cap_now[0] > w.rec_cap[0] || cap_now[1] > w.rec_cap[1] ||
                                            cap_now[2] > w.rec_cap[2]);
     if (w.cap_pairs < n || grown) {
         n = std::max<int64_t>(n, w.cap_pairs);
         free_workspace(h);
-        w.name_cap = h->sp.name_cap;
+        const uint64_t kNameSlack = 32;
+        w.name_cap = h->sp.name_cap + (int32_t)kNameSlack;
+        record_caps(h, cap_now, kNameSlack);
         for (int k = 0; k < 3; ++k) w.rec_cap[k] = cap_now[k];
         const int64_t nblk = (n + kScanTile - 1) / kScanTile;
         CUDA_TRY(h, cudaMalloc((void **)&w.recs, (size_t)n * sizeof(PairRec)));
         CUDA_TRY(h, cudaMalloc((void **)&w.seqs, (size_t)n * 4 * (size_t)(h->sp.nw[0] + h->sp.nw[1] + 1)));
         CUDA_TRY(h, cudaMalloc((void **)&w.serial, (size_t)n * 8));
         CUDA_TRY(h, cudaMalloc((void **)&w.lens, (size_t)n * 12));
-        CUDA_TRY(h, cudaMalloc((void **)&w.names, (size_t)n * 2 * (size_t)h->sp.name_cap));
+        CUDA_TRY(h, cudaMalloc((void **)&w.names, (size_t)n * 2 * (size_t)w.name_cap));
         CUDA_TRY(h, cudaMalloc((void **)&w.name_len, (size_t)n * 4));
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_rand, (size_t)nblk * 8));
         CUDA_TRY(h, cudaMalloc((void **)&w.blk_len, (size_t)nblk * 24));
@@ -694,8 +708,7 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         CUDA_TRY(h, cudaMemset(w.status, 0, 48));
         CUDA_TRY(h, cudaMalloc((void **)&w.jobs, (size_t)n * 2 * sizeof(uint2)));
         CUDA_TRY(h, cudaMallocHost((void **)&w.h_totals, 128));
-        uint64_t cap[3];
-        record_caps(h, cap);
+        const uint64_t *cap = cap_now;
         for (int k = 0; k < 3; ++k) {
             w.out_cap[k] = align_up(cap[k] * (uint64_t)n + 256, 256);
             if (w.out_cap[k] >= (1ull << 32)) { h->last_error = "batch too large: a stream would exceed 4 GiB"; return DWGSIM_GPU_EINVAL; }
@@ -1097,7 +1110,7 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     cudaFree(h->blob_spare);
     cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.qtab); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
     for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
-    cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix);
+    cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix); cudaFree(h->dt.flow_gap[0]); cudaFree(h->dt.flow_gap[1]);
     for (int k = 0; k < 3; ++k) { cudaFree(h->gz_code[k]); cudaFree(h->gz_prefix[k]); }
     cudaFree(h->gz_crc);
     for (auto &e : h->ev_t) if (e) cudaEventDestroy(e);
@@ -1106,25 +1119,67 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     delete h;
 }
 
+struct dwgsim_gpu_packed {
+    HostContig c;
+    double ms_pack = 0;
+};
+
+// Packing is host-only work on the caller's arrays: it may run on another thread while dwgsim_gpu_run is in flight on
+// the same handle (it reads nothing of the handle but its packer-thread count and read-prefix length).
+int dwgsim_gpu_pack_contig(const dwgsim_gpu_t *h, int32_t contig_i, const char *name, const uint8_t *seq_ascii, int32_t len,
+                           const uint64_t *hap1, const uint64_t *hap2, uint8_t *const *ins1, int32_t ins1_n,
+                           uint8_t *const *ins2, int32_t ins2_n, int64_t n_pairs, dwgsim_gpu_packed_t **out)
+{
+    if (!h || !out || !name || !seq_ascii || !hap1 || !hap2 || len <= 0 || n_pairs < 0) return DWGSIM_GPU_EINVAL;
+    *out = nullptr;
+    const size_t nl = strlen(name);
+    if (nl + h->prefix_s.size() + 128 > 1024) return DWGSIM_GPU_EUNSUPPORTED;       // read name too long for the device formatter
+    const double t0 = now_ms();
+    dwgsim_gpu_packed *p = new dwgsim_gpu_packed();
+    HostContig &c = p->c;
+    c.name = name; c.contig_i = contig_i; c.len = len; c.n_pairs = n_pairs;
+    const uint64_t *hap[2] = {hap1, hap2};
+    uint8_t *const *ins[2] = {ins1, ins2};
+    const int32_t ins_n[2] = {ins1_n, ins2_n};
+    std::string err;
+    const int rc = pack_contig(h->host_threads, err, c, seq_ascii, hap, ins, ins_n);
+    if (rc) { delete p; return rc; }
+    p->ms_pack = now_ms() - t0;
+    *out = p;
+    return DWGSIM_GPU_OK;
+}
+
+void dwgsim_gpu_packed_free(dwgsim_gpu_packed_t *p) { delete p; }
+
+int dwgsim_gpu_add_packed(dwgsim_gpu_t *h, dwgsim_gpu_packed_t *p)
+{
+    if (!h || !p) return DWGSIM_GPU_EINVAL;
+    if (h->blob) { h->last_error = "add_contig after the genome was finalized: call run() first"; return DWGSIM_GPU_ESTATE; }
+    h->max_name_len = std::max(h->max_name_len, (int)p->c.name.size());
+    h->ms_pack += p->ms_pack;
+    h->queue.emplace_back(std::move(p->c));
+    delete p;
+    return DWGSIM_GPU_OK;
+}
+
 int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name, const uint8_t *seq_ascii, int32_t len,
                           const uint64_t *hap1, const uint64_t *hap2, uint8_t *const *ins1, int32_t ins1_n,
                           uint8_t *const *ins2, int32_t ins2_n, int64_t n_pairs)
 {
     if (!h || !name || !seq_ascii || !hap1 || !hap2 || len <= 0 || n_pairs < 0) return DWGSIM_GPU_EINVAL;
     if (h->blob) { h->last_error = "add_contig after the genome was finalized: call run() first"; return DWGSIM_GPU_ESTATE; }
-    const size_t nl = strlen(name);
-    if (nl + h->prefix_s.size() + 128 > 1024) { h->last_error = "read name too long for the device formatter"; return DWGSIM_GPU_EUNSUPPORTED; }
-    const double t0 = now_ms();
-    h->queue.emplace_back();
-    HostContig &c = h->queue.back();
-    c.name = name; c.contig_i = contig_i; c.len = len; c.n_pairs = n_pairs;
-    const uint64_t *hap[2] = {hap1, hap2};
-    uint8_t *const *ins[2] = {ins1, ins2};
-    const int32_t ins_n[2] = {ins1_n, ins2_n};
-    int rc = pack_contig(h, c, seq_ascii, hap, ins, ins_n);
-    if (rc) { h->queue.pop_back(); return rc; }
-    h->max_name_len = std::max(h->max_name_len, (int)nl);
-    h->ms_pack += now_ms() - t0;
+    dwgsim_gpu_packed_t *p = nullptr;
+    const int rc = dwgsim_gpu_pack_contig(h, contig_i, name, seq_ascii, len, hap1, hap2, ins1, ins1_n, ins2, ins2_n, n_pairs, &p);
+    if (rc == DWGSIM_GPU_EUNSUPPORTED && !p) h->last_error = "read name too long for the device formatter, or an insertion longer than 2^27-1 bases";
+    else if (rc) h->last_error = "packing the contig failed (long insertion index out of range?)";
+    if (rc) return rc;
+    return dwgsim_gpu_add_packed(h, p);
+}
+
+int dwgsim_gpu_set_host_threads(dwgsim_gpu_t *h, int32_t n)
+{
+    if (!h || n < 0 || n > 1024) return DWGSIM_GPU_EINVAL;
+    h->host_threads = n;
     return DWGSIM_GPU_OK;
 }
 
@@ -1241,6 +1296,7 @@ int dwgsim_gpu_tables(const dwgsim_gpu_t *h, dwgsim_gpu_tables_t *t)
         t->n_cycles[e] = (int32_t)h->err_gap[e].size() - 1;
         t->err_gap[e] = h->err_gap[e].data(); t->err_acc[e] = h->err_acc[e].data(); t->qbase[e] = h->qbase[e].data();
         t->flow_thr[e] = h->flow_thr[e];
+        t->flow_gap[e] = h->flow_gap[e].data(); t->flow_gap_n[e] = (int32_t)h->flow_gap[e].size();
     }
     return DWGSIM_GPU_OK;
 }
@@ -1653,6 +1709,63 @@ int dwgsim_gpu_sink_fd(void *user, int file_id, const char *buf, size_t n)
         buf += w; n -= (size_t)w;
     }
     return 0;
+}
+
+// ---- file sink: one writer thread per file -------------------------------------------------------------------
+// Copying into the page cache is what bounds a file sink (a few GB/s per file: buffered writes to one file serialise
+// on its inode lock), so the three files of a batch are written side by side and while the device works on the next
+// batch: a chunk is handed to the file's writer and joined at the next chunk for that file (the buffer stays valid
+// until then, see dwgsim_gpu_sink_fn) or by dwgsim_gpu_file_sink_close.
+int dwgsim_gpu_pwrite_all(int fd, const char *buf, size_t n, int64_t offset)
+{
+    if (fd < 0) return 0;
+    while (n) {
+        ssize_t w = pwrite(fd, buf, n, (off_t)offset);
+        if (w < 0 && errno == ESPIPE) w = write(fd, buf, n);         // not seekable (pipe, character device)
+        if (w <= 0) return 1;
+        buf += w; n -= (size_t)w; offset += w;
+    }
+    return 0;
+}
+
+struct dwgsim_gpu_file_sink {
+    int fd[3];
+    int64_t offset[3];
+    std::thread writer[3];
+    int status[3];
+};
+
+dwgsim_gpu_file_sink_t *dwgsim_gpu_file_sink_open(const int32_t fd[3], const int64_t offset[3])
+{
+    dwgsim_gpu_file_sink *f = new dwgsim_gpu_file_sink();
+    for (int k = 0; k < 3; ++k) { f->fd[k] = fd ? fd[k] : -1; f->offset[k] = offset ? offset[k] : 0; f->status[k] = 0; }
+    return f;
+}
+static int file_sink_join(dwgsim_gpu_file_sink *f, int k)
+{
+    if (f->writer[k].joinable()) f->writer[k].join();
+    return f->status[k];
+}
+int dwgsim_gpu_sink_files(void *user, int file_id, const char *buf, size_t n)
+{
+    dwgsim_gpu_file_sink *f = (dwgsim_gpu_file_sink *)user;
+    if (!f || file_id < 0 || file_id > 2) return 1;
+    if (file_sink_join(f, file_id)) return 1;
+    const int fd = f->fd[file_id];
+    const int64_t at = f->offset[file_id];
+    f->offset[file_id] += (int64_t)n;
+    if (fd < 0 || n == 0) return 0;
+    int *st = &f->status[file_id];
+    f->writer[file_id] = std::thread([fd, buf, n, at, st]() { if (dwgsim_gpu_pwrite_all(fd, buf, n, at)) *st = 1; });
+    return 0;
+}
+int dwgsim_gpu_file_sink_close(dwgsim_gpu_file_sink_t *f, int64_t offset_out[3])
+{
+    if (!f) return 0;
+    int rc = 0;
+    for (int k = 0; k < 3; ++k) { if (file_sink_join(f, k)) rc = 1; if (offset_out) offset_out[k] = f->offset[k]; }
+    delete f;
+    return rc;
 }
 
 }  // extern "C"

@@ -996,15 +996,20 @@ struct Writer {
     // write has been joined: by the next write to the same file, or by flush() -- the host shell calls it after every
     // dwgsim_gpu_run, before the library can reuse its pinned slots.
     std::future<bool> pending[3];
+    int64_t offset[3] = {0, 0, 0};  // bytes handed to each file so far (positional writes)
     bool join(int id) { return pending[id].valid() ? pending[id].get() : true; }
     bool flush() { bool ok = true; for (int k = 0; k < 3; k++) ok = join(k) && ok; return ok; }
     bool write(int id, const char *buf, size_t n)
     {
         if (!fp[id] || n == 0) return true;
         if (!gz) {
+            // a positional write of the batch, started here and joined by the next write to the file or by flush(): the three
+            // files of a batch go out side by side and while the device works on the next batch
             if (!join(id)) return false;
-            FILE *f = fp[id];
-            pending[id] = std::async(std::launch::async, [f, buf, n]() { return fwrite(buf, 1, n, f) == n; });
+            const int fd = fileno(fp[id]);
+            const int64_t at = offset[id];
+            offset[id] += (int64_t)n;
+            pending[id] = std::async(std::launch::async, [fd, buf, n, at]() { return dwgsim_gpu_pwrite_all(fd, buf, n, at) == 0; });
             return true;
         }
         const size_t nblk = (n + kBlock - 1) / kBlock;
@@ -1040,7 +1045,8 @@ struct Writer {
     {
         flush();
         for (auto &f : fp) if (f) {
-            if (gz_file && ftell(f) == 0) {      // an empty gzip member, like gzclose on an untouched gzFile
+            const int k = (int)(&f - fp);
+            if (gz_file && ftell(f) == 0 && offset[k] == 0) {      // an empty gzip member, like gzclose on an untouched gzFile
                 gzFile g = gzdopen(dup(fileno(f)), "wb");
                 if (g) gzclose(g);
             }
@@ -1296,19 +1302,50 @@ int main(int argc, char **argv)
         }
         return nullptr;
     };
-    auto consume = [&](Job &j) -> bool {                                 // false: stop (the GPU path reported an error)
+    // The consumer side in two halves so they can run on two threads: prepare() writes the contig's mutation records and packs
+    // it for the device (host-only work on the dense arrays, which go back to the pool right after); execute() queues the
+    // packed contig, runs the read loop on the device(s) and writes the FASTQ files.
+    struct RunJob {
+        std::string name;
+        int seq_l = 0, l = 0, contig_i = 0;
+        long long n_pairs = 0;
+        std::vector<uint32_t> reg_start, reg_end;
+        dwgsim_gpu_packed_t *packed = nullptr;
+        double t_mut = 0, t_print = 0, t_pack = 0;
+        bool failed = false;
+    };
+    std::mutex gpu_mu;
+    auto prepare = [&](Job &j) -> std::unique_ptr<RunJob> {
+        std::unique_ptr<RunJob> r(new RunJob);
+        r->name = j.name; r->seq_l = j.seq_l; r->l = j.l; r->contig_i = j.contig_i; r->n_pairs = j.n_pairs; r->t_mut = j.t_mut;
+        r->reg_start = j.reg_start; r->reg_end = j.reg_end;
         double t0 = now();
-        t_mut += j.t_mut;
         if (o.output_type != 1) print_mutations(j.name.c_str(), j.seq, j.h1, j.h2, fp_txt, fp_vcf, j.have_events ? &j.events : nullptr);
-        t_print += now() - t0;
-        bases_in += j.seq_l;
+        r->t_print = now() - t0;
         if (o.output_type != 2 && j.n_pairs > 0) {
-            if (!gpu) gpu_open();
+            { std::lock_guard<std::mutex> g(gpu_mu); if (!gpu) gpu_open(); }
             t0 = now();
-            int rc = dwgsim_gpu_add_contig(gpu, j.contig_i, j.name.c_str(), j.seq.data(), j.seq_l, j.h1.s.data(), j.h2.s.data(), j.h1.ins.data(),
-                                           (int32_t)j.h1.ins.size(), j.h2.ins.data(), (int32_t)j.h2.ins.size(), j.n_pairs);
+            const int rc = dwgsim_gpu_pack_contig(gpu, j.contig_i, j.name.c_str(), j.seq.data(), j.seq_l, j.h1.s.data(), j.h2.s.data(), j.h1.ins.data(),
+                                                  (int32_t)j.h1.ins.size(), j.h2.ins.data(), (int32_t)j.h2.ins.size(), j.n_pairs, &r->packed);
+            r->t_pack = now() - t0;
+            if (rc != DWGSIM_GPU_OK) {
+                fprintf(stderr, "\r[dwgsim_core] %s: packing '%s' for the device failed\n", dwgsim_gpu_strerror(rc), j.name.c_str());
+                r->failed = true;
+            }
+        }
+        return r;
+    };
+    auto execute = [&](RunJob &j) -> bool {                              // false: stop (the GPU path reported an error)
+        t_mut += j.t_mut; t_print += j.t_print;
+        bases_in += j.seq_l;
+        if (j.failed) { rc_exit = 1; return false; }
+        if (j.packed) {
+            const double t0 = now();
+            int rc = dwgsim_gpu_add_packed(gpu, j.packed);
+            j.packed = nullptr;
             if (rc == DWGSIM_GPU_OK && use_regions) rc = dwgsim_gpu_set_regions(gpu, j.reg_start.data(), j.reg_end.data(), (int32_t)j.reg_start.size(), j.l);
             dwgsim_gpu_stats_t st;
+            memset(&st, 0, sizeof st);
             if (rc == DWGSIM_GPU_OK) rc = dwgsim_gpu_run(gpu, sink_cb, &wr, &st);
             if (!wr.flush() && rc == DWGSIM_GPU_OK) { fprintf(stderr, "\r[dwgsim_core] Error: writing the FASTQ files failed\n"); rc_exit = 1; return false; }
             if (rc != DWGSIM_GPU_OK) {
@@ -1316,49 +1353,88 @@ int main(int argc, char **argv)
                 rc_exit = 1;
                 return false;
             }
-            t_gpu += now() - t0; t_pack += st.ms_pack * 1e-3; t_kernels += (st.ms_simulate + st.ms_layout + st.ms_format) * 1e-3;
+            t_gpu += now() - t0; t_pack += j.t_pack; t_kernels += (st.ms_simulate + st.ms_layout + st.ms_format) * 1e-3;
             bytes_out += st.bytes[0] + st.bytes[1] + st.bytes[2];
             ctr += (unsigned long long)j.n_pairs; n_sim += j.n_pairs;
             fprintf(stderr, "\r[dwgsim_core] %llu", ctr);
         }
         return true;
     };
-    // The prologue is memory-bound (17 B/base of dense arrays): a second thread only pays when there is GPU work to hide
+    // The prologue is memory-bound (17 B/base of dense arrays): more threads only pay when there is GPU work to hide
     // behind it.  DWGSIM_PIPELINE=0/1 overrides.
     const char *pipe_env = getenv("DWGSIM_PIPELINE");
     const bool pipelined = pipe_env ? atoi(pipe_env) != 0 : (o.output_type != 2 && (o.N > 0 || o.C > 0));
     if (!pipelined) {
-        for (;;) { std::unique_ptr<Job> j = produce(); if (!j || !consume(*j)) break; recycle(std::move(j)); }
+        for (;;) {
+            std::unique_ptr<Job> j = produce();
+            if (!j) break;
+            std::unique_ptr<RunJob> r = prepare(*j);
+            recycle(std::move(j));
+            if (!execute(*r)) break;
+        }
     } else {
-        // bounded hand-over: at most one finished contig waits while the next is being prepared (three contigs in memory)
-        std::mutex mu;
-        std::condition_variable cv;
-        std::unique_ptr<Job> slot;
-        bool slot_full = false, done = false, stop = false;
+        // Three stages, one contig each: mut_diref (producer thread; the drand48 stream stays in contig order) -> mutation
+        // files + packing (packer thread) -> device read loop + FASTQ files (this thread).  Bounded hand-over: one finished
+        // item waits per stage, so at most three contigs hold dense arrays.
+        struct Slot {
+            std::mutex mu;
+            std::condition_variable cv;
+            bool full = false, done = false, stop = false;
+        } sa, sb;
+        std::unique_ptr<Job> slot_a;
+        std::unique_ptr<RunJob> slot_b;
         std::thread producer([&]() {
             for (;;) {
                 std::unique_ptr<Job> j = produce();
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&]() { return !slot_full || stop; });
-                if (stop) return;
-                if (!j) { done = true; cv.notify_all(); return; }
-                slot = std::move(j); slot_full = true;
-                cv.notify_all();
+                std::unique_lock<std::mutex> lk(sa.mu);
+                sa.cv.wait(lk, [&]() { return !sa.full || sa.stop; });
+                if (sa.stop) return;
+                if (!j) { sa.done = true; sa.cv.notify_all(); return; }
+                slot_a = std::move(j); sa.full = true;
+                sa.cv.notify_all();
             }
         });
-        for (;;) {
-            std::unique_ptr<Job> j;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&]() { return slot_full || done; });
-                if (!slot_full) break;
-                j = std::move(slot); slot_full = false;
-                cv.notify_all();
+        std::thread packer([&]() {
+            for (;;) {
+                std::unique_ptr<Job> j;
+                {
+                    std::unique_lock<std::mutex> lk(sa.mu);
+                    sa.cv.wait(lk, [&]() { return sa.full || sa.done || sa.stop; });
+                    if (sa.stop) return;
+                    if (!sa.full) break;                                  // done
+                    j = std::move(slot_a); sa.full = false;
+                    sa.cv.notify_all();
+                }
+                std::unique_ptr<RunJob> r = prepare(*j);
+                recycle(std::move(j));
+                std::unique_lock<std::mutex> lk(sb.mu);
+                sb.cv.wait(lk, [&]() { return !sb.full || sb.stop; });
+                if (sb.stop) { if (r->packed) dwgsim_gpu_packed_free(r->packed); return; }
+                slot_b = std::move(r); sb.full = true;
+                sb.cv.notify_all();
             }
-            if (!consume(*j)) { std::unique_lock<std::mutex> lk(mu); stop = true; cv.notify_all(); break; }
-            recycle(std::move(j));
+            std::unique_lock<std::mutex> lk(sb.mu);
+            sb.done = true;
+            sb.cv.notify_all();
+        });
+        for (;;) {
+            std::unique_ptr<RunJob> r;
+            {
+                std::unique_lock<std::mutex> lk(sb.mu);
+                sb.cv.wait(lk, [&]() { return sb.full || sb.done; });
+                if (!sb.full) break;
+                r = std::move(slot_b); sb.full = false;
+                sb.cv.notify_all();
+            }
+            if (!execute(*r)) {
+                { std::unique_lock<std::mutex> lk(sb.mu); sb.stop = true; sb.cv.notify_all(); }
+                { std::unique_lock<std::mutex> lk(sa.mu); sa.stop = true; sa.cv.notify_all(); }
+                break;
+            }
         }
+        packer.join();
         producer.join();
+        if (slot_b && slot_b->packed) dwgsim_gpu_packed_free(slot_b->packed);
     }
     if (!rc_exit) fprintf(stderr, "\n[dwgsim_core] Complete!\n");
     if (getenv("DWGSIM_STATS")) {

@@ -280,11 +280,25 @@ struct FlowRng {
     uint32_t end, next;
     uint4 blk;
     int have;
+    // the per-flow error coin ("drand48() < e", src/dwgsim.c:290,372) as a Bernoulli process generated from its geometric
+    // gaps: `left` failures are still to come before the next success (succ) or the next draw (!succ); one FLOW draw per
+    // success instead of one per trial (oracle: flow_coin)
+    int left = 0;
+    bool succ = false, need = true;
     __device__ __forceinline__ uint32_t draw()
     {
         const int b = (int)(next >> 2);
         if (b != have) { have = b; blk = draw_block(key, kStFlow, end, (uint32_t)b); }
         return word_of(blk, next++ & 3u);
+    }
+    __device__ __forceinline__ bool coin(const uint32_t *__restrict__ gap)
+    {
+        for (;;) {
+            if (need) { const int g = table_rank(gap, kFlowGapN, draw()); left = g; succ = g < kFlowGapN; need = false; }
+            if (left > 0) { --left; return false; }
+            need = true;
+            if (succ) return true;
+        }
     }
 };
 __device__ __forceinline__ void warp_reverse(uint8_t *seq, int len, int lane)
@@ -318,7 +332,7 @@ __device__ __forceinline__ void warp_shift_down(uint8_t *seq, int i, int len, in
 }
 // returns the new length, -1 when the first base is not in the flow order (src/dwgsim.c:275-278);
 // *overflow is set when the read would grow past `cap` symbols
-__device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int strand, uint32_t thr, const int8_t *fo,
+__device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int strand, const uint32_t *__restrict__ gap, const int8_t *fo,
                                            int fl, uint8_t *mask, FlowRng &rng, int *n_err_out, int *overflow, int lane)
 {
     for (int j = lane; j < len; j += 32) if (seq[j] >= 4) seq[j] = 0;          // src/dwgsim.c:253-257
@@ -339,7 +353,7 @@ __device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int s
         if (prev_c != c) {
             if (lane == 0) mask[flow_i] = 0;
             int n_err = 0;
-            while (rng.draw() < thr) ++n_err;
+            while (rng.coin(gap)) ++n_err;
             if (n_err > 0) {
                 if (!(rng.draw() >> 31)) {                                       // U < 0.5: insertion
                     if (len + n_err >= cap) { *overflow = 1; return len; }
@@ -378,7 +392,7 @@ __device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int s
         const int c = seq[i];
         while (c != fo[flow_i]) {
             int n_err = 0;
-            while (rng.draw() < thr) ++n_err;
+            while (rng.coin(gap)) ++n_err;
             if (n_err > 0 && mask[flow_i] == 0) {
                 if (len + n_err >= cap) { *overflow = 1; return len; }
                 __syncwarp();
@@ -530,7 +544,7 @@ simulate_pairs_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64
                     int nerr = 0, ovf = 0, nl = 0;
                     if (s[j] > 0) {
                         FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
-                        nl = flow_errors(code[j], s[j], P.cap[j], strand[j], P.flow_thr[j], flow_order, P.flow_order_len,
+                        nl = flow_errors(code[j], s[j], P.cap[j], strand[j], P.flow_gap[j], flow_order, P.flow_order_len,
                                          flow_mask, rng, &nerr, &ovf, lane);
                     }
                     if (ovf && lane == 0) atomicOr(status, 2ull);
@@ -857,7 +871,7 @@ __device__ __forceinline__ void nib_reverse(uint32_t *r, int len)
     for (int dw = 0; dw < nw; ++dw) r[dw] = tmp[dw];
     if (len & 7) r[nw - 1] &= ~(~0u << ((len & 7) << 2));
 }
-__device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int cap, int strand, uint32_t thr, const int8_t *fo, int fl,
+__device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int cap, int strand, const uint32_t *__restrict__ gap, const int8_t *fo, int fl,
                                                   uint32_t *mask /* ceil(fl/32) words of this thread */, FlowRng &rng, int *n_err_out,
                                                   int *overflow)
 {
@@ -885,7 +899,7 @@ __device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int ca
         if (prev_c != c) {                                          // first base of a homopolymer
             mask[flow_i >> 5] &= ~(1u << (flow_i & 31));
             int n_err = 0;
-            while (rng.draw() < thr) ++n_err;
+            while (rng.coin(gap)) ++n_err;
             if (n_err > 0) {
                 if (!(rng.draw() >> 31)) {
                     if (len + n_err >= cap) { *overflow = 1; return len; }
@@ -919,7 +933,7 @@ __device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int ca
     while (i < len) {                                              // pass 2, src/dwgsim.c:366-406
         if (c2 == fo[flow_i]) { ++i; if (i < len) c2 = (int)nib_get(row, i); continue; }
         int n_err = 0;
-        while (rng.draw() < thr) ++n_err;
+        while (rng.coin(gap)) ++n_err;
         if (n_err > 0 && !((mask[flow_i >> 5] >> (flow_i & 31)) & 1u)) {
             if (len + n_err >= cap) { *overflow = 1; return len; }
             nib_insert(row, i, len, n_err, (uint32_t)fo[flow_i]);
@@ -1224,7 +1238,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     if (s <= 0) continue;
                     int nerr = 0, ovf = 0;
                     FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
-                    const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_thr[j], T.flow_order,
+                    const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_gap[j], T.flow_order,
                                                       P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
                     if (ovf) atomicOr(status, 2ull);
                     rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);

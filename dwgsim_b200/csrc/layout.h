@@ -116,7 +116,9 @@ struct SimParams {
     const uint32_t *err_gap[2], *err_acc[2];   // substitution errors by thinning (DESIGN.md "RNG addressing")
     const uint8_t  *qbase[2];
     const int8_t   *flow_order;
+    const uint32_t *flow_gap[2];               // Ion Torrent: [kFlowGapN] geometric gap CDF of the per-flow error coin of each end
     const char     *prefix;
 };
+constexpr int kFlowGapN = 4096;                // a draw beyond the table: kFlowGapN failures, then a new draw (oracle: ORC_FLOW_GAP_N)
 
 }  // namespace dwg

@@ -84,7 +84,10 @@ typedef struct {
     double  ms_compress;           /* device time of the gzip kernels                               */
 } dwgsim_gpu_stats_t;
 
-/* receives FASTQ bytes strictly in pair-index order per file id; buf is only valid during the call.
+/* receives FASTQ bytes strictly in pair-index order per file id.  buf points into the library's pinned ring and stays
+ * valid until the NEXT sink call for the same file id or the return of dwgsim_gpu_run, whichever comes first (the ring
+ * has at least two slots and a slot is reused only after the following batch was handed over): a sink may return at
+ * once and finish writing in the background, provided it joins that write at its next call for the file.
  * Return 0 to continue, non-zero to abort the run (-> DWGSIM_GPU_ESINK). */
 typedef int (*dwgsim_gpu_sink_fn)(void *user, int file_id, const char *buf, size_t n);
 
@@ -114,6 +117,19 @@ int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name,
                           uint8_t *const *ins1, int32_t ins1_n,
                           uint8_t *const *ins2, int32_t ins2_n,
                           int64_t n_pairs);
+/* The same in two calls, for hosts that pipeline: pack_contig does all the host work of add_contig on the caller's arrays
+ * (they may be freed when it returns) and may run on another thread while dwgsim_gpu_run is in flight on the handle;
+ * add_packed queues the result (and takes ownership of it) between two runs. */
+typedef struct dwgsim_gpu_packed dwgsim_gpu_packed_t;
+int dwgsim_gpu_pack_contig(const dwgsim_gpu_t *h, int32_t contig_i, const char *name,
+                           const uint8_t *seq_ascii, int32_t len, const uint64_t *hap1, const uint64_t *hap2,
+                           uint8_t *const *ins1, int32_t ins1_n, uint8_t *const *ins2, int32_t ins2_n,
+                           int64_t n_pairs, dwgsim_gpu_packed_t **out);
+int dwgsim_gpu_add_packed(dwgsim_gpu_t *h, dwgsim_gpu_packed_t *p);
+void dwgsim_gpu_packed_free(dwgsim_gpu_packed_t *p);
+/* threads the packer may use per contig (0 = default: the hardware threads, at most 32; several ranks on one host
+ * should share the cores) */
+int dwgsim_gpu_set_host_threads(dwgsim_gpu_t *h, int32_t n);
 /* -x (targeted regions) for the contig just queued by add_contig: its regions as regions_bed_init leaves them
  * (src/regions_bed.c:43-115: BED half-open, sorted by start, overlapping ones merged) and `sample_len`, the `l`
  * the reference's sampler draws in at that point (src/dwgsim.c:539-553: the total region length, except for the
@@ -205,6 +221,16 @@ int dwgsim_gpu_sink_count(void *user, int file_id, const char *buf, size_t n);
 /* user = int[3]: a file descriptor per file id (-1 discards); write(2)s every chunk */
 int dwgsim_gpu_sink_fd(void *user, int file_id, const char *buf, size_t n);
 
+/* File sink with one writer thread per file id: user = the handle of dwgsim_gpu_file_sink_open (fd[k] = -1 discards,
+ * offset[k] = where the first byte of file k goes; NULL: 0).  A chunk is written positionally in the background and joined
+ * at the next chunk for the same file or by close(), which also reports the end offsets and returns non-zero if any write
+ * failed.  Call close() after dwgsim_gpu_run returned and before the next run on the same handle. */
+typedef struct dwgsim_gpu_file_sink dwgsim_gpu_file_sink_t;
+dwgsim_gpu_file_sink_t *dwgsim_gpu_file_sink_open(const int32_t fd[3], const int64_t offset[3]);
+int dwgsim_gpu_sink_files(void *user, int file_id, const char *buf, size_t n);
+int dwgsim_gpu_file_sink_close(dwgsim_gpu_file_sink_t *f, int64_t offset_out[3]);
+int dwgsim_gpu_pwrite_all(int fd, const char *buf, size_t n, int64_t offset);   /* 0 when every byte was written */
+
 /* -- derived tables (exposed so tests can compare them with the oracle's) ---------------------- */
 typedef struct {
     uint64_t thr_genomic, thr_hap0;
@@ -216,6 +242,8 @@ typedef struct {
     const uint32_t *err_gap[2], *err_acc[2];
     const uint8_t  *qbase[2];
     uint32_t flow_thr[2];
+    const uint32_t *flow_gap[2];   /* Ion Torrent: geometric gap CDF of the per-flow error coin (flow_gap_n entries; 1 otherwise) */
+    int32_t  flow_gap_n[2];
 } dwgsim_gpu_tables_t;
 int dwgsim_gpu_tables(const dwgsim_gpu_t *h, dwgsim_gpu_tables_t *out);   /* host copies */
 

@@ -83,8 +83,11 @@ typedef struct {
     uint32_t *err_gap[2];       /* candidate gap = #{g : u32 >= err_gap[end][g]}, g < read length  */
     uint32_t *err_acc[2];       /* candidate at cycle i becomes an error iff u32 < err_acc[end][i] */
     uint8_t  *qbase[2];         /* Phred before noise, 0..40, per cycle                           */
-    uint32_t flow_thr[2];       /* Ion Torrent: per-flow error coin of each end, u32 < flow_thr   */
+    uint32_t flow_thr[2];       /* Ion Torrent: per-flow error probability of each end as a 32-bit threshold */
+    uint32_t *flow_gap[2];      /* Ion Torrent: failures before the next success of the per-flow coin =          */
+                                /* #{g < ORC_FLOW_GAP_N : u32 >= flow_gap[end][g]}; ORC_FLOW_GAP_N = "no success yet" */
 } orc_tables_t;
+#define ORC_FLOW_GAP_N 4096
 
 typedef struct {
     int64_t n_pairs_total;      /* pairs written (genomic + random)                               */

@@ -39,7 +39,11 @@ class OrcTables(C.Structure):
         ("qdelta_lo", C.c_int32), ("qdelta_n", C.c_int32), ("qdelta_cdf", C.POINTER(C.c_uint32)),
         ("n_cycles", C.c_int32 * 2), ("err_gap", C.POINTER(C.c_uint32) * 2), ("err_acc", C.POINTER(C.c_uint32) * 2),
         ("qbase", C.POINTER(C.c_uint8) * 2), ("flow_thr", C.c_uint32 * 2),
+        ("flow_gap", C.POINTER(C.c_uint32) * 2),
     ]
+
+
+FLOW_GAP_N = 4096
 
 
 class OrcStats(C.Structure):

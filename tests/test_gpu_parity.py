@@ -138,3 +138,16 @@ def test_contig_names_grow_between_runs(oracle, growing_names_fa, tmp_path, data
     """run() once per contig with ever longer contig names: the name, stream and pinned buffers must grow with them"""
     opts = dict(seed=8, N=6000, data_type=data_type, length=(50, 50) if data_type else (100, 100))
     check(oracle, opts, growing_names_fa, tmp_path, per_contig_runs=True, batch=4096)
+
+
+def test_flow_gap_tables_equal_oracle(oracle):
+    """Ion Torrent: the geometric gap table of the per-flow error coin == the oracle's"""
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    opts = dict(seed=1, C=1, data_type=2, length=(200, 100), e=0.013, E=0.04, flow_order=make_golden.FLOW)
+    o = oracle.make_opt(**opts)
+    t = oracle.lib().orc_tables_build(o).contents
+    with DwgsimGpu(params_from_options(**{k: v for k, v in opts.items() if k in gh.GPU_KEYS})) as gpu:
+        g = gpu.tables()
+        for e in range(2):
+            assert g.flow_gap_n[e] == oracle.FLOW_GAP_N
+            assert [g.flow_gap[e][i] for i in range(oracle.FLOW_GAP_N)] == [t.flow_gap[e][i] for i in range(oracle.FLOW_GAP_N)]

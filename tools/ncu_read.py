@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""tools/ncu_read.py <file.ncu-rep>: key metrics per kernel from an ncu capture (runs without a GPU)."""
-import csv, io, subprocess, sys
+"""tools/ncu_read.py <file.ncu-rep> [--traffic out.json]: key metrics per kernel from an ncu capture (runs without a GPU).
+--traffic: the capture holds the launches of ONE device batch (tools/ncu_capture.sh with SKIP/COUNT on a batch boundary);
+their DRAM bytes are summed into out.json, which bench.py reports as roofline.traffic."""
+import csv, io, json, subprocess, sys
 
 KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -16,6 +18,18 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
+    if "--traffic" in sys.argv:
+        out_json = sys.argv[sys.argv.index("--traffic") + 1]
+        num = lambda r, k: float(r[col[k]].replace(",", ""))
+        scale = lambda k: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[col[k]]]
+        per = []
+        for r in rows[2:]:
+            rd, wr = num(r, "dram__bytes_read.sum") * scale("dram__bytes_read.sum"), num(r, "dram__bytes_write.sum") * scale("dram__bytes_write.sum")
+            per.append({"kernel": r[col["Kernel Name"]].split("(")[0], "us": num(r, "gpu__time_duration.sum"), "dram_read": rd, "dram_write": wr})
+        rec = {"dram_bytes_per_batch": sum(k["dram_read"] + k["dram_write"] for k in per), "pairs_per_batch": 1 << 20, "kernels": per,
+               "source": "ncu --set full capture of the launches of one 2^20-pair device batch of bench.py (%s), dram__bytes_read.sum + dram__bytes_write.sum" % rep}
+        json.dump(rec, open(out_json, "w"), indent=1)
+        print("wrote", out_json, rec["dram_bytes_per_batch"])
     for r in rows[2:]:
         print("----", r[col["Kernel Name"]][:60])
         for k in KEYS:
