@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdwgsim_b200.so")
 SOURCES = ["dwgsim_gpu.cu"]
-DEPS = ["dwgsim_gpu.cu", "kernels.cuh", "layout.h", "gz_device.cuh", "gz_host.h", os.path.join("..", "..", "include", "dwgsim_gpu.h")]
+DEPS = ["dwgsim_gpu.cu", "kernels.cuh", "layout.h", "flow_model.h", "gz_device.cuh", "gz_host.h", os.path.join("..", "..", "include", "dwgsim_gpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
 

@@ -80,6 +80,7 @@ struct Workspace {
     unsigned long long *totals = nullptr;     // [8]: 0 n_random, 1..3 stream bytes
     unsigned long long *status = nullptr;     // [4]: error bits, failed attempts, sizes of the job lists F1, R1
     uint2 *jobs = nullptr;                    // [2][cap]: retry and random job lists of the simulate passes
+    uint32_t *flow_scratch = nullptr;         // Ion Torrent: one scratch row per resident thread of the simulate kernel (flow_model.h)
     char *out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint64_t out_cap[3] = {0, 0, 0};
     int32_t name_cap = 0;                     // the name / record bounds the buffers were sized with (update_caps raises them
@@ -222,8 +223,9 @@ size_t tp_smem_bytes(const SimParams &sp)
 {
     size_t words = (((size_t)kTpThreads * sp.row_stride + 3) & ~(size_t)3) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
     words += 2 * (size_t)sp.win_slots * kTpThreads;                                                 // the reference window
-    for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);
-    const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4;
+    if (sp.data_type != 2) for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);   // (not used by the flow model)
+    const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4 +
+                        (size_t)sp.flow_order_len * 8 + 32 + (size_t)kTpThreads * kFlowGapsAhead * 2;  // flow order, masks, nd table, gaps drawn ahead
     return words * 4 + 3 * 1026 * 2 + flow + 32;
 }
 
@@ -396,7 +398,7 @@ int upload_tables(dwgsim_gpu *h)
         // in place word by word and keep the conflict-free odd stride
         const int nw = s.nw[0] + s.nw[1];
         s.row_stride = (p.data_type != 2 && (nw & 3) == 2) ? nw : (nw | 1);
-        if (const char *e = getenv("DWGSIM_ROW_PAD")) if (atoi(e)) s.row_stride = nw | 1;
+        if (const char *e = getenv("DWGSIM_ROW_PAD")) if (atoi(e) && p.data_type != 2) s.row_stride = nw | 1;
     }
     s.inv_groups = (uint32_t)(4294967296.0 / std::max((s.cap[0] + 7) / 8 + (s.cap[1] + 7) / 8, 1)) + 1u;
     if (s.fmt_v2)                                              // format_fastq2_kernel: 16 bases per lane
@@ -667,7 +669,7 @@ void free_workspace(dwgsim_gpu *h)
 {
     Workspace &w = h->ws;
     cudaFree(w.recs); cudaFree(w.seqs); cudaFree(w.serial); cudaFree(w.lens); cudaFree(w.names); cudaFree(w.name_len);
-    cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status); cudaFree(w.jobs);
+    cudaFree(w.blk_rand); cudaFree(w.blk_len); cudaFree(w.totals); cudaFree(w.status); cudaFree(w.jobs); cudaFree(w.flow_scratch);
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(w.out[s][k]);
     for (int k = 0; k < 3; ++k) { cudaFree(w.gz_slots[k]); cudaFree(w.gz_out[0][k]); cudaFree(w.gz_out[1][k]); }
     cudaFree(w.gz_sizes); cudaFree(w.gz_offs); cudaFree(w.gz_totals); cudaFree(w.gz_hist);
@@ -707,6 +709,11 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         CUDA_TRY(h, cudaMalloc((void **)&w.status, 48));
         CUDA_TRY(h, cudaMemset(w.status, 0, 48));
         CUDA_TRY(h, cudaMalloc((void **)&w.jobs, (size_t)n * 2 * sizeof(uint2)));
+        if (h->sp.data_type == 2) {                             // at most 16 CTAs of the simulate kernel per SM
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+            CUDA_TRY(h, cudaMalloc((void **)&w.flow_scratch, (size_t)sms * 16 * kTpThreads * (size_t)std::max(h->sp.nw[0], h->sp.nw[1]) * 4 + 256));
+        }
         CUDA_TRY(h, cudaMallocHost((void **)&w.h_totals, 128));
         const uint64_t *cap = cap_now;
         for (int k = 0; k < 3; ++k) {
@@ -774,16 +781,16 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         int occ_tp = 1;
         if (sp.data_type == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<true>, kTpThreads, smem_tp);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<false>, kTpThreads, smem_tp);
-        const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::max(occ_tp, 1));
+        const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::min(std::max(occ_tp, 1), 16));
         JobLists J;
         J.retry = w.jobs; J.random = w.jobs + (size_t)w.cap_pairs; J.count = w.status + 2;
         // two passes (kernels.cuh "Job lists"): fresh pairs, then the retries and random pairs they left behind
         const int n_pass = sp.data_type == 2 ? 1 : 2;          // (Ion Torrent lanes finish their own retries)
         for (int pass = 0; pass < n_pass; ++pass) {
             if (sp.data_type == 2)
-                simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);
+                simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status, w.flow_scratch);
             else
-                simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status);
+                simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status, w.flow_scratch);
         }
         extra_launches = n_pass - 1;
     }
@@ -1054,7 +1061,7 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         const size_t smem_tp = tp_smem_bytes(sp);
         // one staging row per thread in shared memory bounds the combined read length (about 3,400 symbols); Ion Torrent
         // rows hold 2*len+64 symbols and longer ones fall back to the warp-per-pair kernel
-        const bool tp_fits = smem_tp <= 220 * 1024 && (sp.data_type != 2 || std::max(sp.nw[0], sp.nw[1]) <= kIonRowWordsMax);
+        const bool tp_fits = smem_tp <= 220 * 1024;
         const char *force = getenv("DWGSIM_ION_KERNEL");
         h->ion_warp_kernel = sp.data_type == 2 && (!tp_fits || (force && strcmp(force, "warp") == 0));
         if (sp.data_type != 2 && !tp_fits) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }

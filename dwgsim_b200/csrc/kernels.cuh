@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "layout.h"
+#include "flow_model.h"
 
 namespace dwg {
 
@@ -285,11 +286,17 @@ struct FlowRng {
     // success instead of one per trial (oracle: flow_coin)
     int left = 0;
     bool succ = false, need = true;
-    __device__ __forceinline__ uint32_t draw()
+    __device__ __forceinline__ uint32_t draw()                 // next word of the gap stream
     {
         const int b = (int)(next >> 2);
         if (b != have) { have = b; blk = draw_block(key, kStFlow, end, (uint32_t)b); }
         return word_of(blk, next++ & 3u);
+    }
+    uint32_t unext = 0;
+    __device__ __forceinline__ uint32_t unif()                 // next word of the events' uniform stream (oracle: flow_unif)
+    {
+        const uint4 b = draw_block(key, kStFlowU, end, unext >> 2);
+        return word_of(b, unext++ & 3u);
     }
     __device__ __forceinline__ bool coin(const uint32_t *__restrict__ gap)
     {
@@ -355,7 +362,7 @@ __device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int s
             int n_err = 0;
             while (rng.coin(gap)) ++n_err;
             if (n_err > 0) {
-                if (!(rng.draw() >> 31)) {                                       // U < 0.5: insertion
+                if (!(rng.unif() >> 31)) {                                       // U < 0.5: insertion
                     if (len + n_err >= cap) { *overflow = 1; return len; }
                     __syncwarp();
                     warp_shift_up(seq, i, len, n_err, lane);
@@ -374,7 +381,7 @@ __device__ __forceinline__ int flow_errors(uint8_t *seq, int len, int cap, int s
                         int j = 0;
                         while (next_c != fo[(flow_i + j) % fl]) ++j;
                         if (j <= 0) { *overflow = 2; return len; }
-                        const int k = (int)__umulhi(rng.draw(), (uint32_t)j);
+                        const int k = (int)__umulhi(rng.unif(), (uint32_t)j);
                         if (len + 1 >= cap) { *overflow = 1; return len; }
                         warp_shift_up(seq, i, len, 1, lane);
                         if (lane == 0) seq[i] = (uint8_t)fo[(flow_i + k) % fl];
@@ -684,6 +691,8 @@ struct TpTables {                     // shared-memory copies of the sampling ta
     const uint32_t *isize_cdf; const uint16_t *isize_guide;
     const uint32_t *gap[2], *acc[2]; const uint16_t *gap_guide[2];
     const int8_t *flow_order; uint32_t *flow_mask;
+    const uint16_t *flow_nd;           // [flow_order_len][4] steps to a base's next flow (flow_model.h)
+    uint16_t *flow_q;                  // this thread's kFlowGapsAhead gaps drawn ahead
 };
 __device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int solid)
 {
@@ -817,7 +826,6 @@ __device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int star
 // ---- Ion Torrent flow model, one thread per read, on a nibble-packed row (thread-per-pair kernel) ---------------
 // Same algorithm and draw order as flow_errors() above (src/dwgsim.c:246-417); the read lives in the thread's row of
 // the shared staging tile (8 symbols per word), so insertions / deletions are word-wise funnel shifts.
-constexpr int kIonRowWordsMax = 264;           // rows up to 2,112 symbols (reads up to 1,024 bases): bound of the local scratch
 
 __device__ __forceinline__ uint32_t nib_get(const uint32_t *r, int k) { return (r[k >> 3] >> ((k & 7) << 2)) & 15u; }
 __device__ __forceinline__ void nib_set(uint32_t *r, int k, uint32_t v)
@@ -826,125 +834,23 @@ __device__ __forceinline__ void nib_set(uint32_t *r, int k, uint32_t v)
     r[k >> 3] = (r[k >> 3] & ~(15u << sh)) | (v << sh);
 }
 __device__ __forceinline__ uint32_t nib_mask_ge(int k) { return (k & 7) ? ~0u << ((k & 7) << 2) : ~0u; }   // nibbles >= k&7 of k's word
-// symbols [i, len) move up by n, symbols [i, i+n) become v
-__device__ __forceinline__ void nib_insert(uint32_t *r, int i, int len, int n, uint32_t v)
-{
-    const int q = n >> 3, rr = n & 7, first_w = (i + n) >> 3;
-    for (int dw = (len + n - 1) >> 3; dw >= first_w; --dw) {
-        uint32_t x;
-        if (rr == 0) x = r[dw - q];
-        else { const int sw = dw - q - 1; x = __funnelshift_r(sw >= 0 ? r[sw] : 0u, r[sw + 1], (8 - rr) << 2); }
-        if (dw == first_w) { const uint32_t m = nib_mask_ge(i + n); x = (x & m) | (r[dw] & ~m); }
-        r[dw] = x;
-    }
-    for (int j = i; j < i + n; ++j) nib_set(r, j, v);
-}
-// symbols [i+n, len) move down by n
-__device__ __forceinline__ void nib_delete(uint32_t *r, int i, int len, int n)
-{
-    const int q = n >> 3, rr = n & 7, first_w = i >> 3, last_w = (len - n - 1) >> 3;
-    for (int dw = first_w; dw <= last_w; ++dw) {
-        const int sw = dw + q;
-        uint32_t x = rr == 0 ? r[sw] : __funnelshift_r(r[sw], r[sw + 1], rr << 2);
-        if (dw == first_w) { const uint32_t m = nib_mask_ge(i); x = (x & m) | (r[dw] & ~m); }
-        r[dw] = x;
-    }
-}
-__device__ __forceinline__ uint32_t rev_nibbles(uint32_t x)
-{
-    x = __brev(x);
-    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
-    return ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
-}
-// in-place reversal of the first len symbols through a thread-local scratch
-__device__ __forceinline__ void nib_reverse(uint32_t *r, int len)
-{
-    uint32_t tmp[kIonRowWordsMax];
-    const int nw = (len + 7) >> 3;
-    for (int dw = 0; dw < nw; ++dw) {
-        const int a = len - 8 - 8 * dw;                       // source symbol of the word's LAST nibble
-        uint32_t x;
-        if (a >= 0) x = (a & 7) ? __funnelshift_r(r[a >> 3], r[(a >> 3) + 1], (a & 7) << 2) : r[a >> 3];
-        else x = r[0] << ((-a) << 2);
-        tmp[dw] = rev_nibbles(x);
-    }
-    for (int dw = 0; dw < nw; ++dw) r[dw] = tmp[dw];
-    if (len & 7) r[nw - 1] &= ~(~0u << ((len & 7) << 2));
-}
-__device__ __forceinline__ int flow_errors_thread(uint32_t *row, int len, int cap, int strand, const uint32_t *__restrict__ gap, const int8_t *fo, int fl,
-                                                  uint32_t *mask /* ceil(fl/32) words of this thread */, FlowRng &rng, int *n_err_out,
-                                                  int *overflow)
-{
-    for (int w = 0; w < ((len + 7) >> 3); ++w) { const uint32_t x = row[w]; row[w] = x & ~(((x & 0x44444444u) >> 2) * 15u); }   // N -> A
-    for (int w = 0; w < ((fl + 31) >> 5); ++w) mask[w] = 0;
-    if (strand) nib_reverse(row, len);
-    int i, flow_i;
+// the draw sources of flow_model.h's FlowCoin for one (pair, attempt, end): sequential words of the FLOW stream (gaps of the
+// error coin) and of the FLOWU stream (uniforms of the events)
+struct FlowDraw {
+    PairKey key;
+    uint32_t end, next, unext;
+    __device__ __forceinline__ uint32_t gap_word()
     {
-        const int c = len > 0 ? (int)nib_get(row, 0) : 0;
-        for (i = 0; i < fl; ++i) if (c == fo[i]) break;
-        if (i == fl) return -1;
+        const uint4 b = draw_block(key, kStFlow, end, next >> 2);
+        return word_of(b, next++ & 3u);
     }
-    flow_i = i;
-    // Both passes are written as ONE loop each whose iterations either step one flow or consume one base, so the
-    // threads of a warp (32 different reads) stay in the same loop body; the control flow is that of the reference.
-    int prev_c = 4;
-    i = 0;
-    while (i < len) {                                              // pass 1, src/dwgsim.c:281-364
-        const int c = (int)nib_get(row, i);
-        if (c != fo[flow_i]) {                                      // an empty flow
-            mask[flow_i >> 5] &= ~(1u << (flow_i & 31));
-            flow_i = flow_i + 1 == fl ? 0 : flow_i + 1;
-            continue;
-        }
-        if (prev_c != c) {                                          // first base of a homopolymer
-            mask[flow_i >> 5] &= ~(1u << (flow_i & 31));
-            int n_err = 0;
-            while (rng.coin(gap)) ++n_err;
-            if (n_err > 0) {
-                if (!(rng.draw() >> 31)) {
-                    if (len + n_err >= cap) { *overflow = 1; return len; }
-                    nib_insert(row, i, len, n_err, (uint32_t)c);
-                    len += n_err;
-                } else {
-                    int hp_l = 0, next_c = 4;
-                    for (int j = i; j < len; ++j, ++hp_l) { next_c = (int)nib_get(row, j); if (c != next_c) break; }
-                    if (hp_l < n_err) n_err = hp_l;
-                    nib_delete(row, i, len, n_err);
-                    len -= n_err;
-                    mask[flow_i >> 5] |= 1u << (flow_i & 31);
-                    if (n_err == hp_l && (i == 0 || prev_c == next_c)) {
-                        int j = 0;
-                        while (next_c != fo[(flow_i + j) % fl]) ++j;
-                        if (j <= 0) { *overflow = 2; return len; }
-                        const int k = (int)__umulhi(rng.draw(), (uint32_t)j);
-                        if (len + 1 >= cap) { *overflow = 1; return len; }
-                        nib_insert(row, i, len, 1, (uint32_t)fo[(flow_i + k) % fl]);
-                        len += 1;
-                    }
-                }
-                *n_err_out += n_err;
-            }
-            prev_c = c;
-        }
-        ++i;
+    __device__ __forceinline__ uint32_t unif_word()
+    {
+        const uint4 b = draw_block(key, kStFlowU, end, unext >> 2);
+        return word_of(b, unext++ & 3u);
     }
-    i = 0;
-    int c2 = len > 0 ? (int)nib_get(row, 0) : 0;                    // the base being matched: read once per position
-    while (i < len) {                                              // pass 2, src/dwgsim.c:366-406
-        if (c2 == fo[flow_i]) { ++i; if (i < len) c2 = (int)nib_get(row, i); continue; }
-        int n_err = 0;
-        while (rng.coin(gap)) ++n_err;
-        if (n_err > 0 && !((mask[flow_i >> 5] >> (flow_i & 31)) & 1u)) {
-            if (len + n_err >= cap) { *overflow = 1; return len; }
-            nib_insert(row, i, len, n_err, (uint32_t)fo[flow_i]);
-            len += n_err;
-            *n_err_out += n_err;
-        }
-        flow_i = flow_i + 1 == fl ? 0 : flow_i + 1;
-    }
-    if (strand) nib_reverse(row, len);
-    return len;
-}
+};
+constexpr int kFlowGapsAhead = 16;     // gaps every lane draws (four Philox blocks, sixteen table searches) before its read starts
 
 // Substitution errors (__gen_errors_mismatches, src/dwgsim.c:233-244) by thinning (DESIGN.md "RNG addressing"), applied to
 // the read's staged row after the walk: candidate n of a read sits 1 + rank(gap table, x_n) symbols after candidate
@@ -1016,7 +922,8 @@ __device__ __forceinline__ void list_push(uint2 *list, unsigned long long *count
 template <bool kIon>
 __global__ void __launch_bounds__(kTpThreads, kTpMinBlocks)
 simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n, int pass,
-                         JobLists J, PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status)
+                         JobLists J, PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status,
+                         uint32_t *__restrict__ flow_scratch /* Ion Torrent: [warps of the grid][max(nw0, nw1)][32] words */)
 {
     // the jobs of this pass: fresh pairs, or the two lists of the previous pass back to back
     const int n_f = pass == 0 ? 0 : (int)J.count[0], n_r = pass == 0 ? 0 : (int)J.count[1];
@@ -1038,25 +945,32 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         const bool isz_smem = P.isize_n <= kIsizeSmemMax;  // wider insert-size tables stay in HBM / L2 (one lookup per pair)
         uint32_t *isz = p32; p32 += isz_smem ? ((P.isize_n + 1) & ~1) : 0;
         uint32_t *gp[2], *ac[2];
-        for (int e = 0; e < 2; ++e) { gp[e] = p32; p32 += (P.len[e] + 1) & ~1; ac[e] = p32; p32 += (P.len[e] + 1) & ~1; }
+        // (the substitution-error tables are not used by the Ion Torrent flow model: no room taken for them there)
+        for (int e = 0; e < 2; ++e) { gp[e] = p32; p32 += kIon ? 0 : (P.len[e] + 1) & ~1; ac[e] = p32; p32 += kIon ? 0 : (P.len[e] + 1) & ~1; }
         uint16_t *p16 = reinterpret_cast<uint16_t *>(p32);
         uint16_t *ig = p16; p16 += 1026;
-        uint16_t *gg[2] = {p16, p16 + 1026};
+        uint16_t *gg[2] = {p16, kIon ? p16 : p16 + 1026};
         if (isz_smem) for (int j = threadIdx.x; j < P.isize_n; j += kTpThreads) isz[j] = P.isize_cdf[j];
         for (int j = threadIdx.x; j < 1025; j += kTpThreads) ig[j] = P.isize_guide[j];
-        for (int e = 0; e < 2; ++e) {
-            for (int j = threadIdx.x; j < P.len[e]; j += kTpThreads) { gp[e][j] = P.err_gap[e][j]; ac[e][j] = P.err_acc[e][j]; }
-            for (int j = threadIdx.x; j < 1025; j += kTpThreads) gg[e][j] = P.gap_guide[e][j];
-        }
+        if (!kIon)
+            for (int e = 0; e < 2; ++e) {
+                for (int j = threadIdx.x; j < P.len[e]; j += kTpThreads) { gp[e][j] = P.err_gap[e][j]; ac[e][j] = P.err_acc[e][j]; }
+                for (int j = threadIdx.x; j < 1025; j += kTpThreads) gg[e][j] = P.gap_guide[e][j];
+            }
         T.isize_cdf = isz_smem ? isz : P.isize_cdf; T.isize_guide = ig;
         for (int e = 0; e < 2; ++e) { T.gap[e] = gp[e]; T.acc[e] = ac[e]; T.gap_guide[e] = gg[e]; }
         // Ion Torrent: flow order (codes) and one flow-mask bit vector per thread
-        T.flow_order = nullptr; T.flow_mask = nullptr;
+        T.flow_order = nullptr; T.flow_mask = nullptr; T.flow_nd = nullptr; T.flow_q = nullptr;
         if (kIon) {
-            int8_t *fo = reinterpret_cast<int8_t *>(gg[1] + 1026);
+            int8_t *fo = reinterpret_cast<int8_t *>(p16);           // (behind the insert-size guide)
             for (int j = threadIdx.x; j < P.flow_order_len; j += kTpThreads) fo[j] = P.flow_order[j];
             T.flow_order = fo;
-            T.flow_mask = reinterpret_cast<uint32_t *>(fo + ((P.flow_order_len + 15) & ~15)) + (size_t)threadIdx.x * ((P.flow_order_len + 31) >> 5);
+            uint32_t *masks = reinterpret_cast<uint32_t *>(fo + ((P.flow_order_len + 15) & ~15));
+            T.flow_mask = masks + (size_t)threadIdx.x * ((P.flow_order_len + 31) >> 5);
+            uint16_t *nd = reinterpret_cast<uint16_t *>(masks + (size_t)kTpThreads * ((P.flow_order_len + 31) >> 5));
+            for (int j = threadIdx.x; j < 4 * P.flow_order_len; j += kTpThreads) nd[j] = (uint16_t)fm_build_nd_entry(P.flow_order, P.flow_order_len, j >> 2, j & 3);
+            T.flow_nd = nd;
+            T.flow_q = nd + ((4 * P.flow_order_len + 7) & ~7) + (size_t)threadIdx.x * kFlowGapsAhead;
         }
         __syncthreads();                                                 // the only CTA-wide barrier
     }
@@ -1237,9 +1151,22 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     const int s = j ? s1 : s0;
                     if (s <= 0) continue;
                     int nerr = 0, ovf = 0;
-                    FlowRng rng{key, (uint32_t)j, 0u, make_uint4(0, 0, 0, 0), -1};
-                    const int nl = flow_errors_thread(j ? dst1 : dst0, s, P.cap[j], j ? strand1 : strand0, P.flow_gap[j], T.flow_order,
-                                                      P.flow_order_len, T.flow_mask, rng, &nerr, &ovf);
+                    // the first gaps of the error coin, drawn while the lanes of the warp are together (a draw inside the
+                    // model runs for one lane at a time: a Philox block and a 12-step table search each)
+                    for (int b = 0; b < kFlowGapsAhead / 4; ++b) {
+                        const uint4 blk = draw_block(key, kStFlow, (uint32_t)j, (uint32_t)b);
+                        T.flow_q[4 * b + 0] = (uint16_t)table_rank(P.flow_gap[j], kFlowGapN, blk.x);
+                        T.flow_q[4 * b + 1] = (uint16_t)table_rank(P.flow_gap[j], kFlowGapN, blk.y);
+                        T.flow_q[4 * b + 2] = (uint16_t)table_rank(P.flow_gap[j], kFlowGapN, blk.z);
+                        T.flow_q[4 * b + 3] = (uint16_t)table_rank(P.flow_gap[j], kFlowGapN, blk.w);
+                    }
+                    FlowCoin<FlowDraw> rng(FlowDraw{key, (uint32_t)j, (uint32_t)kFlowGapsAhead, 0u}, P.flow_gap[j], T.flow_q, kFlowGapsAhead);
+                    // the read streams between its row in shared memory and a scratch row in HBM / L2 whose words are interleaved
+                    // with those of the warp's other lanes (coalesced: the lanes advance through their reads together)
+                    const int max_nw = P.nw[0] > P.nw[1] ? P.nw[0] : P.nw[1];
+                    const FlowRow ra{j ? dst1 : dst0, 1}, rb{flow_scratch + (size_t)(blockIdx.x * kTpWarps + warp) * max_nw * 32 + lane, 32};
+                    const int nl = flow_model_rows(ra, rb, s, P.cap[j], j ? strand1 : strand0, T.flow_order,
+                                                   P.flow_order_len, T.flow_nd, T.flow_mask, rng, &nerr, &ovf);
                     if (ovf) atomicOr(status, 2ull);
                     rec.len[j] = (uint16_t)(nl > 0 ? nl : 0);
                     rec.n_err[j] = (uint16_t)nerr;

@@ -76,7 +76,8 @@ constexpr uint8_t kRecRandom = 1, kRecStrand0 = 2, kRecStrand1 = 4, kRecHap1 = 8
 
 // ---- Philox addressing (DESIGN.md "RNG addressing"; oracle/dwgsim_oracle.c restates it) ---------
 constexpr uint32_t kPhiloxKey1 = 0x44574753u;  // "DWGS"
-enum : uint32_t { kStPair = 0, kStRandBase = 1, kStErr = 2, kStSub = 3, kStQual = 4, kStFlow = 5 };
+enum : uint32_t { kStPair = 0, kStRandBase = 1, kStErr = 2, kStFlowU = 3, kStQual = 4, kStFlow = 5 };   // kStFlow: gaps of the
+                                               // Ion Torrent error coin, kStFlowU: the uniforms of its events
 enum : uint32_t { kPairGate = 0, kPairIsize = 1, kPairPosHi = 2, kPairPosLo = 3, kPairHap = 4, kPairStrand = 5 };
 
 // ---- kernel parameters ---------------------------------------------------------------------------
