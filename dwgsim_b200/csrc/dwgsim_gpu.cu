@@ -399,6 +399,7 @@ int upload_tables(dwgsim_gpu *h)
         const int nw = s.nw[0] + s.nw[1];
         s.row_stride = (p.data_type != 2 && (nw & 3) == 2) ? nw : (nw | 1);
         if (const char *e = getenv("DWGSIM_ROW_PAD")) if (atoi(e) && p.data_type != 2) s.row_stride = nw | 1;
+        if (p.data_type == 2) s.row_stride = 0;                 // Ion Torrent rows live in HBM / L2 (Workspace::flow_scratch)
     }
     s.inv_groups = (uint32_t)(4294967296.0 / std::max((s.cap[0] + 7) / 8 + (s.cap[1] + 7) / 8, 1)) + 1u;
     if (s.fmt_v2)                                              // format_fastq2_kernel: 16 bases per lane
@@ -712,7 +713,8 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         if (h->sp.data_type == 2) {                             // at most 16 CTAs of the simulate kernel per SM
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-            CUDA_TRY(h, cudaMalloc((void **)&w.flow_scratch, (size_t)sms * 16 * kTpThreads * (size_t)std::max(h->sp.nw[0], h->sp.nw[1]) * 4 + 256));
+            const size_t row_words = (size_t)(h->sp.nw[0] + h->sp.nw[1] + std::max(h->sp.nw[0], h->sp.nw[1]));
+            CUDA_TRY(h, cudaMalloc((void **)&w.flow_scratch, (size_t)sms * 16 * kTpThreads * row_words * 4 + 256));
         }
         CUDA_TRY(h, cudaMallocHost((void **)&w.h_totals, 128));
         const uint64_t *cap = cap_now;

@@ -689,6 +689,178 @@ void diref(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, 
     }
 }
 
+// mut_diref for long contigs on several threads, same bytes as diref() above.
+// The draws of mut_diref are the iterates X_1, X_2, ... of one LCG; which of them are BELOW the mutation rate does not
+// depend on the bases, so that question is answered for a whole range of iterates in parallel (phase B: thread t jumps to
+// its sub-range and lists the hits with the state before each).  Filling the dense arrays with the plain bases (16 B per
+// base, the memory-bound bulk of the work) is parallel too (phase A, which also counts the A/C/G/T bases per block: an
+// N consumes no draw).  What stays sequential is one step per mutation (phase C): from (base i, n draws consumed) the
+// next mutated base is the k-th A/C/G/T base from i on, k = next hit - n; the mutation itself -- its extra draws and a
+// deletion's extension -- runs through the scalar code of diref() with the generator set to the state before the hit.
+struct DirefHit { uint64_t n, x_before; };                      // iterate index (1-based) and the state before it
+uint64_t lcg_jump(uint64_t x, uint64_t n)                        // x advanced by n steps
+{
+    uint64_t a = 0x5DEECE66Dull, c = 0xBull;
+    const uint64_t M = 0xFFFFFFFFFFFFull;
+    for (; n; n >>= 1) {
+        if (n & 1) x = (a * x + c) & M;
+        c = (a * c + c) & M; a = (a * a) & M;
+    }
+    return x;
+}
+
+void diref_parallel(const Options &o, const std::vector<uint8_t> &seq, Hap &h1, Hap &h2, std::vector<int64_t> *events,
+                    std::vector<int64_t> *touched, int n_threads)
+{
+    const int64_t l = (int64_t)seq.size();
+    h1.reset((size_t)l); h2.reset((size_t)l);
+    Hap *ret[2] = {&h1, &h2};
+    const uint64_t thr = (uint64_t)std::ceil(std::ldexp(o.mut_rate, 48)), M = 0xFFFFFFFFFFFFull;
+    std::vector<int64_t> local;
+    std::vector<int64_t> &ev = events ? *events : local;
+    ev.clear();
+    if (touched) touched->clear();
+    const uint8_t *sq = seq.data();
+    uint64_t *s1 = h1.s.data(), *s2 = h2.s.data();
+    constexpr int kBlk = 256;                                    // bases per block of the A/C/G/T census
+    const int64_t nblk = (l + kBlk - 1) / kBlk;
+    std::vector<uint32_t> blk_acgt((size_t)nblk);
+    const int T = std::max(1, n_threads);
+    auto parallel = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto &x : th) x.join();
+    };
+    const bool timing = getenv("DWGSIM_DIREF_TIMING") != nullptr;
+    auto clk = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tA = clk();
+    // phase A: plain bases into both haplotypes, A/C/G/T census per block
+    parallel([&](int t) {
+        const int64_t b0 = nblk * t / T, b1 = nblk * (t + 1) / T;
+        for (int64_t b = b0; b < b1; ++b) {
+            const int64_t i0 = b * kBlk, i1 = std::min<int64_t>(l, i0 + kBlk);
+            uint32_t cnt = 0;
+            for (int64_t i = i0; i < i1; ++i) { const uint64_t c = g_nt4[sq[i]]; s1[i] = c; s2[i] = c; cnt += c < 4; }
+            blk_acgt[(size_t)b] = cnt;
+        }
+    });
+    uint64_t total_acgt = 0;
+    for (uint32_t c : blk_acgt) total_acgt += c;
+    // phase B: the hits among the iterates 1 .. n_max (more are listed on demand: deletions draw on N bases too, and every
+    // mutation draws a few times)
+    const uint64_t x0 = g_rng.x;
+    std::vector<DirefHit> hits;
+    uint64_t listed = 0;                                         // iterates 1 .. listed are covered by `hits`
+    auto list_hits = [&](uint64_t upto) {
+        if (upto <= listed) return;
+        const uint64_t from = listed, span = upto - from;
+        std::vector<std::vector<DirefHit>> part((size_t)T);
+        parallel([&](int t) {
+            const uint64_t a = from + span * (uint64_t)t / (uint64_t)T, b = from + span * (uint64_t)(t + 1) / (uint64_t)T;
+            uint64_t x = lcg_jump(x0, a), n = a;
+            std::vector<DirefHit> &out = part[(size_t)t];
+            while (n + 8 <= b) {                                 // eight independent jump-ahead steps at a time
+                uint64_t y[9];
+                y[0] = x;
+                uint64_t any = 0;
+                for (int k = 1; k <= 8; k++) { y[k] = (kJump.a[k] * x + kJump.c[k]) & M; any |= (uint64_t)(y[k] < thr); }
+                if (any) for (int k = 1; k <= 8; k++) if (y[k] < thr) out.push_back(DirefHit{n + (uint64_t)k, y[k - 1]});
+                x = y[8]; n += 8;
+            }
+            for (; n < b; ++n) { const uint64_t y = (x * 0x5DEECE66Dull + 0xBull) & M; if (y < thr) out.push_back(DirefHit{n + 1, x}); x = y; }
+        });
+        for (auto &v : part) hits.insert(hits.end(), v.begin(), v.end());
+        listed = upto;
+    };
+    const double tB = clk();
+    list_hits(total_acgt + total_acgt / 64 + 4096);
+    const double tC = clk();
+    // phase C: one step per mutation
+    int64_t i = 0;                                               // next base to look at
+    uint64_t n = 0;                                              // draws consumed so far
+    size_t hp = 0;
+    // the k-th (k >= 1) A/C/G/T base at or after i, or -1 when fewer remain
+    auto kth_acgt = [&](int64_t from, uint64_t k) -> int64_t {
+        int64_t p = from;
+        // the rest of from's block, then whole blocks, then inside the block that holds it
+        while (p < l) {
+            const int64_t b = p / kBlk, bend = std::min<int64_t>(l, (b + 1) * kBlk);
+            if (p == b * kBlk) {
+                const uint32_t c = blk_acgt[(size_t)b];
+                if (c < k) { k -= c; p = bend; continue; }
+                if (c == (uint32_t)(bend - p)) return p + (int64_t)k - 1;        // no N in the block
+            }
+            for (; p < bend; ++p) if (g_nt4[sq[p]] < 4 && --k == 0) return p;
+        }
+        return -1;
+    };
+    for (;;) {
+        while (hp < hits.size() && hits[hp].n <= n) ++hp;
+        if (hp == hits.size()) {
+            // no listed hit left: either the contig ends first, or more iterates have to be looked at (a long insertion or
+            // deletion can also have drawn past the listed range)
+            uint64_t rest = 0;
+            for (int64_t p = i; p < l; ++p) rest += g_nt4[sq[p]] < 4;
+            if (rest == 0) break;
+            if (listed >= n + rest) { n += rest; break; }        // the remaining bases draw listed iterates: none of them hits
+            if (listed < n) listed = n;                          // (iterates already consumed need no listing)
+            list_hits(std::min<uint64_t>(n + rest, listed + std::max<uint64_t>(listed / 8, 1 << 16)));
+            continue;
+        }
+        const int64_t t = kth_acgt(i, hits[hp].n - n);
+        if (t < 0) { for (int64_t p = i; p < l; ++p) n += g_nt4[sq[p]] < 4; break; }      // the contig ends before the hit
+        // base t draws iterate hits[hp].n, which is below the rate: the scalar code of diref() from here, until the mutation
+        // (and the deletion it may start) is over
+        g_rng.x = hits[hp].x_before;
+        uint64_t drawn = hits[hp].n - 1;
+        auto next = [&]() { ++drawn; return g_rng.next(); };
+        int deleting = 0, del_len = 0;
+        int64_t p = t;
+        for (; p < l; ++p) {
+            uint64_t c = (uint64_t)g_nt4[sq[p]];
+            if (deleting) {
+                if (del_len < o.indel_min || next() < o.indel_extend) {
+                    if (deleting & 1) s1[p] |= T_DELETE | c;
+                    if (deleting & 2) s2[p] |= T_DELETE | c;
+                    ev.push_back(p);
+                    del_len++;
+                    continue;
+                }
+                deleting = del_len = 0;
+            }
+            if (p != t) break;                                   // the mutation is over: back to skipping along the hit list
+            next();                                              // the draw that hit
+            ev.push_back(p);
+            if (next() >= o.indel_frac) {
+                const double r = next();
+                c = (c + (uint64_t)(r * 3.0 + 1)) & 3;
+                if (o.is_hap || next() < 0.333333) s1[p] = s2[p] = T_SUBST | c;
+                else ret[next() < 0.5 ? 0 : 1]->s[p] = T_SUBST | c;
+            } else if (next() < 0.5) {
+                if (o.is_hap || next() < 0.3333333) { s1[p] = s2[p] = T_DELETE | c; deleting = 3; }
+                else { deleting = next() < 0.5 ? 1 : 2; ret[deleting - 1]->s[p] = T_DELETE | c; }
+                del_len = 1;
+            } else {
+                const uint64_t before = g_rng.x;
+                add_insertion(o, h1, h2, p, c);
+                for (uint64_t y = before; y != g_rng.x; y = (y * 0x5DEECE66Dull + 0xBull) & M) ++drawn;   // its draws, counted
+            }
+        }
+        i = p; n = drawn;
+    }
+    g_rng.x = lcg_jump(x0, n);
+    const double tD = clk();
+    left_justify(seq, h1, h2, events ? &ev : nullptr, touched);
+    if (events && touched && !touched->empty()) {
+        ev.insert(ev.end(), touched->begin(), touched->end());
+        std::sort(ev.begin(), ev.end());
+        ev.erase(std::unique(ev.begin(), ev.end()), ev.end());
+    }
+    if (timing) fprintf(stderr, "[diref_parallel] %lld bases, %d threads: fill %.3f s, hits %.3f s (%zu), mutations %.3f s, justify %.3f s\n",
+                        (long long)l, T, tB - tA, tC - tB, hits.size(), tD - tC, clk() - tD);
+}
+
 // ---- mutations to replay: -m TXT (src/mut_txt.c), -b BED (src/mut_bed.c), -v VCF (src/mut_vcf.c) ------------------------
 struct ContigList { std::vector<std::string> name; std::vector<uint32_t> len; };
 struct MutRec {
@@ -1238,6 +1410,11 @@ int main(int argc, char **argv)
     std::mutex pool_mu;
     std::vector<std::unique_ptr<Job>> pool;         // finished jobs: their vectors keep capacity (and mapped pages) for the next contig
     auto recycle = [&](std::unique_ptr<Job> j) { std::lock_guard<std::mutex> g(pool_mu); pool.push_back(std::move(j)); };
+    // mut_diref of long contigs runs on several threads (diref_parallel); DWGSIM_DIREF_THREADS / DWGSIM_DIREF_PAR_MIN override
+    int diref_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2));
+    if (const char *e = getenv("DWGSIM_DIREF_THREADS")) diref_threads = std::max(1, atoi(e));
+    int64_t diref_par_min = 1 << 20;
+    if (const char *e = getenv("DWGSIM_DIREF_PAR_MIN")) diref_par_min = atoll(e);
     auto produce = [&]() -> std::unique_ptr<Job> {   // next simulated contig, or null at the end of the FASTA
         std::unique_ptr<Job> j;
         {
@@ -1292,6 +1469,8 @@ int main(int argc, char **argv)
             const double t0 = now();
             j->have_events = muts.kind < 0 && !getenv("DWGSIM_FULL_SCAN");
             if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, contig_i, muts, j->name.c_str());
+            else if (j->have_events && diref_threads > 1 && (int64_t)j->seq.size() >= diref_par_min)
+                diref_parallel(o, j->seq, j->h1, j->h2, &j->events, &j->touched, diref_threads);
             else if (j->have_events) diref(o, j->seq, j->h1, j->h2, &j->events, &j->touched);
             else diref(o, j->seq, j->h1, j->h2);
             j->t_mut = now() - t0;

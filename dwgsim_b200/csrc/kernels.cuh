@@ -681,8 +681,10 @@ __device__ __forceinline__ uint32_t fetch_codes(const ContigView &c, RefWindow &
     return x;
 }
 
-struct Emit {                          // emission state of one read
-    uint32_t *dst;                     // this thread's row of the CTA's shared staging tile (word w at dst[w])
+template <int kStride>
+struct EmitT {                         // emission state of one read
+    uint32_t *dst;                     // this thread's row: word w at dst[w * kStride] (the CTA's shared staging tile, stride 1;
+                                       //   Ion Torrent: a row in HBM interleaved with those of the warp's other lanes, stride 32)
     uint64_t acc; int na, w;           // pending nibbles, their count, next word index
     int k, nN;                         // symbols emitted, N bases seen (src/dwgsim.c:823-831)
     int solid; uint32_t prev;          // colour space: previous base, adaptor = 0 (src/dwgsim.c:845-858)
@@ -694,13 +696,15 @@ struct TpTables {                     // shared-memory copies of the sampling ta
     const uint16_t *flow_nd;           // [flow_order_len][4] steps to a base's next flow (flow_model.h)
     uint16_t *flow_q;                  // this thread's kFlowGapsAhead gaps drawn ahead
 };
-__device__ __forceinline__ void emit_begin(Emit &E, uint32_t *dst, int solid)
+template <int kStride>
+__device__ __forceinline__ void emit_begin(EmitT<kStride> &E, uint32_t *dst, int solid)
 {
     E.dst = dst; E.acc = 0; E.na = 0; E.w = 0; E.k = 0; E.nN = 0;
     E.solid = solid; E.prev = 0;
 }
 // append m <= 8 base codes (nibbles in the low bits of `codes`, zero above)
-__device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
+template <int kStride>
+__device__ __forceinline__ void emit_group(EmitT<kStride> &E, uint32_t codes, int m)
 {
     E.nN += __popc(codes & 0x44444444u);
     if (E.solid) {
@@ -711,11 +715,12 @@ __device__ __forceinline__ void emit_group(Emit &E, uint32_t codes, int m)
     }
     E.acc |= (uint64_t)codes << (4 * E.na);
     E.na += m; E.k += m;
-    if (E.na >= 8) { E.dst[E.w] = (uint32_t)E.acc; ++E.w; E.acc >>= 32; E.na -= 8; }
+    if (E.na >= 8) { E.dst[E.w * kStride] = (uint32_t)E.acc; ++E.w; E.acc >>= 32; E.na -= 8; }
 }
-__device__ __forceinline__ void emit_end(Emit &E)
+template <int kStride>
+__device__ __forceinline__ void emit_end(EmitT<kStride> &E)
 {
-    if (E.na > 0) { E.dst[E.w] = (uint32_t)E.acc; ++E.w; }
+    if (E.na > 0) { E.dst[E.w * kStride] = (uint32_t)E.acc; ++E.w; }
 }
 
 // The walk of gen_read() above executed by one thread as ONE loop: every iteration either emits up to eight
@@ -727,7 +732,8 @@ __device__ __forceinline__ int walk_hint(const ContigView &c, int h, int start, 
     if (start < 0 || start >= c.len) return 0;
     return (int)__ldg(c.blk[h] + (start >> kBlkShift) + (strand ? 1 : 0));
 }
-__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, Emit &E, Walk &w, int hint,
+template <int kStride>
+__device__ __forceinline__ bool walk_thread(const ContigView &c, int h, int start, int strand, int s, EmitT<kStride> &E, Walk &w, int hint,
                                             RefWindow &C)
 {
     const int dir = strand ? -1 : 1;
@@ -981,6 +987,12 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     const int solid = P.data_type == 1;
     const int s0 = P.len[0], s1 = P.len[1];
     uint32_t *dst0 = row, *dst1 = row + P.nw[0];
+    // Ion Torrent: the rows live in HBM / L2 instead, word w of lane l at warp_rows[w * 32 + l] (flow_model.h streams every read
+    // through its row and a scratch row; in shared memory the two would leave room for eight warps per SM)
+    constexpr int kRowStride = kIon ? 32 : 1;
+    const int max_nw = P.nw[0] > P.nw[1] ? P.nw[0] : P.nw[1];
+    uint32_t *const warp_rows = kIon ? flow_scratch + (size_t)(blockIdx.x * kTpWarps + warp) * (NW + max_nw) * 32 : nullptr;
+    if (kIon) { dst0 = warp_rows + lane; dst1 = dst0 + P.nw[0] * 32; }
     const uint32_t ring_base = smem_addr(win_mem) + threadIdx.x * 8;
     unsigned failed_total = 0;
 
@@ -1016,7 +1028,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     rec.pos[j] = 0; rec.len[j] = (uint16_t)s;
                     rec.n_err[j] = rec.n_sub[j] = rec.n_indel[j] = rec.n_indel_first[j] = 0;
                     if (s <= 0) continue;
-                    Emit E;
+                    EmitT<kRowStride> E;
                     emit_begin(E, j ? dst1 : dst0, solid);
                     for (int k = 0; k < s; k += 64) {
                         const uint4 blk = draw_block(key, kStRandBase, j, (uint32_t)(k >> 6));
@@ -1065,7 +1077,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                 pos = (int)__umul64hi(range, ((uint64_t)b0.z << 32) | b0.w);
                 if (P.regions && (pos = map_to_regions(blob, q, pos, d)) < 0) ok = false;
             }
-            Emit E0, E1;
+            EmitT<kRowStride> E0, E1;
             if (ok) {
                 const uint4 b1 = draw_block(key, kStPair, 0, 1);
                 hap = ((uint64_t)b1.x < P.thr_hap0) ? 0 : 1;
@@ -1163,8 +1175,7 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
                     FlowCoin<FlowDraw> rng(FlowDraw{key, (uint32_t)j, (uint32_t)kFlowGapsAhead, 0u}, P.flow_gap[j], T.flow_q, kFlowGapsAhead);
                     // the read streams between its row in shared memory and a scratch row in HBM / L2 whose words are interleaved
                     // with those of the warp's other lanes (coalesced: the lanes advance through their reads together)
-                    const int max_nw = P.nw[0] > P.nw[1] ? P.nw[0] : P.nw[1];
-                    const FlowRow ra{j ? dst1 : dst0, 1}, rb{flow_scratch + (size_t)(blockIdx.x * kTpWarps + warp) * max_nw * 32 + lane, 32};
+                    const FlowRow ra{j ? dst1 : dst0, 32}, rb{warp_rows + NW * 32 + lane, 32};
                     const int nl = flow_model_rows(ra, rb, s, P.cap[j], j ? strand1 : strand0, T.flow_order,
                                                    P.flow_order_len, T.flow_nd, T.flow_mask, rng, &nerr, &ovf);
                     if (ovf) atomicOr(status, 2ull);
@@ -1184,7 +1195,13 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
         // flush the warp's staged rows (pair-major in HBM, NW words per pair).  The rows of a pass-0 round are contiguous in
         // HBM; without row padding they are contiguous in shared memory too and leave as 16-byte vectors (rows of deferred
         // pairs go along and are overwritten by pass 1)
-        if (RS == NW && pass == 0 && jbase + 32 <= n_jobs) {
+        if (kIon) {
+            // the rows of the warp, interleaved in HBM / L2 -> pair-major rows of seqw (strided reads, coalesced writes)
+            for (int x = lane; x < 32 * NW; x += 32) {
+                const int r = (int)__umulhi((uint32_t)x, P.inv_nw), dp = __shfl_sync(0xffffffffu, staged, r);
+                if (dp >= 0) seqw[(size_t)dp * NW + (x - r * NW)] = warp_rows[(x - r * NW) * 32 + r];
+            }
+        } else if (RS == NW && pass == 0 && jbase + 32 <= n_jobs) {
             const uint4 *src = reinterpret_cast<const uint4 *>(wtile);
             uint4 *dst = reinterpret_cast<uint4 *>(seqw + (size_t)jbase * NW);
             for (int x = lane; x < 8 * NW; x += 32) dst[x] = src[x];

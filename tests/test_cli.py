@@ -78,6 +78,23 @@ def test_mutation_files_equal_oracle_C0(cli, oracle, synth_fa, ex1_fa, tmp_path,
         assert md5(a + "." + f) == md5(b + "." + f), f
 
 
+@pytest.mark.parametrize("case", ["defaults_ex1", "haploid_indel_min", "long_insertions", "high_rate", "skips_short_contig_paired"])
+@pytest.mark.parametrize("threads", [2, 5])
+def test_parallel_mut_diref_equals_oracle_C0(cli, oracle, synth_fa, ex1_fa, tmp_path, case, threads):
+    """mut_diref on several threads (hit list of the LCG iterates + one sequential step per mutation; long contigs only by
+    default, forced here for every contig) must write the files of the serial path"""
+    opts, which = MUT_CASES[case]
+    fasta = ex1_fa if which == "ex1" else synth_fa
+    opts = make_golden.materialize(dict(opts, C=0), str(tmp_path))
+    a, b = str(tmp_path / "cli"), str(tmp_path / "orc")
+    env = dict(os.environ, DWGSIM_DIREF_PAR_MIN="0", DWGSIM_DIREF_THREADS=str(threads))
+    subprocess.run([cli] + [str(x) for x in oracle.opt_to_ref_argv(**opts) + [fasta, a]], capture_output=True, check=True, env=env)
+    with oracle.Session(oracle.make_opt(**opts), fasta, b) as s:
+        assert s.stats.error == 0
+    for f in ("mutations.txt", "mutations.vcf"):
+        assert md5(a + "." + f) == md5(b + "." + f), f
+
+
 def test_option_surface(cli, synth_fa, tmp_path):
     assert run(cli, ["-h"], check=False).returncode == 1
     assert run(cli, [synth_fa], check=False).returncode == 1                       # needs <ref> <prefix>
