@@ -72,6 +72,7 @@ SYMBOLS = {
     "dwgsim_gpu_add_packed": (C.c_int, [_P, _P]),
     "dwgsim_gpu_packed_free": (None, [_P]),
     "dwgsim_gpu_set_host_threads": (C.c_int, [_P, C.c_int32]),
+    "dwgsim_gpu_warm": (C.c_int, [_P]),
     "dwgsim_gpu_set_regions": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.c_int32]),
     "dwgsim_gpu_run": (C.c_int, [_P, SINK_FN, _P, C.POINTER(Stats)]),
     "dwgsim_gpu_set_batch": (C.c_int, [_P, C.c_int64, C.c_int32]),

@@ -85,7 +85,8 @@ struct Workspace {
     uint64_t out_cap[3] = {0, 0, 0};
     int32_t name_cap = 0;                     // the name / record bounds the buffers were sized with (update_caps raises them
     uint64_t rec_cap[3] = {0, 0, 0};          //   when a later contig has a longer name)
-    unsigned long long *h_totals = nullptr;   // pinned [8 + 2]
+    unsigned long long *h_totals = nullptr;   // pinned, mapped [16]: batch totals the kernels publish straight to the host
+    unsigned long long *h_totals_dev = nullptr;   // its device alias (the copy engines stay free for the FASTQ streams)
     // device gzip writer
     uint8_t *gz_slots[3] = {nullptr, nullptr, nullptr};
     char *gz_out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
@@ -224,7 +225,8 @@ size_t tp_smem_bytes(const SimParams &sp)
     size_t words = (((size_t)kTpThreads * sp.row_stride + 3) & ~(size_t)3) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
     words += 2 * (size_t)sp.win_slots * kTpThreads;                                                 // the reference window
     if (sp.data_type != 2) for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);   // (not used by the flow model)
-    const size_t flow = (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4 +
+    const size_t flow = sp.data_type != 2 ? 0 :                                                      // Ion Torrent only:
+                        (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4 +
                         (size_t)sp.flow_order_len * 8 + 32 + (size_t)kTpThreads * kFlowGapsAhead * 2;  // flow order, masks, nd table, gaps drawn ahead
     return words * 4 + 3 * 1026 * 2 + flow + 32;
 }
@@ -716,7 +718,8 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
             const size_t row_words = (size_t)(h->sp.nw[0] + h->sp.nw[1] + std::max(h->sp.nw[0], h->sp.nw[1]));
             CUDA_TRY(h, cudaMalloc((void **)&w.flow_scratch, (size_t)sms * 16 * kTpThreads * row_words * 4 + 256));
         }
-        CUDA_TRY(h, cudaMallocHost((void **)&w.h_totals, 128));
+        CUDA_TRY(h, cudaHostAlloc((void **)&w.h_totals, 128, cudaHostAllocMapped));
+        CUDA_TRY(h, cudaHostGetDevicePointer((void **)&w.h_totals_dev, w.h_totals, 0));
         const uint64_t *cap = cap_now;
         for (int k = 0; k < 3; ++k) {
             w.out_cap[k] = align_up(cap[k] * (uint64_t)n + 256, 256);
@@ -742,8 +745,8 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
     if (want_pinned && h->pinned_slots == 0) {
         for (int s = 0; s < h->ring; ++s)
             for (int k = 0; k < 3; ++k) {
-                h->pinned_cap[k] = w.out_cap[k];
-                CUDA_TRY(h, cudaMallocHost((void **)&h->pinned[s][k], w.out_cap[k]));
+                h->pinned_cap[k] = std::max(w.out_cap[k], h->gz_mode ? w.gz_cap[k] : 0);
+                CUDA_TRY(h, cudaMallocHost((void **)&h->pinned[s][k], h->pinned_cap[k]));
             }
         h->pinned_slots = h->ring;
     }
@@ -809,7 +812,7 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
 int read_random_count(dwgsim_gpu *h, int64_t *n_random)
 {
     Workspace &w = h->ws;
-    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 8, cudaMemcpyDeviceToHost, h->s_compute));
+    publish_words_kernel<<<1, 32, 0, h->s_compute>>>(w.h_totals_dev, w.totals, 1);
     CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
     *n_random = (int64_t)w.h_totals[0];
     return DWGSIM_GPU_OK;
@@ -858,8 +861,9 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     }
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals, w.totals, 32, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals + 8, w.status, 16, cudaMemcpyDeviceToHost, st));
+    // (a copy would queue behind the batch-sized device-to-host transfers of the previous batches on the copy engine)
+    publish_words_kernel<<<1, 32, 0, st>>>(w.h_totals_dev, w.totals, 4);
+    publish_words_kernel<<<1, 32, 0, st>>>(w.h_totals_dev + 8, w.status, 2);
     *launches = 4;
     return DWGSIM_GPU_OK;
 }
@@ -967,12 +971,12 @@ int gz_batch(dwgsim_gpu *h, int dslot, const uint64_t bytes[3], uint64_t out_byt
         gz_compress_kernel<<<nm, kGzThreads, 0, st>>>((const uint8_t *)w.out[dslot][k], bytes[k], T, h->gz_crc, w.gz_slots[k], sizes);
         CUDA_TRY(h, cudaMemcpyAsync(offs, sizes, (size_t)nm * 8, cudaMemcpyDeviceToDevice, st));
         layout_scan_blocks_kernel<<<1, 1024, 0, st>>>(offs, nm, 1, w.gz_totals + k);
-        gz_compact_kernel<<<nm, 256, 0, st>>>(w.gz_slots[k], sizes, offs, (uint8_t *)w.gz_out[dslot][k]);
+        gz_compact_kernel<<<nm, 256, 0, st>>>(w.gz_slots[k], sizes, offs, (uint8_t *)w.gz_out[dslot][k], w.gz_cap[k]);
         *launches += 3;
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev_t[7], st));
-    CUDA_TRY(h, cudaMemcpyAsync(w.h_totals + 12, w.gz_totals, 24, cudaMemcpyDeviceToHost, st));
+    publish_words_kernel<<<1, 32, 0, st>>>(w.h_totals_dev + 12, w.gz_totals, 3);
     CUDA_TRY(h, cudaStreamSynchronize(st));
     { float ms = 0; cudaEventElapsedTime(&ms, h->ev_t[6], h->ev_t[7]); h->ms_gz += ms; }
     for (int k = 0; k < 3; ++k) {
@@ -1183,6 +1187,30 @@ int dwgsim_gpu_add_contig(dwgsim_gpu_t *h, int32_t contig_i, const char *name, c
     else if (rc) h->last_error = "packing the contig failed (long insertion index out of range?)";
     if (rc) return rc;
     return dwgsim_gpu_add_packed(h, p);
+}
+
+int dwgsim_gpu_warm(dwgsim_gpu_t *h)
+{
+    if (!h) return DWGSIM_GPU_EINVAL;
+    // the batch workspace and the pinned ring (the slow part: page-locking a GB takes about a second) of every device,
+    // sized for the names seen so far plus some room; run() allocates the same on first use otherwise
+    std::vector<dwgsim_gpu *> all{h};
+    all.insert(all.end(), h->peers.begin(), h->peers.end());
+    std::vector<int> rcs(all.size(), DWGSIM_GPU_OK);
+    std::vector<std::thread> th;
+    auto one = [&](size_t i) {
+        dwgsim_gpu *q = all[i];
+        cudaSetDevice(q->device);
+        int rc = update_caps(q);
+        if (rc == DWGSIM_GPU_OK) rc = ensure_workspace(q, q->batch_pairs, true);
+        rcs[i] = rc;
+    };
+    for (size_t i = 1; i < all.size(); ++i) th.emplace_back(one, i);
+    one(0);
+    for (auto &t : th) t.join();
+    cudaSetDevice(h->device);
+    for (size_t i = 0; i < all.size(); ++i) if (rcs[i]) { h->last_error = all[i]->last_error; return rcs[i]; }
+    return DWGSIM_GPU_OK;
 }
 
 int dwgsim_gpu_set_host_threads(dwgsim_gpu_t *h, int32_t n)
@@ -1412,30 +1440,53 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
     if (rc) return rc;
     const int64_t total = h->blob_pairs;
     const int64_t B = std::min<int64_t>(h->batch_pairs, std::max<int64_t>(total, 1));
-    if ((rc = ensure_workspace(h, B, true))) return rc;
+    if ((rc = ensure_workspace(h, B, true))) { free_blob(h); return rc; }
     Workspace &w = h->ws;
+    const int world = h->shard_world, rank = h->shard_rank;
+    if (world > 1 && !h->exchange) { h->last_error = "sharded run needs dwgsim_gpu_set_exchange"; free_blob(h); return DWGSIM_GPU_ESTATE; }
     cudaEvent_t copied[8];
     for (int s = 0; s < h->pinned_slots; ++s) cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming);
     cudaEvent_t computed;
     cudaEventCreateWithFlags(&computed, cudaEventDisableTiming);
-    struct Pending { bool live = false; uint64_t bytes[3] = {0, 0, 0}; int pslot = 0; int64_t batch = 0; } pend;
+    // every exit below goes through the clean-up at the end (events, copy stream, genome, counters)
+#define RUN_TRY(expr)                                                                                          \
+    {                                                                                                          \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            h->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                               \
+            rc = _e == cudaErrorMemoryAllocation ? DWGSIM_GPU_ENOMEM : DWGSIM_GPU_ECUDA;                       \
+            break;                                                                                             \
+        }                                                                                                      \
+    }
+    // Batches whose device-to-host copy is in flight or finished but not handed to the sink yet, oldest first.  Two of them
+    // keep the copy engine busy: the copy of batch j is enqueued while that of batch j-1 still runs, and the sink gets batch
+    // j-2 meanwhile (with a ring of two pinned slots: one).
+    struct Pending { uint64_t bytes[3] = {0, 0, 0}; int pslot = 0; int64_t batch = 0; };
+    std::vector<Pending> pend;
+    const size_t depth = h->pinned_slots >= 3 ? 2 : 1;
     GroupSync *const grp = h->group;                            // ranks of a device group: the sink sees the batches in order
-    auto drain = [&](Pending &pd) -> int {
-        if (!pd.live) return DWGSIM_GPU_OK;
-        CUDA_TRY(h, cudaEventSynchronize(copied[pd.pslot]));
+    double t_copy_wait = 0, t_turn_wait = 0, t_sink = 0, t_collect = 0, t_gz = 0, t_launch = 0;   // DWGSIM_RUN_TIMING
+    auto drain_one = [&]() -> int {
+        const Pending pd = pend.front();
+        pend.erase(pend.begin());
+        double t0 = now_ms();
+        if (cudaEventSynchronize(copied[pd.pslot]) != cudaSuccess) { h->last_error = "device to host copy failed"; return DWGSIM_GPU_ECUDA; }
+        double t1 = now_ms();
+        t_copy_wait += t1 - t0;
         if (grp && !grp->wait_turn(pd.batch)) { h->last_error = "another device of the group failed"; return DWGSIM_GPU_ESTATE; }
+        t0 = now_ms();
+        t_turn_wait += t0 - t1;
         for (int k = 0; k < 3; ++k)
             if (pd.bytes[k]) {
                 if (sink(user, k, h->pinned[pd.pslot][k], (size_t)pd.bytes[k])) { h->last_error = "sink callback failed"; return DWGSIM_GPU_ESINK; }
                 st.bytes[k] += (int64_t)pd.bytes[k];
             }
         if (grp) grp->pass_turn();
-        pd.live = false;
+        t_sink += now_ms() - t0;
         return DWGSIM_GPU_OK;
     };
+    auto drain_to = [&](size_t keep) -> int { int r = DWGSIM_GPU_OK; while (pend.size() > keep && r == DWGSIM_GPU_OK) r = drain_one(); return r; };
     int launches = 0;
-    const int world = h->shard_world, rank = h->shard_rank;
-    if (world > 1 && !h->exchange) { h->last_error = "sharded run needs dwgsim_gpu_set_exchange"; return DWGSIM_GPU_ESTATE; }
     const int64_t n_batches = (total + B - 1) / B;
     const int64_t n_rounds = (n_batches + world - 1) / world;
     int64_t mine = 0;                                           // batches this rank has processed
@@ -1447,17 +1498,18 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
         const int dslot = (int)(mine & 1), pslot = (int)(mine % h->pinned_slots);
         int l = 0;
         int64_t rand_base = h->rand_serial, my_random = 0, round_total = 0;
+        // the device slot was last used two batches ago: its copy to the host has to be over before the kernels write it again
+        if (active && mine >= 2) RUN_TRY(cudaStreamWaitEvent(h->s_compute, copied[(int)((mine - 2) % h->pinned_slots)], 0));
         if (world == 1) {
-            // the device slot was last used two batches ago, whose copy finished before the previous batch was drained
             if ((rc = launch_batch(h, first, n, rand_base, dslot, true, &l))) break;
             launches += l;
-            if ((rc = drain(pend))) break;                     // the sink works on the previous batch meanwhile
+            if ((rc = drain_to(depth - 1))) break;             // the sink works on an earlier batch meanwhile
         } else {
             if (active) {
                 if ((rc = launch_simulate(h, first, n, true, &l))) break;
                 launches += l;
             }
-            if ((rc = drain(pend))) break;
+            if ((rc = drain_to(depth - 1))) break;
             if (active && (rc = read_random_count(h, &my_random))) break;
             // the one exchange of the path: random-pair counts of this round, in batch order
             int64_t before_me = 0;
@@ -1470,7 +1522,9 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
         }
         if (!active) { h->rand_serial += round_total; continue; }
         BatchResult r;
+        const double tc0 = now_ms();
         if ((rc = collect_batch(h, true, &r))) break;
+        t_collect += now_ms() - tc0;
         st.ms_simulate += r.ms[0]; st.ms_layout += r.ms[1]; st.ms_format += r.ms[2];
         st.n_random += r.n_random; st.n_failed_attempts += r.n_failed; st.n_pairs += n;
         h->rand_serial += world == 1 ? r.n_random : round_total;
@@ -1478,24 +1532,35 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
         for (int k = 0; k < 3; ++k) st.raw_bytes[k] += (int64_t)r.bytes[k];
         if (h->gz_mode) {                                          // gzip members on the device: fewer bytes over PCIe
             int lz = 0;
+            const double tg0 = now_ms();
             if ((rc = gz_batch(h, dslot, r.bytes, send, &lz))) break;
+            t_gz += now_ms() - tg0;
             launches += lz;
         }
-        CUDA_TRY(h, cudaEventRecord(computed, h->s_compute));
-        CUDA_TRY(h, cudaStreamWaitEvent(h->s_copy, computed, 0));
         for (int k = 0; k < 3; ++k)
+            if (send[k] > h->pinned_cap[k]) { h->last_error = "a batch is larger than its pinned slot"; rc = DWGSIM_GPU_EOVERFLOW; }
+        if (rc) break;
+        RUN_TRY(cudaEventRecord(computed, h->s_compute));
+        RUN_TRY(cudaStreamWaitEvent(h->s_copy, computed, 0));
+        bool copy_failed = false;
+        for (int k = 0; k < 3 && !copy_failed; ++k)
             if (send[k]) {
-                CUDA_TRY(h, cudaMemcpyAsync(h->pinned[pslot][k], h->gz_mode ? w.gz_out[dslot][k] : w.out[dslot][k], send[k],
-                                            cudaMemcpyDeviceToHost, h->s_copy));
+                if (cudaMemcpyAsync(h->pinned[pslot][k], h->gz_mode ? w.gz_out[dslot][k] : w.out[dslot][k], send[k],
+                                    cudaMemcpyDeviceToHost, h->s_copy) != cudaSuccess) copy_failed = true;
                 st.d2h_bytes += (int64_t)send[k];
             }
-        CUDA_TRY(h, cudaEventRecord(copied[pslot], h->s_copy));
-        pend.live = true; pend.pslot = pslot; pend.batch = bi;
-        for (int k = 0; k < 3; ++k) pend.bytes[k] = send[k];
+        if (copy_failed) { h->last_error = "device to host copy failed"; rc = DWGSIM_GPU_ECUDA; break; }
+        RUN_TRY(cudaEventRecord(copied[pslot], h->s_copy));
+        Pending pd;
+        pd.pslot = pslot; pd.batch = bi;
+        for (int k = 0; k < 3; ++k) pd.bytes[k] = send[k];
+        pend.push_back(pd);
         ++st.n_batches; ++mine;
     }
-    if (rc == DWGSIM_GPU_OK) rc = drain(pend);
+#undef RUN_TRY
+    if (rc == DWGSIM_GPU_OK) rc = drain_to(0);
     cudaStreamSynchronize(h->s_copy);
+    cudaStreamSynchronize(h->s_compute);
     for (int s = 0; s < h->pinned_slots; ++s) cudaEventDestroy(copied[s]);
     cudaEventDestroy(computed);
     h->gidx_origin += total;
@@ -1505,6 +1570,10 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
     st.ms_pack = h->ms_pack; h->ms_pack = 0;
     st.ms_compress = h->ms_gz; h->ms_gz = 0;
     st.ms_total = now_ms() - t_start;
+    if (getenv("DWGSIM_RUN_TIMING"))
+        fprintf(stderr, "[dwgsim_gpu_run] rank %d: %lld pairs in %d batches, %.1f ms: waits copy %.1f turn %.1f, sink %.1f, collect %.1f, gz %.1f (launch %.1f) | kernels %.1f gz kernels %.1f | d2h %.1f MB\n",
+                rank, (long long)st.n_pairs, st.n_batches, st.ms_total, t_copy_wait, t_turn_wait, t_sink, t_collect, t_gz, t_launch,
+                st.ms_simulate + st.ms_layout + st.ms_format, st.ms_compress, st.d2h_bytes / 1e6);
     if (stats) *stats = st;
     return rc;
 }

@@ -185,12 +185,15 @@ gz_compress_kernel(const uint8_t *__restrict__ raw, unsigned long long n_raw, co
 // members -> contiguous stream; offs = exclusive scan of sizes
 __global__ void __launch_bounds__(256)
 gz_compact_kernel(const uint8_t *__restrict__ slots, const unsigned long long *__restrict__ sizes,
-                  const unsigned long long *__restrict__ offs, uint8_t *__restrict__ out)
+                  const unsigned long long *__restrict__ offs, uint8_t *__restrict__ out, unsigned long long cap)
 {
     const unsigned long long m = blockIdx.x;
     const uint8_t *src = slots + m * (unsigned long long)kGzSlotStride;
     uint8_t *dst = out + offs[m];
     const uint32_t n = (uint32_t)sizes[m];
+    // a code fitted to the first batch can expand later data up to 15 bits per byte: members that would not fit the stream's
+    // buffer are not written (the host sees the total, reports the overflow and nothing leaves the device)
+    if (offs[m] + n > cap) return;
     // aligned middle of the destination with 4-byte stores, source read byte-wise shifted (slots are 4-byte aligned)
     const uint32_t lead = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
     for (uint32_t x = threadIdx.x; x < min(lead, n); x += blockDim.x) dst[x] = src[x];

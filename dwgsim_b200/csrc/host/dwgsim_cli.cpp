@@ -398,6 +398,32 @@ struct Fasta {                                 // seq_read_fasta, src/mut.c:49-8
             return len;
         }
         seq.resize(span + 1);
+        const unsigned hw = std::thread::hardware_concurrency();
+        const size_t T = span >= ((size_t)8 << 20) ? std::max<size_t>(1, std::min<size_t>(8, hw / 2)) : 1;
+        if (T > 1) {
+            // long records: every thread counts what its part of the text keeps, then filters it to its place
+            std::vector<size_t> kept(T + 1, 0);
+            auto part = [&](size_t t, size_t *a, size_t *b) { *a = span * t / T; *b = span * (t + 1) / T; };
+            {
+                std::vector<std::thread> th;
+                for (size_t t = 0; t < T; t++) th.emplace_back([&, t]() { size_t a, b, c = 0; part(t, &a, &b); for (size_t i = a; i < b; i++) c += keep[(unsigned char)beg[i]]; kept[t + 1] = c; });
+                for (auto &x : th) x.join();
+            }
+            for (size_t t = 0; t < T; t++) kept[t + 1] += kept[t];
+            {
+                std::vector<std::thread> th;
+                uint8_t *base = seq.data();
+                for (size_t t = 0; t < T; t++) th.emplace_back([&, t]() {
+                    size_t a, b; part(t, &a, &b);
+                    uint8_t *out = base + kept[t], *stop = base + kept[t + 1];
+                    for (size_t i = a; i < b && out < stop; i++) { const unsigned char ch = (unsigned char)beg[i]; *out = ch; out += keep[ch]; }
+                });
+                for (auto &x : th) x.join();
+            }
+            len = (int64_t)kept[T];
+            seq.resize((size_t)len);
+            return len;
+        }
         uint8_t *out = seq.data();
         for (size_t i = 0; i < span; i++) { const unsigned char ch = (unsigned char)beg[i]; *out = ch; out += keep[ch]; }   // branch-free filter
         len = (int64_t)(out - seq.data());
@@ -1319,9 +1345,19 @@ int main(int argc, char **argv)
             if (rc != DWGSIM_GPU_ENODEV || (o.gpus > 0 || devs.size() == 1)) break;
         }
         if (rc != DWGSIM_GPU_OK) { fprintf(stderr, "\n[dwgsim_core] Error: %s\n", dwgsim_gpu_strerror(rc)); exit(1); }
-        if (o.batch > 0) dwgsim_gpu_set_batch(gpu, o.batch, 3);
+        dwgsim_gpu_set_batch(gpu, o.batch > 0 ? o.batch : (1 << 18), 3);   // (2^18 pairs: the per-batch launch costs are small against it)
         if (!o.uncompressed && !o.host_gzip) dwgsim_gpu_set_compression(gpu, 1);
     };
+
+    // With reads to simulate, the device handle, its batch workspace and the pinned ring are set up on a helper thread while
+    // the census and the first contig's prologue run (CUDA start-up and page-locking the ring take about two seconds)
+    std::future<void> gpu_ready;
+    if (o.output_type != 2 && (o.N > 0 || o.C > 0) && !getenv("DWGSIM_LAZY_GPU"))
+        gpu_ready = std::async(std::launch::async, [&]() {
+            gpu_open();
+            const int rc = dwgsim_gpu_warm(gpu);
+            if (rc != DWGSIM_GPU_OK) { fprintf(stderr, "\n[dwgsim_core] Error: %s: %s\n", dwgsim_gpu_strerror(rc), dwgsim_gpu_last_error(gpu)); exit(1); }
+        });
 
     // census, src/dwgsim.c:465-492
     std::vector<uint8_t> seq;
@@ -1466,20 +1502,24 @@ int main(int argc, char **argv)
                 } else if (n_pairs < 0) { fprintf(stderr, "[dwgsim_core] #5 skip sequence '%s' as not enough pairs found\n", name.c_str()); continue; }
                 P.prev_skip = 0;
             }
-            const double t0 = now();
-            j->have_events = muts.kind < 0 && !getenv("DWGSIM_FULL_SCAN");
-            if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, contig_i, muts, j->name.c_str());
-            else if (j->have_events && diref_threads > 1 && (int64_t)j->seq.size() >= diref_par_min)
-                diref_parallel(o, j->seq, j->h1, j->h2, &j->events, &j->touched, diref_threads);
-            else if (j->have_events) diref(o, j->seq, j->h1, j->h2, &j->events, &j->touched);
-            else diref(o, j->seq, j->h1, j->h2);
-            j->t_mut = now() - t0;
             j->seq_l = seq_l; j->l = l; j->contig_i = contig_i; j->n_pairs = n_pairs;
             if (o.output_type != 2 && n_pairs > 0) P.n_sim += n_pairs;
             P.contig_i++;
             return j;
         }
         return nullptr;
+    };
+    // mut_diref of one contig (the drand48 stream: strictly in contig order, on one thread at a time)
+    auto mutate = [&](Job &jb) {
+        Job *j = &jb;
+        const double t0 = now();
+        j->have_events = muts.kind < 0 && !getenv("DWGSIM_FULL_SCAN");
+        if (muts.kind >= 0) diref_replay(o, j->seq, j->h1, j->h2, j->contig_i, muts, j->name.c_str());
+        else if (j->have_events && diref_threads > 1 && (int64_t)j->seq.size() >= diref_par_min)
+            diref_parallel(o, j->seq, j->h1, j->h2, &j->events, &j->touched, diref_threads);
+        else if (j->have_events) diref(o, j->seq, j->h1, j->h2, &j->events, &j->touched);
+        else diref(o, j->seq, j->h1, j->h2);
+        j->t_mut = now() - t0;
     };
     // The consumer side in two halves so they can run on two threads: prepare() writes the contig's mutation records and packs
     // it for the device (host-only work on the dense arrays, which go back to the pool right after); execute() queues the
@@ -1502,7 +1542,7 @@ int main(int argc, char **argv)
         if (o.output_type != 1) print_mutations(j.name.c_str(), j.seq, j.h1, j.h2, fp_txt, fp_vcf, j.have_events ? &j.events : nullptr);
         r->t_print = now() - t0;
         if (o.output_type != 2 && j.n_pairs > 0) {
-            { std::lock_guard<std::mutex> g(gpu_mu); if (!gpu) gpu_open(); }
+            { std::lock_guard<std::mutex> g(gpu_mu); if (gpu_ready.valid()) gpu_ready.get(); if (!gpu) gpu_open(); }
             t0 = now();
             const int rc = dwgsim_gpu_pack_contig(gpu, j.contig_i, j.name.c_str(), j.seq.data(), j.seq_l, j.h1.s.data(), j.h2.s.data(), j.h1.ins.data(),
                                                   (int32_t)j.h1.ins.size(), j.h2.ins.data(), (int32_t)j.h2.ins.size(), j.n_pairs, &r->packed);
@@ -1547,72 +1587,79 @@ int main(int argc, char **argv)
         for (;;) {
             std::unique_ptr<Job> j = produce();
             if (!j) break;
+            mutate(*j);
             std::unique_ptr<RunJob> r = prepare(*j);
             recycle(std::move(j));
             if (!execute(*r)) break;
         }
     } else {
-        // Three stages, one contig each: mut_diref (producer thread; the drand48 stream stays in contig order) -> mutation
-        // files + packing (packer thread) -> device read loop + FASTQ files (this thread).  Bounded hand-over: one finished
-        // item waits per stage, so at most three contigs hold dense arrays.
+        // Four stages, one contig each: FASTA record + budget / skip rules (reader thread) -> mut_diref (mutator thread; the
+        // drand48 stream stays in contig order) -> mutation files + packing (packer thread) -> device read loop + FASTQ files
+        // (this thread).  Bounded hand-over: one finished item waits per stage, so at most four contigs hold dense arrays.
         struct Slot {
             std::mutex mu;
             std::condition_variable cv;
             bool full = false, done = false, stop = false;
-        } sa, sb;
-        std::unique_ptr<Job> slot_a;
+        } sr, sa, sb;
+        std::unique_ptr<Job> slot_r, slot_a;
         std::unique_ptr<RunJob> slot_b;
-        std::thread producer([&]() {
+        auto put = [](Slot &sl, auto &slot, auto item) -> bool {      // false: the pipeline was stopped
+            std::unique_lock<std::mutex> lk(sl.mu);
+            sl.cv.wait(lk, [&]() { return !sl.full || sl.stop; });
+            if (sl.stop) return false;
+            slot = std::move(item); sl.full = true;
+            sl.cv.notify_all();
+            return true;
+        };
+        auto finish = [](Slot &sl) { std::unique_lock<std::mutex> lk(sl.mu); sl.done = true; sl.cv.notify_all(); };
+        auto take = [](Slot &sl, auto &slot, auto &item) -> int {     // 1: item taken, 0: upstream finished, -1: stopped
+            std::unique_lock<std::mutex> lk(sl.mu);
+            sl.cv.wait(lk, [&]() { return sl.full || sl.done || sl.stop; });
+            if (sl.stop) return -1;
+            if (!sl.full) return 0;
+            item = std::move(slot); sl.full = false;
+            sl.cv.notify_all();
+            return 1;
+        };
+        auto halt = [](Slot &sl) { std::unique_lock<std::mutex> lk(sl.mu); sl.stop = true; sl.cv.notify_all(); };
+        std::thread reader([&]() {
             for (;;) {
                 std::unique_ptr<Job> j = produce();
-                std::unique_lock<std::mutex> lk(sa.mu);
-                sa.cv.wait(lk, [&]() { return !sa.full || sa.stop; });
-                if (sa.stop) return;
-                if (!j) { sa.done = true; sa.cv.notify_all(); return; }
-                slot_a = std::move(j); sa.full = true;
-                sa.cv.notify_all();
+                if (!j) { finish(sr); return; }
+                if (!put(sr, slot_r, std::move(j))) return;
+            }
+        });
+        std::thread mutator([&]() {
+            for (;;) {
+                std::unique_ptr<Job> j;
+                const int got = take(sr, slot_r, j);
+                if (got < 0) return;
+                if (got == 0) { finish(sa); return; }
+                mutate(*j);
+                if (!put(sa, slot_a, std::move(j))) return;
             }
         });
         std::thread packer([&]() {
             for (;;) {
                 std::unique_ptr<Job> j;
-                {
-                    std::unique_lock<std::mutex> lk(sa.mu);
-                    sa.cv.wait(lk, [&]() { return sa.full || sa.done || sa.stop; });
-                    if (sa.stop) return;
-                    if (!sa.full) break;                                  // done
-                    j = std::move(slot_a); sa.full = false;
-                    sa.cv.notify_all();
-                }
+                const int got = take(sa, slot_a, j);
+                if (got < 0) return;
+                if (got == 0) { finish(sb); return; }
                 std::unique_ptr<RunJob> r = prepare(*j);
                 recycle(std::move(j));
-                std::unique_lock<std::mutex> lk(sb.mu);
-                sb.cv.wait(lk, [&]() { return !sb.full || sb.stop; });
-                if (sb.stop) { if (r->packed) dwgsim_gpu_packed_free(r->packed); return; }
-                slot_b = std::move(r); sb.full = true;
-                sb.cv.notify_all();
+                dwgsim_gpu_packed_t *pk = r->packed;
+                if (!put(sb, slot_b, std::move(r))) { if (pk) dwgsim_gpu_packed_free(pk); return; }
             }
-            std::unique_lock<std::mutex> lk(sb.mu);
-            sb.done = true;
-            sb.cv.notify_all();
         });
         for (;;) {
             std::unique_ptr<RunJob> r;
-            {
-                std::unique_lock<std::mutex> lk(sb.mu);
-                sb.cv.wait(lk, [&]() { return sb.full || sb.done; });
-                if (!sb.full) break;
-                r = std::move(slot_b); sb.full = false;
-                sb.cv.notify_all();
-            }
-            if (!execute(*r)) {
-                { std::unique_lock<std::mutex> lk(sb.mu); sb.stop = true; sb.cv.notify_all(); }
-                { std::unique_lock<std::mutex> lk(sa.mu); sa.stop = true; sa.cv.notify_all(); }
-                break;
-            }
+            const int got = take(sb, slot_b, r);
+            if (got <= 0) break;
+            if (!execute(*r)) { halt(sb); halt(sa); halt(sr); break; }
         }
         packer.join();
-        producer.join();
+        mutator.join();
+        reader.join();
         if (slot_b && slot_b->packed) dwgsim_gpu_packed_free(slot_b->packed);
     }
     if (!rc_exit) fprintf(stderr, "\n[dwgsim_core] Complete!\n");
@@ -1623,6 +1670,7 @@ int main(int argc, char **argv)
                 bases_in, n_sim, bytes_out, total, t_mut, bases_in ? 1e9 * t_mut / bases_in : 0.0, t_print, t_gpu, t_pack, t_kernels,
                 o.uncompressed ? "" : " incl. gzip", total > 0 ? n_sim / total / 1e6 : 0.0, t_gpu > 0 ? n_sim / t_gpu / 1e6 : 0.0);
     }
+    if (gpu_ready.valid()) gpu_ready.get();
     if (fp_txt) fclose(fp_txt);
     if (fp_vcf) fclose(fp_vcf);
     wr.close_all();

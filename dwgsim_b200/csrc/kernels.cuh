@@ -1217,6 +1217,13 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
 }
 
+// a few 64-bit results to mapped host memory (no copy engine involved)
+__global__ void publish_words_kernel(unsigned long long *__restrict__ dst_host, const unsigned long long *__restrict__ src, int n)
+{
+    if ((int)threadIdx.x < n) dst_host[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
 // ---- record geometry shared by the layout and format kernels --------------------------------------------
 __device__ __forceinline__ int ndigits10(uint32_t v)
 {

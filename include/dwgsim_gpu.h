@@ -127,6 +127,10 @@ int dwgsim_gpu_pack_contig(const dwgsim_gpu_t *h, int32_t contig_i, const char *
                            int64_t n_pairs, dwgsim_gpu_packed_t **out);
 int dwgsim_gpu_add_packed(dwgsim_gpu_t *h, dwgsim_gpu_packed_t *p);
 void dwgsim_gpu_packed_free(dwgsim_gpu_packed_t *p);
+/* Optional: allocate the batch workspace and the pinned ring now (they are allocated by the first run() otherwise; page-locking
+ * the ring takes about a second per GB).  Call it after set_batch / set_compression, from the thread that will call run() or
+ * strictly before it; a host can hide it behind its own start-up work. */
+int dwgsim_gpu_warm(dwgsim_gpu_t *h);
 /* threads the packer may use per contig (0 = default: the hardware threads, at most 32; several ranks on one host
  * should share the cores) */
 int dwgsim_gpu_set_host_threads(dwgsim_gpu_t *h, int32_t n);
