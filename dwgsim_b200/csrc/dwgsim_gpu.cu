@@ -743,11 +743,12 @@ int ensure_workspace(dwgsim_gpu *h, int64_t n, bool want_pinned)
         w.cap_pairs = n;
     }
     if (want_pinned && h->pinned_slots == 0) {
+        // Page-locking host memory costs about a second per GB, so the ring is sized for what the streams are expected to
+        // need: the worst case of the FASTQ text, or 5/8 of it for gzip members (FASTQ under the literal-only code comes out
+        // near 0.54; a batch that needs more makes run() enlarge the ring, see grow_ring)
+        for (int k = 0; k < 3; ++k) h->pinned_cap[k] = h->gz_mode ? align_up(w.out_cap[k] / 8 * 5 + (64 << 10), 4096) : w.out_cap[k];
         for (int s = 0; s < h->ring; ++s)
-            for (int k = 0; k < 3; ++k) {
-                h->pinned_cap[k] = std::max(w.out_cap[k], h->gz_mode ? w.gz_cap[k] : 0);
-                CUDA_TRY(h, cudaMallocHost((void **)&h->pinned[s][k], h->pinned_cap[k]));
-            }
+            for (int k = 0; k < 3; ++k) CUDA_TRY(h, cudaMallocHost((void **)&h->pinned[s][k], h->pinned_cap[k]));
         h->pinned_slots = h->ring;
     }
     return DWGSIM_GPU_OK;
@@ -1537,9 +1538,22 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
             t_gz += now_ms() - tg0;
             launches += lz;
         }
-        for (int k = 0; k < 3; ++k)
-            if (send[k] > h->pinned_cap[k]) { h->last_error = "a batch is larger than its pinned slot"; rc = DWGSIM_GPU_EOVERFLOW; }
-        if (rc) break;
+        bool grow = false;
+        for (int k = 0; k < 3; ++k) grow = grow || send[k] > h->pinned_cap[k];
+        if (grow) {
+            // a batch compressed worse than the ring was sized for: hand over what is pending, then page-lock larger slots
+            if ((rc = drain_to(0))) break;
+            cudaStreamSynchronize(h->s_copy);
+            for (int k = 0; k < 3; ++k) {
+                if (send[k] <= h->pinned_cap[k]) continue;
+                h->pinned_cap[k] = align_up(send[k] + send[k] / 4, 4096);
+                for (int s2 = 0; s2 < h->pinned_slots && rc == DWGSIM_GPU_OK; ++s2) {
+                    cudaFreeHost(h->pinned[s2][k]); h->pinned[s2][k] = nullptr;
+                    if (cudaMallocHost((void **)&h->pinned[s2][k], h->pinned_cap[k]) != cudaSuccess) { h->last_error = "out of pinned host memory"; rc = DWGSIM_GPU_ENOMEM; }
+                }
+            }
+            if (rc) break;
+        }
         RUN_TRY(cudaEventRecord(computed, h->s_compute));
         RUN_TRY(cudaStreamWaitEvent(h->s_copy, computed, 0));
         bool copy_failed = false;

@@ -1345,7 +1345,9 @@ int main(int argc, char **argv)
             if (rc != DWGSIM_GPU_ENODEV || (o.gpus > 0 || devs.size() == 1)) break;
         }
         if (rc != DWGSIM_GPU_OK) { fprintf(stderr, "\n[dwgsim_core] Error: %s\n", dwgsim_gpu_strerror(rc)); exit(1); }
-        dwgsim_gpu_set_batch(gpu, o.batch > 0 ? o.batch : (1 << 18), 3);   // (2^18 pairs: the per-batch launch costs are small against it)
+        // 2^18 pairs per device batch (the per-batch launch costs are small against it); with four or more devices half of
+        // that, so that page-locking the devices' rings stays a matter of seconds
+        dwgsim_gpu_set_batch(gpu, o.batch > 0 ? o.batch : (dwgsim_gpu_group_size(gpu) >= 4 ? (1 << 17) : (1 << 18)), 3);
         if (!o.uncompressed && !o.host_gzip) dwgsim_gpu_set_compression(gpu, 1);
     };
 
@@ -1674,6 +1676,9 @@ int main(int argc, char **argv)
     if (fp_txt) fclose(fp_txt);
     if (fp_vcf) fclose(fp_vcf);
     wr.close_all();
+    // every file is closed: leave without tearing the CUDA contexts and the pinned rings down page by page (seconds with
+    // several devices); DWGSIM_CLEAN_EXIT=1 keeps the orderly shutdown (leak checkers)
+    if (gpu && !getenv("DWGSIM_CLEAN_EXIT")) { fflush(stdout); fflush(stderr); _exit(rc_exit); }
     if (gpu) dwgsim_gpu_destroy(gpu);
     return rc_exit;
 }
