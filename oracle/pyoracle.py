@@ -64,11 +64,25 @@ def build(force=False):
     ref_bin = os.path.join(_HERE, "_ref", "dwgsim_ref")
     if os.path.isdir("/root/reference/src") and (force or not os.path.exists(ref_bin)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    # the reference with the binding of INTEGRATION.md in place of its read-pair loop, linked against libdwgsim_b200.so
+    gpu_bin = os.path.join(_HERE, "_ref", "dwgsim_ref_gpu")
+    lib_so = os.path.join(os.path.dirname(_HERE), "dwgsim_b200", "libdwgsim_b200.so")
+    deps = [os.path.join(os.path.dirname(_HERE), "integration", f) for f in ("dwgsim_b200_binding.c", "dwgsim_b200_binding.h")] + \
+           [os.path.join(_HERE, "patch_reference.py"), os.path.join(os.path.dirname(_HERE), "include", "dwgsim_gpu.h")]
+    if os.path.isdir("/root/reference/src") and os.path.exists(lib_so) and \
+            (force or not os.path.exists(gpu_bin) or any(os.path.getmtime(d) > os.path.getmtime(gpu_bin) for d in deps)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref_gpu"])
     return so
 
 
 def ref_binary():
     p = os.path.join(_HERE, "_ref", "dwgsim_ref")
+    return p if os.path.exists(p) else None
+
+
+def ref_gpu_binary():
+    """the reference built with integration/dwgsim_b200_binding.c in place of its read-pair loop (needs a GPU to run)"""
+    p = os.path.join(_HERE, "_ref", "dwgsim_ref_gpu")
     return p if os.path.exists(p) else None
 
 

@@ -1,8 +1,8 @@
-# tools/fmt_sweep.sh: format-kernel time over kernel variants x generation (DWGSIM_FORMAT) x warps x pairs per tile
-run() { echo -n "lib=$1 format=$2 warps=$3 TP=$4: "; DWGSIM_LIB=$PWD/variants/$1 DWGSIM_FORMAT=$2 DWGSIM_FMT_WARPS=$3 DWGSIM_TILE_PAIRS=$4 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,1), d['roofline']['ms_per_step_by_kernel']['format_fastq_kernel'])"; }
-run lib_pf1.so 3 10 48
-run lib_pf0.so 3 10 48
-run lib_pf1.so 3 12 48
-run lib_pf0.so 3 12 48
-run lib_pf1.so 3 12 36
-run lib_pf1.so 2 24 4
+# tools/fmt_sweep.sh: format-kernel time over warps per CTA x pairs per mini-tile (DWGSIM_FMT_WARPS, DWGSIM_TILE_PAIRS)
+run() { echo -n "warps=$1 WP=$2: "; DWGSIM_FMT_WARPS=$1 DWGSIM_TILE_PAIRS=$2 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --no-e2e-cli 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,1), d['roofline']['ms_per_batch_by_kernel']['format_fastq_kernel'])"; }
+run 24 4
+run 24 3
+run 20 5
+run 16 6
+run 16 8
+run 12 8
