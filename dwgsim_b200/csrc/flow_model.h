@@ -128,7 +128,11 @@ struct FlowEmit {
     {
         acc |= c << sh;
         sh += 4; ++n;
-        if (sh == 32) { dst[w++] = acc; acc = 0; sh = 0; }
+        // (written so that it compiles to one predicated store and selects: the lanes of a warp fill their words at different
+        // symbols once their reads have had different edits, and a branch would run once per group of lanes)
+        const bool full = sh == 32;
+        if (full) dst[w] = acc;
+        w += full ? 1 : 0; acc = full ? 0u : acc; sh = full ? 0 : sh;
     }
     DWG_HD void flush() { if (sh) dst[w] = acc; }               // (the word keeps zeros above the last symbol)
 };

@@ -151,3 +151,37 @@ def test_flow_gap_tables_equal_oracle(oracle):
         for e in range(2):
             assert g.flow_gap_n[e] == oracle.FLOW_GAP_N
             assert [g.flow_gap[e][i] for i in range(oracle.FLOW_GAP_N)] == [t.flow_gap[e][i] for i in range(oracle.FLOW_GAP_N)]
+
+
+def test_pack_then_add_packed_and_the_file_sink(oracle, synth_fa, tmp_path):
+    """the two-call form of add_contig (pack on one thread, queue later) and the library's file sink (one writer thread
+    per file, positional writes) must give the oracle's bytes"""
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    from concurrent.futures import ThreadPoolExecutor
+    opts = dict(seed=4, N=5000, length=(100, 100), mut_rate=0.01)
+    sess, want = gh.oracle_expected(oracle, opts, synth_fa, str(tmp_path / "orc"))
+    try:
+        names = [str(tmp_path / ("out." + f)) for f in gh.FILE_NAMES]
+        fds = [os.open(p, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644) for p in names]
+        offs = [0, 0, 0]
+        with DwgsimGpu(params_from_options(**{k: v for k, v in opts.items() if k in gh.GPU_KEYS})) as gpu, ThreadPoolExecutor(1) as pool:
+            gpu.set_batch(900, 3)
+            gpu.set_host_threads(2)
+            cs = [sess.contig(k) for k in range(sess.n_contigs)]
+
+            def pack(c):
+                return gpu.pack_contig(c["contig_i"], c["name"], c["seq"], c["len"], c["hap"][0], c["hap"][1], c["ins"][0],
+                                       c["n_ins"][0], c["ins"][1], c["n_ins"][1], c["n_pairs"])
+            nxt = pool.submit(pack, cs[0])
+            for k in range(len(cs)):                       # contig k+1 is packed while contig k runs
+                gpu.add_packed(nxt.result())
+                if k + 1 < len(cs):
+                    nxt = pool.submit(pack, cs[k + 1])
+                st, offs = gpu.run_to_files(fds, offs)
+        for fd in fds:
+            os.close(fd)
+        for i, p in enumerate(names):
+            got = open(p, "rb").read()
+            assert got == want[i], "%s: %s" % (gh.FILE_NAMES[i], gh.first_diff(want[i], got))
+    finally:
+        sess.close()
