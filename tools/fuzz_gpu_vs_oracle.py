@@ -51,6 +51,8 @@ for it in range(int(sys.argv[2])):
     kw = {}
     if rnd.random() < 0.3: kw["batch"] = rnd.choice([100, 257, 1000, 4096])
     if rnd.random() < 0.15: kw["compression"] = 1
+    if rnd.random() < 0.15: kw["devices"] = rnd.choice([[0, 0], [0, 0, 0]])       # a device group whose ranks share cuda:0
+    if rnd.random() < 0.15: kw["per_contig_runs"] = True
     sub = os.path.join(WD, "case"); shutil.rmtree(sub, ignore_errors=True); os.makedirs(sub)
     try:
         sess, want = gh.oracle_expected(po, o, fa, os.path.join(sub, "orc"))
