@@ -565,6 +565,8 @@ int update_caps(dwgsim_gpu *h)
     if (h->sp.fmt_v2) {
         // one CTA per SM (the noise table takes 64 KB of its shared memory): as many warps as fit with the mini-tile wanted
         h->sp.fmt_warps = kFmt2WarpsMax;
+        h->sp.fmt_run = 0;
+        if (const char *e = getenv("DWGSIM_FMT_RUN")) h->sp.fmt_run = std::max(0, atoi(e));     // experiments: 1 = every mini-tile on its own
         if (const char *e = getenv("DWGSIM_FMT_WARPS")) h->sp.fmt_warps = std::max(1, std::min(kFmt2WarpsMax, atoi(e)));
         const int warps_floor = getenv("DWGSIM_TILE_PAIRS") ? 1 : std::min(h->sp.fmt_warps, 20);
         while (h->sp.fmt_warps > warps_floor && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.fmt_warps;
@@ -841,14 +843,15 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[2], st));
     if (sp.fmt_v2) {
         const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmt2WarpsMax, fmt_threads = 32 * fmt_warps;
-        const size_t smem_2 = (size_t)format2_smem_layout(sp).total;
+        const Format2Smem L2 = format2_smem_layout(sp);
+        const size_t smem_2 = (size_t)L2.total;
         const int ctas = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;  // CTAs that have a mini-tile per warp
         const int grid_f = std::min(ctas, sm_count);
         if (sp.data_type == 1)
-            format_fastq2_kernel<true><<<grid_f, fmt_threads, smem_2, st>>>(sp, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
+            format_fastq2_kernel<true><<<grid_f, fmt_threads, smem_2, st>>>(sp, L2, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
                                                                             w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
         else
-            format_fastq2_kernel<false><<<grid_f, fmt_threads, smem_2, st>>>(sp, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
+            format_fastq2_kernel<false><<<grid_f, fmt_threads, smem_2, st>>>(sp, L2, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
                                                                              w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
     } else {
         const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmtWarps, fmt_threads = 32 * fmt_warps;

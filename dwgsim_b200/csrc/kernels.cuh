@@ -1813,8 +1813,13 @@ struct NameMeta {                      // per record (pair, end, bwa | bfast), 1
     uint32_t len;                      // read length (bytes of bases in the record: len - from for bwa)
 };
 
-struct Format2Smem {
+struct Format2Smem {                    // computed on the host, passed by value: every field is a constant-bank operand
     int qtab_off, cdf_off, qb_off[2], warp_off, warp_stride, meta_off, rmeta_off, nmeta_off, stage_off[3], total;
+    int pre_off, pre_bytes;            // per warp, two of each: the next mini-tile's FmtPrefetch words (32 bytes per lane 0..WP)
+    int names_off, names_bytes;        //   and its read names (WP * nvar rows of name_cap bytes), both filled by cp.async
+    int carry_off;                     // per warp: 3 x 16 bytes, the chunk a mini-tile leaves to the next one of its run
+    int g0, h0, G, G2;                 // 8-base groups / 16-base lane items of end 0, code words / lane items per pair
+    int run;                           // mini-tiles a warp takes at a stretch; 0: one contiguous range per warp
 };
 __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
 {
@@ -1830,9 +1835,15 @@ __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
     L.meta_off = w; w += WP * (int)sizeof(PairMeta);
     L.rmeta_off = w; w += 2 * WP * (int)sizeof(ReadMeta);
     L.nmeta_off = w; w += 4 * WP * (int)sizeof(NameMeta);
+    L.pre_off = w; L.pre_bytes = (WP + 1) * 32; w += 2 * L.pre_bytes;
+    L.names_off = w; L.names_bytes = WP * ((P.data_type == 1 && P.out_bwa) ? 2 : 1) * P.name_cap; w += 2 * L.names_bytes;
+    L.carry_off = w; w += 64;
     for (int k = 0; k < 3; ++k) { L.stage_off[k] = w; w += (WP * P.rec_cap[k] + 32 + 15) & ~15; }
     L.warp_stride = w;
     L.total = o + (P.fmt_warps > 0 ? P.fmt_warps : kFmt2WarpsMax) * w;
+    L.g0 = (P.cap[0] + 7) >> 3; L.G = P.nw[0] + P.nw[1];
+    L.h0 = (L.g0 + 1) >> 1; L.G2 = L.h0 + ((L.G - L.g0 + 1) >> 1);      // (P.inv_groups = 2^32 / G2 + 1)
+    L.run = P.fmt_run;
     return L;
 }
 
@@ -1840,6 +1851,13 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// PRMT with the selector used as it is (__byte_perm masks it with 0x7777 first): every selector below has nibbles <= 7
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
 }
 
 // Philox4x32-10 with the first key word's round keys taken from the kernel parameters (P.qkey[r] = seed + r * 0x9E3779B9:
@@ -1856,29 +1874,19 @@ __device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint
     return make_uint4(c0, c1, c2, c3);
 }
 
-// one field (bases or qualities of one record): the lane's 8 bytes {lo, hi} belong at byte address p; `prev` is the last
-// word of the previous group of the same read (anything for the first group).
+// one field (bases or qualities of one record): the lane's 16 bytes x[0..3] belong at byte address p; `prev` is the last
+// word of the previous 16 bytes of the same read (anything for the first).
 // `skip1`: the lane's first byte is not part of the field (first colour of a SOLiD bwa record): when it is the last byte
 // of its word that word holds nothing of the field, and writing it would reach four bytes back
-__device__ __forceinline__ void store_field(uint32_t p, uint32_t prev, uint32_t lo, uint32_t hi, bool tail, int cnt, bool skip1 = false)
-{
-    const uint32_t bs = p & 3u, w = p - bs, sel = 0x7654u - 0x1111u * bs;       // bytes [4 - bs, 8 - bs) of {first, second}
-    const int v = (int)bs + cnt;                                                 // end of the lane's bytes in its 12-byte window
-    if (!(skip1 && bs == 3u)) sts32(w, __byte_perm(prev, lo, sel));
-    if (!tail || v > 4) sts32(w + 4, __byte_perm(lo, hi, sel));
-    if (tail && v > 8) sts32(w + 8, __byte_perm(hi, 0u, sel));
-}
-
-// the same for a lane that holds 16 bytes x[0..3]
 __device__ __forceinline__ void store_field16(uint32_t p, uint32_t prev, const uint32_t (&x)[4], bool tail, int cnt, bool skip1)
 {
-    const uint32_t bs = p & 3u, w = p - bs, sel = 0x7654u - 0x1111u * bs;
+    const uint32_t bs = p & 3u, w = p - bs, sel = 0x7654u - 0x1111u * bs;       // bytes [4 - bs, 8 - bs) of {first, second}
     const int v = (int)bs + cnt;                                                 // end of the lane's bytes in its 20-byte window
-    if (!(skip1 && bs == 3u)) sts32(w, __byte_perm(prev, x[0], sel));
-    if (!tail || v > 4) sts32(w + 4, __byte_perm(x[0], x[1], sel));
-    if (!tail || v > 8) sts32(w + 8, __byte_perm(x[1], x[2], sel));
-    if (!tail || v > 12) sts32(w + 12, __byte_perm(x[2], x[3], sel));
-    if (tail && v > 16) sts32(w + 16, __byte_perm(x[3], 0u, sel));
+    if (!(skip1 && bs == 3u)) sts32(w, prmt(prev, x[0], sel));
+    if (!tail || v > 4) sts32(w + 4, prmt(x[0], x[1], sel));
+    if (!tail || v > 8) sts32(w + 8, prmt(x[1], x[2], sel));
+    if (!tail || v > 12) sts32(w + 12, prmt(x[2], x[3], sel));
+    if (tail && v > 16) sts32(w + 16, prmt(x[3], 0u, sel));
 }
 
 // the draws of a group whose table cell holds a CDF threshold: full 32-bit draw, rank by binary search
@@ -1905,9 +1913,22 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Ampere-style asynchronous copies global -> shared (LDGSTS): no register holds the data in flight
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// the low `nb` bytes of c, the others of v (nb <= 0: v, nb >= 4: c)
+__device__ __forceinline__ uint32_t merge_low(uint32_t c, uint32_t v, int nb)
+{
+    const uint32_t m = nb <= 0 ? 0u : (nb >= 4 ? 0xFFFFFFFFu : (1u << (8 * nb)) - 1u);
+    return (c & m) | (v & ~m);
+}
+template <typename T> __device__ __forceinline__ T pick3(int k, T a, T b, T c) { return k == 0 ? a : (k == 1 ? b : c); }
+
 template <bool kSolid>
 __global__ void __launch_bounds__(kFmt2ThreadsMax, 1)
-format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int n,
+format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int64_t gidx_origin, int n,
                      const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
                      const uint32_t *__restrict__ offs /* [3][n] */,
                      const unsigned long long *__restrict__ totals /* bytes of the batch per stream */,
@@ -1917,10 +1938,9 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
     extern __shared__ __align__(16) uint8_t smem[];
     const int WP = P.tile_pairs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qmode = P.fixed_quality ? 2 : (P.qdelta_n > 0 ? 1 : 0);          // 0: no noise, 1: noise table, 2: fixed character
-    uint32_t a_qtab, a_qb0, a_qb1, a_meta, a_rm, a_nm, a_st0, a_st1, a_st2;
+    uint32_t a_qtab, a_qb0, a_qb1, a_meta, a_rm, a_nm, a_st0, a_st1, a_st2, a_pre, a_names, a_carry;
     const uint32_t *cdf;
     {
-        const Format2Smem L = format2_smem_layout(P);
         if (qmode == 1) {
             const uint4 *src = reinterpret_cast<const uint4 *>(P.qtab);
             uint4 *dst = reinterpret_cast<uint4 *>(smem + L.qtab_off);
@@ -1937,6 +1957,7 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
         const uint32_t a_warp = a_base + L.warp_off + warp * L.warp_stride;
         a_meta = a_warp + L.meta_off; a_rm = in_register(a_warp + L.rmeta_off); a_nm = in_register(a_warp + L.nmeta_off);
         a_st0 = a_warp + L.stage_off[0]; a_st1 = a_warp + L.stage_off[1]; a_st2 = a_warp + L.stage_off[2];
+        a_pre = a_warp + L.pre_off; a_names = a_warp + L.names_off; a_carry = a_warp + L.carry_off + lane * 16;
         cdf = reinterpret_cast<const uint32_t *>(smem + L.cdf_off);
     }
     __syncthreads();                                                 // the only CTA-wide barrier
@@ -1946,62 +1967,90 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
     constexpr int sfx_f = kSolid ? 2 : 1;                           // bytes between a bfast name and its first base: "\n" ("\nA")
     const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
     const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
-    const int g0 = (P.cap[0] + 7) >> 3, G = P.nw[0] + P.nw[1];      // 8-base groups (= code words) per pair; end 0 owns the first g0
-    const int h0 = (g0 + 1) >> 1, G2 = h0 + ((G - g0 + 1) >> 1);    // 16-base lane items per pair (P.inv_groups = 2^32 / G2 + 1)
     const int ntiles = (n + WP - 1) / WP;
-    const int n_warps = (int)blockDim.x >> 5;
-    const int tstride = gridDim.x * n_warps;
     constexpr uint32_t full = 0xffffffffu;
+    const uint32_t al0 = (uint32_t)reinterpret_cast<uintptr_t>(out0) & 15u, al1 = (uint32_t)reinterpret_cast<uintptr_t>(out1) & 15u,
+                   al2 = (uint32_t)reinterpret_cast<uintptr_t>(out2) & 15u;
 
-    auto prefetch = [&](int tile) {
-        FmtPrefetch f;
-        f.lens = f.tail = 0; f.off[0] = f.off[1] = f.off[2] = 0; f.nl = 0;
-        if (tile >= ntiles) return f;
+    // step 0 of a mini-tile, one mini-tile ahead: the FmtPrefetch words of lane j (pair j; lane np: the end offsets) and the
+    // read names on their way to shared memory buffer `b` (cp.async: nothing of it lives in registers meanwhile)
+    auto issue = [&](int tile, int b) {
+        if (tile >= ntiles) return;
         const int p0 = tile * WP, np = min(WP, n - p0), p = p0 + lane;
+        const uint32_t slot = a_pre + b * L.pre_bytes + lane * 32;
         if (lane < np) {
             const uint32_t *r = reinterpret_cast<const uint32_t *>(recs + p);
-            f.lens = __ldg(r + 2); f.tail = __ldg(r + 7);
-            f.nl = __ldg(reinterpret_cast<const uint32_t *>(gname_len) + p);
+            cp_async4(slot, r + 2); cp_async4(slot + 4, r + 7);
+            cp_async4(slot + 8, reinterpret_cast<const uint32_t *>(gname_len) + p);
         }
         if (lane <= np) {
-            if (on0) { f.off[0] = p < n ? __ldg(offs + p) : (uint32_t)totals[0]; f.off[1] = p < n ? __ldg(offs + (size_t)n + p) : (uint32_t)totals[1]; }
-            if (on2) f.off[2] = p < n ? __ldg(offs + (size_t)2 * n + p) : (uint32_t)totals[2];
+            if (on0) {
+                cp_async4(slot + 12, p < n ? static_cast<const void *>(offs + p) : static_cast<const void *>(totals));
+                cp_async4(slot + 16, p < n ? static_cast<const void *>(offs + (size_t)n + p) : static_cast<const void *>(totals + 1));
+            }
+            if (on2) cp_async4(slot + 20, p < n ? static_cast<const void *>(offs + (size_t)2 * n + p) : static_cast<const void *>(totals + 2));
+        }
+        const int nchunk = (np * nvar * P.name_cap) >> 4;
+        const char *src = gnames + (size_t)p0 * nvar * P.name_cap;
+        for (int c = lane; c < nchunk; c += 32) cp_async16(a_names + b * L.names_bytes + (c << 4), src + ((size_t)c << 4));
+    };
+    auto take = [&](int b) {
+        FmtPrefetch f;
+        f.lens = f.tail = 0; f.off[0] = f.off[1] = f.off[2] = 0; f.nl = 0;
+        if (lane <= WP) {
+            const uint4 v = lds128(a_pre + b * L.pre_bytes + lane * 32);
+            const uint2 u = lds64(a_pre + b * L.pre_bytes + lane * 32 + 16);
+            f.lens = v.x; f.tail = v.y; f.nl = v.z;
+            if (on0) { f.off[0] = v.w; f.off[1] = u.x; }
+            if (on2) f.off[2] = u.y;
         }
         return f;
     };
 
-    int tile = blockIdx.x * n_warps + warp;
-    FmtPrefetch cur = prefetch(tile);
+    // mini-tiles of a warp: runs of consecutive mini-tiles (L.run of them, the runs dealt round robin; 0: one contiguous
+    // range per warp).  Inside a run the 16-byte chunk two neighbouring mini-tiles share stays in the warp (`carry`)
+    int run_start, run_end, run_stride;
+    {
+        const int n_warps = (int)blockDim.x >> 5, gw = blockIdx.x * n_warps + warp, tw = gridDim.x * n_warps;
+        if (L.run > 0) { run_start = gw * L.run; run_end = min(run_start + L.run, ntiles); run_stride = tw * L.run; }
+        else {
+            run_start = (int)((long long)ntiles * gw / tw); run_end = (int)((long long)ntiles * (gw + 1) / tw);
+            run_stride = ntiles;                                     // (no second run)
+        }
+    }
+    int tile = run_start < run_end ? run_start : ntiles;
+    int buf = 0;
+    issue(tile, 0);
     bool bulk_pending = false;                                       // (lanes 0-2) a bulk store of the previous mini-tile may still read the staging area
-    for (; tile < ntiles; tile += tstride) {
-        const FmtPrefetch nxt = prefetch(tile + tstride);
+    int carry_lo = -1;                                               // (lane k < 3) stream k: first valid byte of the chunk the previous mini-tile
+                                                                     //   of the run left at a_carry; -1: nothing carried
+    while (tile < ntiles) {
+        const bool last_in_run = tile + 1 >= run_end;
+        const int tile_next = last_in_run ? run_start + run_stride : tile + 1;
+        cp_async_wait_all();                                         // this mini-tile's words and names have landed
+        const FmtPrefetch cur = take(buf);
+        issue(tile_next, buf ^ 1);
+        const uint32_t a_nb = a_names + buf * L.names_bytes;          // the names of this mini-tile (other lanes' copies: after the __syncwarp below)
         const int p0 = tile * WP, np = min(WP, n - p0);
-        const uint32_t *seqw_tile = seqw + (size_t)p0 * G;            // code word of item `it` of this mini-tile: seqw_tile[it]
-        const char *gnames_tile = gnames + (size_t)p0 * nvar * P.name_cap;
+        const uint32_t *seqw_tile = seqw + (size_t)p0 * L.G;          // code word of item `it` of this mini-tile: seqw_tile[it]
         {   // the read codes of this mini-tile towards L1, those of the next one towards L2
-            const uintptr_t c0 = reinterpret_cast<uintptr_t>(seqw_tile), a0 = c0 & ~(uintptr_t)127;
-            if (a0 + ((uintptr_t)lane << 7) < c0 + (size_t)np * G * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + ((uintptr_t)lane << 7)));
-            // the names of this mini-tile (np * nvar rows of name_cap bytes, 128-byte lines) towards L1 as well
-            const uintptr_t n0 = reinterpret_cast<uintptr_t>(gnames) + (size_t)p0 * nvar * P.name_cap, na = n0 & ~(uintptr_t)127;
-            if (na + ((uintptr_t)lane << 7) < n0 + (size_t)np * nvar * P.name_cap) asm volatile("prefetch.global.L1 [%0];" ::"l"(na + ((uintptr_t)lane << 7)));
-            const int pn = (tile + tstride) * WP;
+            const uint32_t cb = (uint32_t)np * (uint32_t)L.G * 4u, lo = (uint32_t)lane << 7;
+            if (lo < cb + 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(seqw_tile) + min(lo, cb - 1u)));
+            const int pn = tile_next * WP;
             if (pn < n) {
-                const uintptr_t c1 = reinterpret_cast<uintptr_t>(seqw + (size_t)pn * G), a1 = c1 & ~(uintptr_t)127;
-                if (a1 + ((uintptr_t)lane << 7) < c1 + (size_t)min(WP, n - pn) * G * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(a1 + ((uintptr_t)lane << 7)));
+                const uint32_t cn = (uint32_t)min(WP, n - pn) * (uint32_t)L.G * 4u;
+                if (lo < cn + 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(seqw + (size_t)pn * L.G) + min(lo, cn - 1u)));
             }
         }
         // ---- step 0: geometry of the mini-tile: per-pair, then per-read and per-record metadata ----------------------
-        uint32_t begin[3], shift[3], total[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            begin[k] = __shfl_sync(full, cur.off[k], 0);
-            total[k] = __shfl_sync(full, cur.off[k], np) - begin[k];
-            char *outk = k == 0 ? out0 : (k == 1 ? out1 : out2);
-            shift[k] = (uint32_t)(reinterpret_cast<uintptr_t>(outk + begin[k]) & 15u);
-        }
+        const uint32_t bg0 = __shfl_sync(full, cur.off[0], 0), bg1 = __shfl_sync(full, cur.off[1], 0), bg2 = __shfl_sync(full, cur.off[2], 0);
+        const uint32_t tt0 = __shfl_sync(full, cur.off[0], np) - bg0, tt1 = __shfl_sync(full, cur.off[1], np) - bg1,
+                       tt2 = __shfl_sync(full, cur.off[2], np) - bg2;                          // bytes of the mini-tile per stream
+        const uint32_t sh0 = (al0 + bg0) & 15u, sh1 = (al1 + bg1) & 15u, sh2 = (al2 + bg2) & 15u;   // their misalignment in the output
+        const uint32_t my_bg = pick3(lane, bg0, bg1, bg2), my_tot = pick3(lane, tt0, tt1, tt2), my_sh = pick3(lane, sh0, sh1, sh2);   // (step 4)
         if (lane < np) {
             uint4 m0, m1;                                            // PairMeta
-            m0.x = cur.off[0] - begin[0] + shift[0]; m0.y = cur.off[1] - begin[1] + shift[1]; m0.z = cur.off[2] - begin[2] + shift[2];
+            m0.x = cur.off[0] - bg0 + sh0; m0.y = cur.off[1] - bg1 + sh1; m0.z = cur.off[2] - bg2 + sh2;
             m0.w = cur.lens; m1.x = cur.nl; m1.y = cur.tail >> 16; m1.z = m1.w = 0;
             sts128(a_meta + lane * 32, m0); sts128(a_meta + lane * 32 + 16, m1);
         }
@@ -2025,7 +2074,7 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
             r1.z = (uint32_t)gidx; r1.w = (uint32_t)(gidx >> 32);
             sts128(a_rm + rd * 32, r0); sts128(a_rm + rd * 32 + 16, r1);
             const bool has = Le > 0;
-            const uint32_t src = (uint32_t)t * (uint32_t)nvar * (uint32_t)P.name_cap;   // relative to gnames_tile
+            const uint32_t src = (uint32_t)t * (uint32_t)nvar * (uint32_t)P.name_cap;   // relative to the names of the mini-tile
             sts128(a_nm + (rd * 2) * 16, make_uint4(has && on0 ? rec_b : 0u, (uint32_t)nbwa, src + (uint32_t)(nvar - 1) * P.name_cap, (uint32_t)(Le - from)));
             sts128(a_nm + (rd * 2 + 1) * 16, make_uint4(has && on2 ? rec_f : 0u, (uint32_t)nfull, src, (uint32_t)Le));
             if (has) max_nn = max(max_nn, max(on0 ? nbwa : 0, on2 ? nfull : 0));
@@ -2040,34 +2089,34 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
                 if (rc < 4 * np) nm = lds128(a_nm + rc * 16);
                 const bool act = nm.x != 0 && x0 < (int)nm.y;
                 uint4 v = make_uint4(0, 0, 0, 0);
-                if (act) v = __ldg(reinterpret_cast<const uint4 *>(gnames_tile + nm.z + x0));
+                if (act) v = lds128(a_nb + nm.z + x0);
                 uint32_t pw = __shfl_up_sync(full, v.w, 1);               // last word of the previous chunk of the same name
-                if ((lane & 3) == 0) pw = c0 ? __ldg(reinterpret_cast<const uint32_t *>(gnames_tile + nm.z + x0 - 4)) : 0u;
+                if ((lane & 3) == 0) pw = c0 ? lds32(a_nb + nm.z + x0 - 4) : 0u;
                 if (act) {
                     const uint32_t d = nm.x + x0, bs = d & 3u, w = d - bs, sel = 0x7654u - 0x1111u * bs;
                     const int left = (int)nm.y - x0 + (int)bs;             // name bytes from w on
-                    sts32(w, __byte_perm(pw, v.x, sel));
-                    if (left > 4) sts32(w + 4, __byte_perm(v.x, v.y, sel));
-                    if (left > 8) sts32(w + 8, __byte_perm(v.y, v.z, sel));
-                    if (left > 12) sts32(w + 12, __byte_perm(v.z, v.w, sel));
-                    if (left > 16 && (int)nm.y - x0 <= 16) sts32(w + 16, __byte_perm(v.w, 0u, sel));   // (the next chunk's first word otherwise)
+                    sts32(w, prmt(pw, v.x, sel));
+                    if (left > 4) sts32(w + 4, prmt(v.x, v.y, sel));
+                    if (left > 8) sts32(w + 8, prmt(v.y, v.z, sel));
+                    if (left > 12) sts32(w + 12, prmt(v.z, v.w, sel));
+                    if (left > 16 && (int)nm.y - x0 <= 16) sts32(w + 16, prmt(v.w, 0u, sel));   // (the next chunk's first word otherwise)
                 }
             }
         __syncwarp();
         // ---- step 2: bases and qualities, one lane per (pair, end, 16 bases = two 8-base groups), aligned word stores ----
-        const int items = np * G2, n_iter = (items + 31) >> 5;
+        const int items = np * L.G2, n_iter = (items + 31) >> 5;
         uint32_t carry_a = 0, carry_d = 0, carry_q = 0;
         for (int iter = 0; iter < n_iter; ++iter) {
             const int it = (iter << 5) + lane;
-            const int t = (int)__umulhi((uint32_t)it, P.inv_groups), gi = it - t * G2;
-            const int e = gi < h0 ? 0 : 1, j = gi - (e ? h0 : 0), rd = 2 * t + e, k0 = j << 4;
+            const int t = (int)__umulhi((uint32_t)it, P.inv_groups), gi = it - t * L.G2;
+            const int e = gi < L.h0 ? 0 : 1, j = gi - (e ? L.h0 : 0), rd = 2 * t + e, k0 = j << 4;
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
             if (it < items) { r0 = lds128(a_rm + rd * 32); r1 = lds128(a_rm + rd * 32 + 16); }
             const int Le = (int)r1.x;
             const bool active = k0 < Le, active_b = k0 + 8 < Le;       // (Le == 0 beyond the mini-tile)
             uint32_t cw[2] = {0, 0};
             {
-                const uint32_t *src = seqw_tile + t * G + (e ? g0 : 0) + 2 * j;
+                const uint32_t *src = seqw_tile + (t * L.G + (e ? L.g0 : 0) + 2 * j);
                 if (active) cw[0] = __ldg(src);
                 if (active_b) cw[1] = __ldg(src + 1);
             }
@@ -2084,25 +2133,27 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
                     if (qmode == 1) {
                         const uint32_t blk = (uint32_t)(4 * j + 2 * sub);                       // the group's first QUAL block
                         const uint4 b0 = philox4x32_10_rk(r1.z, r1.w, r1.y, blk, P);
-                        constexpr int dsh = 16 - kQTabBits;
-#define DWG_LK(word, half) lds8(a_qtab + ((half) ? ((word) >> (16 + dsh)) : (((word) & 0xFFFFu) >> dsh)))
-                        r.x = DWG_LK(b0.x, 0) | (DWG_LK(b0.x, 1) << 16);
-                        r.y = DWG_LK(b0.y, 0) | (DWG_LK(b0.y, 1) << 16);
-                        r.z = DWG_LK(b0.z, 0) | (DWG_LK(b0.z, 1) << 16);
-                        r.w = DWG_LK(b0.w, 0) | (DWG_LK(b0.w, 1) << 16);
-#undef DWG_LK
+                        // the table cell of a 16-bit draw: its upper kQTabBits bits
+#define DWG_LK_LO(word) lds8(a_qtab + (((word) << 16) >> (32 - kQTabBits)))
+#define DWG_LK_HI(word) lds8(a_qtab + ((word) >> (32 - kQTabBits)))
+                        r.x = DWG_LK_LO(b0.x) | (DWG_LK_HI(b0.x) << 16);
+                        r.y = DWG_LK_LO(b0.y) | (DWG_LK_HI(b0.y) << 16);
+                        r.z = DWG_LK_LO(b0.z) | (DWG_LK_HI(b0.z) << 16);
+                        r.w = DWG_LK_LO(b0.w) | (DWG_LK_HI(b0.w) << 16);
+#undef DWG_LK_LO
+#undef DWG_LK_HI
                         if ((r.x | r.y | r.z | r.w) & 0x00800080u)
                             r = qual_ranks_slow(r, b0, philox4x32_10_rk(r1.z, r1.w, r1.y, blk + 1u, P), cdf, P.qdelta_n);
                     }
                     // 33 + clamp(base + noise, 0, 40), two qualities per instruction
                     const uint32_t v0 = __viaddmin_s16x2_relu(r.x, qb.x, 0x00280028u), v1 = __viaddmin_s16x2_relu(r.y, qb.y, 0x00280028u);
                     const uint32_t v2 = __viaddmin_s16x2_relu(r.z, qb.z, 0x00280028u), v3 = __viaddmin_s16x2_relu(r.w, qb.w, 0x00280028u);
-                    q[2 * sub] = __byte_perm(v0, v1, 0x6420) + 0x21212121u;
-                    q[2 * sub + 1] = __byte_perm(v2, v3, 0x6420) + 0x21212121u;
+                    q[2 * sub] = prmt(v0, v1, 0x6420u) + 0x21212121u;
+                    q[2 * sub + 1] = prmt(v2, v3, 0x6420u) + 0x21212121u;
                 }
-                // 8 nibble codes -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
-                a[2 * sub] = __byte_perm(0x54474341u, 0x0000004Eu, codes & 0xFFFFu); a[2 * sub + 1] = __byte_perm(0x54474341u, 0x0000004Eu, codes >> 16);
-                if (solid) { d[2 * sub] = __byte_perm(0x33323130u, 0x00000034u, codes & 0xFFFFu); d[2 * sub + 1] = __byte_perm(0x33323130u, 0x00000034u, codes >> 16); }
+                // 8 nibble codes (0-4) -> 8 characters: the nibbles are PRMT selectors into "ACGTN" / "01234"
+                a[2 * sub] = prmt(0x54474341u, 0x0000004Eu, codes); a[2 * sub + 1] = prmt(0x54474341u, 0x0000004Eu, codes >> 16);
+                if (solid) { d[2 * sub] = prmt(0x33323130u, 0x00000034u, codes); d[2 * sub + 1] = prmt(0x33323130u, 0x00000034u, codes >> 16); }
             }
             // the last word of the previous 16 bases (previous lane; lane 0: last lane of the previous round)
             uint32_t pa = __shfl_up_sync(full, a[3], 1), pq = __shfl_up_sync(full, q[3], 1), pd = pa;
@@ -2129,43 +2180,63 @@ format_fastq2_kernel(const SimParams P, int64_t first, int64_t gidx_origin, int 
         for (int rc = lane; rc < 4 * np; rc += 32) {
             const uint4 nm = lds128(a_nm + rc * 16);
             if (nm.x == 0) continue;
-            const int bf = rc & 1, e = (rc >> 1) & 1, nn = (int)nm.y, L = (int)nm.w;
-            const uint32_t head = __ldg(reinterpret_cast<const uint32_t *>(gnames_tile + nm.z));
+            const int bf = rc & 1, e = (rc >> 1) & 1, nn = (int)nm.y, Lr = (int)nm.w;
+            const uint32_t head = lds32(a_nb + nm.z);
             sts8(nm.x, head); sts8(nm.x + 1, head >> 8);
             uint32_t s = nm.x + nn;
-            sts8(s - 2, (uint32_t)(uint8_t)__ldg(gnames_tile + nm.z + nn - 2)); sts8(s - 1, (uint32_t)(uint8_t)__ldg(gnames_tile + nm.z + nn - 1));
+            sts8(s - 2, lds8(a_nb + nm.z + nn - 2)); sts8(s - 1, lds8(a_nb + nm.z + nn - 1));
             if (!bf) { sts8(s, '/'); sts8(s + 1, solid ? (e == 0 ? '2' : '1') : (e == 0 ? '1' : '2')); sts8(s + 2, '\n'); s += 3; }
             else { sts8(s, '\n'); s += 1; if (solid) { sts8(s, 'A'); s += 1; } }
-            sts8(s + L, '\n'); sts8(s + L + 1, '+'); sts8(s + L + 2, '\n');
-            sts8(s + L + 3 + L, '\n');
+            sts8(s + Lr, '\n'); sts8(s + Lr + 1, '+'); sts8(s + Lr + 2, '\n');
+            sts8(s + Lr + 3 + Lr, '\n');
         }
         fence_async_smem();                                          // the bulk engine reads what the lanes wrote
         __syncwarp();
-        // ---- step 4: copy-out: lane k < 3 sends the 16-byte aligned interior of stream k as one bulk store -----------
-        {
-            const int k = lane < 3 ? lane : 0;
-            const uint32_t a_st = k == 0 ? a_st0 : (k == 1 ? a_st1 : a_st2);
-            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin[k] - shift[k];   // 16-byte aligned
-            const int sh = (int)shift[k], end = sh + (int)total[k];
-            const int c_first = sh ? 1 : 0, c_full = end >> 4;          // chunks [c_first, c_full) lie wholly inside the range
-            if (lane < 3 && total[k] != 0 && c_full > c_first) {
-                bulk_store(base + (c_first << 4), a_st + (c_first << 4), (uint32_t)(c_full - c_first) << 4);
-                bulk_commit();
-                bulk_pending = true;
+        // ---- step 4: copy-out, lane k < 3 for stream k.  Staging byte x of the stream belongs at base[x]; the bytes that
+        //      are this warp's to store are [lo, end): lo = sh, or the start of what the previous mini-tile of the run left
+        //      behind in `carry` (the chunk the two share).  Whole 16-byte chunks leave as one bulk store; the partial chunk
+        //      at the end is carried to the next mini-tile of the run; only the ends of a run store single bytes -----------
+        if (lane < 3) {
+            const uint32_t a_st = pick3(lane, a_st0, a_st1, a_st2);
+            const int sh = (int)my_sh, tot = (int)my_tot;
+            if (tot != 0 || carry_lo >= 0) {
+                char *base = pick3(lane, out0, out1, out2) + my_bg - sh;                         // 16-byte aligned
+                const int end = sh + tot;
+                int lo = sh;
+                if (carry_lo >= 0) {                                 // chunk 0: the carried bytes below sh, this mini-tile's from sh on
+                    const uint4 carry = lds128(a_carry);
+                    uint4 c = lds128(a_st);
+                    c.x = merge_low(carry.x, c.x, sh); c.y = merge_low(carry.y, c.y, sh - 4);
+                    c.z = merge_low(carry.z, c.z, sh - 8); c.w = merge_low(carry.w, c.w, sh - 12);
+                    sts128(a_st, c);
+                    fence_async_smem();
+                    lo = carry_lo;
+                }
+                const int c_lo = (lo + 15) >> 4, c_full = end >> 4;  // whole chunks: [c_lo, c_full)
+                if (c_full > c_lo) {
+                    bulk_store(base + (c_lo << 4), a_st + (c_lo << 4), (uint32_t)(c_full - c_lo) << 4);
+                    bulk_commit();
+                    bulk_pending = true;
+                }
+                const bool reach = c_full >= c_lo;                   // the staged bytes reach the chunk boundary c_lo
+                if (reach && (lo & 15)) {                            // head of a run: bytes [lo, 16)
+#pragma unroll
+                    for (int x = 1; x < 16; ++x) if (x >= lo) base[x] = (char)lds8(a_st + x);
+                }
+                const int t0 = reach ? (c_full << 4) : lo;           // the bytes after the last whole chunk: [t0, end)
+                carry_lo = -1;
+                if (end > t0) {
+                    if (!last_in_run) { sts128(a_carry, lds128(a_st + (c_full << 4))); carry_lo = reach ? 0 : lo; }
+                    else {
+#pragma unroll
+                        for (int xx = 0; xx < 16; ++xx) { const int x = (c_full << 4) + xx; if (x >= t0 && x < end) base[x] = (char)lds8(a_st + x); }
+                    }
+                }
             }
         }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {                                // the two boundary chunks are shared with the neighbouring mini-tiles
-            if (total[k] == 0) continue;
-            const uint32_t a_st = k == 0 ? a_st0 : (k == 1 ? a_st1 : a_st2);
-            char *base = (k == 0 ? out0 : (k == 1 ? out1 : out2)) + begin[k] - shift[k];
-            const int sh = (int)shift[k], end = sh + (int)total[k], nchunk = (end + 15) >> 4;
-            const int c_first = sh ? 1 : 0, c_full = end >> 4;
-            const int c = lane < 16 ? 0 : c_full, x = (c << 4) + (lane & 15);
-            const bool mine = lane < 16 ? c_first != 0 : (c_full < nchunk && (c_full > 0 || !c_first));
-            if (mine && x >= sh && x < end) base[x] = (char)lds8(a_st + x);
-        }
-        cur = nxt;
+        if (last_in_run) { run_start += run_stride; run_end = min(run_start + L.run, ntiles); }
+        tile = tile_next;
+        buf ^= 1;
     }
     if (bulk_pending) bulk_wait_read();
 }
