@@ -565,8 +565,6 @@ int update_caps(dwgsim_gpu *h)
     if (h->sp.fmt_v2) {
         // one CTA per SM (the noise table takes 64 KB of its shared memory): as many warps as fit with the mini-tile wanted
         h->sp.fmt_warps = kFmt2WarpsMax;
-        h->sp.fmt_run = 0;
-        if (const char *e = getenv("DWGSIM_FMT_RUN")) h->sp.fmt_run = std::max(0, atoi(e));     // experiments: 1 = every mini-tile on its own
         if (const char *e = getenv("DWGSIM_FMT_WARPS")) h->sp.fmt_warps = std::max(1, std::min(kFmt2WarpsMax, atoi(e)));
         const int warps_floor = getenv("DWGSIM_TILE_PAIRS") ? 1 : std::min(h->sp.fmt_warps, 20);
         while (h->sp.fmt_warps > warps_floor && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.fmt_warps;

@@ -1819,7 +1819,6 @@ struct Format2Smem {                    // computed on the host, passed by value
     int names_off, names_bytes;        //   and its read names (WP * nvar rows of name_cap bytes), both filled by cp.async
     int carry_off;                     // per warp: 3 x 16 bytes, the chunk a mini-tile leaves to the next one of its run
     int g0, h0, G, G2;                 // 8-base groups / 16-base lane items of end 0, code words / lane items per pair
-    int run;                           // mini-tiles a warp takes at a stretch; 0: one contiguous range per warp
 };
 __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
 {
@@ -1832,7 +1831,7 @@ __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
     for (int e = 0; e < 2; ++e) { L.qb_off[e] = o; o += (((P.cap[e] + 7) & ~7) * 2 + 16) & ~15; }
     L.warp_off = o;
     int w = 0;
-    L.meta_off = w; w += WP * (int)sizeof(PairMeta);
+    L.meta_off = w;
     L.rmeta_off = w; w += 2 * WP * (int)sizeof(ReadMeta);
     L.nmeta_off = w; w += 4 * WP * (int)sizeof(NameMeta);
     L.pre_off = w; L.pre_bytes = (WP + 1) * 32; w += 2 * L.pre_bytes;
@@ -1843,7 +1842,6 @@ __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
     L.total = o + (P.fmt_warps > 0 ? P.fmt_warps : kFmt2WarpsMax) * w;
     L.g0 = (P.cap[0] + 7) >> 3; L.G = P.nw[0] + P.nw[1];
     L.h0 = (L.g0 + 1) >> 1; L.G2 = L.h0 + ((L.G - L.g0 + 1) >> 1);      // (P.inv_groups = 2^32 / G2 + 1)
-    L.run = P.fmt_run;
     return L;
 }
 
@@ -1938,7 +1936,7 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
     extern __shared__ __align__(16) uint8_t smem[];
     const int WP = P.tile_pairs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qmode = P.fixed_quality ? 2 : (P.qdelta_n > 0 ? 1 : 0);          // 0: no noise, 1: noise table, 2: fixed character
-    uint32_t a_qtab, a_qb0, a_qb1, a_meta, a_rm, a_nm, a_st0, a_st1, a_st2, a_pre, a_names, a_carry;
+    uint32_t a_qtab, a_qb0, a_qb1, a_rm, a_nm, a_st0, a_st1, a_st2, a_pre, a_names, a_carry;
     const uint32_t *cdf;
     {
         if (qmode == 1) {
@@ -1955,7 +1953,7 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
         const uint32_t a_base = smem_addr(smem);
         a_qtab = in_register(a_base + L.qtab_off); a_qb0 = a_base + L.qb_off[0]; a_qb1 = a_base + L.qb_off[1];
         const uint32_t a_warp = a_base + L.warp_off + warp * L.warp_stride;
-        a_meta = a_warp + L.meta_off; a_rm = in_register(a_warp + L.rmeta_off); a_nm = in_register(a_warp + L.nmeta_off);
+        a_rm = in_register(a_warp + L.rmeta_off); a_nm = in_register(a_warp + L.nmeta_off);
         a_st0 = a_warp + L.stage_off[0]; a_st1 = a_warp + L.stage_off[1]; a_st2 = a_warp + L.stage_off[2];
         a_pre = a_warp + L.pre_off; a_names = a_warp + L.names_off; a_carry = a_warp + L.carry_off + lane * 16;
         cdf = reinterpret_cast<const uint32_t *>(smem + L.cdf_off);
@@ -1984,53 +1982,39 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
             cp_async4(slot + 8, reinterpret_cast<const uint32_t *>(gname_len) + p);
         }
         if (lane <= np) {
-            if (on0) {
-                cp_async4(slot + 12, p < n ? static_cast<const void *>(offs + p) : static_cast<const void *>(totals));
-                cp_async4(slot + 16, p < n ? static_cast<const void *>(offs + (size_t)n + p) : static_cast<const void *>(totals + 1));
+            if (p < n) {
+                if (on0) { cp_async4(slot + 12, offs + p); cp_async4(slot + 16, offs + (size_t)n + p); }
+                if (on2) cp_async4(slot + 20, offs + (size_t)2 * n + p);
+            } else {                                                 // the end of the batch
+                if (on0) { cp_async4(slot + 12, totals); cp_async4(slot + 16, totals + 1); }
+                if (on2) cp_async4(slot + 20, totals + 2);
             }
-            if (on2) cp_async4(slot + 20, p < n ? static_cast<const void *>(offs + (size_t)2 * n + p) : static_cast<const void *>(totals + 2));
         }
         const int nchunk = (np * nvar * P.name_cap) >> 4;
         const char *src = gnames + (size_t)p0 * nvar * P.name_cap;
         for (int c = lane; c < nchunk; c += 32) cp_async16(a_names + b * L.names_bytes + (c << 4), src + ((size_t)c << 4));
     };
-    auto take = [&](int b) {
-        FmtPrefetch f;
-        f.lens = f.tail = 0; f.off[0] = f.off[1] = f.off[2] = 0; f.nl = 0;
-        if (lane <= WP) {
-            const uint4 v = lds128(a_pre + b * L.pre_bytes + lane * 32);
-            const uint2 u = lds64(a_pre + b * L.pre_bytes + lane * 32 + 16);
-            f.lens = v.x; f.tail = v.y; f.nl = v.z;
-            if (on0) { f.off[0] = v.w; f.off[1] = u.x; }
-            if (on2) f.off[2] = u.y;
-        }
-        return f;
-    };
-
-    // mini-tiles of a warp: runs of consecutive mini-tiles (L.run of them, the runs dealt round robin; 0: one contiguous
-    // range per warp).  Inside a run the 16-byte chunk two neighbouring mini-tiles share stays in the warp (`carry`)
-    int run_start, run_end, run_stride;
+    // every warp formats one contiguous range of mini-tiles: the 16-byte chunk two neighbouring mini-tiles share stays in
+    // the warp (a_carry), only the two ends of the range meet another warp's bytes
+    int tile, run_end;
     {
         const int n_warps = (int)blockDim.x >> 5, gw = blockIdx.x * n_warps + warp, tw = gridDim.x * n_warps;
-        if (L.run > 0) { run_start = gw * L.run; run_end = min(run_start + L.run, ntiles); run_stride = tw * L.run; }
-        else {
-            run_start = (int)((long long)ntiles * gw / tw); run_end = (int)((long long)ntiles * (gw + 1) / tw);
-            run_stride = ntiles;                                     // (no second run)
-        }
+        tile = (int)((long long)ntiles * gw / tw); run_end = (int)((long long)ntiles * (gw + 1) / tw);
     }
-    int tile = run_start < run_end ? run_start : ntiles;
     int buf = 0;
     issue(tile, 0);
     bool bulk_pending = false;                                       // (lanes 0-2) a bulk store of the previous mini-tile may still read the staging area
     int carry_lo = -1;                                               // (lane k < 3) stream k: first valid byte of the chunk the previous mini-tile
                                                                      //   of the run left at a_carry; -1: nothing carried
-    while (tile < ntiles) {
-        const bool last_in_run = tile + 1 >= run_end;
-        const int tile_next = last_in_run ? run_start + run_stride : tile + 1;
-        cp_async_wait_all();                                         // this mini-tile's words and names have landed
-        const FmtPrefetch cur = take(buf);
+    for (; tile < run_end; ++tile) {
+        const bool last_in_run = tile + 1 == run_end;
+        const int tile_next = last_in_run ? ntiles : tile + 1;
+        cp_async_wait_all();                                         // this lane's copies for this mini-tile have landed
+        if (bulk_pending) { bulk_wait_read(); bulk_pending = false; }   // the staging area is free again
+        __syncwarp();                                                // ... and every other lane's
+        const uint32_t a_pb = a_pre + buf * L.pre_bytes;              // slot j (32 bytes): lens, tail, name lengths, the three offsets of pair j
+        const uint32_t a_nb = a_names + buf * L.names_bytes;          // the read names of the mini-tile
         issue(tile_next, buf ^ 1);
-        const uint32_t a_nb = a_names + buf * L.names_bytes;          // the names of this mini-tile (other lanes' copies: after the __syncwarp below)
         const int p0 = tile * WP, np = min(WP, n - p0);
         const uint32_t *seqw_tile = seqw + (size_t)p0 * L.G;          // code word of item `it` of this mini-tile: seqw_tile[it]
         {   // the read codes of this mini-tile towards L1, those of the next one towards L2
@@ -2042,35 +2026,27 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
                 if (lo < cn + 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(seqw + (size_t)pn * L.G) + min(lo, cn - 1u)));
             }
         }
-        // ---- step 0: geometry of the mini-tile: per-pair, then per-read and per-record metadata ----------------------
-        const uint32_t bg0 = __shfl_sync(full, cur.off[0], 0), bg1 = __shfl_sync(full, cur.off[1], 0), bg2 = __shfl_sync(full, cur.off[2], 0);
-        const uint32_t tt0 = __shfl_sync(full, cur.off[0], np) - bg0, tt1 = __shfl_sync(full, cur.off[1], np) - bg1,
-                       tt2 = __shfl_sync(full, cur.off[2], np) - bg2;                          // bytes of the mini-tile per stream
+        // ---- step 0: geometry of the mini-tile, then per-read and per-record metadata ----------------------------------
+        uint32_t bg0 = 0, bg1 = 0, bg2 = 0, tt0 = 0, tt1 = 0, tt2 = 0;      // first byte and bytes of the mini-tile per stream
+        if (on0) { bg0 = lds32(a_pb + 12); bg1 = lds32(a_pb + 16); tt0 = lds32(a_pb + np * 32 + 12) - bg0; tt1 = lds32(a_pb + np * 32 + 16) - bg1; }
+        if (on2) { bg2 = lds32(a_pb + 20); tt2 = lds32(a_pb + np * 32 + 20) - bg2; }
         const uint32_t sh0 = (al0 + bg0) & 15u, sh1 = (al1 + bg1) & 15u, sh2 = (al2 + bg2) & 15u;   // their misalignment in the output
         const uint32_t my_bg = pick3(lane, bg0, bg1, bg2), my_tot = pick3(lane, tt0, tt1, tt2), my_sh = pick3(lane, sh0, sh1, sh2);   // (step 4)
-        if (lane < np) {
-            uint4 m0, m1;                                            // PairMeta
-            m0.x = cur.off[0] - bg0 + sh0; m0.y = cur.off[1] - bg1 + sh1; m0.z = cur.off[2] - bg2 + sh2;
-            m0.w = cur.lens; m1.x = cur.nl; m1.y = cur.tail >> 16; m1.z = m1.w = 0;
-            sts128(a_meta + lane * 32, m0); sts128(a_meta + lane * 32 + 16, m1);
-        }
-        if (bulk_pending) { bulk_wait_read(); bulk_pending = false; }   // the staging area is free again
-        __syncwarp();
         int max_nn = 0;
         for (int rd = lane; rd < 2 * np; rd += 32) {                  // ReadMeta + the read's two NameMeta
             const int t = rd >> 1, e = rd & 1;
-            const uint4 m0 = lds128(a_meta + t * 32);
-            const uint2 m1 = lds64(a_meta + t * 32 + 16);
-            const int len0 = (int)(m0.w & 0xFFFFu), Le = e ? (int)(m0.w >> 16) : len0;
-            const int nfull = (int)(m1.x & 0xFFFFu), nbwa = (int)(m1.x >> 16);
-            const uint32_t rec_b = (e ? a_st1 + m0.y : a_st0 + m0.x);
+            const uint4 pv = lds128(a_pb + t * 32);                    // lens, tail, name lengths, offset in stream 0
+            const uint2 pu = lds64(a_pb + t * 32 + 16);                // offsets in streams 1 and 2
+            const int len0 = (int)(pv.x & 0xFFFFu), Le = e ? (int)(pv.x >> 16) : len0;
+            const int nfull = (int)(pv.z & 0xFFFFu), nbwa = (int)(pv.z >> 16);
+            const uint32_t rec_b = e ? a_st1 + (pu.x - bg1 + sh1) : a_st0 + (pv.w - bg0 + sh0);
             const int rec0 = len0 > 0 ? nfull + sfx_f + 2 * len0 + 4 : 0;
-            const uint32_t rec_f = a_st2 + m0.z + (e ? rec0 : 0);
+            const uint32_t rec_f = a_st2 + (pu.y - bg2 + sh2) + (e ? rec0 : 0);
             const uint64_t gidx = (uint64_t)(gidx_origin + first + p0 + t);
             uint4 r0, r1;
             r0.x = rec_b + nbwa + 3 - from; r0.y = r0.x + (Le - from) + 3;
             r0.z = rec_f + nfull + sfx_f; r0.w = r0.z + Le + 3;
-            r1.x = (uint32_t)Le; r1.y = (m1.y & 0xFFFFu) | (kStQual << 16) | ((uint32_t)e << 24);
+            r1.x = (uint32_t)Le; r1.y = (pv.y >> 16) | (kStQual << 16) | ((uint32_t)e << 24);
             r1.z = (uint32_t)gidx; r1.w = (uint32_t)(gidx >> 32);
             sts128(a_rm + rd * 32, r0); sts128(a_rm + rd * 32 + 16, r1);
             const bool has = Le > 0;
@@ -2234,8 +2210,6 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
                 }
             }
         }
-        if (last_in_run) { run_start += run_stride; run_end = min(run_start + L.run, ntiles); }
-        tile = tile_next;
         buf ^= 1;
     }
     if (bulk_pending) bulk_wait_read();
