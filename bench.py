@@ -62,7 +62,7 @@ WORKLOADS = {
 
 def traffic_record():
     """DRAM bytes of one 2^20-pair step from the committed ncu --set full capture (tools/ncu_read.py --traffic writes it)"""
-    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02b_traffic.json")
     try:
         return json.load(open(p))
     except Exception:

@@ -1775,7 +1775,7 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
 
 
 // ---- kernel B2: format, word-granular -----------------------------------------------------------------------
-// Same mini-tile organisation, inputs and output bytes as format_fastq_kernel above, rebuilt around three changes:
+// Same mini-tile organisation, inputs and output bytes as format_fastq_kernel above, rebuilt around these changes:
 //   * qualities: the 8 QUAL draws of a group are the eight 16-bit fields of ONE Philox block; a byte table indexed by the
 //     16-bit draw gives the noise rank directly (P.qtab, 2^kQTabBits entries in shared memory), bit 7 marks the draws whose
 //     table cell contains a CDF threshold: only those (about 5e-4 of the draws) take their lower 16 bits from the group's
@@ -1788,6 +1788,15 @@ format_fastq_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t
 //     and up to two name bytes after the qualities), then one lane per record rewrites exactly those bytes
 //   * the 16-byte aligned interior of every stream range leaves with one cp.async.bulk.global.shared::cta per stream
 //     (UBLKCP) while the warp goes on with its next mini-tile; the staging area is reused after wait_group.read
+//   * a warp formats one contiguous range of mini-tiles.  The 16-byte chunk two neighbouring mini-tiles share is handed
+//     from one to the next in shared memory (a_carry) and leaves inside the next bulk store; single bytes are stored
+//     only where the range meets another warp's (two chunks per warp and stream)
+//   * what step 0 needs of the NEXT mini-tile - six words per pair of PairRec / name lengths / stream offsets and the
+//     read names - is on its way to shared memory while this one is formatted (cp.async, LDGSTS): no register holds
+//     it, no load latency is left in the names pass.  The code words are loaded where they are used (their latency
+//     hides behind the Philox rounds), the next mini-tile's lines are prefetched to L2
+//   * the geometry that only depends on the read lengths (Format2Smem) is computed on the host and arrives in the
+//     constant bank
 // Specialisation: colour space.  Configurations whose quality sum can wrap in int8 or whose noise table has 128 or
 // more steps (quality_std >= 7.8) stay on format_fastq_kernel.
 #ifndef DWG_QTAB_BITS
@@ -1814,7 +1823,7 @@ struct NameMeta {                      // per record (pair, end, bwa | bfast), 1
 };
 
 struct Format2Smem {                    // computed on the host, passed by value: every field is a constant-bank operand
-    int qtab_off, cdf_off, qb_off[2], warp_off, warp_stride, meta_off, rmeta_off, nmeta_off, stage_off[3], total;
+    int qtab_off, cdf_off, qb_off[2], warp_off, warp_stride, rmeta_off, nmeta_off, stage_off[3], total;
     int pre_off, pre_bytes;            // per warp, two of each: the next mini-tile's FmtPrefetch words (32 bytes per lane 0..WP)
     int names_off, names_bytes;        //   and its read names (WP * nvar rows of name_cap bytes), both filled by cp.async
     int carry_off;                     // per warp: 3 x 16 bytes, the chunk a mini-tile leaves to the next one of its run
@@ -1831,7 +1840,6 @@ __host__ __device__ inline Format2Smem format2_smem_layout(const SimParams &P)
     for (int e = 0; e < 2; ++e) { L.qb_off[e] = o; o += (((P.cap[e] + 7) & ~7) * 2 + 16) & ~15; }
     L.warp_off = o;
     int w = 0;
-    L.meta_off = w;
     L.rmeta_off = w; w += 2 * WP * (int)sizeof(ReadMeta);
     L.nmeta_off = w; w += 4 * WP * (int)sizeof(NameMeta);
     L.pre_off = w; L.pre_bytes = (WP + 1) * 32; w += 2 * L.pre_bytes;
@@ -2017,9 +2025,8 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
         issue(tile_next, buf ^ 1);
         const int p0 = tile * WP, np = min(WP, n - p0);
         const uint32_t *seqw_tile = seqw + (size_t)p0 * L.G;          // code word of item `it` of this mini-tile: seqw_tile[it]
-        {   // the read codes of this mini-tile towards L1, those of the next one towards L2
-            const uint32_t cb = (uint32_t)np * (uint32_t)L.G * 4u, lo = (uint32_t)lane << 7;
-            if (lo < cb + 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(seqw_tile) + min(lo, cb - 1u)));
+        {   // the read codes of the next mini-tile towards L2 (measured: -2% kernel time; an L1 prefetch of this one's: nothing)
+            const uint32_t lo = (uint32_t)lane << 7;
             const int pn = tile_next * WP;
             if (pn < n) {
                 const uint32_t cn = (uint32_t)min(WP, n - pn) * (uint32_t)L.G * 4u;
