@@ -220,15 +220,24 @@ format_kernel_t format_kernel_of(const SimParams &sp)
 }
 
 // dynamic shared memory of simulate_pairs_tp_kernel: staging tile + sampling tables (see the kernel prologue)
+// the instance of the thread-per-pair simulate kernel for a configuration (SimParams.tp_tables is 3 or 0)
+using tp_kernel_t = void (*)(const SimParams, const uint8_t *, int64_t, int64_t, int, int, JobLists, PairRec *, uint32_t *, unsigned long long *, uint32_t *);
+tp_kernel_t tp_kernel_of(const SimParams &sp)
+{
+    if (sp.data_type == 2) return simulate_pairs_tp_kernel<true, 3>;
+    return sp.tp_tables >= 3 ? simulate_pairs_tp_kernel<false, 3> : simulate_pairs_tp_kernel<false, 0>;
+}
+
 size_t tp_smem_bytes(const SimParams &sp)
 {
-    size_t words = (((size_t)kTpThreads * sp.row_stride + 3) & ~(size_t)3) + (sp.isize_n <= kIsizeSmemMax ? ((sp.isize_n + 1) & ~1) : 0);
+    size_t words = (((size_t)kTpThreads * sp.row_stride + 3) & ~(size_t)3) +
+                   (sp.isize_n <= kIsizeSmemMax && sp.tp_tables >= 1 ? ((sp.isize_n + 1) & ~1) : 0);
     words += 2 * (size_t)sp.win_slots * kTpThreads;                                                 // the reference window
-    if (sp.data_type != 2) for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);   // (not used by the flow model)
+    if (sp.data_type != 2 && sp.tp_tables >= 2) for (int e = 0; e < 2; ++e) words += 2 * (size_t)((sp.len[e] + 1) & ~1);   // (not used by the flow model)
     const size_t flow = sp.data_type != 2 ? 0 :                                                      // Ion Torrent only:
                         (size_t)((sp.flow_order_len + 15) & ~15) + (size_t)kTpThreads * ((sp.flow_order_len + 31) >> 5) * 4 +
                         (size_t)sp.flow_order_len * 8 + 32 + (size_t)kTpThreads * kFlowGapsAhead * 2;  // flow order, masks, nd table, gaps drawn ahead
-    return words * 4 + 3 * 1026 * 2 + flow + 32;
+    return words * 4 + (sp.tp_tables >= 3 ? 3 * 1026 * 2 : 0) + flow + 32;
 }
 
 #define CUDA_TRY(h, expr)                                                                              \
@@ -785,18 +794,15 @@ int launch_simulate(dwgsim_gpu *h, int64_t first, int n, bool timed, int *launch
         // persistent grid: exactly the CTAs that are resident at once (a partial second wave would idle most SMs)
         const size_t smem_tp = tp_smem_bytes(sp);
         int occ_tp = 1;
-        if (sp.data_type == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<true>, kTpThreads, smem_tp);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, simulate_pairs_tp_kernel<false>, kTpThreads, smem_tp);
+        const tp_kernel_t tp = tp_kernel_of(sp);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tp, tp, kTpThreads, smem_tp);
         const int grid_tp = std::min((n + kTpThreads - 1) / kTpThreads, sm_count * std::min(std::max(occ_tp, 1), 16));
         JobLists J;
         J.retry = w.jobs; J.random = w.jobs + (size_t)w.cap_pairs; J.count = w.status + 2;
         // two passes (kernels.cuh "Job lists"): fresh pairs, then the retries and random pairs they left behind
         const int n_pass = sp.data_type == 2 ? 1 : 2;          // (Ion Torrent lanes finish their own retries)
         for (int pass = 0; pass < n_pass; ++pass) {
-            if (sp.data_type == 2)
-                simulate_pairs_tp_kernel<true><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status, w.flow_scratch);
-            else
-                simulate_pairs_tp_kernel<false><<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status, w.flow_scratch);
+            tp<<<grid_tp, kTpThreads, smem_tp, st>>>(sp, h->blob, first, h->gidx_origin, n, pass, J, w.recs, w.seqs, w.status, w.flow_scratch);
         }
         extra_launches = n_pass - 1;
     }
@@ -1059,12 +1065,22 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         // still fit an SM or when it does not cost a CTA (long Ion Torrent rows leave room for two or three CTAs only)
         {
             auto ctas = [&](size_t bytes) { return (int)std::min<size_t>(6, (227 * 1024) / (bytes + 1024)); };
+            h->sp.tp_tables = 3;
             h->sp.win_slots = 0;
             const int without = ctas(tp_smem_bytes(h->sp));
             h->sp.win_slots = std::max(window_slots(sp.len[0]), window_slots(sp.len[1]));
             const int with = ctas(tp_smem_bytes(h->sp));
             if (const char *e = getenv("DWGSIM_WINDOW")) { if (atoi(e) == 0) h->sp.win_slots = 0; }
             else if (with < 4 && with < without) h->sp.win_slots = 0;
+            // the sampling tables leave shared memory (guides first, then the error tables, then the insert-size CDF) when
+            // that lets one more CTA fit: a pair reads a handful of their entries, an SM gains four warps
+            if (sp.data_type != 2) {
+                h->sp.tp_tables = 0;
+                const int without_tables = ctas(tp_smem_bytes(h->sp));
+                h->sp.tp_tables = 3;
+                if (ctas(tp_smem_bytes(h->sp)) < without_tables) h->sp.tp_tables = 0;
+                if (const char *e = getenv("DWGSIM_TP_TABLES")) h->sp.tp_tables = atoi(e) >= 3 ? 3 : 0;
+            }
         }
         const size_t smem_tp = tp_smem_bytes(sp);
         // one staging row per thread in shared memory bounds the combined read length (about 3,400 symbols); Ion Torrent
@@ -1074,8 +1090,7 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         h->ion_warp_kernel = sp.data_type == 2 && (!tp_fits || (force && strcmp(force, "warp") == 0));
         if (sp.data_type != 2 && !tp_fits) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }
         if (!h->ion_warp_kernel &&
-            (sp.data_type == 2 ? cudaFuncSetAttribute(simulate_pairs_tp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp)
-                               : cudaFuncSetAttribute(simulate_pairs_tp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp)) != cudaSuccess) {
+            cudaFuncSetAttribute(tp_kernel_of(sp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp) != cudaSuccess) {
             dwgsim_gpu_destroy(h); return DWGSIM_GPU_ECUDA;
         }
         if (smem_a > 227 * 1024) { dwgsim_gpu_destroy(h); return DWGSIM_GPU_EUNSUPPORTED; }

@@ -925,7 +925,7 @@ __device__ __forceinline__ void list_push(uint2 *list, unsigned long long *count
     if (push) list[base + __popc(m & ((1u << lane) - 1u))] = item;
 }
 
-template <bool kIon>
+template <bool kIon, int kTables /* = SimParams.tp_tables: which sampling tables are copied to shared memory */>
 __global__ void __launch_bounds__(kTpThreads, kTpMinBlocks)
 simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, int64_t first, int64_t gidx_origin, int n, int pass,
                          JobLists J, PairRec *__restrict__ recs, uint32_t *__restrict__ seqw, unsigned long long *__restrict__ status,
@@ -948,23 +948,30 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     TpTables T;
     {
         uint32_t *p32 = reinterpret_cast<uint32_t *>(win_mem + (size_t)P.win_slots * kTpThreads);
-        const bool isz_smem = P.isize_n <= kIsizeSmemMax;  // wider insert-size tables stay in HBM / L2 (one lookup per pair)
+        // (kTables: which of them are copied; the others are read where they lie, a few L1 / L2 hits per pair, when that
+        //  lets one more CTA fit the SM.  A template parameter: the loads keep their address space)
+        const bool isz_smem = P.isize_n <= kIsizeSmemMax && kTables >= 1;  // wider insert-size tables stay in HBM / L2 (one lookup per pair)
+        constexpr bool err_smem = !kIon && kTables >= 2, guide_smem = kTables >= 3;
         uint32_t *isz = p32; p32 += isz_smem ? ((P.isize_n + 1) & ~1) : 0;
         uint32_t *gp[2], *ac[2];
         // (the substitution-error tables are not used by the Ion Torrent flow model: no room taken for them there)
-        for (int e = 0; e < 2; ++e) { gp[e] = p32; p32 += kIon ? 0 : (P.len[e] + 1) & ~1; ac[e] = p32; p32 += kIon ? 0 : (P.len[e] + 1) & ~1; }
+        for (int e = 0; e < 2; ++e) { gp[e] = p32; p32 += err_smem ? (P.len[e] + 1) & ~1 : 0; ac[e] = p32; p32 += err_smem ? (P.len[e] + 1) & ~1 : 0; }
         uint16_t *p16 = reinterpret_cast<uint16_t *>(p32);
-        uint16_t *ig = p16; p16 += 1026;
+        uint16_t *ig = p16; p16 += guide_smem ? 1026 : 0;
         uint16_t *gg[2] = {p16, kIon ? p16 : p16 + 1026};
+        if (guide_smem && !kIon) p16 += 2 * 1026;
         if (isz_smem) for (int j = threadIdx.x; j < P.isize_n; j += kTpThreads) isz[j] = P.isize_cdf[j];
-        for (int j = threadIdx.x; j < 1025; j += kTpThreads) ig[j] = P.isize_guide[j];
+        if (guide_smem) for (int j = threadIdx.x; j < 1025; j += kTpThreads) ig[j] = P.isize_guide[j];
         if (!kIon)
             for (int e = 0; e < 2; ++e) {
-                for (int j = threadIdx.x; j < P.len[e]; j += kTpThreads) { gp[e][j] = P.err_gap[e][j]; ac[e][j] = P.err_acc[e][j]; }
-                for (int j = threadIdx.x; j < 1025; j += kTpThreads) gg[e][j] = P.gap_guide[e][j];
+                if (err_smem) for (int j = threadIdx.x; j < P.len[e]; j += kTpThreads) { gp[e][j] = P.err_gap[e][j]; ac[e][j] = P.err_acc[e][j]; }
+                if (guide_smem) for (int j = threadIdx.x; j < 1025; j += kTpThreads) gg[e][j] = P.gap_guide[e][j];
             }
-        T.isize_cdf = isz_smem ? isz : P.isize_cdf; T.isize_guide = ig;
-        for (int e = 0; e < 2; ++e) { T.gap[e] = gp[e]; T.acc[e] = ac[e]; T.gap_guide[e] = gg[e]; }
+        T.isize_cdf = isz_smem ? isz : P.isize_cdf; T.isize_guide = guide_smem ? ig : P.isize_guide;
+        for (int e = 0; e < 2; ++e) {
+            T.gap[e] = err_smem ? gp[e] : P.err_gap[e]; T.acc[e] = err_smem ? ac[e] : P.err_acc[e];
+            T.gap_guide[e] = guide_smem ? gg[e] : P.gap_guide[e];
+        }
         // Ion Torrent: flow order (codes) and one flow-mask bit vector per thread
         T.flow_order = nullptr; T.flow_mask = nullptr; T.flow_nd = nullptr; T.flow_q = nullptr;
         if (kIon) {

@@ -113,6 +113,8 @@ struct SimParams {
     const uint8_t  *qtab;                      // [2^kQTabBits] noise rank by the upper bits of a draw; bit 7: the cell holds a threshold
     uint32_t qkey[10];                         // Philox round keys of the seed: seed + r * 0x9E3779B9
     int32_t  fmt_v2;                           // 1: format_fastq2_kernel (word-granular), 0: format_fastq_kernel (int8 wrap / wide noise)
+    int32_t  tp_tables;                        // simulate kernel, sampling tables copied to shared memory: 3 all, 2 without the three
+                                               // guides, 1 also without the error gap / accept tables, 0 none (chosen by occupancy)
     const uint16_t *isize_guide, *gap_guide[2]; // [1025] the same for isize_cdf and err_gap[end] (first len[end] entries)
     const uint32_t *err_gap[2], *err_acc[2];   // substitution errors by thinning (DESIGN.md "RNG addressing")
     const uint8_t  *qbase[2];
