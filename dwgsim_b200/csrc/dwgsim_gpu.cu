@@ -1064,7 +1064,7 @@ int dwgsim_gpu_create(dwgsim_gpu_t **out, const dwgsim_gpu_params_t *p, int devi
         // the reference window of the thread-per-pair kernel costs shared memory: keep it when at least four CTAs (16 warps)
         // still fit an SM or when it does not cost a CTA (long Ion Torrent rows leave room for two or three CTAs only)
         {
-            auto ctas = [&](size_t bytes) { return (int)std::min<size_t>(6, (227 * 1024) / (bytes + 1024)); };
+            auto ctas = [&](size_t bytes) { return (int)std::min<size_t>(kTpMinBlocks, (227 * 1024) / (bytes + 1024)); };
             h->sp.tp_tables = 3;
             h->sp.win_slots = 0;
             const int without = ctas(tp_smem_bytes(h->sp));
