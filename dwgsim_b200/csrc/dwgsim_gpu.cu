@@ -1504,14 +1504,25 @@ int run_one(dwgsim_gpu_t *h, dwgsim_gpu_sink_fn sink, void *user, dwgsim_gpu_sta
     };
     auto drain_to = [&](size_t keep) -> int { int r = DWGSIM_GPU_OK; while (pend.size() > keep && r == DWGSIM_GPU_OK) r = drain_one(); return r; };
     int launches = 0;
-    const int64_t n_batches = (total + B - 1) / B;
+    // batch b covers the pairs [starts[b], starts[b + 1]).  A run starts with shorter batches (B/4, B/2, then B): the first
+    // device-to-host copy, which everything after it queues behind, begins after a quarter of a batch's kernel time.  The
+    // devices of a group follow the same schedule (their output is that of one device, gzip members included); runs sharded
+    // across processes keep equal batches: batch index -> rank is part of the exchange protocol (dwgsim_b200/shard.py).
+    std::vector<int64_t> starts;
+    {
+        static const bool no_ramp = getenv("DWGSIM_NO_RAMP") != nullptr;
+        int64_t sz = ((world == 1 || h->group) && !no_ramp) ? std::max<int64_t>(B / 4, 1) : B;
+        for (int64_t at = 0; at < total; at += std::min(sz, total - at), sz = std::min(B, sz * 2)) starts.push_back(at);
+        starts.push_back(total);
+    }
+    const int64_t n_batches = (int64_t)starts.size() - 1;
     const int64_t n_rounds = (n_batches + world - 1) / world;
     int64_t mine = 0;                                           // batches this rank has processed
     for (int64_t round = 0; round < n_rounds && rc == DWGSIM_GPU_OK; ++round) {
         const int64_t bi = round * world + rank;               // batch index owned by this rank in this round
         const bool active = bi < n_batches;
-        const int64_t first = bi * B;
-        const int n = active ? (int)std::min<int64_t>(B, total - first) : 0;
+        const int64_t first = active ? starts[(size_t)bi] : total;
+        const int n = active ? (int)(starts[(size_t)bi + 1] - first) : 0;
         const int dslot = (int)(mine & 1), pslot = (int)(mine % h->pinned_slots);
         int l = 0;
         int64_t rand_base = h->rand_serial, my_random = 0, round_total = 0;
