@@ -1284,32 +1284,75 @@ __device__ __forceinline__ void record_lengths(const SimParams &P, const PairRec
     }
 }
 
-__device__ __forceinline__ int put_dec(char *p, uint32_t v)      // writes v in decimal, returns the digit count
-{
-    if (v < 10u) { p[0] = (char)('0' + v); return 1; }              // strands, flags and most counts are one digit
-    const int nd = ndigits10(v);
-    for (int d = nd - 1; d >= 0; --d) { p[d] = (char)('0' + v % 10u); v /= 10u; }
-    return nd;
-}
-// '@' prefix contig _pos1_pos2_s1_s2_r_r_e:s:i_e:s:i_hex   (src/dwgsim.c:923-929); returns the length
-__device__ __forceinline__ int write_name(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
-                                          int cname_len, int variant, char *buf)
-{
-    const bool rnd = r.flags & kRecRandom;
-    int o = 0;
-    buf[o++] = '@';
-    for (int j = 0; j < P.prefix_len; ++j) buf[o++] = P.prefix[j];
-    if (rnd) { buf[o++] = 'r'; buf[o++] = 'a'; buf[o++] = 'n'; buf[o++] = 'd'; }
-    else for (int j = 0; j < cname_len; ++j) buf[o++] = cname[j];
-#pragma unroll
-    for (int f = 0; f < 12; ++f) {
-        buf[o++] = (f == 7 || f == 8 || f == 10 || f == 11) ? ':' : '_';
-        o += put_dec(buf + o, (uint32_t)name_field(r, serial, f, variant));
+// '@' prefix contig _pos1_pos2_s1_s2_r_r_e:s:i_e:s:i_hex   (src/dwgsim.c:923-929), assembled in a 64-bit register and stored
+// eight bytes at a time straight into the name row (16-byte aligned, name_cap bytes): no byte stores, no local staging
+// buffer.  Values handed to put() carry their first byte lowest and nothing above their n bytes.
+struct NameEmit {
+    unsigned long long acc;
+    int o;
+    char *dst;
+    __device__ __forceinline__ void put(unsigned long long v, int n)        // 1 <= n <= 8
+    {
+        const int k = o & 7;
+        acc |= v << (8 * k);
+        if (k + n >= 8) {
+            *reinterpret_cast<unsigned long long *>(dst + (o - k)) = acc;
+            acc = k ? v >> (8 * (8 - k)) : 0ull;
+        }
+        o += n;
     }
-    buf[o++] = '_';
+    __device__ __forceinline__ void finish() { if (o & 7) *reinterpret_cast<unsigned long long *>(dst + (o & ~7)) = acc; }
+};
+// the decimal digits of v < 10^8 as ASCII bytes, first digit lowest; *nd = how many (`fixed`: exactly 8, zero padded)
+__device__ __forceinline__ unsigned long long dec_bytes(uint32_t v, int *nd, bool fixed = false)
+{
+    unsigned long long d = 0;
+    int n = 0;
+    do { d = (d << 8) | (unsigned long long)('0' + v % 10u); v /= 10u; ++n; } while (fixed ? n < 8 : v != 0u);
+    *nd = n;
+    return d;
+}
+// separator + decimal number
+__device__ __forceinline__ void put_field(NameEmit &E, uint32_t sep, uint32_t v)
+{
+    if (v < 10u) { E.put(sep | ((unsigned long long)('0' + v) << 8), 2); return; }     // strands, flags and most counts
+    int nd;
+    if (v >= 100000000u) {
+        const unsigned long long hi = dec_bytes(v / 100000000u, &nd);
+        E.put(sep | (hi << 8), nd + 1);
+        E.put(dec_bytes(v % 100000000u, &nd, true), 8);
+        return;
+    }
+    const unsigned long long d = dec_bytes(v, &nd);
+    if (nd < 8) E.put(sep | (d << 8), nd + 1);
+    else { E.put(sep, 1); E.put(d, 8); }
+}
+__device__ __forceinline__ unsigned long long hex_bytes(uint32_t v, int nd)      // nd <= 8 hexadecimal digits of v, first digit lowest
+{
+    unsigned long long d = 0;
+    for (int j = 0; j < nd; ++j) { const uint32_t h = v & 15u; d = (d << 8) | (unsigned long long)('0' + h + (h > 9u ? 39u : 0u)); v >>= 4; }
+    return d;
+}
+__device__ __forceinline__ int write_name_words(const SimParams &P, const PairRec &r, uint64_t serial, const char *cname,
+                                                int cname_len, int variant, char *row)
+{
+    NameEmit E;
+    E.acc = 0; E.o = 0; E.dst = row;
+    E.put('@', 1);
+    for (int j = 0; j < P.prefix_len; ++j) E.put((unsigned long long)(uint8_t)P.prefix[j], 1);
+    if (r.flags & kRecRandom) E.put(0x646e6172ull, 4);                          // "rand"
+    else for (int j = 0; j < cname_len; ++j) E.put((unsigned long long)(uint8_t)cname[j], 1);
+#pragma unroll
+    for (int f = 0; f < 12; ++f)
+        put_field(E, (f == 7 || f == 8 || f == 10 || f == 11) ? ':' : '_', (uint32_t)name_field(r, serial, f, variant));
     const int nd = ndigits16(serial);
-    for (int d = nd - 1; d >= 0; --d) { const uint32_t h = (uint32_t)(serial >> (4 * d)) & 15u; buf[o++] = (char)(h < 10 ? '0' + h : 'a' + h - 10); }
-    return o;
+    if (nd > 8) {
+        E.put('_' | (hex_bytes((uint32_t)(serial >> 32), nd - 8) << 8), nd - 7);
+        E.put(hex_bytes((uint32_t)serial, 8), 8);
+    } else if (nd == 8) { E.put('_', 1); E.put(hex_bytes((uint32_t)serial, 8), 8); }
+    else E.put('_' | (hex_bytes((uint32_t)serial, nd) << 8), nd + 1);
+    E.finish();
+    return E.o;
 }
 
 // ---- layout kernels --------------------------------------------------------------------------------------
@@ -1376,7 +1419,10 @@ layout_scan_blocks_kernel(unsigned long long *__restrict__ v, int m, int n_array
 }
 
 // serial (ii or rand_ii) + record lengths per pair, block sums of the lengths
-__global__ void __launch_bounds__(kThreads)
+#ifndef DWG_LAYOUT_MIN_BLOCKS
+#define DWG_LAYOUT_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kThreads, DWG_LAYOUT_MIN_BLOCKS)
 layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const PairRec *__restrict__ recs, int n,
                       int64_t first, unsigned long long rand_base, const unsigned long long *__restrict__ rand_base_dev,
                       const unsigned long long *__restrict__ blk_rand_excl,
@@ -1412,13 +1458,7 @@ layout_lengths_kernel(const SimParams P, const uint8_t *__restrict__ blob, const
             const int nvar = (P.data_type == 1 && P.out_bwa) ? 2 : 1;
             for (int v = 0; v < nvar; ++v) {
                 char *dst = names + ((size_t)(base + t) * nvar + v) * P.name_cap;   // name_cap is a multiple of 16
-                int nl;
-                if (P.name_cap <= 256) {               // assemble locally, store 16 bytes at a time
-                    __align__(16) char tmp[256];
-                    nl = write_name(P, rt, ser, cname, (int)cd->name_len, v, tmp);
-                    for (int x = 0; x < nl; x += 16) *reinterpret_cast<uint4 *>(dst + x) = *reinterpret_cast<const uint4 *>(tmp + x);
-                } else nl = write_name(P, rt, ser, cname, (int)cd->name_len, v, dst);
-                nl_v[v] = nl;
+                nl_v[v] = write_name_words(P, rt, ser, cname, (int)cd->name_len, v, dst);
             }
             if (nvar == 1) nl_v[1] = nl_v[0];
             *reinterpret_cast<uint32_t *>(name_len + (size_t)(base + t) * 2) = (uint32_t)nl_v[0] | ((uint32_t)nl_v[1] << 16);
