@@ -870,8 +870,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());
     // (a copy would queue behind the batch-sized device-to-host transfers of the previous batches on the copy engine)
-    publish_words_kernel<<<1, 32, 0, st>>>(w.h_totals_dev, w.totals, 4);
-    publish_words_kernel<<<1, 32, 0, st>>>(w.h_totals_dev + 8, w.status, 2);
+    publish_batch_kernel<<<1, 32, 0, st>>>(w.h_totals_dev, w.totals, w.status);
     *launches = 4;
     return DWGSIM_GPU_OK;
 }

@@ -1224,6 +1224,14 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
     if (failed_total) atomicAdd(status + 1, (unsigned long long)failed_total);
 }
 
+// the result words of a batch to mapped host memory in one launch: totals[0..3] -> dst[0..3], status[0..1] -> dst[8..9]
+__global__ void publish_batch_kernel(unsigned long long *__restrict__ dst_host, const unsigned long long *__restrict__ totals,
+                                     const unsigned long long *__restrict__ status)
+{
+    if (threadIdx.x < 4) dst_host[threadIdx.x] = totals[threadIdx.x];
+    else if (threadIdx.x < 6) dst_host[8 + threadIdx.x - 4] = status[threadIdx.x - 4];
+    __threadfence_system();
+}
 // a few 64-bit results to mapped host memory (no copy engine involved)
 __global__ void publish_words_kernel(unsigned long long *__restrict__ dst_host, const unsigned long long *__restrict__ src, int n)
 {
