@@ -73,3 +73,27 @@ def test_determinism_and_batch_split_independence(gpu):
     h2, _ = streams(gpu, first + 25_000, n - 25_000, rand_base=777 + b1.n_random)
     for k in range(3):
         assert h1[k] + h2[k] == whole[k]
+
+
+@pytest.mark.parametrize("base", [0xFFFFFFF0, (1 << 36) + 5])
+def test_random_pair_serials_of_eight_and_more_hex_digits(gpu, base):
+    """the running count of random pairs (rand_ii, src/dwgsim.c:1096) is printed in hexadecimal at the end of the name: the
+    name writer assembles eight digits per store, so cross 2^32 and go past it"""
+    first, n = 150_000_000, 4_000
+    (r1, r2, bf), b = streams(gpu, first, n, rand_base=base)
+    (s1, _, _), _ = streams(gpu, first, n, rand_base=0)
+    l0, l1 = s1.split(b"\n"), r1.split(b"\n")
+    assert l0[1::4] == l1[1::4] and l0[3::4] == l1[3::4]          # bases and qualities do not depend on the count
+    k = 0
+    for small, big in zip(l0[0:-1:4], l1[0:-1:4]):
+        ms, mb = NAME.match(small[:-2]), NAME.match(big[:-2])
+        assert ms and mb, (small, big)
+        if mb.group(1) == b"rand":
+            assert int(ms.group(14), 16) == k and int(mb.group(14), 16) == base + k
+            assert mb.group(14) == b"%x" % (base + k)              # no leading zeros
+            k += 1
+        else:
+            assert small == big
+    assert k == b.n_random and k > 100
+    names2 = r2.split(b"\n")[0:-1:4]
+    assert [x[:-2] for x in names2] == [x[:-2] for x in l1[0:-1:4]] and bf.split(b"\n")[0::8][:-1] == [x[:-2] for x in l1[0:-1:4]]
