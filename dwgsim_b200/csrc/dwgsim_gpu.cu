@@ -220,6 +220,23 @@ format_kernel_t format_kernel_of(const SimParams &sp)
 }
 
 // dynamic shared memory of simulate_pairs_tp_kernel: staging tile + sampling tables (see the kernel prologue)
+// the instance of the word-granular format kernel for a configuration: colour space x quality mode
+using format2_kernel_t = void (*)(const SimParams, const Format2Smem, int64_t, int64_t, int, const PairRec *, const uint32_t *, const uint32_t *,
+                                  const unsigned long long *, const char *, const uint16_t *, char *, char *, char *);
+template <bool kSolid, int kQMode>
+format2_kernel_t format2_kernel_out(int out)
+{
+    return out == 1 ? format_fastq2_kernel<kSolid, kQMode, 1> : (out == 2 ? format_fastq2_kernel<kSolid, kQMode, 2> : format_fastq2_kernel<kSolid, kQMode, 3>);
+}
+format2_kernel_t format2_kernel_of(const SimParams &sp)
+{
+    const int qmode = sp.fixed_quality ? 2 : (sp.qdelta_n > 0 ? 1 : 0);       // 0: no noise, 1: noise table, 2: fixed character
+    const int out = (sp.out_bwa ? 1 : 0) | (sp.out_bfast ? 2 : 0);
+    if (sp.data_type == 1)
+        return qmode == 2 ? format2_kernel_out<true, 2>(out) : (qmode == 1 ? format2_kernel_out<true, 1>(out) : format2_kernel_out<true, 0>(out));
+    return qmode == 2 ? format2_kernel_out<false, 2>(out) : (qmode == 1 ? format2_kernel_out<false, 1>(out) : format2_kernel_out<false, 0>(out));
+}
+
 // the instance of the thread-per-pair simulate kernel for a configuration (SimParams.tp_tables is 3 or 0)
 using tp_kernel_t = void (*)(const SimParams, const uint8_t *, int64_t, int64_t, int, int, JobLists, PairRec *, uint32_t *, unsigned long long *, uint32_t *);
 tp_kernel_t tp_kernel_of(const SimParams &sp)
@@ -581,8 +598,7 @@ int update_caps(dwgsim_gpu *h)
         while (h->sp.fmt_warps > 1 && format2_smem_layout(h->sp).total > 227 * 1024) --h->sp.fmt_warps;
         const Format2Smem L2 = format2_smem_layout(h->sp);
         if (L2.total > 227 * 1024) { h->last_error = "reads / names too long for the format kernel's shared memory"; return DWGSIM_GPU_EUNSUPPORTED; }
-        if (h->sp.data_type == 1) CUDA_TRY(h, cudaFuncSetAttribute(format_fastq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
-        else CUDA_TRY(h, cudaFuncSetAttribute(format_fastq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+        CUDA_TRY(h, cudaFuncSetAttribute(format2_kernel_of(h->sp), cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
         return DWGSIM_GPU_OK;
     }
     h->sp.fmt_warps = kFmtWarps;
@@ -851,12 +867,8 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
         const size_t smem_2 = (size_t)L2.total;
         const int ctas = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;  // CTAs that have a mini-tile per warp
         const int grid_f = std::min(ctas, sm_count);
-        if (sp.data_type == 1)
-            format_fastq2_kernel<true><<<grid_f, fmt_threads, smem_2, st>>>(sp, L2, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
-                                                                            w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
-        else
-            format_fastq2_kernel<false><<<grid_f, fmt_threads, smem_2, st>>>(sp, L2, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
-                                                                             w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
+        format2_kernel_of(sp)<<<grid_f, fmt_threads, smem_2, st>>>(sp, L2, first, h->gidx_origin, n, w.recs, w.seqs, w.lens, w.totals + 1,
+                                                                  w.names, w.name_len, w.out[slot][0], w.out[slot][1], w.out[slot][2]);
     } else {
         const int fmt_warps = sp.fmt_warps > 0 ? sp.fmt_warps : kFmtWarps, fmt_threads = 32 * fmt_warps;
         const int ntiles = ((n + sp.tile_pairs - 1) / sp.tile_pairs + fmt_warps - 1) / fmt_warps;    // CTAs that have a mini-tile per warp

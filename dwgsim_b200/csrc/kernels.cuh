@@ -1987,7 +1987,8 @@ __device__ __forceinline__ uint32_t merge_low(uint32_t c, uint32_t v, int nb)
 }
 template <typename T> __device__ __forceinline__ T pick3(int k, T a, T b, T c) { return k == 0 ? a : (k == 1 ? b : c); }
 
-template <bool kSolid>
+template <bool kSolid, int kQMode /* qualities: 0 no noise, 1 noise table, 2 fixed character (-Q / fixed quality) */,
+          int kOut /* bit 0: the two bwa files, bit 1: the bfast file (-o) */>
 __global__ void __launch_bounds__(kFmt2ThreadsMax, 1)
 format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int64_t gidx_origin, int n,
                      const PairRec *__restrict__ recs, const uint32_t *__restrict__ seqw,
@@ -1998,7 +1999,7 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int WP = P.tile_pairs, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qmode = P.fixed_quality ? 2 : (P.qdelta_n > 0 ? 1 : 0);          // 0: no noise, 1: noise table, 2: fixed character
+    constexpr int qmode = kQMode;
     uint32_t a_qtab, a_qb0, a_qb1, a_rm, a_nm, a_st0, a_st1, a_st2, a_pre, a_names, a_carry;
     const uint32_t *cdf;
     {
@@ -2026,8 +2027,8 @@ format_fastq2_kernel(const SimParams P, const Format2Smem L, int64_t first, int6
     constexpr bool solid = kSolid;
     constexpr int from = kSolid ? 1 : 0;                            // bwa drops the first colour (src/dwgsim.c:949-953)
     constexpr int sfx_f = kSolid ? 2 : 1;                           // bytes between a bfast name and its first base: "\n" ("\nA")
-    const int nvar = (solid && P.out_bwa) ? 2 : 1;                  // SOLiD bwa names carry reduced counts (:945-946)
-    const bool on0 = P.out_bwa != 0, on2 = P.out_bfast != 0;
+    constexpr int nvar = (kSolid && (kOut & 1)) ? 2 : 1;            // SOLiD bwa names carry reduced counts (:945-946)
+    constexpr bool on0 = (kOut & 1) != 0, on2 = (kOut & 2) != 0;
     const int ntiles = (n + WP - 1) / WP;
     constexpr uint32_t full = 0xffffffffu;
     const uint32_t al0 = (uint32_t)reinterpret_cast<uintptr_t>(out0) & 15u, al1 = (uint32_t)reinterpret_cast<uintptr_t>(out1) & 15u,
