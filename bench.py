@@ -11,6 +11,8 @@ A step = `device_batches_per_step` consecutive device batches of PAIRS_PER_BATCH
 whole hot path (simulate -> layout -> format), genome resident in HBM, FASTQ bytes left in HBM (`value`); the number of
 batches per step is chosen after the warm-up so that the K timed steps last at least MIN_TIMED_S seconds (the whole
 326 M-pair job is well under a second of kernel time, so the timed region walks the job's pair indices more than once).
+The batches of a step are queued back to back on the library's stream (dwgsim_gpu_resident_enqueue; rand_ii continues in
+device memory) with one host wait per step; the per-kernel times of the roofline are those of each step's last batch.
 `configs` repeats the kernel-path measurement for BASELINE.json configs[2..4] (-R 0.15, SOLiD 2x50, Ion Torrent 400 bp SE).
 `e2e` drives the C ABI the way the reference host would: dense seq_t/mutseq_t host arrays in (dwgsim_gpu_add_contig),
 .fastq.gz bytes out through dwgsim_gpu_run to host memory in pair order; `e2e.file_sink` also writes them to new files
@@ -323,7 +325,9 @@ class KernelPath:
             self.base_t = torch.zeros(1, dtype=torch.int64, device="cuda")
             self.running_t = torch.zeros(1, dtype=torch.int64, device="cuda")
 
-    def batch(self):
+    def enqueue(self):
+        """one device batch queued behind the previous ones on the library's stream: no host wait (rand_ii continues in device
+        memory: the library's running counter at N = 1, the all-gathered counts at N > 1)"""
         torch, dist, gpu = self.torch, self.dist, self.gpu
         first = ((self.batch_no % self.n_avail) * self.world + self.rank) * self.B
         self.batch_no += 1
@@ -333,12 +337,15 @@ class KernelPath:
             with torch.cuda.stream(self.stream):
                 dist.all_gather_into_tensor(self.allc, cnt)
                 torch.add(self.running_t, self.allc[:self.rank].sum(), out=self.base_t)
-                b = gpu.resident_finish_dev(self.base_t.data_ptr())
+                gpu.resident_finish_async(self.base_t.data_ptr())
                 self.running_t.add_(self.allc.sum())
         else:
-            b = gpu.simulate_resident(first, self.B, self.rand_base)
-            self.rand_base += b.n_random
-        return b
+            gpu.resident_enqueue(first, self.B)
+
+    def batch(self):
+        """one device batch, waited for"""
+        self.enqueue()
+        return self.gpu.resident_wait()
 
     def measure(self, steps, warmup, min_seconds, sampler=None):
         """`warmup` untimed steps, then exactly `steps` timed steps of `per_step` device batches each"""
@@ -368,14 +375,18 @@ class KernelPath:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(self.stream)
         ms = [0.0, 0.0, 0.0]
-        out_bytes = launches = 0
+        out_bytes = launches = sampled = 0
         t_wall0 = time.perf_counter()
         for _ in range(steps):
+            # the batches of a step are queued back to back; one host wait per step.  The kernel times and sizes of the step's
+            # last batch are the sample of the per-kernel figures below
             for _ in range(per_step):
-                b = self.batch()
-                ms[0] += b.ms_simulate; ms[1] += b.ms_layout; ms[2] += b.ms_format
-                out_bytes += sum(b.n_bytes)
-                launches += b.n_launches
+                self.enqueue()
+            b = self.gpu.resident_wait()
+            ms[0] += b.ms_simulate; ms[1] += b.ms_layout; ms[2] += b.ms_format
+            out_bytes += sum(b.n_bytes)
+            launches += b.n_launches
+            sampled += 1
         ev1.record(self.stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -393,23 +404,24 @@ class KernelPath:
         peak, peak_src = peak_hbm()
         L = self.w["opts"]["length"]
         read_bytes = sum(((x + 3) // 4) * 1.5 for x in L if x > 0) + 5.0
-        fastq_per_unit = out_bytes / (self.B * n_batches)
+        fastq_per_unit = out_bytes / (self.B * sampled)
         algo = ALGO_BYTES_PER_PAIR if self.name == "illumina_2x150" else read_bytes + fastq_per_unit
-        kern_ms = sum(ms) / n_batches
+        kern_ms = sum(ms) / sampled
         achieved = algo * self.B / (kern_ms * 1e-3) / 1e9
         names = ["simulate_pairs_tp_kernel", "layout_* (5 scan kernels)", "format_fastq_kernel"]
         dom = max(range(3), key=lambda i: ms[i])
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "algorithmic_bytes_per_unit": algo, "fastq_bytes_per_unit": fastq_per_unit,
                     "kernel": "whole device batch = simulate + layout + format; dominant: %s" % names[dom],
-                    "ms_per_batch_by_kernel": {n: m / n_batches for n, m in zip(names, ms)}}
-        fmt_ms = ms[2] / n_batches
+                    "ms_per_batch_by_kernel": {n: m / sampled for n, m in zip(names, ms)},
+                    "sampled_batches": sampled}
+        fmt_ms = ms[2] / sampled
         if fmt_ms > 0:        # the formatter alone: its algorithmic bytes are the FASTQ text it writes
-            fmt_bytes = out_bytes / n_batches
+            fmt_bytes = out_bytes / sampled
             roofline["dominant_kernel" if dom == 2 else "format_kernel"] = {
                 "name": "format_fastq_kernel", "ms": fmt_ms, "algorithmic_bytes": fmt_bytes,
                 "achieved": fmt_bytes / (fmt_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": fmt_bytes / (fmt_ms * 1e-3) / 1e9 / peak}
-        sim_ms = ms[0] / n_batches
+        sim_ms = ms[0] / sampled
         if dom == 0 and sim_ms > 0:
             roofline["dominant_kernel"] = {"name": "simulate_pairs_tp_kernel", "ms": sim_ms,
                                            "algorithmic_bytes": algo * self.B, "achieved": algo * self.B / (sim_ms * 1e-3) / 1e9,

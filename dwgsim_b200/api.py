@@ -276,6 +276,22 @@ class DwgsimGpu:
         self._check(self._L.dwgsim_gpu_resident_finish_dev(self._h, rand_serial_base_device_ptr, C.byref(b)))
         return b
 
+    def resident_set_running(self, rand_serial):
+        self._check(self._L.dwgsim_gpu_resident_set_running(self._h, rand_serial))
+
+    def resident_enqueue(self, first, n):
+        """queue one batch behind the previous ones (no host sync); rand_ii continues in device memory"""
+        self._check(self._L.dwgsim_gpu_resident_enqueue(self._h, first, n))
+
+    def resident_finish_async(self, rand_serial_base_device_ptr):
+        self._check(self._L.dwgsim_gpu_resident_finish_async(self._h, rand_serial_base_device_ptr))
+
+    def resident_wait(self):
+        """wait for the queued batches; describes the last one"""
+        b = Batch()
+        self._check(self._L.dwgsim_gpu_resident_wait(self._h, C.byref(b)))
+        return b
+
     def copy_stream(self, file_id, n_bytes):
         buf = C.create_string_buffer(max(int(n_bytes), 1))
         self._check(self._L.dwgsim_gpu_copy_stream(self._h, file_id, buf, n_bytes))

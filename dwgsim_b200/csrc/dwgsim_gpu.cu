@@ -198,6 +198,11 @@ struct dwgsim_gpu {
     dwgsim_gpu_exchange_fn exchange = nullptr;
     void *exchange_user = nullptr;
     int64_t pending_first = -1; int pending_n = 0, pending_launches = 0;
+    // batches queued without a host sync (dwgsim_gpu_resident_enqueue / _finish_async)
+    unsigned long long *queue_dev = nullptr;   // [0] running count of random pairs, [1] error bits since the last wait
+    bool queue_active = false;                 // the batch being launched belongs to the queue; advance [0] with it?
+    bool queue_advance = false;
+    int queued_launches = 0, queued_n = 0;
     Workspace ws;
     char *pinned[8][3] = {};
     uint64_t pinned_cap[3] = {0, 0, 0};
@@ -882,7 +887,7 @@ int launch_format(dwgsim_gpu *h, int64_t first, int n, int64_t rand_base, int sl
     if (timed) CUDA_TRY(h, cudaEventRecord(h->ev_t[3], st));
     CUDA_TRY(h, cudaGetLastError());
     // (a copy would queue behind the batch-sized device-to-host transfers of the previous batches on the copy engine)
-    publish_batch_kernel<<<1, 32, 0, st>>>(w.h_totals_dev, w.totals, w.status);
+    publish_batch_kernel<<<1, 32, 0, st>>>(w.h_totals_dev, w.totals, w.status, h->queue_active ? h->queue_dev : nullptr, h->queue_advance ? 1 : 0);
     *launches = 4;
     return DWGSIM_GPU_OK;
 }
@@ -1149,6 +1154,7 @@ void dwgsim_gpu_destroy(dwgsim_gpu_t *h)
     free_workspace(h);
     free_blob(h);
     cudaFree(h->blob_spare);
+    cudaFree(h->queue_dev);
     cudaFree(h->dt.isize_cdf); cudaFree(h->dt.qdelta_cdf); cudaFree(h->dt.qguide); cudaFree(h->dt.qtab); cudaFree(h->dt.isize_guide); cudaFree(h->dt.gap_guide[0]); cudaFree(h->dt.gap_guide[1]);
     for (int e = 0; e < 2; ++e) { cudaFree(h->dt.err_gap[e]); cudaFree(h->dt.err_acc[e]); cudaFree(h->dt.qbase[e]); }
     cudaFree(h->dt.flow_order); cudaFree(h->dt.prefix); cudaFree(h->dt.flow_gap[0]); cudaFree(h->dt.flow_gap[1]);
@@ -1406,6 +1412,82 @@ int resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, const unsigned lo
 int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim_gpu_batch_t *out)
 {
     return resident_finish(h, rand_serial_base, nullptr, out);
+}
+
+// ---- batches queued back to back: no host round trip between them -----------------------------------------------------
+namespace {
+int queue_ready(dwgsim_gpu_t *h)
+{
+    if (h->queue_dev) return DWGSIM_GPU_OK;
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMalloc((void **)&h->queue_dev, 16));
+    CUDA_TRY(h, cudaMemset(h->queue_dev, 0, 16));
+    return DWGSIM_GPU_OK;
+}
+// layout + format of the batch begun last, queued behind its simulate passes; nothing is waited for
+int queue_finish(dwgsim_gpu_t *h, const unsigned long long *rand_base_dev, bool advance)
+{
+    if (h->pending_first < 0) return DWGSIM_GPU_ESTATE;
+    int launches = 0;
+    const int64_t first = h->pending_first;
+    const int n = h->pending_n;
+    h->pending_first = -1;
+    h->queue_active = true; h->queue_advance = advance;
+    const int rc = launch_format(h, first, n, 0, 0, true, &launches, rand_base_dev);
+    h->queue_active = h->queue_advance = false;
+    if (rc) return rc;
+    h->queued_launches += launches + h->pending_launches;
+    h->queued_n = n;
+    return DWGSIM_GPU_OK;
+}
+}  // namespace
+
+int dwgsim_gpu_resident_set_running(dwgsim_gpu_t *h, int64_t rand_serial)
+{
+    if (!h || rand_serial < 0) return DWGSIM_GPU_EINVAL;
+    int rc = queue_ready(h);
+    if (rc) return rc;
+    const unsigned long long v = (unsigned long long)rand_serial;
+    CUDA_TRY(h, cudaMemcpyAsync(h->queue_dev, &v, 8, cudaMemcpyHostToDevice, h->s_compute));
+    CUDA_TRY(h, cudaStreamSynchronize(h->s_compute));
+    return DWGSIM_GPU_OK;
+}
+
+int dwgsim_gpu_resident_enqueue(dwgsim_gpu_t *h, int64_t first, int64_t n)
+{
+    if (!h) return DWGSIM_GPU_EINVAL;
+    int rc = queue_ready(h);
+    if (rc || (rc = dwgsim_gpu_resident_begin(h, first, n, nullptr))) return rc;
+    return queue_finish(h, h->queue_dev, true);
+}
+
+int dwgsim_gpu_resident_finish_async(dwgsim_gpu_t *h, uint64_t rand_serial_base_device_ptr)
+{
+    if (!h || !rand_serial_base_device_ptr) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    int rc = queue_ready(h);
+    if (rc) return rc;
+    return queue_finish(h, reinterpret_cast<const unsigned long long *>((uintptr_t)rand_serial_base_device_ptr), false);
+}
+
+int dwgsim_gpu_resident_wait(dwgsim_gpu_t *h, dwgsim_gpu_batch_t *out)
+{
+    if (!h || !out || !h->queue_dev || h->queued_n <= 0) return DWGSIM_GPU_ESTATE;
+    cudaSetDevice(h->device);
+    BatchResult r;
+    int rc = collect_batch(h, true, &r);
+    const unsigned long long bits = h->ws.h_totals[10];            // error bits of every batch since the last wait
+    CUDA_TRY(h, cudaMemsetAsync(h->queue_dev + 1, 0, 8, h->s_compute));
+    if (rc == DWGSIM_GPU_OK && (bits & 1ull)) { h->last_error = "failed to generate a read after 10001 trials"; rc = DWGSIM_GPU_ETRIALS; }
+    if (rc == DWGSIM_GPU_OK && (bits & 2ull)) { h->last_error = "Ion Torrent read grew past 2*len+64 bases"; rc = DWGSIM_GPU_EOVERFLOW; }
+    memset(out, 0, sizeof *out);
+    for (int k = 0; k < 3; ++k) { out->dev_ptr[k] = (uint64_t)(uintptr_t)h->ws.out[0][k]; out->n_bytes[k] = r.bytes[k]; h->last_bytes[k] = r.bytes[k]; }
+    h->last_slot = 0;
+    out->n_pairs = h->queued_n; out->n_random = r.n_random; out->n_failed_attempts = r.n_failed;
+    out->ms_simulate = r.ms[0]; out->ms_layout = r.ms[1]; out->ms_format = r.ms[2];
+    out->n_launches = h->queued_launches;
+    h->queued_launches = 0; h->queued_n = 0;
+    return rc;
 }
 
 int dwgsim_gpu_resident_count_ptr(dwgsim_gpu_t *h, uint64_t *count_device_ptr)

@@ -1225,11 +1225,19 @@ simulate_pairs_tp_kernel(const SimParams P, const uint8_t *__restrict__ blob, in
 }
 
 // the result words of a batch to mapped host memory in one launch: totals[0..3] -> dst[0..3], status[0..1] -> dst[8..9]
+// `queue` (batches queued without a host sync in between, dwgsim_gpu_resident_enqueue): [0] the running count of random
+// pairs, advanced by this batch when `advance`; [1] the error bits of all batches since the last wait -> dst[10]
 __global__ void publish_batch_kernel(unsigned long long *__restrict__ dst_host, const unsigned long long *__restrict__ totals,
-                                     const unsigned long long *__restrict__ status)
+                                     const unsigned long long *__restrict__ status, unsigned long long *__restrict__ queue, int advance)
 {
     if (threadIdx.x < 4) dst_host[threadIdx.x] = totals[threadIdx.x];
     else if (threadIdx.x < 6) dst_host[8 + threadIdx.x - 4] = status[threadIdx.x - 4];
+    else if (threadIdx.x == 6 && queue) {
+        if (advance) queue[0] += totals[0];
+        const unsigned long long bits = queue[1] | status[0];
+        queue[1] = bits;
+        dst_host[10] = bits;
+    }
     __threadfence_system();
 }
 // a few 64-bit results to mapped host memory (no copy engine involved)

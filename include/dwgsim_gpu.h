@@ -202,6 +202,16 @@ int dwgsim_gpu_resident_finish(dwgsim_gpu_t *h, int64_t rand_serial_base, dwgsim
  * collective and the prefix arithmetic between the two calls on that stream. */
 int dwgsim_gpu_resident_count_ptr(dwgsim_gpu_t *h, uint64_t *count_device_ptr);
 int dwgsim_gpu_resident_finish_dev(dwgsim_gpu_t *h, uint64_t rand_serial_base_device_ptr, dwgsim_gpu_batch_t *out);
+/* Batches queued back to back, no host round trip between them.  enqueue() = begin + finish on the library's stream, returning
+ * at once; the running count of random pairs (rand_ii, src/dwgsim.c:1096) lives in device memory: set_running() sets it,
+ * every enqueue()d batch starts from it and adds its own.  finish_async() is finish_dev() without the wait (sharded runs: the
+ * caller's collective wrote rand_serial_base to device memory; the library's counter is left alone).  wait() waits for
+ * everything queued and describes the LAST batch (sizes, pointers, timings); n_launches and the error status cover every
+ * batch since the previous wait.  Each batch overwrites the previous one's device buffers. */
+int dwgsim_gpu_resident_set_running(dwgsim_gpu_t *h, int64_t rand_serial);
+int dwgsim_gpu_resident_enqueue(dwgsim_gpu_t *h, int64_t first, int64_t n);
+int dwgsim_gpu_resident_finish_async(dwgsim_gpu_t *h, uint64_t rand_serial_base_device_ptr);
+int dwgsim_gpu_resident_wait(dwgsim_gpu_t *h, dwgsim_gpu_batch_t *out);
 /* copy one stream of the last resident batch to host memory (tests) */
 int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap);
 /* Queue a synthetic genome built procedurally inside the library (benchmarks only; no dense

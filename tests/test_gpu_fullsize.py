@@ -97,3 +97,25 @@ def test_random_pair_serials_of_eight_and_more_hex_digits(gpu, base):
     assert k == b.n_random and k > 100
     names2 = r2.split(b"\n")[0:-1:4]
     assert [x[:-2] for x in names2] == [x[:-2] for x in l1[0:-1:4]] and bf.split(b"\n")[0::8][:-1] == [x[:-2] for x in l1[0:-1:4]]
+
+
+def test_queued_batches_equal_waited_batches(gpu):
+    """dwgsim_gpu_resident_enqueue queues batches without a host wait; rand_ii continues from the counter in device memory"""
+    first, n, base = 120_000_000, 30_000, 4242
+    want, run = [], base
+    for k in range(3):                                   # three waited batches, the running count carried on the host
+        s, b = streams(gpu, first + k * n, n, rand_base=run)
+        want.append(s)
+        run += b.n_random
+        per_batch = b.n_launches
+    gpu.resident_set_running(base)
+    for k in range(3):
+        gpu.resident_enqueue(first + k * n, n)
+    b = gpu.resident_wait()
+    got = [gpu.copy_stream(k, b.n_bytes[k]) for k in range(3)]
+    assert got == want[2] and b.n_pairs == n and b.n_launches == 3 * per_batch
+    gpu.resident_enqueue(first + 3 * n, n)               # the counter went on: batch 3 continues where batch 2 ended
+    b3 = gpu.resident_wait()
+    got3 = [gpu.copy_stream(k, b3.n_bytes[k]) for k in range(3)]
+    s3, _ = streams(gpu, first + 3 * n, n, rand_base=run)
+    assert got3 == s3
