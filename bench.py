@@ -336,9 +336,7 @@ class KernelPath:
             cnt = torch.as_tensor(_CudaArray(gpu.resident_count_ptr(), 8), device="cuda").view(torch.int64)
             with torch.cuda.stream(self.stream):
                 dist.all_gather_into_tensor(self.allc, cnt)
-                torch.add(self.running_t, self.allc[:self.rank].sum(), out=self.base_t)
-                gpu.resident_finish_async(self.base_t.data_ptr())
-                self.running_t.add_(self.allc.sum())
+                gpu.resident_finish_gathered(self.allc.data_ptr(), self.world, self.rank)   # prefix of the counts: one kernel of the library
         else:
             gpu.resident_enqueue(first, self.B)
 

@@ -86,6 +86,7 @@ SYMBOLS = {
     "dwgsim_gpu_resident_set_running": (C.c_int, [_P, C.c_int64]),
     "dwgsim_gpu_resident_enqueue": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "dwgsim_gpu_resident_finish_async": (C.c_int, [_P, C.c_uint64]),
+    "dwgsim_gpu_resident_finish_gathered": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
     "dwgsim_gpu_resident_wait": (C.c_int, [_P, C.POINTER(Batch)]),
     "dwgsim_gpu_set_origin": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "dwgsim_gpu_genome_finalize": (C.c_int, [_P]),

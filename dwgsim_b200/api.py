@@ -286,6 +286,9 @@ class DwgsimGpu:
     def resident_finish_async(self, rand_serial_base_device_ptr):
         self._check(self._L.dwgsim_gpu_resident_finish_async(self._h, rand_serial_base_device_ptr))
 
+    def resident_finish_gathered(self, counts_device_ptr, world, rank):
+        self._check(self._L.dwgsim_gpu_resident_finish_gathered(self._h, counts_device_ptr, world, rank))
+
     def resident_wait(self):
         """wait for the queued batches; describes the last one"""
         b = Batch()

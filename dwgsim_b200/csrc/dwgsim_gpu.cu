@@ -199,7 +199,8 @@ struct dwgsim_gpu {
     void *exchange_user = nullptr;
     int64_t pending_first = -1; int pending_n = 0, pending_launches = 0;
     // batches queued without a host sync (dwgsim_gpu_resident_enqueue / _finish_async)
-    unsigned long long *queue_dev = nullptr;   // [0] running count of random pairs, [1] error bits since the last wait
+    unsigned long long *queue_dev = nullptr;   // [0] running count of random pairs, [1] error bits since the last wait,
+                                               // [2] count before this rank's batch (dwgsim_gpu_resident_finish_gathered)
     bool queue_active = false;                 // the batch being launched belongs to the queue; advance [0] with it?
     bool queue_advance = false;
     int queued_launches = 0, queued_n = 0;
@@ -1420,8 +1421,8 @@ int queue_ready(dwgsim_gpu_t *h)
 {
     if (h->queue_dev) return DWGSIM_GPU_OK;
     cudaSetDevice(h->device);
-    CUDA_TRY(h, cudaMalloc((void **)&h->queue_dev, 16));
-    CUDA_TRY(h, cudaMemset(h->queue_dev, 0, 16));
+    CUDA_TRY(h, cudaMalloc((void **)&h->queue_dev, 32));
+    CUDA_TRY(h, cudaMemset(h->queue_dev, 0, 32));
     return DWGSIM_GPU_OK;
 }
 // layout + format of the batch begun last, queued behind its simulate passes; nothing is waited for
@@ -1468,6 +1469,16 @@ int dwgsim_gpu_resident_finish_async(dwgsim_gpu_t *h, uint64_t rand_serial_base_
     int rc = queue_ready(h);
     if (rc) return rc;
     return queue_finish(h, reinterpret_cast<const unsigned long long *>((uintptr_t)rand_serial_base_device_ptr), false);
+}
+
+int dwgsim_gpu_resident_finish_gathered(dwgsim_gpu_t *h, uint64_t counts_device_ptr, int32_t world, int32_t rank)
+{
+    if (!h || !counts_device_ptr || world < 1 || rank < 0 || rank >= world) return DWGSIM_GPU_EINVAL;
+    cudaSetDevice(h->device);
+    int rc = queue_ready(h);
+    if (rc) return rc;
+    gathered_base_kernel<<<1, 32, 0, h->s_compute>>>(reinterpret_cast<const unsigned long long *>((uintptr_t)counts_device_ptr), world, rank, h->queue_dev);
+    return queue_finish(h, h->queue_dev + 2, false);
 }
 
 int dwgsim_gpu_resident_wait(dwgsim_gpu_t *h, dwgsim_gpu_batch_t *out)

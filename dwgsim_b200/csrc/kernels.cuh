@@ -1240,6 +1240,16 @@ __global__ void publish_batch_kernel(unsigned long long *__restrict__ dst_host, 
     }
     __threadfence_system();
 }
+// sharded runs: from the all-gathered random-pair counts of a round (counts[world], rank order = batch order) the count before
+// this rank's batch -> queue[2], and the running count of the whole job queue[0] += all of them
+__global__ void gathered_base_kernel(const unsigned long long *__restrict__ counts, int world, int rank, unsigned long long *__restrict__ queue)
+{
+    unsigned long long before = 0, all = 0;
+    for (int r = threadIdx.x; r < world; r += 32) { const unsigned long long c = counts[r]; all += c; if (r < rank) before += c; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+    if (threadIdx.x == 0) { queue[2] = queue[0] + before; queue[0] += all; }
+}
 // a few 64-bit results to mapped host memory (no copy engine involved)
 __global__ void publish_words_kernel(unsigned long long *__restrict__ dst_host, const unsigned long long *__restrict__ src, int n)
 {

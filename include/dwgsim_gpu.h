@@ -211,6 +211,10 @@ int dwgsim_gpu_resident_finish_dev(dwgsim_gpu_t *h, uint64_t rand_serial_base_de
 int dwgsim_gpu_resident_set_running(dwgsim_gpu_t *h, int64_t rand_serial);
 int dwgsim_gpu_resident_enqueue(dwgsim_gpu_t *h, int64_t first, int64_t n);
 int dwgsim_gpu_resident_finish_async(dwgsim_gpu_t *h, uint64_t rand_serial_base_device_ptr);
+/* the same with the prefix arithmetic done by the library: counts_device_ptr = the all-gathered random-pair counts of the round
+ * (uint64[world], rank order = batch order, on the library's stream); this rank's batch starts at the running count + the counts
+ * of the ranks before it, and the running count advances by all of them */
+int dwgsim_gpu_resident_finish_gathered(dwgsim_gpu_t *h, uint64_t counts_device_ptr, int32_t world, int32_t rank);
 int dwgsim_gpu_resident_wait(dwgsim_gpu_t *h, dwgsim_gpu_batch_t *out);
 /* copy one stream of the last resident batch to host memory (tests) */
 int dwgsim_gpu_copy_stream(dwgsim_gpu_t *h, int file_id, char *dst, uint64_t cap);

@@ -94,3 +94,37 @@ def test_device_side_rand_base_equals_host_path():
         assert seen == b1.n_random == b0.n_random and b0.n_random > 0
         assert [gpu.copy_stream(k, b1.n_bytes[k]) for k in range(3)] == want
         assert b"rand_0_0_0_0_1_1_0:0:0_0:0:0_%x" % base in want[0]          # the first random pair carries the base as rand_ii
+
+
+def test_finish_gathered_takes_the_prefix_of_the_counts_on_the_device():
+    """dwgsim_gpu_resident_finish_gathered (bench.py at N > 1): rand_serial_base = running count + counts of the ranks before
+    this one, computed by a kernel of the library from the all-gathered counts; the running count advances by all of them"""
+    import torch
+    from dwgsim_b200 import DwgsimGpu, params_from_options
+    with DwgsimGpu(params_from_options(seed=5, length=(100, 100), rand_read=0.1)) as gpu:
+        gpu.genome_synthetic([300000, 200000], 11, 0.002, 0.2, 0.01, 10.0)
+        gpu.genome_finalize()
+        n, start = 10000, 1000
+        stream = torch.cuda.ExternalStream(gpu.cuda_stream())
+
+        class Arr:
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        gpu.resident_set_running(700)
+        running = 700
+        for rnd, (before, after) in enumerate(((17, 5), (0, 9))):          # this rank is rank 1 of 3
+            first = start + rnd * n
+            gpu.resident_begin(first, n, False)
+            cnt = torch.as_tensor(Arr(gpu.resident_count_ptr(), 8), device="cuda").view(torch.int64)
+            allc = torch.zeros(3, dtype=torch.int64, device="cuda")
+            with torch.cuda.stream(stream):
+                allc[0] = before
+                allc[1:2].copy_(cnt)
+                allc[2] = after
+                gpu.resident_finish_gathered(allc.data_ptr(), 3, 1)
+            b = gpu.resident_wait()
+            got = [gpu.copy_stream(k, b.n_bytes[k]) for k in range(3)]
+            want_b = gpu.simulate_resident(first, n, running + before)
+            assert got == [gpu.copy_stream(k, want_b.n_bytes[k]) for k in range(3)] and b.n_random == want_b.n_random > 0
+            running += before + b.n_random + after
