@@ -362,7 +362,7 @@ class KernelPath:
             t = torch.tensor([t_batch], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_batch = float(t.item())
-        per_step = max(1, int(min_seconds / (steps * t_batch) + 0.999))
+        per_step = max(1, int(1.05 * min_seconds / (steps * t_batch) + 0.999))     # (the calibration carries some start-up time)
         for _ in range(warmup):
             for _ in range(per_step):
                 self.batch()
